@@ -1,0 +1,134 @@
+"""ctypes binding of libcrgpu.so (include/crgpu.h).  There is no CPU fallback: if the library is
+missing or no B200 is visible, every entry point raises."""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcrgpu.so")
+
+MEM_HOST, MEM_DEVICE = 0, 1
+E_CUDA, E_ARG, E_ALIGN, E_NOMEM = 1, 2, 3, 4
+
+ALN_REC = np.dtype([("score_x2", "<i4"), ("alnlen", "<i4"), ("ident", "<i4"), ("tenths", "<i4"),
+                    ("aln_off", "<i4"), ("start1", "<i4"), ("start2", "<i4"), ("read_len", "<i4")])
+READ_REC = np.dtype([("cls", "u1"), ("pad", "u1", (3,)), ("n_mutated", "<i4"), ("n_inserted", "<i4"),
+                     ("n_deleted", "<i4")])
+NUM_VECTORS = 15
+NUM_COUNTERS = 4
+Q_HAS_HDR, Q_IGNORE_SUBS, Q_IGNORE_INS, Q_IGNORE_DEL, Q_WINDOW, Q_HIDE_OUTSIDE, Q_FRAMESHIFT, Q_MASK_N = (
+    1, 2, 4, 8, 16, 32, 64, 128)
+C_UNMODIFIED, C_NHEJ, C_HDR, C_MIXED = 1, 2, 4, 8
+
+
+class QuantParams(ctypes.Structure):
+    _fields_ = [("amplicon_len", ctypes.c_int32), ("flags", ctypes.c_int32),
+                ("hdr_perfect_alignment_threshold", ctypes.c_double),
+                ("include_mask", ctypes.c_void_p), ("exon_mask", ctypes.c_void_p), ("splice_mask", ctypes.c_void_p)]
+
+
+class PathParams(ctypes.Structure):
+    _fields_ = [("gapopen", ctypes.c_double), ("gapextend", ctypes.c_double), ("min_identity_score", ctypes.c_double),
+                ("hdr_amplicon", ctypes.c_char_p), ("hdr_amplicon_len", ctypes.c_int32), ("rc_rescue", ctypes.c_int32)]
+
+
+class CrgpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libcrgpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load libcrgpu.so.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("crispresso_b200: %s is missing -- run `python -m crispresso_b200.build` "
+                          "(there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
+    lib.crgpu_abi_version.restype = i32
+    lib.crgpu_create.argtypes = [ctypes.POINTER(vp), i32]
+    lib.crgpu_destroy.argtypes = [vp]
+    lib.crgpu_destroy.restype = None
+    lib.crgpu_last_error.argtypes = [vp]
+    lib.crgpu_last_error.restype = ctypes.c_char_p
+    lib.crgpu_set_traceback_budget.argtypes = [vp, ctypes.c_size_t]
+    lib.crgpu_last_timing.argtypes = [vp, vp, vp]
+    lib.crgpu_sync.argtypes = [vp]
+    lib.crgpu_qualfilter.argtypes = [vp, i32, vp, vp, i64, i32, i32, vp]
+    lib.crgpu_align.argtypes = [vp, i32, ctypes.c_char_p, i32, vp, vp, i64, dbl, dbl, vp, vp, vp, vp, i64]
+    lib.crgpu_quantify.argtypes = [vp, i32, ctypes.POINTER(QuantParams), vp, vp, vp, i64, vp, vp, vp, vp, vp, i64,
+                                   vp, vp, vp, vp, ctypes.c_int32, ctypes.c_int32, vp]
+    lib.crgpu_align_quantify.argtypes = [vp, i32, ctypes.c_char_p, i32, ctypes.POINTER(PathParams),
+                                         ctypes.POINTER(QuantParams), vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64,
+                                         vp, vp, vp, ctypes.c_int32, ctypes.c_int32, vp, vp]
+    lib.crgpu_int_peak.argtypes = [vp, i32, ctypes.POINTER(dbl)]
+    for name in ("crgpu_create", "crgpu_set_traceback_budget", "crgpu_last_timing", "crgpu_sync", "crgpu_qualfilter",
+                 "crgpu_align", "crgpu_quantify", "crgpu_align_quantify", "crgpu_int_peak"):
+        getattr(lib, name).restype = i32
+    _lib = lib
+    return lib
+
+
+def ptr(x):
+    """Raw address of a numpy array, a torch tensor, an int address, or None."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    raise TypeError(type(x))
+
+
+class Context:
+    """One per GPU (crgpu_create).  Not thread-safe."""
+
+    TIMING_NAMES = ("encode", "fill", "walk", "quantify", "qualfilter", "other")
+
+    def __init__(self, device=0):
+        self.lib = load()
+        self.handle = ctypes.c_void_p()
+        rc = self.lib.crgpu_create(ctypes.byref(self.handle), int(device))
+        if rc:
+            raise CrgpuError(rc, "crgpu_create(device=%d) failed: no usable sm_100 GPU (no CPU fallback exists)" % device)
+        self.device = device
+
+    def close(self):
+        if self.handle:
+            self.lib.crgpu_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc:
+            raise CrgpuError(rc, self.lib.crgpu_last_error(self.handle).decode())
+
+    def set_traceback_budget(self, nbytes):
+        self.check(self.lib.crgpu_set_traceback_budget(self.handle, int(nbytes)))
+
+    def last_timing(self):
+        ms = (ctypes.c_float * 6)()
+        ln = (ctypes.c_int64 * 6)()
+        self.check(self.lib.crgpu_last_timing(self.handle, ms, ln))
+        return ({k: float(ms[i]) for i, k in enumerate(self.TIMING_NAMES)},
+                {k: int(ln[i]) for i, k in enumerate(self.TIMING_NAMES)})
+
+    def int_peak(self, which=0):
+        v = ctypes.c_double()
+        self.check(self.lib.crgpu_int_peak(self.handle, int(which), ctypes.byref(v)))
+        return v.value

@@ -1,0 +1,71 @@
+// crgpu_common.cuh -- shared device/host definitions for libcrgpu (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace crgpu {
+
+// ---- score representation -------------------------------------------------------------
+// All DP values are exact integers (needle's float32 scores times `scale`),
+// stored BIASED so that every value is a positive 15-bit number:  stored = value + BIAS.
+// Two alignments (two reads of equal length against the same amplicon) share each 32-bit
+// register: read "lo" in bits 0..15, read "hi" in bits 16..31.  Because both halves are always
+// in [0, 0x7fff], (a) signed and unsigned 16x2 min/max agree, and (b) plain 32-bit adds of
+// (c_hi*65536 + c_lo) and 32-bit subtracts of ordered operands never carry between halves, so
+// they can be issued on either the integer-ALU or the FMA (IMAD) pipe.
+constexpr int BIAS = 0x4000;
+constexpr uint32_t BIAS2 = 0x40004000u;
+constexpr uint32_t ONE2 = 0x00010001u;
+constexpr int MAX_ABS_SCORE = 0x3c00;   // |value| must stay below this (checked on the host)
+
+// read codes: A C G T N ; amplicon codes likewise plus PAD (virtual rows above row 0)
+constexpr int NCODE = 5;
+constexpr int NPAIR = NCODE * NCODE;    // pair code = lo + 5*hi
+
+// traceback flag byte per DP cell ("not equal" bits; the walker inverts them):
+//   bit0 nM : m  != max(m,ix,iy)      bit1 nX : ix != max3      bit2 nY : iy != max3
+//   bit3 nFX: ix != ix[y,x-1]-gex(y)  bit4 nFY: iy != iy[y-1,x]-gey(x)
+// Together they are sufficient for needle's traceback state machine.
+constexpr int F_NM = 1, F_NX = 2, F_NY = 4, F_NFX = 8, F_NFY = 16;
+
+// profile layout (int32 words) for a (G,K) kernel: lane t's strip of K rows starts at
+// t*strip_stride(K); the stride is padded so that stride/4 is odd, i.e. the 8 lanes of a quarter
+// warp hit 8 distinct 16-byte bank groups with their LDS.128.
+__host__ __device__ constexpr int strip_stride(int K) { return ((K / 4) % 2 == 0) ? K + 4 : K; }
+__host__ __device__ constexpr int prof_stride(int G, int K) { return G * strip_stride(K); }
+
+struct FillArgs {
+    const int32_t *prof;      // [NPAIR][prof_stride]  c32 = s_hi*65536 + s_lo (scaled scores)
+    const uint8_t *pc;        // pair codes, pc[pc_off[p] + x]
+    const int64_t *pc_off;    // [npairs+1] prefix sum of pair lengths
+    const int32_t *plen;      // [npairs]
+    const int64_t *tb_off;    // [npairs]  offset (in uint32 words) of pair p inside tb, batch-relative
+    uint32_t *tb;             // traceback flags of this batch
+    uint32_t *lastrow;        // [(pc_off[p]-pc_off[p0]) + x][3]  (m,ix,iy) of amplicon row La-1
+    uint32_t *lastcol;        // [(p-p0)*G*K + r][3]              (m,ix,iy) of read column Lb-1
+    int p0, p1;               // pair range of this batch
+    int open, ext;            // gap open / extend, scaled (positive)
+};
+
+struct WalkArgs {
+    const uint32_t *tb;
+    const int64_t *tb_off;
+    const uint32_t *lastrow;
+    const uint32_t *lastcol;
+    const int64_t *pc_off;
+    const int32_t *plen;
+    const int32_t *pair_lo;   // read index of the lo half
+    const int32_t *pair_hi;   // read index of the hi half (== pair_lo for an unpaired read)
+    const uint8_t *reads;     // original read bytes (device)
+    const int64_t *offsets;   // [n+1]
+    const uint8_t *amplicon;  // La bytes (upper-cased by the host)
+    int La, GK, P;            // rows, padded rows, pad rows on top (P = GK - La)
+    int p0, p1;
+    int open, ext, scale;
+    // outputs, indexed by read
+    void *recs;               // crgpu_aln_rec*
+    uint8_t *ref_out, *mark_out, *qry_out;   // may be null
+    int64_t slot;
+};
+
+}  // namespace crgpu

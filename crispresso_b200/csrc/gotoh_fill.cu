@@ -1,0 +1,263 @@
+// gotoh_fill.cu -- k_gotoh_fill<G,K>: batched Gotoh fill (needle semantics) for sm_100a.
+//
+// Replaces the DP of EMBOSS needle's embAlignPathCalcWithEndGapPenalties as CRISPResso runs it
+// (CRISPResso/CRISPRessoCORE.py:1791-1806; algorithm: SURVEY.md App. A.1-A.3, exact integer
+// form A.6).
+//
+// Work decomposition (DESIGN.md "k_gotoh_fill"):
+//   * one GROUP of G lanes owns one PAIR of reads (equal length, packed in the two 16-bit
+//     halves of every register) and sweeps the read columns x = 0..Lb-1;
+//   * lane t of the group owns K consecutive amplicon rows (virtual rows r = t*K .. t*K+K-1;
+//     the amplicon is padded on TOP with P = G*K - La rows scoring 0 against everything, which
+//     reproduces needle's free-end-gap boundary exactly), whose state MY = max(m,iy)[y,x-1] and
+//     IX = ix[y,x-1] lives in 2K registers;
+//   * the lanes form a systolic pipeline: at step s lane t works on column x = s - t and hands
+//     (max(m,ix), iy, m) of its bottom row to lane t+1 with one warp shuffle each;
+//   * the substitution scores of a column come from a pair profile table in shared memory
+//     (25 read-code pairs x padded rows, one LDS.128 per 4 rows), loaded once per CTA with a
+//     TMA bulk copy (cp.async.bulk -> UBLKCP);
+//   * per cell 5 "not equal" flag bits (crgpu_common.cuh) are packed into one byte and written
+//     with 16-byte vector stores; the last amplicon row and the last read column are written as
+//     values for the traceback's start-cell scan.
+// The kernel is persistent: grid = SMs x resident CTAs, groups stride over the batch's pairs.
+#include "crgpu_common.cuh"
+
+namespace crgpu {
+
+__device__ __forceinline__ uint32_t vmax2(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }      // VIMNMX.U16x2
+__device__ __forceinline__ uint32_t vmin2(uint32_t a, uint32_t b) { return __vminu2(a, b); }
+__device__ __forceinline__ uint32_t vaddmax2(uint32_t a, uint32_t b, uint32_t c)                   // VIADDMNMX.S16x2
+{
+    return __viaddmax_s16x2(a, b, c);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int K>
+struct Strip {
+    uint32_t MY[K];   // max(m,iy)[row, x-1]
+    uint32_t IX[K];   // ix[row, x-1]
+    uint32_t mlast;   // m[row K-1, x-1]; only meaningful in the lane that owns amplicon row La-1
+};
+
+// One read column for the K rows of this lane.
+//  SLOW = true handles the first (x == 0) and last (x == Lb-1) columns, whose iy rule / FY flag
+//  differ (App. A.2/A.3: last column opens from m only with zero penalties; A.4: gey = 0 there).
+template <int K, bool SLOW>
+__device__ __forceinline__ void column_step(Strip<K> &st, const int32_t *__restrict__ prow,
+                                            uint32_t upMX, uint32_t upIY, uint32_t upM, uint32_t hd,
+                                            const uint32_t nopen16, const uint32_t ext32,
+                                            const uint32_t nopen16_last, const uint32_t ext32_last,
+                                            const bool lastLane, const bool isLastCol,
+                                            uint32_t *__restrict__ tbw, uint32_t *__restrict__ lastcol,
+                                            uint32_t &botMX, uint32_t &botIY, uint32_t &botM)
+{
+    uint32_t words[K / 2];
+    uint32_t ceven = 0;
+    int32_t S4[4];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        if ((k & 3) == 0) {
+            const int4 v = *reinterpret_cast<const int4 *>(prow + k);
+            S4[0] = v.x; S4[1] = v.y; S4[2] = v.z; S4[3] = v.w;
+        }
+        const uint32_t S = (uint32_t)S4[k & 3];
+        const uint32_t my0 = st.MY[k], ix0 = st.IX[k];
+        const uint32_t hnext = vmax2(my0, ix0);          // max3[row, x-1]: diagonal input of row+1
+        const uint32_t m = hd + S;                       // m = sub + max3[row-1, x-1]
+        uint32_t t_, ix;
+        if (k == K - 1) {                                // the only row that can be amplicon row La-1
+            const uint32_t src = lastLane ? st.mlast : my0;
+            t_ = ix0 - ext32_last;
+            ix = vaddmax2(src, nopen16_last, t_);
+        } else {
+            t_ = ix0 - ext32;
+            ix = vaddmax2(my0, nopen16, t_);
+        }
+        uint32_t u_, iy, nFY;
+        if (SLOW) {
+            if (isLastCol) { u_ = upIY; iy = vmax2(upM, upIY); }
+            else { u_ = upIY - ext32; iy = vaddmax2(upMX, nopen16, u_); }
+            nFY = vmin2(iy ^ upIY, ONE2);                // gey = 0 on the first and last column
+        } else {
+            u_ = upIY - ext32;
+            iy = vaddmax2(upMX, nopen16, u_);
+            nFY = vmin2(iy - u_, ONE2);
+        }
+        const uint32_t my = vmax2(m, iy);
+        const uint32_t mx = vmax2(m, ix);
+        const uint32_t h3 = vmax2(my, ix);
+        const uint32_t nM = vmin2(h3 - m, ONE2);
+        const uint32_t nX = vmin2(h3 - ix, ONE2);
+        const uint32_t nY = vmin2(h3 - iy, ONE2);
+        const uint32_t nFX = vmin2(ix - t_, ONE2);
+        const uint32_t c = nM + 2u * nX + 4u * nY + 8u * nFX + 16u * nFY;
+        if (k & 1) words[k >> 1] = ceven + (c << 8);
+        else ceven = c;
+        if (SLOW) {
+            if (isLastCol) { lastcol[3 * k] = m; lastcol[3 * k + 1] = ix; lastcol[3 * k + 2] = iy; }
+        }
+        st.MY[k] = my;
+        st.IX[k] = ix;
+        if (k == K - 1) st.mlast = m;
+        upMX = mx; upIY = iy; upM = m; hd = hnext;
+    }
+    botMX = upMX; botIY = upIY; botM = upM;
+    if constexpr ((K % 8) == 0) {
+#pragma unroll
+        for (int j = 0; j < K / 8; ++j)
+            reinterpret_cast<uint4 *>(tbw)[j] = make_uint4(words[4 * j], words[4 * j + 1], words[4 * j + 2], words[4 * j + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < K / 4; ++j)
+            reinterpret_cast<uint2 *>(tbw)[j] = make_uint2(words[2 * j], words[2 * j + 1]);
+    }
+}
+
+template <int G, int K>
+__global__ void __launch_bounds__(128) k_gotoh_fill(const FillArgs a)
+{
+    static_assert(K % 4 == 0 && (32 % G) == 0, "bad tile");
+    constexpr int PS = prof_stride(G, K);
+    constexpr int GK = G * K;
+    extern __shared__ __align__(128) int32_t sprof[];
+    __shared__ __align__(8) uint64_t mbar;
+
+    // ---- stage the pair profile with one TMA bulk copy -------------------------------------
+    const uint32_t prof_bytes = NPAIR * PS * 4;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(prof_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(sprof)), "l"(a.prof), "r"(prof_bytes), "r"(smem_u32(&mbar)) : "memory");
+    }
+    {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0u) : "memory");
+        }
+    }
+
+    const int lane = threadIdx.x & 31;
+    const int t = lane % G;
+    const int gl = lane / G;
+    constexpr int GPW = 32 / G;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const bool lastLane = (t == G - 1);
+
+    const uint32_t Z = BIAS2;                                             // stored 0
+    const uint32_t NOPEN_ST = BIAS2 - (uint32_t)a.open * 0x10001u;        // stored -open
+    const uint32_t nopen16 = ((uint32_t)(-a.open) & 0xffffu) * 0x10001u;  // per-half two's complement
+    const uint32_t ext32 = (uint32_t)a.ext * 0x10001u;
+    const uint32_t nopen16_last = lastLane ? 0u : nopen16;                // amplicon row La-1: zero end-gap penalties
+    const uint32_t ext32_last = lastLane ? 0u : ext32;
+
+    for (int base = a.p0 + warp_global * GPW; base < a.p1; base += nwarps * GPW) {
+        const int p = base + gl;
+        const bool valid = p < a.p1;
+        const int Lb = valid ? a.plen[p] : 0;
+        const int steps = __reduce_max_sync(0xffffffffu, Lb) + G - 1;
+        const int64_t pco = valid ? a.pc_off[p] : 0;
+        const uint8_t *pcp = a.pc + pco;
+        uint32_t *tbp = a.tb + (valid ? a.tb_off[p] : 0) + t * (K / 2);
+        uint32_t *lrp = a.lastrow + (pco - a.pc_off[a.p0]) * 3;
+        uint32_t *lcp = a.lastcol + ((int64_t)(p - a.p0) * GK + t * K) * 3;
+
+        Strip<K> st;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { st.MY[k] = Z; st.IX[k] = NOPEN_ST; }
+        st.mlast = Z;
+        uint32_t botMX = Z, botIY = NOPEN_ST, botM = Z;
+        uint32_t hd0 = Z;
+        int cp_next = (t == 0 && Lb > 0) ? pcp[0] : 0;
+
+        for (int s = 0; s < steps; ++s) {
+            const int x = s - t;
+            uint32_t rMX = __shfl_up_sync(0xffffffffu, botMX, 1, G);
+            uint32_t rIY = __shfl_up_sync(0xffffffffu, botIY, 1, G);
+            uint32_t rM = __shfl_up_sync(0xffffffffu, botM, 1, G);
+            if (t == 0) { rMX = Z; rIY = NOPEN_ST; rM = Z; }          // free boundary above the padded top
+            const bool active = (x >= 0) && (x < Lb);
+            const int cp = cp_next;
+            if (x + 1 >= 0 && x + 1 < Lb) cp_next = pcp[x + 1];
+            if (active) {
+                const int32_t *prow = sprof + cp * PS + t * strip_stride(K);
+                uint32_t *tbw = tbp + (int64_t)x * (GK / 2);
+                if (x == 0 || x == Lb - 1)
+                    column_step<K, true>(st, prow, rMX, rIY, rM, hd0, nopen16, ext32, nopen16_last, ext32_last,
+                                         lastLane, x == Lb - 1, tbw, lcp, botMX, botIY, botM);
+                else
+                    column_step<K, false>(st, prow, rMX, rIY, rM, hd0, nopen16, ext32, nopen16_last, ext32_last,
+                                          lastLane, false, tbw, lcp, botMX, botIY, botM);
+                hd0 = vmax2(rMX, rIY);                                // max3[row above, x] for column x+1
+                if (lastLane) {
+                    uint32_t *lr = lrp + (int64_t)x * 3;
+                    lr[0] = botM; lr[1] = st.IX[K - 1]; lr[2] = botIY;
+                }
+            }
+        }
+    }
+}
+
+// ---- host-side dispatch ----------------------------------------------------------------
+struct Tile { int G, K; };
+
+template <int G, int K>
+static cudaError_t launch_tile(const FillArgs &a, int num_sms, cudaStream_t stream)
+{
+    const size_t smem = (size_t)NPAIR * prof_stride(G, K) * 4;
+    static bool configured = false;
+    static int blocks_per_sm = 1;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_gotoh_fill<G, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_gotoh_fill<G, K>, 128, smem);
+        if (e != cudaSuccess) return e;
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+        configured = true;
+    }
+    const int npairs = a.p1 - a.p0;
+    const int groups_per_block = 4 * (32 / G);
+    int grid = (npairs + groups_per_block - 1) / groups_per_block;
+    const int cap = num_sms * blocks_per_sm;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    k_gotoh_fill<G, K><<<grid, 128, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+// Smallest padded tile G*K >= La from the compiled menu.
+bool choose_tile(int La, int *G, int *K)
+{
+    static const Tile menu[] = {
+        {4, 16}, {4, 24}, {4, 32}, {8, 20}, {8, 24}, {8, 28}, {8, 32}, {8, 36}, {8, 40},
+        {16, 24}, {16, 28}, {16, 32}, {16, 36}, {16, 40}, {32, 24}, {32, 28}, {32, 32},
+    };
+    int best = -1, bestgk = 1 << 30;
+    for (unsigned i = 0; i < sizeof(menu) / sizeof(menu[0]); ++i) {
+        const int gk = menu[i].G * menu[i].K;
+        if (gk >= La && gk < bestgk) { bestgk = gk; best = (int)i; }
+    }
+    if (best < 0) return false;
+    *G = menu[best].G; *K = menu[best].K;
+    return true;
+}
+
+cudaError_t launch_fill(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream)
+{
+#define CASE(g, k) if (G == g && K == k) return launch_tile<g, k>(a, num_sms, stream);
+    CASE(4, 16) CASE(4, 24) CASE(4, 32)
+    CASE(8, 20) CASE(8, 24) CASE(8, 28) CASE(8, 32) CASE(8, 36) CASE(8, 40)
+    CASE(16, 24) CASE(16, 28) CASE(16, 32) CASE(16, 36) CASE(16, 40)
+    CASE(32, 24) CASE(32, 28) CASE(32, 32)
+#undef CASE
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace crgpu

@@ -1,0 +1,57 @@
+// int_peak.cu -- integer issue-rate micro-benchmark ("measure it").
+// Dependency-free chains (16 independent accumulators per thread) of one instruction kind,
+// 1024 threads x 2 CTAs per SM.  The op count reported is lane-ops: one SASS instruction on
+// one lane.  `cuobjdump -sass` of this file must show the unrolled body made of exactly the
+// named instruction (checked in profiles/r01_sass_notes.md).
+#include "crgpu_common.cuh"
+
+namespace crgpu {
+
+constexpr int PEAK_CHAINS = 16;
+constexpr int PEAK_UNROLL = 8;
+
+template <int WHICH>
+__global__ void __launch_bounds__(1024) k_int_peak(int iters, unsigned *sink, unsigned b, unsigned c)
+{
+    unsigned a[PEAK_CHAINS];
+#pragma unroll
+    for (int j = 0; j < PEAK_CHAINS; ++j) a[j] = threadIdx.x * 2654435761u + j * 40503u + blockIdx.x;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < PEAK_UNROLL; ++u) {
+#pragma unroll
+            for (int j = 0; j < PEAK_CHAINS; ++j) {
+                if (WHICH == 0) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[j]) : "r"(b));
+                else if (WHICH == 1) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[j]) : "r"(b), "r"(c));
+                else if (WHICH == 2) a[j] = (u & 1) ? __vmaxs2(a[j], b) : __vmins2(a[j], c);
+                else if (WHICH == 3) a[j] = __viaddmax_s16x2(a[j], b, c);
+                else {
+                    if (j & 1) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[j]) : "r"(b), "r"(c));
+                    else asm volatile("add.u32 %0, %0, %1;" : "+r"(a[j]) : "r"(b));
+                }
+            }
+        }
+    }
+    unsigned r = 0;
+#pragma unroll
+    for (int j = 0; j < PEAK_CHAINS; ++j) r ^= a[j];
+    if (r == 0x12345678u) sink[0] = r;   // practically never: keeps the chains alive
+}
+
+cudaError_t launch_int_peak(int which, int num_sms, int iters, unsigned *sink, cudaStream_t s, double *lane_ops)
+{
+    const int grid = num_sms * 2, block = 1024;
+    const unsigned b = 3u + (unsigned)(iters & 1), c = 0x00050007u;
+    switch (which) {
+    case 0: k_int_peak<0><<<grid, block, 0, s>>>(iters, sink, b, c); break;
+    case 1: k_int_peak<1><<<grid, block, 0, s>>>(iters, sink, b, c); break;
+    case 2: k_int_peak<2><<<grid, block, 0, s>>>(iters, sink, b, c); break;
+    case 3: k_int_peak<3><<<grid, block, 0, s>>>(iters, sink, b, c); break;
+    case 4: k_int_peak<4><<<grid, block, 0, s>>>(iters, sink, b, c); break;
+    default: return cudaErrorInvalidValue;
+    }
+    *lane_ops = (double)grid * block * (double)iters * PEAK_UNROLL * PEAK_CHAINS;
+    return cudaGetLastError();
+}
+
+}  // namespace crgpu

@@ -1,0 +1,200 @@
+/*
+ * crgpu.h -- C ABI of libcrgpu.so: the B200 (sm_100a) implementation of CRISPResso's
+ * read->amplicon alignment + indel quantification hot path.
+ *
+ * The reference (tonyreina/CRISPResso) has no FFI; the path is three in-process seams in
+ * CRISPResso/CRISPRessoCORE.py::run_crispresso plus one subprocess:
+ *
+ *   S1  quality filter      filter_se_fastq_by_qual / filter_pe_fastq_by_qual /
+ *                           get_ids_reads_to_remove            CORE:162-310, call site 1547-1583
+ *   S2  alignment           `needle` subprocess + parse_needle_output
+ *                                                               CORE:1791-1828, 1707-1786, 1911-1936
+ *   S3  quantification      process_df_chunk                    CORE:428-753 (driver 2773-2864)
+ *
+ * Every entry point below names the seam it replaces.  Conventions:
+ *   - plain C, no torch / C++ types; `int` return: 0 = ok, non-zero = CRGPU_E_* (message via
+ *     crgpu_last_error).  The Python shim maps CRGPU_E_ALIGN to NeedleException (CLI exit 6,
+ *     CORE:4349-4356).
+ *   - the caller owns every buffer.  `mem` says where the caller's buffers live:
+ *     CRGPU_MEM_HOST (library stages them through pinned memory, copies are part of the call)
+ *     or CRGPU_MEM_DEVICE (device pointers on the context's GPU; nothing is copied).
+ *   - one opaque context per GPU; a context is not thread-safe.
+ *   - there is NO CPU fallback: without a CUDA device crgpu_create fails.
+ */
+#ifndef CRGPU_H
+#define CRGPU_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRGPU_ABI_VERSION 1
+
+enum {
+    CRGPU_OK = 0,
+    CRGPU_E_CUDA = 1,       /* CUDA runtime error (no device, OOM, launch failure) */
+    CRGPU_E_ARG = 2,        /* bad argument (null pointer, negative size, bad enum) */
+    CRGPU_E_ALIGN = 3,      /* input the aligner cannot honour exactly: a base outside ACGTN(U),
+                               read/amplicon length out of range, gap penalties not exactly
+                               representable -> NeedleException in the shim */
+    CRGPU_E_NOMEM = 4
+};
+
+enum { CRGPU_MEM_HOST = 0, CRGPU_MEM_DEVICE = 1 };
+
+/* Limits of the exact int16x2 aligner (DESIGN.md "Score range"). */
+#define CRGPU_MAX_AMPLICON 1024
+#define CRGPU_MAX_READ 2048
+#define CRGPU_MIN_LEN 2
+
+typedef struct crgpu_ctx crgpu_ctx;
+
+/* ---- context -------------------------------------------------------------------------- */
+int crgpu_abi_version(void);
+int crgpu_create(crgpu_ctx **ctx, int device);
+void crgpu_destroy(crgpu_ctx *ctx);
+const char *crgpu_last_error(const crgpu_ctx *ctx);
+/* Cap on the traceback scratch held in HBM per batch (bytes; default 8 GiB).  Reads are
+ * processed in batches sized to this cap; results do not depend on it. */
+int crgpu_set_traceback_budget(crgpu_ctx *ctx, size_t bytes);
+/* Device time (ms, CUDA events on the context's stream) spent in each kernel family during
+ * the LAST call on this context, and launch counts.  out_ms[0..5] = encode, fill, walk,
+ * quantify, qualfilter, other;  out_launches likewise. */
+int crgpu_last_timing(const crgpu_ctx *ctx, float out_ms[6], int64_t out_launches[6]);
+/* Synchronise the context's stream. */
+int crgpu_sync(crgpu_ctx *ctx);
+
+/* ---- S1: quality filter (CORE:162-193, 270-310) --------------------------------------- *
+ * keep[i] = 1 iff mean(phred) >= min_mean_q and min(phred) >= min_single_q, phred = byte - 33,
+ * evaluated in exact integer form (sum >= q*len).  For paired ends the caller ANDs the two
+ * masks (CORE:216-227 drops a pair if either mate fails). An empty read has keep = 0. */
+int crgpu_qualfilter(crgpu_ctx *ctx, int mem, const uint8_t *qual, const int64_t *offsets, int64_t n,
+                     int min_mean_q, int min_single_q, uint8_t *keep);
+
+/* ---- S2: alignment (needle subprocess + parse_needle_output, CORE:1791-1806, 1707-1786) -- */
+typedef struct {
+    int32_t score_x2;     /* needle "# Score:" times `scale` (see crgpu_align; 2 for the defaults) */
+    int32_t alnlen;       /* alignment columns incl. end gaps ("# Length:") */
+    int32_t ident;        /* identical columns ("# Identity: ident/alnlen") */
+    int32_t tenths;       /* identity %% as printed by "%4.1f", times 10: what the parser's
+                             score_<name> column holds (CORE:1732-1738) */
+    int32_t aln_off;      /* the three strings occupy [aln_off, aln_off+alnlen) of the read's slot */
+    int32_t start1;       /* traceback start cell: amplicon index */
+    int32_t start2;       /* traceback start cell: read index */
+    int32_t read_len;     /* the parser's `length` column (CORE:1754) */
+} crgpu_aln_rec;
+
+/* Align each of n reads (bytes reads[offsets[i]..offsets[i+1])) globally to `amplicon` exactly
+ * as `needle -gapopen G -gapextend E` (EDNAFULL, end gaps free) does, including its traceback
+ * tie-breaking.  recs[n] always written.  ref_out/mark_out/qry_out (each n*slot bytes, slot >=
+ * amplicon_len + longest read) receive the three srspair rows -- aligned amplicon, markup
+ * ('|' '.' ' '), aligned read -- right-aligned in the read's slot (see aln_off); pass NULL for
+ * all three to skip them (score-only use, CORE:1833-1835 just_score=True).
+ * Reads shorter than CRGPU_MIN_LEN or with a base outside ACGTN(U) fail the call (CRGPU_E_ALIGN). */
+int crgpu_align(crgpu_ctx *ctx, int mem, const char *amplicon, int amplicon_len,
+                const uint8_t *reads, const int64_t *offsets, int64_t n,
+                double gapopen, double gapextend,
+                crgpu_aln_rec *recs, uint8_t *ref_out, uint8_t *mark_out, uint8_t *qry_out, int64_t slot);
+
+/* ---- S3: quantification (process_df_chunk, CORE:428-753) ------------------------------- */
+enum {                        /* crgpu_quant_params.flags */
+    CRGPU_Q_HAS_HDR = 1,          /* args.expected_hdr_amplicon_seq non-empty (CORE:537) */
+    CRGPU_Q_IGNORE_SUBS = 2,      /* CORE:490 */
+    CRGPU_Q_IGNORE_INS = 4,       /* CORE:517 */
+    CRGPU_Q_IGNORE_DEL = 8,       /* CORE:503 */
+    CRGPU_Q_WINDOW = 16,          /* args.window_around_sgrna != 0 (CORE:611) */
+    CRGPU_Q_HIDE_OUTSIDE = 32,    /* args.hide_mutations_outside_window_NHEJ (CORE:591,645) */
+    CRGPU_Q_FRAMESHIFT = 64,      /* args.coding_seq non-empty (CORE:446) */
+    CRGPU_Q_MASK_N = 128          /* amplicon contains N: apply ignore_n_in_alignment (CORE:2033-2052) */
+};
+
+enum {                        /* class bits in crgpu_read_rec.cls (DataFrame columns CORE:2014-2019) */
+    CRGPU_C_UNMODIFIED = 1, CRGPU_C_NHEJ = 2, CRGPU_C_HDR = 4, CRGPU_C_MIXED = 8
+};
+
+/* order of the 15 per-position vectors in `vectors` (process_df_chunk's return tuple, CORE:730-753) */
+enum {
+    CRGPU_V_INS = 0, CRGPU_V_DEL, CRGPU_V_MUT, CRGPU_V_ANY,
+    CRGPU_V_INS_MIXED, CRGPU_V_DEL_MIXED, CRGPU_V_MUT_MIXED,
+    CRGPU_V_INS_HDR, CRGPU_V_DEL_HDR, CRGPU_V_MUT_HDR,
+    CRGPU_V_INS_NONCODING, CRGPU_V_DEL_NONCODING, CRGPU_V_MUT_NONCODING,
+    CRGPU_V_AVG_DEL, CRGPU_V_AVG_INS,
+    CRGPU_NUM_VECTORS
+};
+enum { CRGPU_K_MOD_FRAMESHIFT = 0, CRGPU_K_MOD_NON_FRAMESHIFT, CRGPU_K_NON_MOD_NON_FRAMESHIFT,
+       CRGPU_K_SPLICING_MODIFIED, CRGPU_NUM_COUNTERS };
+
+typedef struct {
+    int32_t amplicon_len;                  /* LEN_AMPLICON (CORE:1288) */
+    int32_t flags;                         /* CRGPU_Q_* */
+    double hdr_perfect_alignment_threshold;/* CORE:541 */
+    const uint8_t *include_mask;           /* [amplicon_len] 1 = in INCLUDE_IDXS (CORE:2739-2762); host memory */
+    const uint8_t *exon_mask;              /* [amplicon_len] EXON_POSITIONS (CORE:1418-1451) or NULL; host */
+    const uint8_t *splice_mask;            /* [amplicon_len] SPLICING_POSITIONS (CORE:1444-1455) or NULL; host */
+} crgpu_quant_params;
+
+typedef struct {
+    uint8_t cls;          /* CRGPU_C_* after classification */
+    uint8_t pad[3];
+    int32_t n_mutated;    /* CORE:654 */
+    int32_t n_inserted;   /* CORE:657 */
+    int32_t n_deleted;    /* CORE:660 */
+} crgpu_read_rec;
+
+/* Quantify n aligned reads.  Strings as produced by crgpu_align: row i occupies
+ * X[i*slot + aln_off[i] .. +alnlen[i]) (aln_off may be all zeros for left-aligned rows).
+ * tenths_ref[i] / tenths_rep[i]: identity tenths vs the amplicon / the HDR amplicon
+ * (tenths_rep < 0 = NaN: the reverse-complement rows of CORE:1924-1949).  unmodified_in[i] =
+ * the UNMODIFIED column on entry (CORE:2014, 2047).
+ * Outputs: out_recs[n]; vectors[CRGPU_NUM_VECTORS][amplicon_len] int64 ADDED to the caller's
+ * values; hist_inframe / hist_frameshift: int64[hist_len] ADDED, bin index = key + hist_zero
+ * (key = effective exon length change, CORE:710-717); counters[CRGPU_NUM_COUNTERS] ADDED.
+ * vectors/hist/counters are always HOST memory (small); per-read arrays follow `mem`. */
+int crgpu_quantify(crgpu_ctx *ctx, int mem, const crgpu_quant_params *params,
+                   const uint8_t *ref_rows, const uint8_t *mark_rows, const uint8_t *qry_rows, int64_t slot,
+                   const int32_t *aln_off, const int32_t *alnlen,
+                   const int32_t *tenths_ref, const int32_t *tenths_rep, const uint8_t *unmodified_in,
+                   int64_t n, crgpu_read_rec *out_recs,
+                   int64_t *vectors, int64_t *hist_inframe, int64_t *hist_frameshift, int32_t hist_len,
+                   int32_t hist_zero, int64_t *counters);
+
+/* ---- fused hot path: S2 (+HDR pass, + reverse-complement rescue) + S3 in one call -------- *
+ * Reproduces CORE:1791-2072 + 2773-2864 for one amplicon without materialising the needle text:
+ *  1. align all reads to `amplicon` (and to `hdr_amplicon` when non-NULL, CORE:1810-1828);
+ *  2. reads with identity < min_identity are re-aligned to the reverse complements
+ *     (CORE:1873-2000; their HDR score stays NaN, CORE:1924-1949);
+ *  3. rows kept iff score_ref > min_identity (or score_repaired > min_identity, CORE:1849-1852);
+ *  4. quantify the kept rows (crgpu_quantify semantics).
+ * Per-read outputs (all length n, indexed like the input): kept[i] (1 = forward row kept,
+ * 2 = kept through the RC rescue, 0 = dropped), aln[i] = the alignment vs the amplicon that the
+ * row carries, tenths_rep[i], recs[i].  Strings optional as in crgpu_align. */
+typedef struct {
+    double gapopen, gapextend;             /* parsed from --needle_options_string (CORE:4226-4231) */
+    double min_identity_score;             /* CORE:4092 */
+    const char *hdr_amplicon;              /* expected HDR amplicon or NULL */
+    int32_t hdr_amplicon_len;
+    int32_t rc_rescue;                     /* 1 = run the reverse-complement rescue (reference behaviour) */
+} crgpu_path_params;
+
+int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int amplicon_len,
+                         const crgpu_path_params *path, const crgpu_quant_params *quant,
+                         const uint8_t *reads, const int64_t *offsets, int64_t n,
+                         uint8_t *kept, crgpu_aln_rec *aln, int32_t *tenths_rep, crgpu_read_rec *recs,
+                         uint8_t *ref_out, uint8_t *mark_out, uint8_t *qry_out, int64_t slot,
+                         int64_t *vectors, int64_t *hist_inframe, int64_t *hist_frameshift,
+                         int32_t hist_len, int32_t hist_zero, int64_t *counters,
+                         int64_t *n_cells /* DP cells actually computed (for GCUPS), may be NULL */);
+
+/* ---- measurement helper ---------------------------------------------------------------- *
+ * Integer-ALU peak micro-benchmark ("measure it"): dependent-free 32-bit
+ * IADD3/VIMNMX chains on every SM.  Returns lane-ops per second.  which: 0 = IADD3 (alu pipe),
+ * 1 = IMAD (fma pipe), 2 = VIMNMX.S16x2, 3 = VIADDMNMX.S16x2, 4 = 1:1 IADD3+IMAD mix. */
+int crgpu_int_peak(crgpu_ctx *ctx, int which, double *lane_ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRGPU_H */
