@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "libcrgpu.so")
 MEM_HOST, MEM_DEVICE = 0, 1
 E_CUDA, E_ARG, E_ALIGN, E_NOMEM = 1, 2, 3, 4
 
-ALN_REC = np.dtype([("score_x2", "<i4"), ("alnlen", "<i4"), ("ident", "<i4"), ("tenths", "<i4"),
+ALN_REC = np.dtype([("score", "<f4"), ("alnlen", "<i4"), ("ident", "<i4"), ("tenths", "<i4"),
                     ("aln_off", "<i4"), ("start1", "<i4"), ("start2", "<i4"), ("read_len", "<i4")])
 READ_REC = np.dtype([("cls", "u1"), ("pad", "u1", (3,)), ("n_mutated", "<i4"), ("n_inserted", "<i4"),
                      ("n_deleted", "<i4")])
@@ -31,6 +31,18 @@ class QuantParams(ctypes.Structure):
 class PathParams(ctypes.Structure):
     _fields_ = [("gapopen", ctypes.c_double), ("gapextend", ctypes.c_double), ("min_identity_score", ctypes.c_double),
                 ("hdr_amplicon", ctypes.c_char_p), ("hdr_amplicon_len", ctypes.c_int32), ("rc_rescue", ctypes.c_int32)]
+
+
+class PathOut(ctypes.Structure):
+    _fields_ = [("kept", ctypes.c_void_p), ("aln", ctypes.c_void_p), ("tenths_rep", ctypes.c_void_p),
+                ("recs", ctypes.c_void_p), ("ref_rows", ctypes.c_void_p), ("mark_rows", ctypes.c_void_p),
+                ("qry_rows", ctypes.c_void_p), ("slot", ctypes.c_int64),
+                ("rc_cap", ctypes.c_int64), ("rc_n", ctypes.c_int64), ("rc_read", ctypes.c_void_p),
+                ("rc_aln", ctypes.c_void_p), ("rc_recs", ctypes.c_void_p), ("rc_ref_rows", ctypes.c_void_p),
+                ("rc_mark_rows", ctypes.c_void_p), ("rc_qry_rows", ctypes.c_void_p),
+                ("vectors", ctypes.c_void_p), ("hist_inframe", ctypes.c_void_p), ("hist_frameshift", ctypes.c_void_p),
+                ("hist_len", ctypes.c_int32), ("hist_zero", ctypes.c_int32), ("counters", ctypes.c_void_p),
+                ("class_counts", ctypes.c_int64 * 4), ("n_total", ctypes.c_int64), ("n_cells", ctypes.c_int64)]
 
 
 class CrgpuError(RuntimeError):
@@ -66,8 +78,7 @@ def load():
     lib.crgpu_quantify.argtypes = [vp, i32, ctypes.POINTER(QuantParams), vp, vp, vp, i64, vp, vp, vp, vp, vp, i64,
                                    vp, vp, vp, vp, ctypes.c_int32, ctypes.c_int32, vp]
     lib.crgpu_align_quantify.argtypes = [vp, i32, ctypes.c_char_p, i32, ctypes.POINTER(PathParams),
-                                         ctypes.POINTER(QuantParams), vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64,
-                                         vp, vp, vp, ctypes.c_int32, ctypes.c_int32, vp, vp]
+                                         ctypes.POINTER(QuantParams), vp, vp, i64, ctypes.POINTER(PathOut)]
     lib.crgpu_int_peak.argtypes = [vp, i32, ctypes.POINTER(dbl)]
     for name in ("crgpu_create", "crgpu_set_traceback_budget", "crgpu_last_timing", "crgpu_sync", "crgpu_qualfilter",
                  "crgpu_align", "crgpu_quantify", "crgpu_align_quantify", "crgpu_int_peak"):

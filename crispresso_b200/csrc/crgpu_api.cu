@@ -1,129 +1,7 @@
-// crgpu_api.cu -- the C ABI declared in include/crgpu.h: context, batching, host-side pairing.
-#include "../../include/crgpu.h"
-#include "crgpu_common.cuh"
-
-#include <algorithm>
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
-#include <string>
-#include <vector>
-
-namespace crgpu {
-bool choose_tile(int La, int *G, int *K);
-cudaError_t launch_fill(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream);
-cudaError_t launch_encode(const uint8_t *reads, const int64_t *offsets, const int32_t *pair_lo, const int32_t *pair_hi,
-                          const int64_t *pc_off, int npairs, uint8_t *pc, int *err, int num_sms, cudaStream_t s);
-cudaError_t launch_walk(const WalkArgs &a, cudaStream_t s);
-cudaError_t launch_qualfilter(const uint8_t *qual, const int64_t *offsets, int64_t n, int q, int sq, uint8_t *keep,
-                              int num_sms, cudaStream_t s);
-struct QuantDev;
-int quantify_device(crgpu_ctx *ctx, const crgpu_quant_params *params, const uint8_t *d_ref, const uint8_t *d_mark,
-                    const uint8_t *d_qry, int64_t slot, const int32_t *d_aln_off, const int32_t *d_alnlen,
-                    const int32_t *d_tenths_ref, const int32_t *d_tenths_rep, const uint8_t *d_unmod, int64_t n,
-                    crgpu_read_rec *d_recs, int64_t *vectors, int64_t *hist_inframe, int64_t *hist_frameshift,
-                    int32_t hist_len, int32_t hist_zero, int64_t *counters);
-cudaError_t launch_int_peak(int which, int num_sms, int iters, unsigned *sink, cudaStream_t s, double *lane_ops);
-}  // namespace crgpu
+// crgpu_api.cu -- the C ABI declared in include/crgpu.h: context, S1, S2, batching, host-side pairing.
+#include "crgpu_internal.h"
 
 using namespace crgpu;
-
-enum { T_ENCODE = 0, T_FILL, T_WALK, T_QUANT, T_QUAL, T_OTHER, T_N };
-
-struct DBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t bytes)
-    {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
-};
-
-struct TimedSpan { int family; cudaEvent_t a, b; };
-
-struct crgpu_ctx {
-    int device = 0;
-    int num_sms = 0;
-    cudaStream_t stream = nullptr;
-    size_t tb_budget = (size_t)8 << 30;
-    std::string err;
-    // device scratch
-    DBuf reads, offsets, amp, prof, pc, pc_off, plen, pair_lo, pair_hi, tb_off, tb, lastrow, lastcol, errflag;
-    DBuf recs, sref, smark, sqry;
-    DBuf q_in[8], q_out[4];
-    DBuf aux[8];
-    // timing
-    std::vector<cudaEvent_t> ev_pool;
-    size_t ev_used = 0;
-    std::vector<TimedSpan> spans;
-    float ms[T_N] = {0};
-    int64_t launches[T_N] = {0};
-};
-
-static int fail(crgpu_ctx *c, int code, const char *fmt, ...)
-{
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
-    va_end(ap);
-    if (c) c->err = buf;
-    return code;
-}
-
-#define CK(call)                                                                                         \
-    do {                                                                                                 \
-        cudaError_t e_ = (call);                                                                         \
-        if (e_ != cudaSuccess)                                                                           \
-            return fail(ctx, e_ == cudaErrorMemoryAllocation ? CRGPU_E_NOMEM : CRGPU_E_CUDA, "%s: %s (%s:%d)", #call, \
-                        cudaGetErrorString(e_), __FILE__, __LINE__);                                     \
-    } while (0)
-
-static cudaEvent_t next_event(crgpu_ctx *c)
-{
-    if (c->ev_used == c->ev_pool.size()) {
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        c->ev_pool.push_back(e);
-    }
-    return c->ev_pool[c->ev_used++];
-}
-static void span_begin(crgpu_ctx *c, int family)
-{
-    TimedSpan s{family, next_event(c), next_event(c)};
-    cudaEventRecord(s.a, c->stream);
-    c->spans.push_back(s);
-}
-static void span_end(crgpu_ctx *c)
-{
-    cudaEventRecord(c->spans.back().b, c->stream);
-    c->launches[c->spans.back().family]++;
-}
-static void timing_reset(crgpu_ctx *c)
-{
-    c->ev_used = 0;
-    c->spans.clear();
-    for (int i = 0; i < T_N; ++i) { c->ms[i] = 0; c->launches[i] = 0; }
-}
-static void timing_collect(crgpu_ctx *c)
-{
-    for (auto &s : c->spans) {
-        float ms = 0;
-        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) c->ms[s.family] += ms;
-    }
-    c->spans.clear();
-    c->ev_used = 0;
-}
 
 extern "C" {
 
@@ -260,8 +138,9 @@ namespace crgpu {
 // subset: optional list of read indices to align (device reads/offsets cover ALL reads); when
 // null all n_total reads are aligned.  recs/strings are indexed by ORIGINAL read index.
 int align_core(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_reads, const int64_t *d_offsets,
-               const int64_t *h_offsets, const int32_t *subset, int64_t nsub, double gapopen, double gapextend,
-               crgpu_aln_rec *d_recs, uint8_t *d_ref, uint8_t *d_mark, uint8_t *d_qry, int64_t slot, int64_t *n_cells)
+               const int64_t *h_offsets, const int32_t *subset, int64_t nsub, const int32_t *d_out_index, int rc_out,
+               double gapopen, double gapextend, crgpu_aln_rec *d_recs, uint8_t *d_ref, uint8_t *d_mark, uint8_t *d_qry,
+               int64_t slot, int64_t *n_cells)
 {
     if (La < CRGPU_MIN_LEN || La > CRGPU_MAX_AMPLICON)
         return fail(ctx, CRGPU_E_ALIGN, "amplicon length %d outside [%d, %d]", La, CRGPU_MIN_LEN, CRGPU_MAX_AMPLICON);
@@ -424,6 +303,7 @@ int align_core(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_re
         wa.La = La; wa.GK = GK; wa.P = P; wa.p0 = fa.p0; wa.p1 = fa.p1;
         wa.open = open_s; wa.ext = ext_s; wa.scale = scale;
         wa.recs = d_recs; wa.ref_out = d_ref; wa.mark_out = d_mark; wa.qry_out = d_qry; wa.slot = slot;
+        wa.out_index = d_out_index; wa.rc_out = rc_out;
         span_begin(ctx, T_WALK);
         CK(launch_walk(wa, s));
         span_end(ctx);
@@ -475,7 +355,7 @@ int crgpu_align(crgpu_ctx *ctx, int mem, const char *amplicon, int amplicon_len,
             d_ref = ctx->sref.as<uint8_t>(); d_mark = ctx->smark.as<uint8_t>(); d_qry = ctx->sqry.as<uint8_t>();
         }
     }
-    int rc = align_core(ctx, amplicon, amplicon_len, d_reads, d_off, h_off, nullptr, n, gapopen, gapextend, d_recs,
+    int rc = align_core(ctx, amplicon, amplicon_len, d_reads, d_off, h_off, nullptr, n, nullptr, 0, gapopen, gapextend, d_recs,
                         d_ref, d_mark, d_qry, slot, nullptr);
     if (rc != CRGPU_OK) { cudaStreamSynchronize(s); return rc; }
     if (mem == CRGPU_MEM_HOST) {

@@ -66,6 +66,9 @@ struct WalkArgs {
     void *recs;               // crgpu_aln_rec*
     uint8_t *ref_out, *mark_out, *qry_out;   // may be null
     int64_t slot;
+    const int32_t *out_index; // optional: output row of read r (null: row r)
+    int rc_out;               // 1: the amplicon is a reverse complement; emit rows flipped back to the
+                              // forward strand (CORE:1982-1990), left-aligned in the slot
 };
 
 }  // namespace crgpu

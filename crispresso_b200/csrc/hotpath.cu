@@ -1,0 +1,367 @@
+// hotpath.cu -- host side of seam S3 (crgpu_quantify) and of the fused path crgpu_align_quantify
+// (CRISPResso/CRISPRessoCORE.py:1791-2072 + 2773-2864 in one call, no needle text in between).
+#include "crgpu_internal.h"
+
+#include "quant_args.cuh"
+
+namespace crgpu {
+
+cudaError_t launch_quantify(const QuantArgs &a, cudaStream_t s);
+cudaError_t launch_prepare_rows(const crgpu_aln_rec *ref, const crgpu_aln_rec *rep, int64_t n, double min_identity,
+                                int32_t *tenths_ref, int32_t *tenths_rep, int32_t *aln_off, int32_t *alnlen, uint8_t *unmod,
+                                uint8_t *flags_out, cudaStream_t s);
+cudaError_t launch_prepare_rc_rows(const crgpu_aln_rec *rc, const int32_t *rc_read, int64_t n, double min_identity,
+                                   int32_t *tenths_ref, int32_t *aln_off, int32_t *alnlen, uint8_t *unmod, uint8_t *active,
+                                   uint8_t *kept, cudaStream_t s);
+
+constexpr int N_ACC_TAIL = CRGPU_NUM_COUNTERS + 5;   // counters + 4 class counts + rows seen
+
+// Device accumulators for one amplicon: [vectors 15*L][hist_in][hist_fs][counters tail]
+struct Accum {
+    int L = 0, hist_len = 0;
+    size_t words() const { return (size_t)CRGPU_NUM_VECTORS * L + 2 * (size_t)hist_len + N_ACC_TAIL; }
+    unsigned long long *base = nullptr;
+    unsigned long long *vectors() const { return base; }
+    unsigned long long *hist_in() const { return base + (size_t)CRGPU_NUM_VECTORS * L; }
+    unsigned long long *hist_fs() const { return hist_in() + hist_len; }
+    unsigned long long *tail() const { return hist_fs() + hist_len; }
+};
+
+static void pack_mask(const uint8_t *mask, int L, std::vector<uint32_t> &bits, int W, int which)
+{
+    for (int w = 0; w < W; ++w) bits[(size_t)which * W + w] = 0;
+    if (!mask) return;
+    for (int p = 0; p < L; ++p) if (mask[p]) bits[(size_t)which * W + (p >> 5)] |= 1u << (p & 31);
+}
+
+static int quant_setup(crgpu_ctx *ctx, const crgpu_quant_params *q, int hist_len, Accum *acc, const uint32_t **d_bits, int *W_out)
+{
+    const int L = q->amplicon_len;
+    if (L < CRGPU_MIN_LEN || L > CRGPU_MAX_AMPLICON) return fail(ctx, CRGPU_E_ARG, "quantify: amplicon_len %d out of range", L);
+    if (!q->include_mask) return fail(ctx, CRGPU_E_ARG, "quantify: include_mask is required");
+    if ((q->flags & CRGPU_Q_FRAMESHIFT) && (!q->exon_mask || !q->splice_mask || hist_len <= 0))
+        return fail(ctx, CRGPU_E_ARG, "quantify: frameshift analysis needs exon_mask, splice_mask and histograms");
+    const int W = (L + 31) / 32;
+    std::vector<uint32_t> bits((size_t)3 * W);
+    pack_mask(q->include_mask, L, bits, W, 0);
+    pack_mask(q->exon_mask, L, bits, W, 1);
+    pack_mask(q->splice_mask, L, bits, W, 2);
+    CK(ctx->q_in[0].reserve(bits.size() * 4));
+    CK(cudaMemcpyAsync(ctx->q_in[0].p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    acc->L = L; acc->hist_len = hist_len > 0 ? hist_len : 0;
+    CK(ctx->q_out[0].reserve(acc->words() * 8));
+    acc->base = ctx->q_out[0].as<unsigned long long>();
+    CK(cudaMemsetAsync(acc->base, 0, acc->words() * 8, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));    // `bits` is a local
+    *d_bits = ctx->q_in[0].as<uint32_t>();
+    *W_out = W;
+    return CRGPU_OK;
+}
+
+// Add the device accumulators into the caller's host arrays.
+static int quant_collect(crgpu_ctx *ctx, const Accum &acc, int64_t *vectors, int64_t *hist_in, int64_t *hist_fs,
+                         int64_t *counters, int64_t *class_counts, int64_t *n_total)
+{
+    std::vector<unsigned long long> h(acc.words());
+    CK(cudaMemcpyAsync(h.data(), acc.base, acc.words() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const size_t nv = (size_t)CRGPU_NUM_VECTORS * acc.L;
+    if (vectors) for (size_t i = 0; i < nv; ++i) vectors[i] += (int64_t)h[i];
+    if (hist_in) for (int i = 0; i < acc.hist_len; ++i) hist_in[i] += (int64_t)h[nv + i];
+    if (hist_fs) for (int i = 0; i < acc.hist_len; ++i) hist_fs[i] += (int64_t)h[nv + acc.hist_len + i];
+    const unsigned long long *tail = h.data() + nv + 2 * (size_t)acc.hist_len;
+    if (counters) for (int i = 0; i < CRGPU_NUM_COUNTERS; ++i) counters[i] += (int64_t)tail[i];
+    if (class_counts) for (int i = 0; i < 4; ++i) class_counts[i] += (int64_t)tail[CRGPU_NUM_COUNTERS + i];
+    if (n_total) *n_total += (int64_t)tail[CRGPU_NUM_COUNTERS + 4];
+    return CRGPU_OK;
+}
+
+static void fill_quant_args(QuantArgs *qa, const crgpu_quant_params *q, const Accum &acc, const uint32_t *d_bits, int W,
+                            int hist_zero)
+{
+    qa->L = q->amplicon_len; qa->W = W; qa->flags = q->flags; qa->hdr_thr = q->hdr_perfect_alignment_threshold;
+    qa->inc = d_bits; qa->exon = d_bits + W; qa->splice = d_bits + 2 * W;
+    qa->vectors = acc.vectors(); qa->hist_in = acc.hist_in(); qa->hist_fs = acc.hist_fs();
+    qa->hist_len = acc.hist_len; qa->hist_zero = hist_zero; qa->counters = acc.tail();
+}
+
+}  // namespace crgpu
+
+using namespace crgpu;
+
+extern "C" {
+
+int crgpu_quantify(crgpu_ctx *ctx, int mem, const crgpu_quant_params *params,
+                   const uint8_t *ref_rows, const uint8_t *mark_rows, const uint8_t *qry_rows, int64_t slot,
+                   const int32_t *aln_off, const int32_t *alnlen,
+                   const int32_t *tenths_ref, const int32_t *tenths_rep, const uint8_t *unmodified_in,
+                   int64_t n, crgpu_read_rec *out_recs,
+                   int64_t *vectors, int64_t *hist_inframe, int64_t *hist_frameshift, int32_t hist_len,
+                   int32_t hist_zero, int64_t *counters)
+{
+    if (!ctx) return CRGPU_E_ARG;
+    if (!params || n < 0 || slot <= 0) return fail(ctx, CRGPU_E_ARG, "crgpu_quantify: bad argument");
+    if (n > 0 && (!ref_rows || !mark_rows || !qry_rows || !alnlen || !tenths_ref || !unmodified_in || !out_recs))
+        return fail(ctx, CRGPU_E_ARG, "crgpu_quantify: null per-read array");
+    if (mem != CRGPU_MEM_HOST && mem != CRGPU_MEM_DEVICE) return fail(ctx, CRGPU_E_ARG, "bad mem");
+    timing_reset(ctx);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    Accum acc; const uint32_t *d_bits; int W;
+    int rc = quant_setup(ctx, params, hist_len, &acc, &d_bits, &W);
+    if (rc) return rc;
+    QuantArgs qa{};
+    fill_quant_args(&qa, params, acc, d_bits, W, hist_zero);
+    qa.slot = slot; qa.n = n; qa.active = nullptr; qa.active_bit = 0;
+    if (mem == CRGPU_MEM_DEVICE) {
+        qa.ref = ref_rows; qa.mark = mark_rows; qa.qry = qry_rows; qa.aln_off = aln_off; qa.alnlen = alnlen;
+        qa.tenths_ref = tenths_ref; qa.tenths_rep = tenths_rep; qa.unmod_in = unmodified_in; qa.recs = out_recs;
+    } else if (n > 0) {
+        const size_t rb = (size_t)n * slot;
+        CK(ctx->sref.reserve(rb)); CK(ctx->smark.reserve(rb)); CK(ctx->sqry.reserve(rb));
+        CK(ctx->q_in[1].reserve((size_t)n * 4)); CK(ctx->q_in[2].reserve((size_t)n * 4));
+        CK(ctx->q_in[3].reserve((size_t)n * 4)); CK(ctx->q_in[4].reserve((size_t)n * 4));
+        CK(ctx->q_in[5].reserve((size_t)n)); CK(ctx->q_out[1].reserve((size_t)n * sizeof(crgpu_read_rec)));
+        CK(cudaMemcpyAsync(ctx->sref.p, ref_rows, rb, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->smark.p, mark_rows, rb, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->sqry.p, qry_rows, rb, cudaMemcpyHostToDevice, s));
+        if (aln_off) CK(cudaMemcpyAsync(ctx->q_in[1].p, aln_off, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->q_in[2].p, alnlen, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->q_in[3].p, tenths_ref, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        if (tenths_rep) CK(cudaMemcpyAsync(ctx->q_in[4].p, tenths_rep, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->q_in[5].p, unmodified_in, (size_t)n, cudaMemcpyHostToDevice, s));
+        qa.ref = ctx->sref.as<uint8_t>(); qa.mark = ctx->smark.as<uint8_t>(); qa.qry = ctx->sqry.as<uint8_t>();
+        qa.aln_off = aln_off ? ctx->q_in[1].as<int32_t>() : nullptr; qa.alnlen = ctx->q_in[2].as<int32_t>();
+        qa.tenths_ref = ctx->q_in[3].as<int32_t>(); qa.tenths_rep = tenths_rep ? ctx->q_in[4].as<int32_t>() : nullptr;
+        qa.unmod_in = ctx->q_in[5].as<uint8_t>(); qa.recs = ctx->q_out[1].as<crgpu_read_rec>();
+    }
+    span_begin(ctx, T_QUANT);
+    CK(launch_quantify(qa, s));
+    span_end(ctx);
+    if (mem == CRGPU_MEM_HOST && n > 0)
+        CK(cudaMemcpyAsync(out_recs, qa.recs, (size_t)n * sizeof(crgpu_read_rec), cudaMemcpyDeviceToHost, s));
+    rc = quant_collect(ctx, acc, vectors, hist_inframe, hist_frameshift, counters, nullptr, nullptr);
+    if (rc) return rc;
+    timing_collect(ctx);
+    return CRGPU_OK;
+}
+
+static std::string revcomp_upper(const char *s, int n)
+{
+    std::string out((size_t)n, 'N');
+    for (int i = 0; i < n; ++i) {
+        char c = s[n - 1 - i];
+        switch (c) {
+        case 'A': case 'a': c = 'T'; break;
+        case 'C': case 'c': c = 'G'; break;
+        case 'G': case 'g': c = 'C'; break;
+        case 'T': case 't': c = 'A'; break;
+        default: c = 'N'; break;
+        }
+        out[(size_t)i] = c;
+    }
+    return out;
+}
+
+int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int amplicon_len,
+                         const crgpu_path_params *path, const crgpu_quant_params *quant,
+                         const uint8_t *reads, const int64_t *offsets, int64_t n, crgpu_path_out *out)
+{
+    if (!ctx) return CRGPU_E_ARG;
+    if (!amplicon || !path || !quant || !out || n < 0 || (n > 0 && (!reads || !offsets)))
+        return fail(ctx, CRGPU_E_ARG, "crgpu_align_quantify: null pointer or negative count");
+    if (mem != CRGPU_MEM_HOST && mem != CRGPU_MEM_DEVICE) return fail(ctx, CRGPU_E_ARG, "bad mem");
+    if (quant->amplicon_len != amplicon_len) return fail(ctx, CRGPU_E_ARG, "quant->amplicon_len != amplicon_len");
+    if (n >= (int64_t)1 << 31) return fail(ctx, CRGPU_E_ARG, "too many reads in one call");
+    const bool want_rows = out->ref_rows || out->mark_rows || out->qry_rows;
+    if (want_rows && !(out->ref_rows && out->mark_rows && out->qry_rows)) return fail(ctx, CRGPU_E_ARG, "pass all three row buffers or none");
+    const bool want_rc_rows = out->rc_ref_rows || out->rc_mark_rows || out->rc_qry_rows;
+    if (want_rc_rows && !(out->rc_ref_rows && out->rc_mark_rows && out->rc_qry_rows)) return fail(ctx, CRGPU_E_ARG, "pass all three rc row buffers or none");
+    const bool has_hdr = path->hdr_amplicon != nullptr && path->hdr_amplicon_len > 0;
+    if (has_hdr != ((quant->flags & CRGPU_Q_HAS_HDR) != 0)) return fail(ctx, CRGPU_E_ARG, "CRGPU_Q_HAS_HDR must match path->hdr_amplicon");
+    timing_reset(ctx);
+    out->rc_n = 0;
+    if (n == 0) return CRGPU_OK;
+    if (!out->kept || !out->aln || !out->recs) return fail(ctx, CRGPU_E_ARG, "kept/aln/recs are required");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const bool host = mem == CRGPU_MEM_HOST;
+
+    // ---- inputs on the device, offsets on the host ----
+    std::vector<int64_t> h_off_copy;
+    const int64_t *h_off = offsets;
+    const uint8_t *d_reads = reads; const int64_t *d_off = offsets;
+    if (!host) {
+        h_off_copy.resize((size_t)n + 1);
+        CK(cudaMemcpyAsync(h_off_copy.data(), offsets, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        h_off = h_off_copy.data();
+    } else {
+        const int64_t total = offsets[n];
+        CK(ctx->reads.reserve((size_t)std::max<int64_t>(total, 1)));
+        CK(ctx->offsets.reserve((size_t)(n + 1) * 8));
+        CK(cudaMemcpyAsync(ctx->reads.p, reads, (size_t)total, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->offsets.p, offsets, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s));
+        d_reads = ctx->reads.as<uint8_t>(); d_off = ctx->offsets.as<int64_t>();
+    }
+    int maxlen = 0;
+    for (int64_t i = 0; i < n; ++i) maxlen = std::max<int64_t>(maxlen, h_off[i + 1] - h_off[i]);
+    const int max_amp = std::max(amplicon_len, has_hdr ? path->hdr_amplicon_len : 0);
+    // rows are always produced on the device (the quantifier reads them); slot = caller's or minimal
+    int64_t slot = out->slot > 0 ? out->slot : (int64_t)max_amp + maxlen;
+    if (slot < (int64_t)amplicon_len + maxlen) return fail(ctx, CRGPU_E_ARG, "slot %lld too small", (long long)slot);
+
+    // ---- device outputs ----
+    uint8_t *d_kept; crgpu_aln_rec *d_aln; crgpu_read_rec *d_recs; int32_t *d_trep;
+    uint8_t *d_ref, *d_mark, *d_qry;
+    if (host) {
+        CK(ctx->aux[0].reserve((size_t)n)); CK(ctx->recs.reserve((size_t)n * sizeof(crgpu_aln_rec)));
+        CK(ctx->q_out[1].reserve((size_t)n * sizeof(crgpu_read_rec))); CK(ctx->q_in[4].reserve((size_t)n * 4));
+        d_kept = ctx->aux[0].as<uint8_t>(); d_aln = ctx->recs.as<crgpu_aln_rec>();
+        d_recs = ctx->q_out[1].as<crgpu_read_rec>(); d_trep = ctx->q_in[4].as<int32_t>();
+    } else {
+        d_kept = out->kept; d_aln = out->aln; d_recs = out->recs;
+        if (out->tenths_rep) d_trep = out->tenths_rep;
+        else { CK(ctx->q_in[4].reserve((size_t)n * 4)); d_trep = ctx->q_in[4].as<int32_t>(); }
+    }
+    if (!host && want_rows) { d_ref = out->ref_rows; d_mark = out->mark_rows; d_qry = out->qry_rows; }
+    else {
+        const size_t rb = (size_t)n * slot;
+        CK(ctx->sref.reserve(rb)); CK(ctx->smark.reserve(rb)); CK(ctx->sqry.reserve(rb));
+        d_ref = ctx->sref.as<uint8_t>(); d_mark = ctx->smark.as<uint8_t>(); d_qry = ctx->sqry.as<uint8_t>();
+    }
+
+    // ---- 1. forward alignments ----
+    int64_t cells = 0;
+    int rc = align_core(ctx, amplicon, amplicon_len, d_reads, d_off, h_off, nullptr, n, nullptr, 0, path->gapopen,
+                        path->gapextend, d_aln, d_ref, d_mark, d_qry, slot, &cells);
+    if (rc) { cudaStreamSynchronize(s); return rc; }
+    crgpu_aln_rec *d_aln_hdr = nullptr;
+    if (has_hdr) {
+        CK(ctx->aux[1].reserve((size_t)n * sizeof(crgpu_aln_rec)));
+        d_aln_hdr = ctx->aux[1].as<crgpu_aln_rec>();
+        rc = align_core(ctx, path->hdr_amplicon, path->hdr_amplicon_len, d_reads, d_off, h_off, nullptr, n, nullptr, 0,
+                        path->gapopen, path->gapextend, d_aln_hdr, nullptr, nullptr, nullptr, slot, &cells);
+        if (rc) { cudaStreamSynchronize(s); return rc; }
+    }
+
+    // ---- 2. keep / rescue decision ----
+    CK(ctx->q_in[1].reserve((size_t)n * 4)); CK(ctx->q_in[2].reserve((size_t)n * 4)); CK(ctx->q_in[3].reserve((size_t)n * 4));
+    CK(ctx->q_in[5].reserve((size_t)n));
+    int32_t *d_aln_off = ctx->q_in[1].as<int32_t>(), *d_alnlen = ctx->q_in[2].as<int32_t>(), *d_tref = ctx->q_in[3].as<int32_t>();
+    uint8_t *d_unmod = ctx->q_in[5].as<uint8_t>();
+    span_begin(ctx, T_OTHER);
+    CK(launch_prepare_rows(d_aln, d_aln_hdr, n, path->min_identity_score, d_tref, d_trep, d_aln_off, d_alnlen, d_unmod, d_kept, s));
+    span_end(ctx);
+
+    std::vector<int32_t> rc_read;
+    if (path->rc_rescue) {
+        std::vector<uint8_t> h_flags((size_t)n);
+        CK(cudaMemcpyAsync(h_flags.data(), d_kept, (size_t)n, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        for (int64_t i = 0; i < n; ++i) if (h_flags[(size_t)i] & 4) rc_read.push_back((int32_t)i);
+    }
+    const int64_t nrc = (int64_t)rc_read.size();
+    out->rc_n = nrc;
+    if (nrc > out->rc_cap && (out->rc_read || out->rc_aln || out->rc_recs || want_rc_rows))
+        return fail(ctx, CRGPU_E_ARG, "rc_cap %lld < %lld reads re-aligned to the reverse complement", (long long)out->rc_cap, (long long)nrc);
+
+    // ---- 3. quantification of the forward rows ----
+    Accum acc; const uint32_t *d_bits; int W;
+    rc = quant_setup(ctx, quant, out->hist_len, &acc, &d_bits, &W);
+    if (rc) return rc;
+    QuantArgs qa{};
+    fill_quant_args(&qa, quant, acc, d_bits, W, out->hist_zero);
+    qa.ref = d_ref; qa.mark = d_mark; qa.qry = d_qry; qa.slot = slot; qa.aln_off = d_aln_off; qa.alnlen = d_alnlen;
+    qa.tenths_ref = d_tref; qa.tenths_rep = has_hdr ? d_trep : nullptr; qa.unmod_in = d_unmod;
+    qa.active = d_kept; qa.active_bit = 1; qa.n = n; qa.recs = d_recs;
+    if (amplicon_len > 0) {
+        bool hasN = false;
+        for (int i = 0; i < amplicon_len; ++i) hasN |= (amplicon[i] == 'N' || amplicon[i] == 'n');
+        if (hasN) qa.flags |= CRGPU_Q_MASK_N;                      // CORE:2033
+    }
+    CK(cudaMemsetAsync(d_recs, 0, (size_t)n * sizeof(crgpu_read_rec), s));
+    span_begin(ctx, T_QUANT);
+    CK(launch_quantify(qa, s));
+    span_end(ctx);
+
+    // ---- 4. reverse-complement rescue (CORE:1873-2000) ----
+    crgpu_aln_rec *d_rc_aln = nullptr; crgpu_read_rec *d_rc_recs = nullptr;
+    uint8_t *d_rc_ref = nullptr, *d_rc_mark = nullptr, *d_rc_qry = nullptr;
+    if (nrc > 0) {
+        const std::string amp_rc = revcomp_upper(amplicon, amplicon_len);
+        // out_index: read -> compact RC row
+        std::vector<int32_t> out_index((size_t)n, -1);
+        for (int64_t j = 0; j < nrc; ++j) out_index[(size_t)rc_read[(size_t)j]] = (int32_t)j;
+        CK(ctx->aux[2].reserve((size_t)n * 4)); CK(ctx->aux[3].reserve((size_t)nrc * 4));
+        CK(cudaMemcpyAsync(ctx->aux[2].p, out_index.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->aux[3].p, rc_read.data(), (size_t)nrc * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+        const size_t rb = (size_t)nrc * slot;
+        if (!host && out->rc_aln) d_rc_aln = out->rc_aln;
+        else { CK(ctx->aux[4].reserve((size_t)nrc * sizeof(crgpu_aln_rec))); d_rc_aln = ctx->aux[4].as<crgpu_aln_rec>(); }
+        if (!host && out->rc_recs) d_rc_recs = out->rc_recs;
+        else { CK(ctx->aux[5].reserve((size_t)nrc * sizeof(crgpu_read_rec))); d_rc_recs = ctx->aux[5].as<crgpu_read_rec>(); }
+        if (!host && want_rc_rows) { d_rc_ref = out->rc_ref_rows; d_rc_mark = out->rc_mark_rows; d_rc_qry = out->rc_qry_rows; }
+        else {
+            CK(ctx->q_out[2].reserve(rb * 3));
+            d_rc_ref = ctx->q_out[2].as<uint8_t>(); d_rc_mark = d_rc_ref + rb; d_rc_qry = d_rc_mark + rb;
+        }
+        rc = align_core(ctx, amp_rc.data(), amplicon_len, d_reads, d_off, h_off, rc_read.data(), nrc, ctx->aux[2].as<int32_t>(), 1,
+                        path->gapopen, path->gapextend, d_rc_aln, d_rc_ref, d_rc_mark, d_rc_qry, slot, &cells);
+        if (rc) { cudaStreamSynchronize(s); return rc; }
+        // per-row SoA for the quantifier (separate scratch: the forward views are still in use by the stream)
+        CK(ctx->q_out[3].reserve((size_t)nrc * 14));
+        int32_t *r_tref = ctx->q_out[3].as<int32_t>();
+        int32_t *r_off = r_tref + nrc, *r_len = r_off + nrc;
+        uint8_t *r_unmod = reinterpret_cast<uint8_t *>(r_len + nrc), *r_active = r_unmod + nrc;
+        span_begin(ctx, T_OTHER);
+        CK(launch_prepare_rc_rows(d_rc_aln, ctx->aux[3].as<int32_t>(), nrc, path->min_identity_score, r_tref, r_off, r_len,
+                                  r_unmod, r_active, d_kept, s));
+        span_end(ctx);
+        QuantArgs qr = qa;
+        qr.ref = d_rc_ref; qr.mark = d_rc_mark; qr.qry = d_rc_qry; qr.aln_off = r_off; qr.alnlen = r_len;
+        qr.tenths_ref = r_tref; qr.tenths_rep = nullptr; qr.unmod_in = r_unmod; qr.active = r_active; qr.active_bit = 1;
+        qr.n = nrc; qr.recs = d_rc_recs;
+        CK(cudaMemsetAsync(d_rc_recs, 0, (size_t)nrc * sizeof(crgpu_read_rec), s));
+        span_begin(ctx, T_QUANT);
+        CK(launch_quantify(qr, s));
+        span_end(ctx);
+    }
+
+    // ---- 5. results ----
+    if (host) {
+        CK(cudaMemcpyAsync(out->kept, d_kept, (size_t)n, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(out->aln, d_aln, (size_t)n * sizeof(crgpu_aln_rec), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(out->recs, d_recs, (size_t)n * sizeof(crgpu_read_rec), cudaMemcpyDeviceToHost, s));
+        if (out->tenths_rep) CK(cudaMemcpyAsync(out->tenths_rep, d_trep, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        if (want_rows) {
+            if (out->slot != slot) return fail(ctx, CRGPU_E_ARG, "out->slot must be set when rows are requested");
+            const size_t rb = (size_t)n * slot;
+            CK(cudaMemcpyAsync(out->ref_rows, d_ref, rb, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(out->mark_rows, d_mark, rb, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(out->qry_rows, d_qry, rb, cudaMemcpyDeviceToHost, s));
+        }
+        if (nrc > 0) {
+            if (out->rc_read) memcpy(out->rc_read, rc_read.data(), (size_t)nrc * 4);
+            if (out->rc_aln) CK(cudaMemcpyAsync(out->rc_aln, d_rc_aln, (size_t)nrc * sizeof(crgpu_aln_rec), cudaMemcpyDeviceToHost, s));
+            if (out->rc_recs) CK(cudaMemcpyAsync(out->rc_recs, d_rc_recs, (size_t)nrc * sizeof(crgpu_read_rec), cudaMemcpyDeviceToHost, s));
+            if (want_rc_rows) {
+                const size_t rb = (size_t)nrc * slot;
+                CK(cudaMemcpyAsync(out->rc_ref_rows, d_rc_ref, rb, cudaMemcpyDeviceToHost, s));
+                CK(cudaMemcpyAsync(out->rc_mark_rows, d_rc_mark, rb, cudaMemcpyDeviceToHost, s));
+                CK(cudaMemcpyAsync(out->rc_qry_rows, d_rc_qry, rb, cudaMemcpyDeviceToHost, s));
+            }
+        }
+    } else if (nrc > 0 && out->rc_read) {
+        CK(cudaMemcpyAsync(out->rc_read, rc_read.data(), (size_t)nrc * 4, cudaMemcpyHostToDevice, s));
+    }
+    rc = quant_collect(ctx, acc, out->vectors, out->hist_inframe, out->hist_frameshift, out->counters, out->class_counts,
+                       &out->n_total);
+    if (rc) return rc;
+    out->n_cells += cells;
+    timing_collect(ctx);
+    return CRGPU_OK;
+}
+
+}  // extern "C"

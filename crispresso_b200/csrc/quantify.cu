@@ -1,17 +1,307 @@
-// quantify.cu -- placeholder translation unit; the kernel lands in the next commit.
+// quantify.cu -- k_quantify: fused indel/substitution extraction, read classification and
+// histogram reduction.  Replaces CRISPResso's per-read Python loop process_df_chunk
+// (CRISPResso/CRISPRessoCORE.py:428-753) together with the per-row preparation that feeds it
+// (ignore_n_in_alignment CORE:2040-2052, compute_ref_positions CORE:2055-2067).
+//
+// One thread per aligned read.  The read's substitution / deletion / insertion-flank position
+// sets are kept as amplicon-length bitmaps (<= 32 words each) in local memory, which makes the
+// reference's set semantics -- INCLUDE_IDXS.intersection(...), numpy's buffered fancy-index
+// `vec[list] += 1` that increments a duplicated index once, negative flank indices wrapping
+// round the amplicon -- plain AND / OR / popcount.
+// Per-position vectors, the frameshift histograms and the counters are reduced with 64-bit
+// global atomics (REDG); per-read results go to crgpu_read_rec.
 #include "../../include/crgpu.h"
 #include "crgpu_common.cuh"
+
+#include "quant_args.cuh"
+
 namespace crgpu {
-int quantify_device(crgpu_ctx *, const crgpu_quant_params *, const uint8_t *, const uint8_t *, const uint8_t *, int64_t,
-                    const int32_t *, const int32_t *, const int32_t *, const int32_t *, const uint8_t *, int64_t,
-                    crgpu_read_rec *, int64_t *, int64_t *, int64_t *, int32_t, int32_t, int64_t *) { return CRGPU_E_ARG; }
+
+constexpr int MAXW = CRGPU_MAX_AMPLICON / 32;
+
+
+// CORE:2059: only upper-case A,T,C,G,N advance the amplicon index
+__device__ __forceinline__ bool is_ref_base(uint8_t c) { return c == 'A' || c == 'T' || c == 'C' || c == 'G' || c == 'N'; }
+
+__device__ __forceinline__ void set_bit(uint32_t *bits, int v) { bits[v >> 5] |= 1u << (v & 31); }
+__device__ __forceinline__ bool get_bit(const uint32_t *bits, int v) { return (bits[v >> 5] >> (v & 31)) & 1u; }
+
+__device__ __forceinline__ void add_bits(unsigned long long *vec, const uint32_t *bits, int W)
+{
+    for (int w = 0; w < W; ++w) {
+        uint32_t x = bits[w];
+        while (x) {
+            const int b = __ffs(x) - 1;
+            x &= x - 1;
+            atomicAdd(vec + w * 32 + b, 1ull);
+        }
+    }
 }
-extern "C" {
-int crgpu_quantify(crgpu_ctx *, int, const crgpu_quant_params *, const uint8_t *, const uint8_t *, const uint8_t *, int64_t,
-                   const int32_t *, const int32_t *, const int32_t *, const int32_t *, const uint8_t *, int64_t,
-                   crgpu_read_rec *, int64_t *, int64_t *, int64_t *, int32_t, int32_t, int64_t *) { return CRGPU_E_ARG; }
-int crgpu_align_quantify(crgpu_ctx *, int, const char *, int, const crgpu_path_params *, const crgpu_quant_params *,
-                         const uint8_t *, const int64_t *, int64_t, uint8_t *, crgpu_aln_rec *, int32_t *, crgpu_read_rec *,
-                         uint8_t *, uint8_t *, uint8_t *, int64_t, int64_t *, int64_t *, int64_t *, int32_t, int32_t,
-                         int64_t *, int64_t *) { return CRGPU_E_ARG; }
+
+__global__ void __launch_bounds__(128) k_quantify(const QuantArgs a)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    if (a.active && !(a.active[i] & a.active_bit)) return;
+    const int L = a.L, W = a.W, flags = a.flags;
+    const int64_t base = i * a.slot + (a.aln_off ? a.aln_off[i] : 0);
+    const uint8_t *R = a.ref + base, *M = a.mark + base, *Q = a.qry + base;
+    const int n = a.alnlen[i];
+    const bool maskN = flags & CRGPU_Q_MASK_N;
+    crgpu_read_rec rec;
+    rec.cls = 0; rec.pad[0] = rec.pad[1] = rec.pad[2] = 0;
+    rec.n_mutated = rec.n_inserted = rec.n_deleted = 0;
+
+    bool unmod = a.unmod_in[i] != 0;
+    if (maskN && !unmod) {
+        // ignore_n_in_alignment (CORE:2040-2048): markup -> '|' where the amplicon row has N; a
+        // markup made of ONE distinct character (whatever it is) marks the read UNMODIFIED.
+        bool uniform = n > 0;
+        const uint8_t first = n > 0 ? (R[0] == 'N' ? (uint8_t)'|' : M[0]) : 0;
+        for (int c = 1; c < n && uniform; ++c) {
+            const uint8_t ch = R[c] == 'N' ? (uint8_t)'|' : M[c];
+            uniform = ch == first;
+        }
+        if (uniform) unmod = true;
+    }
+    atomicAdd(a.counters + CRGPU_NUM_COUNTERS + 4, 1ull);            // rows seen (n_total)
+    if (unmod) {                                                     // CORE:480-481
+        rec.cls = CRGPU_C_UNMODIFIED;
+        a.recs[i] = rec;
+        atomicAdd(a.counters + CRGPU_NUM_COUNTERS + 0, 1ull);
+        return;
+    }
+
+    uint32_t S[MAXW], D[MAXW], I[MAXW], Dk[MAXW];
+    for (int w = 0; w < W; ++w) { S[w] = D[w] = I[w] = Dk[w] = 0; }
+    const bool doS = !(flags & CRGPU_Q_IGNORE_SUBS), doD = !(flags & CRGPU_Q_IGNORE_DEL), doI = !(flags & CRGPU_Q_IGNORE_INS);
+
+    // ---- pass 1: position sets (CORE:488-533) and the INCLUDE_IDXS test (CORE:553-571) ----
+    bool inc_hit = false, ins_splice = false;
+    {
+        int idx = 0;              // amplicon bases consumed so far == ref_positions of the next base column
+        int c = 0;
+        while (c < n) {
+            const uint8_t rc_ = R[c];
+            if (!is_ref_base(rc_)) {
+                // maximal '-' run in the amplicon row: an insertion [st, en)
+                const int st = c;
+                while (c < n && !is_ref_base(R[c])) ++c;
+                if (doI) {
+                    const int fl = st == 0 ? -1 : idx - 1;                       // ref_positions[max(0, st-1)]
+                    const int fr = c < n ? idx : (idx == 0 ? -1 : -idx);         // ref_positions[min(n-1, en)]
+                    if (fl >= 0) { if (get_bit(a.inc, fl)) inc_hit = true; if (a.splice && get_bit(a.splice, fl)) ins_splice = true; }
+                    if (fr >= 0) { if (get_bit(a.inc, fr)) inc_hit = true; if (a.splice && get_bit(a.splice, fr)) ins_splice = true; }
+                    set_bit(I, fl >= 0 ? fl : L + fl);                           // numpy wraps negative indices (Q1)
+                    set_bit(I, fr >= 0 ? fr : L + fr);
+                }
+                continue;
+            }
+            if (Q[c] == '-') { if (doD) set_bit(D, idx); }
+            else if (doS && M[c] == '.' && !(maskN && rc_ == 'N')) set_bit(S, idx);
+            ++idx; ++c;
+        }
+        for (int w = 0; w < W; ++w) if ((S[w] | D[w]) & a.inc[w]) inc_hit = true;
+    }
+
+    // ---- classification (CORE:535-576) ----
+    const bool has_hdr = flags & CRGPU_Q_HAS_HDR;
+    int cls;
+    {
+        const int tr = a.tenths_ref[i];
+        const int tp = (has_hdr && a.tenths_rep) ? a.tenths_rep[i] : -1;
+        const bool diff_neg = tp >= 0 && tr < tp;                         // score_ref - score_repaired < 0 (NaN -> false)
+        if (has_hdr && diff_neg) cls = ((double)tp / 10.0 >= a.hdr_thr) ? CRGPU_C_HDR : CRGPU_C_MIXED;
+        else cls = inc_hit ? CRGPU_C_NHEJ : CRGPU_C_UNMODIFIED;
+    }
+    rec.cls = (uint8_t)cls;
+    const bool hide = flags & CRGPU_Q_HIDE_OUTSIDE;
+    const bool windowed = cls == CRGPU_C_NHEJ && (flags & CRGPU_Q_WINDOW);
+    unsigned long long *V = a.vectors;
+
+    // ---- vectors that show every event (CORE:578-606) ----
+    if (cls == CRGPU_C_MIXED) {
+        add_bits(V + (size_t)CRGPU_V_MUT_MIXED * L, S, W); add_bits(V + (size_t)CRGPU_V_DEL_MIXED * L, D, W);
+        add_bits(V + (size_t)CRGPU_V_INS_MIXED * L, I, W);
+    } else if (cls == CRGPU_C_HDR) {
+        add_bits(V + (size_t)CRGPU_V_MUT_HDR * L, S, W); add_bits(V + (size_t)CRGPU_V_DEL_HDR * L, D, W);
+        add_bits(V + (size_t)CRGPU_V_INS_HDR * L, I, W);
+    } else if (cls == CRGPU_C_NHEJ && !hide) {
+        add_bits(V + (size_t)CRGPU_V_MUT * L, S, W); add_bits(V + (size_t)CRGPU_V_DEL * L, D, W);
+        add_bits(V + (size_t)CRGPU_V_INS * L, I, W);
+    }
+    {
+        uint32_t A[MAXW];
+        for (int w = 0; w < W; ++w) A[w] = S[w] | D[w] | I[w];
+        add_bits(V + (size_t)CRGPU_V_ANY * L, A, W);                  // also for rows re-classified UNMODIFIED (Q8)
+    }
+    const int cls_slot = cls == CRGPU_C_UNMODIFIED ? 0 : cls == CRGPU_C_NHEJ ? 1 : cls == CRGPU_C_HDR ? 2 : 3;
+    atomicAdd(a.counters + CRGPU_NUM_COUNTERS + cls_slot, 1ull);
+    if (cls == CRGPU_C_UNMODIFIED) { a.recs[i] = rec; return; }
+
+    // ---- window filter for NHEJ (CORE:611-641) ----
+    if (windowed) for (int w = 0; w < W; ++w) S[w] &= a.inc[w];
+
+    // ---- pass 2: per-run sizes, average-size vectors, exon lengths (CORE:652-673) ----
+    const bool fs = flags & CRGPU_Q_FRAMESHIFT;
+    int n_ins = 0, n_del = 0, exon_len = 0;
+    bool have_len = false, exons_modified = false, any_del_kept = false;
+    {
+        int idx = 0, c = 0;
+        while (c < n) {
+            if (!is_ref_base(R[c])) {
+                const int st = c;
+                while (c < n && !is_ref_base(R[c])) ++c;
+                if (doI) {
+                    const int size = c - st;
+                    const int fl = st == 0 ? -1 : idx - 1;
+                    const int fr = c < n ? idx : (idx == 0 ? -1 : -idx);
+                    bool keep = true;
+                    if (windowed) keep = (fl >= 0 && get_bit(a.inc, fl)) || (fr >= 0 && get_bit(a.inc, fr));
+                    if (keep) {
+                        n_ins += size;
+                        const int wl = fl >= 0 ? fl : L + fl, wr = fr >= 0 ? fr : L + fr;
+                        atomicAdd(V + (size_t)CRGPU_V_AVG_INS * L + wl, (unsigned long long)size);
+                        if (wr != wl) atomicAdd(V + (size_t)CRGPU_V_AVG_INS * L + wr, (unsigned long long)size);
+                        if (fs && ((fl >= 0 && get_bit(a.exon, fl)) || (fr >= 0 && get_bit(a.exon, fr)))) {
+                            exon_len += size; have_len = true; exons_modified = true;        // CORE:665-670
+                        }
+                    }
+                }
+                continue;
+            }
+            if (Q[c] == '-' && doD) {
+                const int st = c, p0 = idx;
+                while (c < n && Q[c] == '-') { ++c; ++idx; }      // amplicon has bases under a deletion run
+                const int size = c - st;
+                bool keep = true;
+                if (windowed) {
+                    keep = false;
+                    for (int p = p0; p < p0 + size; ++p) if (get_bit(a.inc, p)) { keep = true; break; }
+                }
+                if (keep) {
+                    n_del += size;
+                    any_del_kept = true;
+                    for (int p = p0; p < p0 + size; ++p) {
+                        set_bit(Dk, p);
+                        atomicAdd(V + (size_t)CRGPU_V_AVG_DEL * L + p, (unsigned long long)size);
+                    }
+                }
+                continue;
+            }
+            ++idx; ++c;
+        }
+    }
+    // deletion_positions_flat is rebuilt only when some deletion survived the window (Q3)
+    const uint32_t *Dflat = (windowed && any_del_kept) ? Dk : D;
+
+    if (cls == CRGPU_C_NHEJ && hide) {                                 // CORE:643-649 (Q5)
+        add_bits(V + (size_t)CRGPU_V_MUT * L, S, W); add_bits(V + (size_t)CRGPU_V_DEL * L, Dflat, W);
+        add_bits(V + (size_t)CRGPU_V_INS * L, I, W);
+    }
+    int n_mut = 0;
+    for (int w = 0; w < W; ++w) n_mut += __popc(S[w]);
+    rec.n_mutated = n_mut; rec.n_inserted = n_ins; rec.n_deleted = n_del;
+    a.recs[i] = rec;
+
+    // ---- frameshift / splice analysis (CORE:675-725) ----
+    if (fs) {
+        int del_exon = 0;
+        bool sub_exon = false, spliced = ins_splice;
+        for (int w = 0; w < W; ++w) {
+            del_exon += __popc(Dflat[w] & a.exon[w]);
+            if (S[w] & a.exon[w]) sub_exon = true;
+            if ((S[w] | Dflat[w]) & a.splice[w]) spliced = true;
+        }
+        if (del_exon > 0) { exons_modified = true; exon_len -= del_exon; have_len = true; }
+        if (sub_exon) exons_modified = true;
+        if (spliced) atomicAdd(a.counters + CRGPU_K_SPLICING_MODIFIED, 1ull);
+        if (exons_modified) {
+            const int key = have_len ? exon_len : 0;
+            const int bin = key + a.hist_zero;
+            const bool inframe = !have_len || (key % 3) == 0;
+            if (inframe) {
+                atomicAdd(a.counters + CRGPU_K_MOD_NON_FRAMESHIFT, 1ull);
+                if (bin >= 0 && bin < a.hist_len) atomicAdd(a.hist_in + bin, 1ull);
+            } else {
+                atomicAdd(a.counters + CRGPU_K_MOD_FRAMESHIFT, 1ull);
+                if (bin >= 0 && bin < a.hist_len) atomicAdd(a.hist_fs + bin, 1ull);
+            }
+        } else {
+            atomicAdd(a.counters + CRGPU_K_NON_MOD_NON_FRAMESHIFT, 1ull);
+            add_bits(V + (size_t)CRGPU_V_INS_NONCODING * L, I, W);
+            add_bits(V + (size_t)CRGPU_V_DEL_NONCODING * L, Dflat, W);
+            add_bits(V + (size_t)CRGPU_V_MUT_NONCODING * L, S, W);
+        }
+    }
 }
+
+cudaError_t launch_quantify(const QuantArgs &a, cudaStream_t s)
+{
+    if (a.n <= 0) return cudaSuccess;
+    k_quantify<<<(unsigned)((a.n + 127) / 128), 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+// From the alignment records of the forward pass(es): SoA views the quantifier wants plus the
+// keep / rescue decision of CORE:1843-1871.  flags_out[i]: bit0 = forward row kept, bit2 = goes to
+// the reverse-complement rescue (score_ref < min_identity).
+__global__ void k_prepare_rows(const crgpu_aln_rec *__restrict__ ref, const crgpu_aln_rec *__restrict__ rep, int64_t n,
+                               double min_identity, int32_t *tenths_ref, int32_t *tenths_rep, int32_t *aln_off,
+                               int32_t *alnlen, uint8_t *unmod, uint8_t *flags_out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int tr = ref[i].tenths;
+    const int tp = rep ? rep[i].tenths : -1;
+    tenths_ref[i] = tr;
+    if (tenths_rep) tenths_rep[i] = tp;
+    aln_off[i] = ref[i].aln_off;
+    alnlen[i] = ref[i].alnlen;
+    unmod[i] = tr == 1000;                                    // score_ref == 100 (CORE:2014)
+    const double sr = (double)tr / 10.0;
+    uint8_t f = 0;
+    if (sr > min_identity || (tp >= 0 && (double)tp / 10.0 > min_identity)) f |= 1;
+    if (sr < min_identity) f |= 4;
+    if (flags_out) flags_out[i] = f;
+}
+
+// RC rows (compact): keep iff score_ref(rc) > min_identity (CORE:1956-1959 with NaN score_repaired,
+// 1976-1978); sets bit1 of kept[read].
+__global__ void k_prepare_rc_rows(const crgpu_aln_rec *__restrict__ rc, const int32_t *__restrict__ rc_read, int64_t n,
+                                  double min_identity, int32_t *tenths_ref, int32_t *aln_off, int32_t *alnlen,
+                                  uint8_t *unmod, uint8_t *active, uint8_t *kept)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int tr = rc[j].tenths;
+    tenths_ref[j] = tr;
+    aln_off[j] = rc[j].aln_off;
+    alnlen[j] = rc[j].alnlen;
+    unmod[j] = tr == 1000;
+    const bool k = (double)tr / 10.0 > min_identity;
+    active[j] = k ? 1 : 0;
+    if (k) kept[rc_read[j]] |= 2;
+}
+
+cudaError_t launch_prepare_rows(const crgpu_aln_rec *ref, const crgpu_aln_rec *rep, int64_t n, double min_identity,
+                                int32_t *tenths_ref, int32_t *tenths_rep, int32_t *aln_off, int32_t *alnlen, uint8_t *unmod,
+                                uint8_t *flags_out, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    k_prepare_rows<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ref, rep, n, min_identity, tenths_ref, tenths_rep, aln_off,
+                                                              alnlen, unmod, flags_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_prepare_rc_rows(const crgpu_aln_rec *rc, const int32_t *rc_read, int64_t n, double min_identity,
+                                   int32_t *tenths_ref, int32_t *aln_off, int32_t *alnlen, uint8_t *unmod, uint8_t *active,
+                                   uint8_t *kept, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    k_prepare_rc_rows<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rc, rc_read, n, min_identity, tenths_ref, aln_off, alnlen,
+                                                                 unmod, active, kept);
+    return cudaGetLastError();
+}
+
+}  // namespace crgpu

@@ -52,6 +52,19 @@ __global__ void k_encode_pairs(const uint8_t *__restrict__ reads, const int64_t 
     }
 }
 
+// reverse_complement() of the reference upper-cases and complements (CORE:141-144)
+__device__ __forceinline__ uint8_t comp_upper(uint8_t c)
+{
+    switch (c) {
+    case 'A': case 'a': return 'T';
+    case 'C': case 'c': return 'G';
+    case 'G': case 'g': return 'C';
+    case 'T': case 't': case 'U': case 'u': return 'A';
+    case 'N': case 'n': return 'N';
+    default: return c;
+    }
+}
+
 __device__ __forceinline__ int half16(uint32_t w, int h) { return (int)((w >> (16 * h)) & 0xffffu); }
 
 // ix[0, j] of needle's first row (App. A.2), true scaled value.
@@ -102,12 +115,20 @@ __global__ void __launch_bounds__(128) k_traceback_walk(const WalkArgs a)
 
     const bool want = a.ref_out != nullptr;
     const int64_t slot = a.slot;
-    uint8_t *ro = want ? a.ref_out + (int64_t)r * slot + slot - 1 : nullptr;
-    uint8_t *mo = want ? a.mark_out + (int64_t)r * slot + slot - 1 : nullptr;
-    uint8_t *qo = want ? a.qry_out + (int64_t)r * slot + slot - 1 : nullptr;
+    const int64_t orow = a.out_index ? a.out_index[r] : r;
+    // Columns are produced from the alignment's right end to its left end.  Forward strand: store
+    // them right to left from the end of the slot.  rc_out: storing them left to right from the
+    // start of the slot, complemented, IS the reverse complement the reference applies afterwards.
+    const int dirn = a.rc_out ? 1 : -1;
+    const int64_t first = a.rc_out ? 0 : slot - 1;
+    uint8_t *ro = want ? a.ref_out + orow * slot + first : nullptr;
+    uint8_t *mo = want ? a.mark_out + orow * slot + first : nullptr;
+    uint8_t *qo = want ? a.qry_out + orow * slot + first : nullptr;
+    const bool rc = a.rc_out != 0;
     int n = 0, ident = 0;
-#define EMIT_GAP_A(cb) do { if (want) { ro[-n] = '-'; mo[-n] = ' '; qo[-n] = (cb); } ++n; } while (0)
-#define EMIT_GAP_B(ca) do { if (want) { ro[-n] = (ca); mo[-n] = ' '; qo[-n] = '-'; } ++n; } while (0)
+#define OUTC(c) (rc ? comp_upper(c) : (c))
+#define EMIT_GAP_A(cb) do { if (want) { ro[dirn * n] = '-'; mo[dirn * n] = ' '; qo[dirn * n] = OUTC(cb); } ++n; } while (0)
+#define EMIT_GAP_B(ca) do { if (want) { ro[dirn * n] = OUTC(ca); mo[dirn * n] = ' '; qo[dirn * n] = '-'; } ++n; } while (0)
 
     // ---- walk (App. A.5): trailing end gaps first (the strings are built right to left)
     for (int x = Lb - 1; x > s2; --x) EMIT_GAP_A(b[x]);
@@ -135,7 +156,7 @@ __global__ void __launch_bounds__(128) k_traceback_walk(const WalkArgs a)
             const uint8_t ca = amp[y], cb = b[x];
             const bool same = base_code(ca) == base_code(cb);
             ident += same;
-            if (want) { ro[-n] = ca; mo[-n] = same ? '|' : '.'; qo[-n] = cb; }
+            if (want) { ro[dirn * n] = OUTC(ca); mo[dirn * n] = same ? '|' : '.'; qo[dirn * n] = OUTC(cb); }
             ++n; --x; --y;
         } else if (dir == 1) {
             // the next cell (y, x-1) continues LEFT iff ix[y,x-1] - gex(y) == ix[y,x].  The fill
@@ -158,19 +179,20 @@ __global__ void __launch_bounds__(128) k_traceback_walk(const WalkArgs a)
     for (; y >= 0; --y) EMIT_GAP_B(amp[y]);
 #undef EMIT_GAP_A
 #undef EMIT_GAP_B
+#undef OUTC
 
     crgpu_aln_rec rec;
-    rec.score_x2 = best - BIAS;
+    rec.score = (float)(best - BIAS) / (float)a.scale;
     rec.alnlen = n;
     rec.ident = ident;
     // App. B.3: "%4.1f" of (float)100 * ident / len, as tenths (round-half-even on the exact product)
     const float fpct = __fdiv_rn(100.0f * (float)ident, (float)n);
     rec.tenths = __double2int_rn((double)fpct * 10.0);
-    rec.aln_off = (int32_t)(slot - n);
+    rec.aln_off = rc ? 0 : (int32_t)(slot - n);
     rec.start1 = s1;
     rec.start2 = s2;
     rec.read_len = Lb;
-    reinterpret_cast<crgpu_aln_rec *>(a.recs)[r] = rec;
+    reinterpret_cast<crgpu_aln_rec *>(a.recs)[orow] = rec;
 }
 
 // S1: one warp per read; keep iff sum(phred) >= q*len and min(phred) >= s (CORE:186-190, 300-305).

@@ -1,0 +1,385 @@
+"""Host-side mirror of the reference's interface for the hot path.
+
+* ``include_mask`` / ``exon_masks``: the geometry run_crispresso builds on the host
+  (INCLUDE_IDXS CORE:2739-2762, EXON_POSITIONS / SPLICING_POSITIONS CORE:1414-1455).
+* ``process_df_chunk``: drop-in for CRISPRessoCORE.process_df_chunk (CORE:428-753): same
+  argument (``[df, args]``; the four module globals are passed explicitly), same 22-tuple back.
+* ``run_hot_path``: CORE:1791-2072 + 2773-2869 through crgpu_align_quantify.
+* ``build_dataframe``: the df_needle_alignment the rest of run_crispresso consumes.
+
+Everything here calls libcrgpu through the C ABI; nothing computes on the CPU instead.
+"""
+import ctypes
+from collections import namedtuple
+
+import numpy as np
+
+from . import _lib
+
+HIST_ZERO = 1024            # histogram bin of key 0; keys span [-amplicon_len, +read_len]
+HIST_LEN = 1024 + 2048 + 1
+
+VECTOR_NAMES = (
+    "effect_vector_insertion", "effect_vector_deletion", "effect_vector_mutation", "effect_vector_any",
+    "effect_vector_insertion_mixed", "effect_vector_deletion_mixed", "effect_vector_mutation_mixed",
+    "effect_vector_insertion_hdr", "effect_vector_deletion_hdr", "effect_vector_mutation_hdr",
+    "effect_vector_insertion_noncoding", "effect_vector_deletion_noncoding", "effect_vector_mutation_noncoding",
+    "avg_vector_del_all", "avg_vector_ins_all")
+COUNTER_NAMES = ("modified_frameshift", "modified_non_frameshift", "non_modified_non_frameshift",
+                 "splicing_sites_modified")
+
+
+# --------------------------------------------------------------------------------- geometry
+def include_mask(amplicon_len, cut_points, window_around_sgrna, exclude_bp_from_left, exclude_bp_from_right):
+    """INCLUDE_IDXS as a 0/1 mask (CORE:2739-2762).  Ranges clipped at an amplicon end make the
+    reference's np.ravel ragged; that case raises here as well."""
+    L = amplicon_len
+    if cut_points and window_around_sgrna > 0:
+        half = max(1, window_around_sgrna // 2)
+        ranges = [range(max(0, c - half + 1), min(L - 1, c + half + 1)) for c in cut_points]
+        if len({len(r) for r in ranges}) > 1:
+            raise ValueError("INCLUDE_IDXS ranges have unequal lengths (np.ravel of a ragged list, CORE:2759)")
+        idx = np.ravel([list(r) for r in ranges]).astype(np.int64)
+    else:
+        idx = np.arange(L)
+    excl = []
+    if exclude_bp_from_left:
+        excl += list(range(exclude_bp_from_left))
+    if exclude_bp_from_right:
+        excl += list(range(L)[-exclude_bp_from_right:])
+    keep = np.setdiff1d(idx, np.array(excl, dtype=np.int64))
+    m = np.zeros(L, np.uint8)
+    m[keep] = 1
+    return m
+
+
+def cut_points_from_guides(amplicon, guide_seq, cleavage_offset=-3):
+    """cut_points (CORE:1290-1321)."""
+    import re
+
+    from .synth import revcomp
+    cuts = []
+    for g in guide_seq.strip().upper().split(","):
+        if not g:
+            continue
+        off_fw = cleavage_offset + len(g) - 1
+        off_rc = (-cleavage_offset) - 1
+        cuts += [m.start() + off_fw for m in re.finditer(g, amplicon)]
+        cuts += [m.start() + off_rc for m in re.finditer(revcomp(g), amplicon)]
+    return cuts
+
+
+def exon_masks(amplicon, coding_seq):
+    """EXON_POSITIONS and SPLICING_POSITIONS as masks (CORE:1414-1455)."""
+    L = len(amplicon)
+    exon = np.zeros(L, np.uint8)
+    splicing = []
+    for exon_seq in coding_seq.strip().upper().split(","):
+        st = amplicon.find(exon_seq)
+        if st < 0:
+            raise ValueError("coding subsequence not contained in the amplicon")
+        en = st + len(exon_seq)
+        exon[st:en] = 1
+        splicing += [max(0, st - 2), max(0, st - 1), min(L - 1, en), min(L - 1, en + 1)]
+    splice = np.zeros(L, np.uint8)
+    for p in set(splicing):
+        if not exon[p]:
+            splice[p] = 1
+    return exon, splice
+
+
+def quant_flags(expected_hdr_amplicon_seq="", ignore_substitutions=False, ignore_insertions=False,
+                ignore_deletions=False, window_around_sgrna=1, hide_mutations_outside_window_NHEJ=False,
+                coding_seq="", mask_n=False):
+    f = 0
+    if expected_hdr_amplicon_seq:
+        f |= _lib.Q_HAS_HDR
+    if ignore_substitutions:
+        f |= _lib.Q_IGNORE_SUBS
+    if ignore_insertions:
+        f |= _lib.Q_IGNORE_INS
+    if ignore_deletions:
+        f |= _lib.Q_IGNORE_DEL
+    if window_around_sgrna:
+        f |= _lib.Q_WINDOW
+    if hide_mutations_outside_window_NHEJ:
+        f |= _lib.Q_HIDE_OUTSIDE
+    if coding_seq:
+        f |= _lib.Q_FRAMESHIFT
+    if mask_n:
+        f |= _lib.Q_MASK_N
+    return f
+
+
+def flags_from_args(args, mask_n=False):
+    return quant_flags(getattr(args, "expected_hdr_amplicon_seq", ""), getattr(args, "ignore_substitutions", False),
+                       getattr(args, "ignore_insertions", False), getattr(args, "ignore_deletions", False),
+                       getattr(args, "window_around_sgrna", 0), getattr(args, "hide_mutations_outside_window_NHEJ", False),
+                       getattr(args, "coding_seq", ""), mask_n)
+
+
+class Reductions:
+    """Host accumulators of one amplicon (int64; the reference stores the same integers in float64)."""
+
+    def __init__(self, amplicon_len):
+        self.L = amplicon_len
+        self.vectors = np.zeros((_lib.NUM_VECTORS, amplicon_len), np.int64)
+        self.hist_inframe = np.zeros(HIST_LEN, np.int64)
+        self.hist_frameshift = np.zeros(HIST_LEN, np.int64)
+        self.counters = np.zeros(_lib.NUM_COUNTERS, np.int64)
+        self.class_counts = np.zeros(4, np.int64)      # UNMODIFIED, NHEJ, HDR, MIXED
+        self.n_total = 0
+        self.n_cells = 0
+
+    def flat(self):
+        """One int64 vector (for the multi-GPU all-reduce)."""
+        return np.concatenate([self.vectors.ravel(), self.hist_inframe, self.hist_frameshift, self.counters,
+                               self.class_counts, np.array([self.n_total, self.n_cells], np.int64)])
+
+    def load_flat(self, v):
+        v = np.asarray(v, dtype=np.int64)
+        o = 0
+        for name, shape in (("vectors", self.vectors.shape), ("hist_inframe", (HIST_LEN,)),
+                            ("hist_frameshift", (HIST_LEN,)), ("counters", (_lib.NUM_COUNTERS,)), ("class_counts", (4,))):
+            k = int(np.prod(shape))
+            setattr(self, name, v[o:o + k].reshape(shape).copy())
+            o += k
+        self.n_total, self.n_cells = int(v[o]), int(v[o + 1])
+
+    def vector(self, name):
+        return self.vectors[VECTOR_NAMES.index(name)]
+
+    @staticmethod
+    def hist_dict(h):
+        nz = np.nonzero(h)[0]
+        return {int(k - HIST_ZERO): int(h[k]) for k in nz}
+
+    def counter(self, name):
+        return int(self.counters[COUNTER_NAMES.index(name)])
+
+
+def _quant_params(amplicon_len, flags, hdr_thr, inc, exon, splice, keepalive):
+    qp = _lib.QuantParams()
+    qp.amplicon_len = amplicon_len
+    qp.flags = flags
+    qp.hdr_perfect_alignment_threshold = float(hdr_thr)
+    inc = np.ascontiguousarray(inc, dtype=np.uint8)
+    keepalive.append(inc)
+    qp.include_mask = inc.ctypes.data
+    if exon is not None:
+        exon = np.ascontiguousarray(exon, dtype=np.uint8)
+        splice = np.ascontiguousarray(splice, dtype=np.uint8)
+        keepalive += [exon, splice]
+        qp.exon_mask = exon.ctypes.data
+        qp.splice_mask = splice.ctypes.data
+    return qp
+
+
+def rows_to_buffer(rows, slot=None):
+    """list of equal-role strings -> (uint8 [n, slot] left-aligned, lengths)."""
+    lens = np.array([len(r) for r in rows], dtype=np.int32)
+    slot = int(slot or max(1, lens.max() if len(lens) else 1))
+    buf = np.zeros((len(rows), slot), np.uint8)
+    for i, r in enumerate(rows):
+        buf[i, :len(r)] = np.frombuffer(r.encode() if isinstance(r, str) else r, dtype=np.uint8)
+    return buf, lens
+
+
+def _score_to_tenths(col):
+    a = np.asarray(col, dtype=np.float64)
+    out = np.full(len(a), -1, np.int32)
+    ok = ~np.isnan(a)
+    out[ok] = np.rint(a[ok] * 10.0).astype(np.int32)
+    return out
+
+
+def quantify_rows(ctx, ref_rows, mark_rows, read_rows, score_ref, score_repaired, unmodified, amplicon_len, flags,
+                  hdr_thr, inc, exon=None, splice=None, red=None):
+    """crgpu_quantify on host strings.  Returns (READ_REC array, Reductions)."""
+    n = len(ref_rows)
+    red = red or Reductions(amplicon_len)
+    recs = np.zeros(n, dtype=_lib.READ_REC)
+    if n == 0:
+        return recs, red
+    rb, lens = rows_to_buffer(ref_rows)
+    slot = rb.shape[1]
+    mb, _ = rows_to_buffer(mark_rows, slot)
+    qb, _ = rows_to_buffer(read_rows, slot)
+    tref = _score_to_tenths(score_ref)
+    trep = _score_to_tenths(score_repaired) if score_repaired is not None else None
+    unmod = np.ascontiguousarray(np.asarray(unmodified, dtype=bool).astype(np.uint8))
+    keep = []
+    qp = _quant_params(amplicon_len, flags, hdr_thr, inc, exon, splice, keep)
+    ctx.check(ctx.lib.crgpu_quantify(
+        ctx.handle, _lib.MEM_HOST, ctypes.byref(qp), _lib.ptr(rb), _lib.ptr(mb), _lib.ptr(qb), slot, None,
+        _lib.ptr(lens), _lib.ptr(tref), _lib.ptr(trep), _lib.ptr(unmod), n, _lib.ptr(recs), _lib.ptr(red.vectors),
+        _lib.ptr(red.hist_inframe), _lib.ptr(red.hist_frameshift), HIST_LEN, HIST_ZERO, _lib.ptr(red.counters)))
+    return recs, red
+
+
+def process_df_chunk(chunk_input, ctx, INCLUDE_IDXS, LEN_AMPLICON, EXON_POSITIONS=None, SPLICING_POSITIONS=None):
+    """Drop-in for CRISPRessoCORE.process_df_chunk (CORE:428-753).
+
+    ``chunk_input`` is ``[df_needle_alignment_chunk, args]`` exactly as the reference passes it;
+    the module globals it reads (CORE:1261-1264) are explicit parameters.  Returns the same
+    22-tuple (CORE:730-753) with the same types: the updated DataFrame, 13 float64 effect
+    vectors, two dict histograms, two float64 average-size sums, four ints.
+    """
+    df, args = chunk_input[0], chunk_input[1]
+    L = LEN_AMPLICON
+    inc = np.zeros(L, np.uint8)
+    inc[[int(i) for i in INCLUDE_IDXS]] = 1
+    exon = splice = None
+    if getattr(args, "coding_seq", ""):
+        exon = np.zeros(L, np.uint8)
+        exon[[int(i) for i in EXON_POSITIONS]] = 1
+        splice = np.zeros(L, np.uint8)
+        splice[[int(i) for i in SPLICING_POSITIONS]] = 1
+    has_hdr = bool(getattr(args, "expected_hdr_amplicon_seq", ""))
+    recs, red = quantify_rows(
+        ctx, list(df["ref_seq"]), list(df["align_str"]), list(df["align_seq"]), df["score_ref"].values,
+        df["score_repaired"].values if has_hdr else None, df["UNMODIFIED"].values, L, flags_from_args(args),
+        getattr(args, "hdr_perfect_alignment_threshold", 98.0), inc, exon, splice)
+    df = df.copy()
+    cls = recs["cls"]
+    df["UNMODIFIED"] = (cls & _lib.C_UNMODIFIED) != 0
+    df["NHEJ"] = (cls & _lib.C_NHEJ) != 0
+    df["HDR"] = (cls & _lib.C_HDR) != 0
+    df["MIXED"] = (cls & _lib.C_MIXED) != 0
+    df["n_mutated"] = recs["n_mutated"].astype(np.int64)
+    df["n_inserted"] = recs["n_inserted"].astype(np.int64)
+    df["n_deleted"] = recs["n_deleted"].astype(np.int64)
+    v = [red.vectors[i].astype(np.float64) for i in range(_lib.NUM_VECTORS)]
+    return (df, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12],
+            Reductions.hist_dict(red.hist_inframe), Reductions.hist_dict(red.hist_frameshift), v[13], v[14],
+            red.counter("modified_frameshift"), red.counter("modified_non_frameshift"),
+            red.counter("non_modified_non_frameshift"), red.counter("splicing_sites_modified"))
+
+
+HotPathResult = namedtuple("HotPathResult", [
+    "kept", "aln", "tenths_rep", "recs", "rows", "slot", "rc_read", "rc_aln", "rc_recs", "rc_rows", "red"])
+
+
+def run_hot_path(ctx, amplicon, reads, gapopen=10.0, gapextend=0.5, min_identity_score=60.0, hdr_amplicon=None,
+                 flags=None, hdr_thr=98.0, inc=None, exon=None, splice=None, want_rows=False, rc_rescue=True,
+                 red=None, device_inputs=None):
+    """CORE:1791-2072 + 2773-2869 for one amplicon through crgpu_align_quantify.
+
+    reads: (uint8 buffer, int64 offsets) host arrays, or with ``device_inputs=(ptr_reads,
+    ptr_offsets, n, max_len)`` raw device pointers (HBM-resident inputs; per-read outputs are then
+    NOT returned -- only the reductions -- unless torch tensors are supplied by the caller).
+    Returns HotPathResult; ``red`` carries the vectors / histograms / counters / class counts.
+    """
+    amp = amplicon.upper().encode()
+    L = len(amp)
+    red = red or Reductions(L)
+    if flags is None:
+        flags = quant_flags(expected_hdr_amplicon_seq=hdr_amplicon or "")
+    if inc is None:
+        inc = np.ones(L, np.uint8)
+    keep = []
+    qp = _quant_params(L, flags, hdr_thr, inc, exon, splice, keep)
+    pp = _lib.PathParams()
+    pp.gapopen, pp.gapextend, pp.min_identity_score = float(gapopen), float(gapextend), float(min_identity_score)
+    hdr_b = hdr_amplicon.upper().encode() if hdr_amplicon else None
+    pp.hdr_amplicon = hdr_b
+    pp.hdr_amplicon_len = len(hdr_b) if hdr_b else 0
+    pp.rc_rescue = 1 if rc_rescue else 0
+    po = _lib.PathOut()
+    po.vectors = red.vectors.ctypes.data
+    po.hist_inframe = red.hist_inframe.ctypes.data
+    po.hist_frameshift = red.hist_frameshift.ctypes.data
+    po.hist_len, po.hist_zero = HIST_LEN, HIST_ZERO
+    po.counters = red.counters.ctypes.data
+
+    if device_inputs is not None:
+        d_reads, d_off, n, _maxlen, dev_out = device_inputs
+        po.kept, po.aln, po.recs = dev_out["kept"], dev_out["aln"], dev_out["recs"]
+        po.tenths_rep = dev_out.get("tenths_rep")
+        po.slot = 0
+        po.rc_cap = 0
+        ctx.check(ctx.lib.crgpu_align_quantify(ctx.handle, _lib.MEM_DEVICE, amp, L, ctypes.byref(pp), ctypes.byref(qp),
+                                               d_reads, d_off, n, ctypes.byref(po)))
+        res = HotPathResult(None, None, None, None, None, 0, None, None, None, None, red)
+    else:
+        buf, offsets = reads
+        n = len(offsets) - 1
+        kept = np.zeros(n, np.uint8)
+        aln = np.zeros(n, _lib.ALN_REC)
+        trep = np.full(n, -1, np.int32)
+        recs = np.zeros(n, _lib.READ_REC)
+        maxlb = int(np.max(np.diff(offsets))) if n else 0
+        slot = max(L, len(hdr_b) if hdr_b else 0) + maxlb
+        rows = rc_rows = None
+        po.kept, po.aln, po.tenths_rep, po.recs = kept.ctypes.data, aln.ctypes.data, trep.ctypes.data, recs.ctypes.data
+        po.slot = slot if want_rows else 0
+        if want_rows:
+            rows = [np.zeros((n, slot), np.uint8) for _ in range(3)]
+            po.ref_rows, po.mark_rows, po.qry_rows = (r.ctypes.data for r in rows)
+        rc_cap = n
+        rc_read = np.zeros(rc_cap, np.int32)
+        rc_aln = np.zeros(rc_cap, _lib.ALN_REC)
+        rc_recs = np.zeros(rc_cap, _lib.READ_REC)
+        po.rc_cap = rc_cap
+        po.rc_read, po.rc_aln, po.rc_recs = rc_read.ctypes.data, rc_aln.ctypes.data, rc_recs.ctypes.data
+        rc_bufs = None
+        if want_rows:
+            rc_bufs = [np.zeros((rc_cap, slot), np.uint8) for _ in range(3)]
+            po.rc_ref_rows, po.rc_mark_rows, po.rc_qry_rows = (r.ctypes.data for r in rc_bufs)
+        ctx.check(ctx.lib.crgpu_align_quantify(ctx.handle, _lib.MEM_HOST, amp, L, ctypes.byref(pp), ctypes.byref(qp),
+                                               _lib.ptr(buf), _lib.ptr(offsets), n, ctypes.byref(po)))
+        nrc = int(po.rc_n)
+        if want_rows:
+            # RC rows come back already flipped to the forward strand, left-aligned in their slot
+            rc_rows = [[b[j, :rc_aln["alnlen"][j]].tobytes().decode() for j in range(nrc)] for b in rc_bufs]
+        res = HotPathResult(kept, aln, trep, recs, rows, slot, rc_read[:nrc], rc_aln[:nrc], rc_recs[:nrc], rc_rows, red)
+    red.class_counts += np.array(list(po.class_counts), np.int64)
+    red.n_total += int(po.n_total)
+    red.n_cells += int(po.n_cells)
+    return res
+
+
+def build_dataframe(res, read_names, has_hdr=False, amplicon=None):
+    """df_needle_alignment as run_crispresso holds it after CORE:2072 and the quantification
+    (CORE:2864): index ID, columns score_ref [score_repaired score_diff] length ref_seq align_str
+    align_seq UNMODIFIED MIXED HDR NHEJ n_mutated n_inserted n_deleted, forward rows in read
+    order followed by the ``_RC`` rows (CORE:1993-1998).  Needs want_rows=True."""
+    import pandas as pd
+    if res.rows is None:
+        raise ValueError("run_hot_path(want_rows=True) is required to build the DataFrame")
+    mask_n = amplicon is not None and "N" in amplicon.upper()
+
+    def frame(ids, aln, trep, recs, ref, mark, qry, rc):
+        d = {"score_ref": aln["tenths"] / 10.0}
+        if has_hdr:
+            d["score_repaired"] = np.where(trep >= 0, trep / 10.0, np.nan) if not rc else np.full(len(ids), np.nan)
+        d["length"] = [str(int(x)) for x in aln["read_len"]]
+        if mask_n:
+            mark = ["".join("|" if rch == "N" else c for rch, c in zip(r_, m_)) for r_, m_ in zip(ref, mark)]
+        d["ref_seq"], d["align_str"], d["align_seq"] = ref, mark, qry
+        if has_hdr:
+            d["score_diff"] = d["score_ref"] - d["score_repaired"]
+        cls = recs["cls"]
+        d["UNMODIFIED"] = (cls & _lib.C_UNMODIFIED) != 0
+        d["MIXED"] = (cls & _lib.C_MIXED) != 0
+        d["HDR"] = (cls & _lib.C_HDR) != 0
+        d["NHEJ"] = (cls & _lib.C_NHEJ) != 0
+        d["n_mutated"] = recs["n_mutated"].astype(np.int64)
+        d["n_inserted"] = recs["n_inserted"].astype(np.int64)
+        d["n_deleted"] = recs["n_deleted"].astype(np.int64)
+        return pd.DataFrame(d, index=pd.Index(ids, name="ID"))
+
+    fw = np.nonzero(res.kept & 1)[0]
+    rows = []
+    for arr in res.rows:
+        rows.append([arr[i, res.aln["aln_off"][i]:res.aln["aln_off"][i] + res.aln["alnlen"][i]].tobytes().decode() for i in fw])
+    names = np.asarray(read_names, dtype=object)
+    df = frame(list(names[fw]), res.aln[fw], res.tenths_rep[fw], res.recs[fw], rows[0], rows[1], rows[2], False)
+    if len(res.rc_read):
+        sel = np.nonzero((res.kept[res.rc_read] & 2) != 0)[0]
+        if len(sel):
+            rr = [[res.rc_rows[k][j] for j in sel] for k in range(3)]
+            ids = [names[res.rc_read[j]] + "_RC" for j in sel]
+            df_rc = frame(ids, res.rc_aln[sel], None, res.rc_recs[sel], rr[0], rr[1], rr[2], True)
+            df = pd.concat([df, df_rc])
+    return df

@@ -76,7 +76,7 @@ int crgpu_qualfilter(crgpu_ctx *ctx, int mem, const uint8_t *qual, const int64_t
 
 /* ---- S2: alignment (needle subprocess + parse_needle_output, CORE:1791-1806, 1707-1786) -- */
 typedef struct {
-    int32_t score_x2;     /* needle "# Score:" times `scale` (see crgpu_align; 2 for the defaults) */
+    float score;          /* needle "# Score:" (exact: a multiple of 1/8 far below 2^20) */
     int32_t alnlen;       /* alignment columns incl. end gaps ("# Length:") */
     int32_t ident;        /* identical columns ("# Identity: ident/alnlen") */
     int32_t tenths;       /* identity %% as printed by "%4.1f", times 10: what the parser's
@@ -164,13 +164,15 @@ int crgpu_quantify(crgpu_ctx *ctx, int mem, const crgpu_quant_params *params,
 /* ---- fused hot path: S2 (+HDR pass, + reverse-complement rescue) + S3 in one call -------- *
  * Reproduces CORE:1791-2072 + 2773-2864 for one amplicon without materialising the needle text:
  *  1. align all reads to `amplicon` (and to `hdr_amplicon` when non-NULL, CORE:1810-1828);
- *  2. reads with identity < min_identity are re-aligned to the reverse complements
- *     (CORE:1873-2000; their HDR score stays NaN, CORE:1924-1949);
- *  3. rows kept iff score_ref > min_identity (or score_repaired > min_identity, CORE:1849-1852);
- *  4. quantify the kept rows (crgpu_quantify semantics).
- * Per-read outputs (all length n, indexed like the input): kept[i] (1 = forward row kept,
- * 2 = kept through the RC rescue, 0 = dropped), aln[i] = the alignment vs the amplicon that the
- * row carries, tenths_rep[i], recs[i].  Strings optional as in crgpu_align. */
+ *  2. reads with score_ref < min_identity are re-aligned to the reverse complement of the
+ *     amplicon (CORE:1865-1867, 1873-1921; in HDR mode their score_repaired is NaN because the
+ *     reference's repair-RC needle command is malformed, CORE:1924-1949 / SURVEY Q11);
+ *  3. forward rows are kept iff score_ref > min_identity (HDR mode: or score_repaired >
+ *     min_identity, CORE:1849-1852, 1869-1871); RC rows iff score_ref(rc) > min_identity
+ *     (CORE:1956-1959, 1976-1978);
+ *  4. UNMODIFIED = (score_ref == 100), N-masking when the amplicon has N (CORE:2014-2052), then
+ *     every kept row is quantified with crgpu_quantify semantics.
+ * A read can own a forward row AND an RC row (HDR mode only). */
 typedef struct {
     double gapopen, gapextend;             /* parsed from --needle_options_string (CORE:4226-4231) */
     double min_identity_score;             /* CORE:4092 */
@@ -179,14 +181,36 @@ typedef struct {
     int32_t rc_rescue;                     /* 1 = run the reverse-complement rescue (reference behaviour) */
 } crgpu_path_params;
 
+typedef struct {
+    /* forward rows, indexed by read; per-read arrays follow `mem` */
+    uint8_t *kept;                         /* [n] bit0: forward row kept, bit1: RC row kept,
+                                              bit2: read was re-aligned to the reverse complement */
+    crgpu_aln_rec *aln;                    /* [n] alignment vs the amplicon */
+    int32_t *tenths_rep;                   /* [n] identity tenths vs the HDR amplicon (-1 = NaN / no HDR); may be NULL */
+    crgpu_read_rec *recs;                  /* [n] valid where kept&1 */
+    uint8_t *ref_rows, *mark_rows, *qry_rows;   /* n*slot each (right-aligned, see aln_off) or all NULL */
+    int64_t slot;                          /* >= amplicon_len + longest read; 0 = choose (only without rows) */
+    /* reverse-complement rescue rows: compact, in read order */
+    int64_t rc_cap;                        /* capacity (rows) of the rc_* arrays */
+    int64_t rc_n;                          /* OUT: number of reads re-aligned to the reverse complement */
+    int32_t *rc_read;                      /* [rc_cap] read index of RC row j */
+    crgpu_aln_rec *rc_aln;                 /* [rc_cap] alignment vs revcomp(amplicon) */
+    crgpu_read_rec *rc_recs;               /* [rc_cap] valid where kept[rc_read[j]]&2 */
+    uint8_t *rc_ref_rows, *rc_mark_rows, *rc_qry_rows;  /* rc_cap*slot each or NULL: rows already flipped to
+                                              the forward strand (CORE:1982-1990), LEFT-aligned in the slot */
+    /* reductions: HOST memory, results are ADDED to the caller's values */
+    int64_t *vectors;                      /* [CRGPU_NUM_VECTORS][amplicon_len] */
+    int64_t *hist_inframe, *hist_frameshift;    /* [hist_len], bin = key + hist_zero; may be NULL without -c */
+    int32_t hist_len, hist_zero;
+    int64_t *counters;                     /* [CRGPU_NUM_COUNTERS] */
+    int64_t class_counts[4];               /* OUT (added): UNMODIFIED, NHEJ, HDR, MIXED rows (CORE:2866-2869) */
+    int64_t n_total;                       /* OUT (added): rows kept = df_needle_alignment.shape[0] (CORE:2025) */
+    int64_t n_cells;                       /* OUT (added): DP cells computed, for GCUPS */
+} crgpu_path_out;
+
 int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int amplicon_len,
                          const crgpu_path_params *path, const crgpu_quant_params *quant,
-                         const uint8_t *reads, const int64_t *offsets, int64_t n,
-                         uint8_t *kept, crgpu_aln_rec *aln, int32_t *tenths_rep, crgpu_read_rec *recs,
-                         uint8_t *ref_out, uint8_t *mark_out, uint8_t *qry_out, int64_t slot,
-                         int64_t *vectors, int64_t *hist_inframe, int64_t *hist_frameshift,
-                         int32_t hist_len, int32_t hist_zero, int64_t *counters,
-                         int64_t *n_cells /* DP cells actually computed (for GCUPS), may be NULL */);
+                         const uint8_t *reads, const int64_t *offsets, int64_t n, crgpu_path_out *out);
 
 /* ---- measurement helper ---------------------------------------------------------------- *
  * Integer-ALU peak micro-benchmark ("measure it"): dependent-free 32-bit

@@ -308,7 +308,9 @@ typedef struct {
 static void *batch_worker(void *arg)
 {
     batch_job *j = (batch_job *)arg;
-    const int scale = 2;
+    int scale = 1;   /* smallest power of two making both penalties integral (App. A.6) */
+    while (scale < 8 && (j->gapopen * scale != floor(j->gapopen * scale) || j->gapextend * scale != floor(j->gapextend * scale)))
+        scale *= 2;
     int go = (int)lrint(j->gapopen * scale), ge = (int)lrint(j->gapextend * scale);
     for (;;) {
         int64_t lo, hi;

@@ -18,7 +18,7 @@ def check(La, n, read_len, seed, len_sigma=0.0, n_rate=0.0):
     for i in range(n):
         ok = (r[i] == orr[i] and m[i] == om[i] and q[i] == oq[i] and recs["tenths"][i] == ores["tenths"][i]
               and recs["ident"][i] == ores["ident"][i] and recs["alnlen"][i] == ores["alnlen"][i]
-              and recs["score_x2"][i] == int(round(ores["score"][i] * 2)) and recs["start1"][i] == ores["start1"][i]
+              and float(recs["score"][i]) == ores["score"][i] and recs["start1"][i] == ores["start1"][i]
               and recs["start2"][i] == ores["start2"][i])
         if not ok:
             bad += 1

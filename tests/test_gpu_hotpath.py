@@ -1,0 +1,108 @@
+"""crgpu_align_quantify (the fused hot path) against oracle.quantify.hot_path.  Needs a B200."""
+import numpy as np
+import pytest
+
+from crispresso_b200 import _lib, hotpath, synth
+from oracle import quantify
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(ctx, amp, packed, hdr_amp="", window=1, coding="", guide=None, excl=(15, 15), min_id=60.0, hide=False,
+              want_rows=True):
+    L = len(amp)
+    cuts = hotpath.cut_points_from_guides(amp, guide) if guide else []
+    inc = hotpath.include_mask(L, cuts, window, excl[0], excl[1])
+    exon = splice = None
+    if coding:
+        exon, splice = hotpath.exon_masks(amp, coding)
+    flags = hotpath.quant_flags(hdr_amp, window_around_sgrna=window, hide_mutations_outside_window_NHEJ=hide, coding_seq=coding)
+    res = hotpath.run_hot_path(ctx, amp, packed, min_identity_score=min_id, hdr_amplicon=hdr_amp or None, flags=flags,
+                               inc=inc, exon=exon, splice=splice, want_rows=want_rows)
+    opts = quantify.Opts(coding_seq=coding, expected_hdr_amplicon_seq=hdr_amp, window_around_sgrna=window,
+                         hide_mutations_outside_window_NHEJ=hide)
+    ora = quantify.hot_path(amp, packed, min_identity_score=min_id, hdr_amplicon=hdr_amp, opts=opts,
+                            include=np.nonzero(inc)[0], exon=np.nonzero(exon)[0] if coding else (),
+                            splice=np.nonzero(splice)[0] if coding else ())
+    return res, ora
+
+
+def _assert_same(res, ora, names=None, has_hdr=False, amp=None):
+    red = res.red
+    assert red.n_total == ora["n_total"]
+    assert red.n_cells == ora["n_cells"]
+    assert red.class_counts.tolist() == [ora["classes"][k] for k in ("UNMODIFIED", "NHEJ", "HDR", "MIXED")]
+    for k, name in enumerate(hotpath.VECTOR_NAMES):
+        assert red.vectors[k].tolist() == ora["vectors"][name].tolist(), name
+    assert hotpath.Reductions.hist_dict(red.hist_inframe) == ora["hist_inframe"]
+    assert hotpath.Reductions.hist_dict(red.hist_frameshift) == ora["hist_frameshift"]
+    assert {n: red.counter(n) for n in hotpath.COUNTER_NAMES} == ora["counters"]
+    if res.rows is not None:
+        n = len(res.kept)
+        names = names or ["r%d" % i for i in range(n)]
+        df = hotpath.build_dataframe(res, names, has_hdr=has_hdr, amplicon=amp)
+        assert list(df.index) == [r["ID"] for r in ora["rows"]]
+        for col in ("ref_seq", "align_str", "align_seq", "length"):
+            assert list(df[col]) == [r[col] for r in ora["rows"]], col
+        assert np.array_equal(df["score_ref"].values, np.array([r["score_ref"] for r in ora["rows"]]))
+        for col in ("UNMODIFIED", "NHEJ", "HDR", "MIXED", "n_mutated", "n_inserted", "n_deleted"):
+            assert [int(x) for x in df[col]] == [int(p[col]) for p in ora["per_row"]], col
+
+
+def test_cfg2_shape_with_hdr(ctx):
+    amp, guide, cut, hdr = synth.make_case(1234, 250)
+    packed = synth.make_reads(amp, hdr, cut, 3000, seed=1234, read_len=250)
+    res, ora = _run_both(ctx, amp, packed, hdr_amp=hdr, guide=guide)
+    _assert_same(res, ora, has_hdr=True, amp=amp)
+    assert ora["classes"]["HDR"] > 100 and ora["classes"]["NHEJ"] > 100
+
+
+def test_cfg3_shape_with_coding_sequence(ctx):
+    amp, guide, cut, _ = synth.make_case(77, 300, hdr=False)
+    packed = synth.make_reads(amp, None, cut, 2500, seed=77, read_len=300, len_sigma=8.0, p_exact=0.8)
+    res, ora = _run_both(ctx, amp, packed, coding=amp[cut - 60:cut + 60], guide=guide, window=20)
+    _assert_same(res, ora, amp=amp)
+    assert ora["counters"]["modified_frameshift"] > 0
+
+
+def test_reverse_complement_rescue(ctx):
+    amp, guide, cut, hdr = synth.make_case(5, 200)
+    packed = synth.make_reads(amp, hdr, cut, 1500, seed=5, rc_frac=0.3)
+    for h in ("", hdr):
+        res, ora = _run_both(ctx, amp, packed, hdr_amp=h, guide=guide)
+        assert any(r["rc"] for r in ora["rows"])
+        _assert_same(res, ora, has_hdr=bool(h), amp=amp)
+
+
+def test_amplicon_with_n_and_junk(ctx):
+    rng = np.random.default_rng(6)
+    amp, guide, cut, _ = synth.make_case(6, 180, hdr=False)
+    a = list(amp); a[cut + 9] = "N"; a[40] = "N"; amp = "".join(a)
+    buf, off = synth.make_reads(amp.replace("N", "C"), None, cut, 1200, seed=6, n_rate=0.005)
+    reads = [bytes(buf[off[i]:off[i + 1]]).decode() for i in range(len(off) - 1)]
+    reads += [synth.random_seq(rng, int(rng.integers(20, 220))) for _ in range(100)]          # dropped by the identity filter
+    reads += [amp.replace("N", "A"), amp.replace("N", "G")[:150]]
+    from crispresso_b200.aligner import pack_reads
+    res, ora = _run_both(ctx, amp, pack_reads(reads), guide=None, window=1, min_id=60.0)
+    _assert_same(res, ora, amp=amp)
+
+
+def test_low_identity_threshold_and_hide(ctx):
+    amp, guide, cut, _ = synth.make_case(8, 150, hdr=False)
+    packed = synth.make_reads(amp, None, cut, 1500, seed=8, read_len=151)
+    res, ora = _run_both(ctx, amp, packed, guide=guide, window=10, min_id=30.0, hide=True, excl=(5, 5))
+    _assert_same(res, ora, amp=amp)
+
+
+def test_reductions_do_not_depend_on_sharding(ctx):
+    """What multi-GPU sharding relies on: quantifying two halves and adding == quantifying all."""
+    amp, guide, cut, hdr = synth.make_case(9, 250)
+    buf, off = synth.make_reads(amp, hdr, cut, 2000, seed=9, read_len=250)
+    inc = hotpath.include_mask(250, hotpath.cut_points_from_guides(amp, guide), 1, 15, 15)
+    flags = hotpath.quant_flags(hdr)
+    whole = hotpath.run_hot_path(ctx, amp, (buf, off), hdr_amplicon=hdr, flags=flags, inc=inc).red
+    red = hotpath.Reductions(250)
+    h = 1000
+    hotpath.run_hot_path(ctx, amp, (buf[:off[h]].copy(), off[:h + 1].copy()), hdr_amplicon=hdr, flags=flags, inc=inc, red=red)
+    hotpath.run_hot_path(ctx, amp, (buf[off[h]:].copy(), (off[h:] - off[h]).copy()), hdr_amplicon=hdr, flags=flags, inc=inc, red=red)
+    assert np.array_equal(whole.flat(), red.flat())
