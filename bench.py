@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the CRISPResso hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--reads R]
+
+A "step" = one pass of the hot path (CORE:1791-2072 + 2773-2869: alignment to the amplicon AND the
+HDR amplicon with needle semantics, reverse-complement rescue, classification and all
+histograms) over one batch of synthetic reads.  Workload at any N: BASELINE.json configs[1]
+per GPU -- 2^20 single-end 250-bp reads vs a 250-bp amplicon + HDR amplicon (weak scaling: reads
+shard across ranks, one NCCL all-reduce of the int64 histogram block per step).
+
+Prints ONE JSON line (rank 0).  `value` = reads/s with inputs resident in HBM, `e2e` = the same
+through the C ABI with pinned HOST buffers (H2D of the reads and D2H of the per-read records
+inside the timed region).  `--impl reference` times the CPU restatement of the reference path
+(oracle/: C needle port on all host cores + the Python quantification loop) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OPS_PER_CELL = 13          # algorithmic integer ops per DP cell
+AMPLICON_LEN = 250
+READ_LEN = 250
+SEED = 1234
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--reads", type=int, default=1 << 20, help="reads per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=6000, help="reads in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(n_reads, rank):
+    from crispresso_b200 import hotpath, synth
+    amp, guide, cut, hdr = synth.make_case(SEED, AMPLICON_LEN)
+    buf, off = synth.make_reads_fast(amp, hdr, cut, n_reads, seed=SEED + 17 * rank, read_len=READ_LEN)
+    inc = hotpath.include_mask(AMPLICON_LEN, hotpath.cut_points_from_guides(amp, guide), 1, 15, 15)
+    return amp, guide, cut, hdr, buf, off, inc
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                mx = max(mx, int(float(f[1])))
+                if t0 <= t <= t1 + 0.1:
+                    sm.append(int(float(f[0])))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": 0}
+        return {"sm_mhz": int(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_step(amp, hdr, inc, buf, off, nthreads):
+    """One pass of the reference path restated on the CPU (oracle/): needle port on `nthreads`
+    host threads for the amplicon and the HDR amplicon + RC rescue + the Python per-read loop."""
+    from oracle import quantify
+    t0 = time.time()
+    res = quantify.hot_path(amp, (buf, off), hdr_amplicon=hdr, opts=quantify.Opts(expected_hdr_amplicon_seq=hdr),
+                            include=np.nonzero(inc)[0], nthreads=nthreads, use_int=False)
+    return time.time() - t0, res
+
+
+def cpu_baseline(args, amp, hdr, inc, buf, off):
+    n = min(args.cpu_sample, len(off) - 1)
+    sb, so = buf[:off[n]].copy(), off[:n + 1].copy()
+    cores = os.cpu_count() or 1
+    dt, res = cpu_reference_step(amp, hdr, inc, sb, so, cores)
+    return {"value": n / dt, "unit": "reads/s", "cores": cores, "kind": "port",
+            "gcups": res["n_cells"] / dt / 1e9,
+            "sample": "first %d reads of the rank-0 workload, both amplicons + RC rescue + quantification, "
+                      "C needle port on %d pthreads + single-process Python quantifier, %.1f s" % (n, cores, dt)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    amp, guide, cut, hdr, buf, off, inc = workload(max(args.cpu_sample, 1), 0)
+    n = min(args.cpu_sample, len(off) - 1)
+    sb, so = buf[:off[n]].copy(), off[:n + 1].copy()
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cpu_reference_step(amp, hdr, inc, sb[:so[200]].copy(), so[:201].copy(), cores)
+    t0 = time.time()
+    cells = 0
+    for _ in range(args.steps):
+        _dt, res = cpu_reference_step(amp, hdr, inc, sb, so, cores)
+        cells += res["n_cells"]
+    dt = time.time() - t0
+    value = n * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "aligned_reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "gcups": cells / dt / 1e9,
+        "config": {"workload": "cfg2: single-end %d-bp reads vs %d-bp amplicon + HDR amplicon; CPU arm runs a bounded "
+                               "sample of %d reads per step" % (READ_LEN, AMPLICON_LEN, n), "reads_per_step": n},
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "port",
+                         "sample": "%d reads/step x %d steps; oracle C needle port (float32, as needle) on %d pthreads + "
+                                   "Python quantifier (the reference's own needle is a missing third-party binary)" % (
+                                       n, args.steps, cores)},
+        "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from crispresso_b200 import Context, _lib, hotpath
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = Context(local)
+    ext_stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", local))
+
+    n = args.reads
+    amp, guide, cut, hdr, buf, off, inc = workload(n, rank)
+    L = len(amp)
+    flags = hotpath.quant_flags(hdr)
+    h2d_bytes = int(buf.nbytes + off.nbytes)
+
+    # int-ALU peak, measured live; which=4 interleaves IADD (alu pipe) and IMAD (fma pipe)
+    int_peak = max(ctx.int_peak(4), ctx.int_peak(0) if False else 0.0)
+
+    # ---- device-resident arm ------------------------------------------------------------------
+    d_buf = torch.from_numpy(buf).cuda()
+    d_off = torch.from_numpy(off).cuda()
+    dev_out = {
+        "kept": torch.zeros(n, dtype=torch.uint8, device="cuda"),
+        "aln": torch.zeros(n * _lib.ALN_REC.itemsize, dtype=torch.uint8, device="cuda"),
+        "recs": torch.zeros(n * _lib.READ_REC.itemsize, dtype=torch.uint8, device="cuda"),
+        "tenths_rep": torch.zeros(n, dtype=torch.int32, device="cuda"),
+    }
+    dev_ptrs = {k: v.data_ptr() for k, v in dev_out.items()}
+
+    def allreduce(red):
+        if world > 1:
+            t = torch.from_numpy(red.flat()).cuda()
+            dist.all_reduce(t)
+            red.load_flat(t.cpu().numpy())
+
+    fam_ms = {k: 0.0 for k in Context.TIMING_NAMES}
+    fam_launch = {k: 0 for k in Context.TIMING_NAMES}
+
+    def step_device(record=False):
+        red = hotpath.Reductions(L)
+        hotpath.run_hot_path(ctx, amp, None, hdr_amplicon=hdr, flags=flags, inc=inc, red=red,
+                             device_inputs=(d_buf.data_ptr(), d_off.data_ptr(), n, READ_LEN, dev_ptrs))
+        if record:
+            ms, ln = ctx.last_timing()
+            for k in ms:
+                fam_ms[k] += ms[k]
+                fam_launch[k] += ln[k]
+        allreduce(red)
+        return red
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        red = step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    ev0.record(ext_stream)
+    for _ in range(args.steps):
+        red = step_device(record=True)
+    ev1.record(ext_stream)
+    barrier()
+    t_wall1 = time.time()
+    dev_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    cells_step = red.n_cells if world == 1 else None
+    n_total = red.n_total
+
+    # ---- end-to-end arm: pinned host buffers through the C ABI ----------------------------------
+    p_buf = torch.from_numpy(buf).pin_memory()
+    p_off = torch.from_numpy(off).pin_memory()
+    h_kept = torch.zeros(n, dtype=torch.uint8).pin_memory()
+    h_aln = torch.zeros(n * _lib.ALN_REC.itemsize, dtype=torch.uint8).pin_memory()
+    h_recs = torch.zeros(n * _lib.READ_REC.itemsize, dtype=torch.uint8).pin_memory()
+    h_trep = torch.zeros(n, dtype=torch.int32).pin_memory()
+    import ctypes
+    keep = []
+    qp = hotpath._quant_params(L, flags, 98.0, inc, None, None, keep)
+    pp = _lib.PathParams()
+    pp.gapopen, pp.gapextend, pp.min_identity_score = 10.0, 0.5, 60.0
+    hdr_b = hdr.encode()
+    pp.hdr_amplicon, pp.hdr_amplicon_len, pp.rc_rescue = hdr_b, len(hdr_b), 1
+    rc_cap = n
+    h_rc_read = np.zeros(rc_cap, np.int32)
+    h_rc_aln = np.zeros(rc_cap, _lib.ALN_REC)
+    h_rc_recs = np.zeros(rc_cap, _lib.READ_REC)
+
+    def step_host():
+        red = hotpath.Reductions(L)
+        po = _lib.PathOut()
+        po.kept, po.aln, po.recs, po.tenths_rep = h_kept.data_ptr(), h_aln.data_ptr(), h_recs.data_ptr(), h_trep.data_ptr()
+        po.rc_cap = rc_cap
+        po.rc_read, po.rc_aln, po.rc_recs = h_rc_read.ctypes.data, h_rc_aln.ctypes.data, h_rc_recs.ctypes.data
+        po.vectors, po.hist_inframe, po.hist_frameshift = red.vectors.ctypes.data, red.hist_inframe.ctypes.data, red.hist_frameshift.ctypes.data
+        po.hist_len, po.hist_zero, po.counters = hotpath.HIST_LEN, hotpath.HIST_ZERO, red.counters.ctypes.data
+        ctx.check(ctx.lib.crgpu_align_quantify(ctx.handle, _lib.MEM_HOST, amp.encode(), L, ctypes.byref(pp), ctypes.byref(qp),
+                                               p_buf.data_ptr(), p_off.data_ptr(), n, ctypes.byref(po)))
+        red.class_counts += np.array(list(po.class_counts), np.int64)
+        red.n_total += int(po.n_total)
+        red.n_cells += int(po.n_cells)
+        allreduce(red)
+        return red
+
+    for _ in range(max(1, args.warmup - 1)):
+        red_h = step_host()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext_stream)
+    for _ in range(args.steps):
+        red_h = step_host()
+    e1.record(ext_stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    d2h_bytes = int(n * (1 + _lib.ALN_REC.itemsize + _lib.READ_REC.itemsize + 4) + red_h.flat().nbytes)
+    same = bool(np.array_equal(red_h.flat(), red.flat()))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_reads = n * world * args.steps
+    value = total_reads / (dev_ms * 1e-3)
+    e2e_value = total_reads / (e2e_ms * 1e-3)
+    cells_per_rank_step = 2.0 * L * float(off[-1])          # amplicon + HDR amplicon (RC rescue cells are extra)
+    fill_ms = fam_ms["fill"] / max(1, fam_launch["fill"])   # average fill launch (this rank)
+    cells_per_launch = cells_per_rank_step * args.steps / max(1, fam_launch["fill"])
+    achieved = cells_per_launch * OPS_PER_CELL / (fill_ms * 1e-3) / 1e12
+    peak = int_peak / 1e12
+    tb_bytes_per_cell = 1.0
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        hbm_peak = 6650.0
+    hbm_achieved = cells_per_launch * tb_bytes_per_cell / (fill_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "fill_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    line = {
+        "metric": "aligned_reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int16x2", "data": "synthetic",
+        "gcups": (cells_per_rank_step * world * args.steps) / (dev_ms * 1e-3) / 1e9,
+        "config": {"workload": "cfg2: %d single-end %d-bp reads per GPU vs %d-bp amplicon + HDR amplicon (needle "
+                               "gapopen 10 / gapextend 0.5), RC rescue, classification + histograms" % (n, READ_LEN, L),
+                   "reads_per_gpu_per_step": n, "alignments_per_read": 2, "l2": "inputs and traceback exceed L2 (reads %d MB, "
+                   "traceback scratch 8 GB per batch)" % (buf.nbytes >> 20), "parallelism": "reads sharded x%d" % world},
+        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": e2e_ms / args.steps, "results_equal_device_arm": same},
+        "gpu_launches": int(sum(fam_launch.values())),
+        "kernel_ms_per_step": {k: fam_ms[k] / args.steps for k in fam_ms},
+        "roofline": {"bound": "int_alu", "kernel": "k_gotoh_fill<8,32>", "achieved": achieved, "peak": peak, "unit": "Tiop/s",
+                     "frac": achieved / peak if peak else None, "traffic": traffic,
+                     "ops_per_cell": OPS_PER_CELL, "cells_per_launch": cells_per_launch, "ms_per_launch": fill_ms,
+                     "tcups": cells_per_launch / (fill_ms * 1e-3) / 1e12,
+                     "peak_source": "measured live: crgpu_int_peak(4), 1:1 IADD (alu pipe) + IMAD (fma pipe) chains"},
+        "roofline_hbm": {"bound": "hbm", "kernel": "k_gotoh_fill<8,32>", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": hbm_achieved / hbm_peak, "bytes_per_cell": tb_bytes_per_cell,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else "fallback"},
+        "clocks": clocks,
+        "classes": {"n_total": int(n_total), "unmodified": int(red.class_counts[0]), "nhej": int(red.class_counts[1]),
+                    "hdr": int(red.class_counts[2]), "mixed": int(red.class_counts[3])},
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, amp, hdr, inc, buf, off)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -73,6 +73,8 @@ def load():
     lib.crgpu_set_traceback_budget.argtypes = [vp, ctypes.c_size_t]
     lib.crgpu_last_timing.argtypes = [vp, vp, vp]
     lib.crgpu_sync.argtypes = [vp]
+    lib.crgpu_stream.argtypes = [vp]
+    lib.crgpu_stream.restype = vp
     lib.crgpu_qualfilter.argtypes = [vp, i32, vp, vp, i64, i32, i32, vp]
     lib.crgpu_align.argtypes = [vp, i32, ctypes.c_char_p, i32, vp, vp, i64, dbl, dbl, vp, vp, vp, vp, i64]
     lib.crgpu_quantify.argtypes = [vp, i32, ctypes.POINTER(QuantParams), vp, vp, vp, i64, vp, vp, vp, vp, vp, i64,
@@ -138,6 +140,12 @@ class Context:
         self.check(self.lib.crgpu_last_timing(self.handle, ms, ln))
         return ({k: float(ms[i]) for i, k in enumerate(self.TIMING_NAMES)},
                 {k: int(ln[i]) for i, k in enumerate(self.TIMING_NAMES)})
+
+    def stream_ptr(self):
+        return int(self.lib.crgpu_stream(self.handle) or 0)
+
+    def sync(self):
+        self.check(self.lib.crgpu_sync(self.handle))
 
     def int_peak(self, which=0):
         v = ctypes.c_double()

@@ -68,6 +68,8 @@ int crgpu_sync(crgpu_ctx *ctx)
     return CRGPU_OK;
 }
 
+void *crgpu_stream(crgpu_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
 int crgpu_qualfilter(crgpu_ctx *ctx, int mem, const uint8_t *qual, const int64_t *offsets, int64_t n,
                      int min_mean_q, int min_single_q, uint8_t *keep)
 {

@@ -66,6 +66,9 @@ int crgpu_set_traceback_budget(crgpu_ctx *ctx, size_t bytes);
 int crgpu_last_timing(const crgpu_ctx *ctx, float out_ms[6], int64_t out_launches[6]);
 /* Synchronise the context's stream. */
 int crgpu_sync(crgpu_ctx *ctx);
+/* The context's cudaStream_t (as void*), so that a caller can bracket calls with its own CUDA
+ * events on the stream the kernels are launched on. */
+void *crgpu_stream(crgpu_ctx *ctx);
 
 /* ---- S1: quality filter (CORE:162-193, 270-310) --------------------------------------- *
  * keep[i] = 1 iff mean(phred) >= min_mean_q and min(phred) >= min_single_q, phred = byte - 33,

@@ -195,7 +195,7 @@ def process_rows(rows, opts, include, L, exon=(), splice=()):
 
 
 def hot_path(amplicon, reads, names=None, gapopen=10.0, gapextend=0.5, min_identity_score=60.0, hdr_amplicon="",
-             opts=None, include=None, exon=(), splice=(), nthreads=8):
+             opts=None, include=None, exon=(), splice=(), nthreads=8, use_int=True):
     """CORE:1791-2072 + 2773-2869 on the CPU: needle (oracle) -> parse -> merge/filter -> RC rescue ->
     prep -> process_df_chunk.  reads: list of str or (buffer, offsets).  Returns a dict with the
     row list (forward rows in read order, then _RC rows), per-row results and the reductions."""
@@ -208,11 +208,11 @@ def hot_path(amplicon, reads, names=None, gapopen=10.0, gapextend=0.5, min_ident
     buf, off = packed
     n = len(off) - 1
     names = list(names) if names is not None else ["r%d" % i for i in range(n)]
-    res, ref, mark, qry = needle.align_batch(amplicon, packed, gapopen, gapextend, use_int=True, nthreads=nthreads)
+    res, ref, mark, qry = needle.align_batch(amplicon, packed, gapopen, gapextend, use_int=use_int, nthreads=nthreads)
     score_ref = res["tenths"] / 10.0
     has_hdr = bool(hdr_amplicon)
     if has_hdr:
-        res_h, _, _, _ = needle.align_batch(hdr_amplicon.upper(), packed, gapopen, gapextend, use_int=True, nthreads=nthreads)
+        res_h, _, _, _ = needle.align_batch(hdr_amplicon.upper(), packed, gapopen, gapextend, use_int=use_int, nthreads=nthreads)
         score_rep = res_h["tenths"] / 10.0
     rows = []
     failed = [i for i in range(n) if score_ref[i] < min_identity_score]                  # CORE:1843-1846, 1865-1867
@@ -228,7 +228,7 @@ def hot_path(amplicon, reads, names=None, gapopen=10.0, gapextend=0.5, min_ident
         # are dropped, i.e. the original read is re-aligned (DESIGN.md "RC rescue input")
         sub = [bytes(buf[off[i]:off[i + 1]]) for i in failed]
         amp_rc = reverse_complement(amplicon)
-        res_r, ref_r, mark_r, qry_r = needle.align_batch(amp_rc, sub, gapopen, gapextend, use_int=True, nthreads=nthreads)
+        res_r, ref_r, mark_r, qry_r = needle.align_batch(amp_rc, sub, gapopen, gapextend, use_int=use_int, nthreads=nthreads)
         cells += sum(L * len(s) for s in sub)
         for j, i in enumerate(failed):
             s = res_r["tenths"][j] / 10.0
