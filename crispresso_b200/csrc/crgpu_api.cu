@@ -150,9 +150,9 @@ int align_core(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_re
     if (!scale_penalties(gapopen, gapextend, &scale, &open_s, &ext_s))
         return fail(ctx, CRGPU_E_ALIGN, "gapopen=%g gapextend=%g are not multiples of 1/8: needle's float32 result is not "
                                         "reproducible exactly", gapopen, gapextend);
-    if (gapopen < 4.0 || gapextend < 0.0)
-        return fail(ctx, CRGPU_E_ALIGN, "gapopen=%g gapextend=%g: need gapopen >= 4 (>= -min(EDNAFULL)) and gapextend >= 0",
-                    gapopen, gapextend);
+    if (gapopen < 4.0 || gapextend < 0.0 || gapextend > gapopen)
+        return fail(ctx, CRGPU_E_ALIGN, "gapopen=%g gapextend=%g: need gapopen >= 4 (>= -min(EDNAFULL)) and "
+                                        "0 <= gapextend <= gapopen", gapopen, gapextend);
     std::vector<int> acode(La);
     std::string amp_up(La, 'N');
     for (int i = 0; i < La; ++i) {

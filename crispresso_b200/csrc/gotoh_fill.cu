@@ -9,10 +9,10 @@
 //     halves of every register) and sweeps the read columns x = 0..Lb-1;
 //   * lane t of the group owns K consecutive amplicon rows (virtual rows r = t*K .. t*K+K-1;
 //     the amplicon is padded on TOP with P = G*K - La rows scoring 0 against everything, which
-//     reproduces needle's free-end-gap boundary exactly), whose state MY = max(m,iy)[y,x-1] and
+//     reproduces needle's free-end-gap boundary exactly), whose state H3 = max(m,ix,iy)[y,x-1] and
 //     IX = ix[y,x-1] lives in 2K registers;
 //   * the lanes form a systolic pipeline: at step s lane t works on column x = s - t and hands
-//     (max(m,ix), iy, m) of its bottom row to lane t+1 with one warp shuffle each;
+//     (max3, iy, m) of its bottom row to lane t+1 with one warp shuffle each;
 //   * the substitution scores of a column come from a pair profile table in shared memory
 //     (25 read-code pairs x padded rows, one LDS.128 per 4 rows), loaded once per CTA with a
 //     TMA bulk copy (cp.async.bulk -> UBLKCP);
@@ -35,26 +35,40 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)_
 
 template <int K>
 struct Strip {
-    uint32_t MY[K];   // max(m,iy)[row, x-1]
+    uint32_t H3[K];   // max(m,ix,iy)[row, x-1]
     uint32_t IX[K];   // ix[row, x-1]
     uint32_t mlast;   // m[row K-1, x-1]; only meaningful in the lane that owns amplicon row La-1
 };
 
 // One read column for the K rows of this lane.
-//  SLOW = true handles the first (x == 0) and last (x == Lb-1) columns, whose iy rule / FY flag
-//  differ (App. A.2/A.3: last column opens from m only with zero penalties; A.4: gey = 0 there).
-template <int K, bool SLOW>
+//
+// Recurrences in the form used here, valid because gapopen >= gapextend (checked
+// on the host): the "open" source max(m,iy)[y,x-1] of ix may be replaced by max3[y,x-1] -- if ix is
+// the strict maximum then ix-open <= ix-ext, so the result is unchanged -- and likewise for iy.
+// That leaves per cell: m = S + max3[y-1,x-1]; ix = max(max3[y,x-1]-open, ix[y,x-1]-ext);
+// iy = max(max3[y-1,x]-open, iy[y-1,x]-ext); max3 = VIMNMX3(m,ix,iy).
+//
+//  EDGE = false: interior columns, all penalties are immediates.
+//  EDGE = true : some lane of the warp is on its first (x == 0) or last (x == Lb-1) column, whose
+//  iy rule / FY flag differ (App. A.2/A.3: the last column opens from m only with zero penalties;
+//  A.4: gey = 0 on both).  The whole warp then runs this body with per-lane sources/penalties, so
+//  the special columns cost no divergence.
+template <int K, bool EDGE>
 __device__ __forceinline__ void column_step(Strip<K> &st, const int32_t *__restrict__ prow,
-                                            uint32_t upMX, uint32_t upIY, uint32_t upM, uint32_t hd,
+                                            uint32_t upH3, uint32_t upIY, uint32_t upM, uint32_t hd,
                                             const uint32_t nopen16, const uint32_t ext32,
                                             const uint32_t nopen16_last, const uint32_t ext32_last,
-                                            const bool lastLane, const bool isLastCol,
+                                            const bool lastLane, const bool isFirstCol, const bool isLastCol,
                                             uint32_t *__restrict__ tbw, uint32_t *__restrict__ lastcol,
-                                            uint32_t &botMX, uint32_t &botIY, uint32_t &botM)
+                                            uint32_t &botH3, uint32_t &botIY, uint32_t &botM)
 {
     uint32_t words[K / 2];
     uint32_t ceven = 0;
     int32_t S4[4];
+    // per-lane vertical-gap parameters of this column (EDGE only)
+    const uint32_t nopen16_v = (EDGE && isLastCol) ? 0u : nopen16;
+    const uint32_t ext32_v = (EDGE && isLastCol) ? 0u : ext32;
+    const uint32_t ext32_f = (EDGE && (isLastCol || isFirstCol)) ? 0u : ext32;   // gey of the FY flag
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         if ((k & 3) == 0) {
@@ -62,31 +76,28 @@ __device__ __forceinline__ void column_step(Strip<K> &st, const int32_t *__restr
             S4[0] = v.x; S4[1] = v.y; S4[2] = v.z; S4[3] = v.w;
         }
         const uint32_t S = (uint32_t)S4[k & 3];
-        const uint32_t my0 = st.MY[k], ix0 = st.IX[k];
-        const uint32_t hnext = vmax2(my0, ix0);          // max3[row, x-1]: diagonal input of row+1
+        const uint32_t h0 = st.H3[k], ix0 = st.IX[k];
         const uint32_t m = hd + S;                       // m = sub + max3[row-1, x-1]
         uint32_t t_, ix;
         if (k == K - 1) {                                // the only row that can be amplicon row La-1
-            const uint32_t src = lastLane ? st.mlast : my0;
+            const uint32_t src = lastLane ? st.mlast : h0;
             t_ = ix0 - ext32_last;
             ix = vaddmax2(src, nopen16_last, t_);
         } else {
             t_ = ix0 - ext32;
-            ix = vaddmax2(my0, nopen16, t_);
+            ix = vaddmax2(h0, nopen16, t_);
         }
-        uint32_t u_, iy, nFY;
-        if (SLOW) {
-            if (isLastCol) { u_ = upIY; iy = vmax2(upM, upIY); }
-            else { u_ = upIY - ext32; iy = vaddmax2(upMX, nopen16, u_); }
-            nFY = vmin2(iy ^ upIY, ONE2);                // gey = 0 on the first and last column
+        uint32_t iy, nFY;
+        if (EDGE) {
+            const uint32_t src = isLastCol ? upM : upH3;
+            iy = vaddmax2(src, nopen16_v, upIY - ext32_v);
+            nFY = vmin2(iy ^ (upIY - ext32_f), ONE2);
         } else {
-            u_ = upIY - ext32;
-            iy = vaddmax2(upMX, nopen16, u_);
+            const uint32_t u_ = upIY - ext32;
+            iy = vaddmax2(upH3, nopen16, u_);
             nFY = vmin2(iy - u_, ONE2);
         }
-        const uint32_t my = vmax2(m, iy);
-        const uint32_t mx = vmax2(m, ix);
-        const uint32_t h3 = vmax2(my, ix);
+        const uint32_t h3 = __vimax3_s16x2(m, ix, iy);
         const uint32_t nM = vmin2(h3 - m, ONE2);
         const uint32_t nX = vmin2(h3 - ix, ONE2);
         const uint32_t nY = vmin2(h3 - iy, ONE2);
@@ -94,15 +105,15 @@ __device__ __forceinline__ void column_step(Strip<K> &st, const int32_t *__restr
         const uint32_t c = nM + 2u * nX + 4u * nY + 8u * nFX + 16u * nFY;
         if (k & 1) words[k >> 1] = ceven + (c << 8);
         else ceven = c;
-        if (SLOW) {
+        if (EDGE) {
             if (isLastCol) { lastcol[3 * k] = m; lastcol[3 * k + 1] = ix; lastcol[3 * k + 2] = iy; }
         }
-        st.MY[k] = my;
+        st.H3[k] = h3;
         st.IX[k] = ix;
         if (k == K - 1) st.mlast = m;
-        upMX = mx; upIY = iy; upM = m; hd = hnext;
+        upH3 = h3; upIY = iy; upM = m; hd = h0;
     }
-    botMX = upMX; botIY = upIY; botM = upM;
+    botH3 = upH3; botIY = upIY; botM = upM;
     if constexpr ((K % 8) == 0) {
 #pragma unroll
         for (int j = 0; j < K / 8; ++j)
@@ -114,8 +125,18 @@ __device__ __forceinline__ void column_step(Strip<K> &st, const int32_t *__restr
     }
 }
 
+// 128-thread CTAs, as many per SM as registers / shared memory allow (3 for the K = 32 strips).
+// The register cap per strip height was swept on a B200 (profiles/r01_notes.md): K = 32 runs
+// 2007 GCUPS at 136 registers vs 1845 at ptxas' own choice (133) and 1513 at 128 (4 CTAs/SM but
+// spills + extra moves); one 12-warp CTA per SM under __launch_bounds__(384) is 25 % slower.
+#ifdef FILL_MAXNREG
+template <int K> constexpr int fill_maxnreg() { return FILL_MAXNREG; }
+#else
+template <int K> constexpr int fill_maxnreg() { return K >= 36 ? 144 : (K >= 32 ? 136 : 128); }
+#endif
+
 template <int G, int K>
-__global__ void __launch_bounds__(128) k_gotoh_fill(const FillArgs a)
+__global__ void __maxnreg__(fill_maxnreg<K>()) k_gotoh_fill(const FillArgs a)
 {
     static_assert(K % 4 == 0 && (32 % G) == 0, "bad tile");
     constexpr int PS = prof_stride(G, K);
@@ -171,31 +192,33 @@ __global__ void __launch_bounds__(128) k_gotoh_fill(const FillArgs a)
 
         Strip<K> st;
 #pragma unroll
-        for (int k = 0; k < K; ++k) { st.MY[k] = Z; st.IX[k] = NOPEN_ST; }
+        for (int k = 0; k < K; ++k) { st.H3[k] = Z; st.IX[k] = NOPEN_ST; }
         st.mlast = Z;
-        uint32_t botMX = Z, botIY = NOPEN_ST, botM = Z;
+        uint32_t botH3 = Z, botIY = NOPEN_ST, botM = Z;
         uint32_t hd0 = Z;
         int cp_next = (t == 0 && Lb > 0) ? pcp[0] : 0;
 
         for (int s = 0; s < steps; ++s) {
             const int x = s - t;
-            uint32_t rMX = __shfl_up_sync(0xffffffffu, botMX, 1, G);
+            uint32_t rH3 = __shfl_up_sync(0xffffffffu, botH3, 1, G);
             uint32_t rIY = __shfl_up_sync(0xffffffffu, botIY, 1, G);
             uint32_t rM = __shfl_up_sync(0xffffffffu, botM, 1, G);
-            if (t == 0) { rMX = Z; rIY = NOPEN_ST; rM = Z; }          // free boundary above the padded top
+            if (t == 0) { rH3 = Z; rIY = NOPEN_ST; rM = Z; }          // free boundary above the padded top
             const bool active = (x >= 0) && (x < Lb);
+            const bool firstCol = active && x == 0, lastCol = active && x == Lb - 1;
+            const bool edge = __any_sync(0xffffffffu, firstCol || lastCol);   // warp-uniform
             const int cp = cp_next;
             if (x + 1 >= 0 && x + 1 < Lb) cp_next = pcp[x + 1];
             if (active) {
                 const int32_t *prow = sprof + cp * PS + t * strip_stride(K);
                 uint32_t *tbw = tbp + (int64_t)x * (GK / 2);
-                if (x == 0 || x == Lb - 1)
-                    column_step<K, true>(st, prow, rMX, rIY, rM, hd0, nopen16, ext32, nopen16_last, ext32_last,
-                                         lastLane, x == Lb - 1, tbw, lcp, botMX, botIY, botM);
+                if (edge)
+                    column_step<K, true>(st, prow, rH3, rIY, rM, hd0, nopen16, ext32, nopen16_last, ext32_last,
+                                         lastLane, firstCol, lastCol, tbw, lcp, botH3, botIY, botM);
                 else
-                    column_step<K, false>(st, prow, rMX, rIY, rM, hd0, nopen16, ext32, nopen16_last, ext32_last,
-                                          lastLane, false, tbw, lcp, botMX, botIY, botM);
-                hd0 = vmax2(rMX, rIY);                                // max3[row above, x] for column x+1
+                    column_step<K, false>(st, prow, rH3, rIY, rM, hd0, nopen16, ext32, nopen16_last, ext32_last,
+                                          lastLane, false, false, tbw, lcp, botH3, botIY, botM);
+                hd0 = rH3;                                            // max3[row above, x] for column x+1
                 if (lastLane) {
                     uint32_t *lr = lrp + (int64_t)x * 3;
                     lr[0] = botM; lr[1] = st.IX[K - 1]; lr[2] = botIY;
@@ -225,7 +248,7 @@ static cudaError_t launch_tile(const FillArgs &a, int num_sms, cudaStream_t stre
     const int npairs = a.p1 - a.p0;
     const int groups_per_block = 4 * (32 / G);
     int grid = (npairs + groups_per_block - 1) / groups_per_block;
-    const int cap = num_sms * blocks_per_sm;
+    const int cap = num_sms * blocks_per_sm;      // persistent: a multiple of the SM count
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     k_gotoh_fill<G, K><<<grid, 128, smem, stream>>>(a);

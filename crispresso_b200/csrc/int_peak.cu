@@ -10,6 +10,9 @@ namespace crgpu {
 constexpr int PEAK_CHAINS = 16;
 constexpr int PEAK_UNROLL = 8;
 
+// Every op takes another accumulator as its second operand, so ptxas cannot fold a chain into
+// a*k+b or merge two adds into one IADD3: one source op == one SASS instruction (checked with
+// cuobjdump, profiles/r01_sass_notes.md).
 template <int WHICH>
 __global__ void __launch_bounds__(1024) k_int_peak(int iters, unsigned *sink, unsigned b, unsigned c)
 {
@@ -21,14 +24,18 @@ __global__ void __launch_bounds__(1024) k_int_peak(int iters, unsigned *sink, un
         for (int u = 0; u < PEAK_UNROLL; ++u) {
 #pragma unroll
             for (int j = 0; j < PEAK_CHAINS; ++j) {
-                if (WHICH == 0) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[j]) : "r"(b));
-                else if (WHICH == 1) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[j]) : "r"(b), "r"(c));
-                else if (WHICH == 2) a[j] = (u & 1) ? __vmaxs2(a[j], b) : __vmins2(a[j], c);
-                else if (WHICH == 3) a[j] = __viaddmax_s16x2(a[j], b, c);
-                else {
-                    if (j & 1) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[j]) : "r"(b), "r"(c));
-                    else asm volatile("add.u32 %0, %0, %1;" : "+r"(a[j]) : "r"(b));
+                const unsigned o = a[(j + 1 + u) % PEAK_CHAINS];
+                if (WHICH == 0) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[j]) : "r"(o));                        // IADD3 / VIADD (alu)
+                else if (WHICH == 1) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[j]) : "r"(b), "r"(o));     // IMAD (fma)
+                else if (WHICH == 2) a[j] = (u & 1) ? __vmaxs2(a[j], o) : __vmins2(a[j], o);                        // VIMNMX.S16x2
+                else if (WHICH == 3) a[j] = __viaddmax_s16x2(a[j], b, o);                                           // VIADDMNMX.S16x2
+                else if (WHICH == 4) {                                                                              // 1:1 alu + fma
+                    if (j & 1) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[j]) : "r"(b), "r"(o));
+                    else a[j] = (u & 1) ? __vmaxs2(a[j], o) : __vmins2(a[j], o);
                 }
+                else if (WHICH == 5) a[j] = __vimax3_s16x2(a[j], o, c);                                             // VIMNMX3.S16x2
+                else if (WHICH == 6) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[j]) : "r"(o), "r"(c)); // LOP3
+                else if (WHICH == 7) a[j] = __vminu2(a[j] - o, 0x00010001u) + c;                                    // sub + VIMNMX imm + add
             }
         }
     }
@@ -48,9 +55,12 @@ cudaError_t launch_int_peak(int which, int num_sms, int iters, unsigned *sink, c
     case 2: k_int_peak<2><<<grid, block, 0, s>>>(iters, sink, b, c); break;
     case 3: k_int_peak<3><<<grid, block, 0, s>>>(iters, sink, b, c); break;
     case 4: k_int_peak<4><<<grid, block, 0, s>>>(iters, sink, b, c); break;
+    case 5: k_int_peak<5><<<grid, block, 0, s>>>(iters, sink, b, c); break;
+    case 6: k_int_peak<6><<<grid, block, 0, s>>>(iters, sink, b, c); break;
+    case 7: k_int_peak<7><<<grid, block, 0, s>>>(iters, sink, b, c); break;
     default: return cudaErrorInvalidValue;
     }
-    *lane_ops = (double)grid * block * (double)iters * PEAK_UNROLL * PEAK_CHAINS;
+    *lane_ops = (double)grid * block * (double)iters * PEAK_UNROLL * PEAK_CHAINS * (which == 7 ? 3.0 : 1.0);
     return cudaGetLastError();
 }
 

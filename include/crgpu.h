@@ -216,9 +216,11 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
                          const uint8_t *reads, const int64_t *offsets, int64_t n, crgpu_path_out *out);
 
 /* ---- measurement helper ---------------------------------------------------------------- *
- * Integer-ALU peak micro-benchmark ("measure it"): dependent-free 32-bit
- * IADD3/VIMNMX chains on every SM.  Returns lane-ops per second.  which: 0 = IADD3 (alu pipe),
- * 1 = IMAD (fma pipe), 2 = VIMNMX.S16x2, 3 = VIADDMNMX.S16x2, 4 = 1:1 IADD3+IMAD mix. */
+ * Integer issue-rate micro-benchmark ("measure it"): dependency-free chains of ONE
+ * instruction kind on every SM.  Returns lane-ops per second (one SASS instruction on one lane).
+ * which: 0 = IADD (alu pipe), 1 = IMAD (fma pipe), 2 = VIMNMX.S16x2, 3 = VIADDMNMX.S16x2,
+ * 4 = 1:1 mix of VIMNMX.S16x2 (alu) and IMAD (fma) -- the dual-pipe integer peak the roofline
+ * uses --, 5 = VIMNMX3.S16x2, 6 = LOP3, 7 = (sub, VIMNMX imm, add) triple. */
 int crgpu_int_peak(crgpu_ctx *ctx, int which, double *lane_ops_per_s);
 
 #ifdef __cplusplus
