@@ -1,5 +1,6 @@
 // crgpu_api.cu -- the C ABI declared in include/crgpu.h: context, S1, S2, batching, host-side pairing.
 #include "crgpu_internal.h"
+#include <cstdlib>
 
 using namespace crgpu;
 
@@ -20,7 +21,15 @@ int crgpu_create(crgpu_ctx **out, int device)
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return CRGPU_E_CUDA; }
     if (prop.major != 10) { delete c; return CRGPU_E_CUDA; }   // sm_100a SASS only: no other target, no fallback
     c->num_sms = prop.multiProcessorCount;
+    // The traceback walk reads one byte per visited cell from scattered sectors: ask L2 not to
+    // over-fetch neighbouring sectors from HBM (a hint; DESIGN.md "k_traceback_walk").
+    if (!getenv("CRGPU_NO_L2_HINT")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return CRGPU_E_CUDA; }
+    if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete c; return CRGPU_E_CUDA; }
+    for (int i = 0; i < 2; ++i) {
+        cudaEventCreateWithFlags(&c->fill_done[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->walk_done[i], cudaEventDisableTiming);
+    }
     *out = c;
     return CRGPU_OK;
 }
@@ -30,13 +39,16 @@ void crgpu_destroy(crgpu_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->stream2);
     DBuf *all[] = {&c->reads, &c->offsets, &c->amp, &c->prof, &c->pc, &c->pc_off, &c->plen, &c->pair_lo, &c->pair_hi,
-                   &c->tb_off, &c->tb, &c->lastrow, &c->lastcol, &c->errflag, &c->recs, &c->sref, &c->smark, &c->sqry};
+                   &c->order, &c->plan_hist, &c->plan_tab, &c->tb2, &c->lastrow2, &c->lastcol2, &c->tb, &c->lastrow, &c->lastcol, &c->errflag, &c->recs, &c->sref, &c->smark, &c->sqry, &c->ops, &c->ops_rc};
     for (DBuf *b : all) b->release();
     for (auto &b : c->q_in) b.release();
     for (auto &b : c->q_out) b.release();
     for (auto &b : c->aux) b.release();
     for (auto e : c->ev_pool) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->fill_done[i]); cudaEventDestroy(c->walk_done[i]); }
+    cudaStreamDestroy(c->stream2);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -137,13 +149,98 @@ static bool scale_penalties(double gapopen, double gapextend, int *scale, int *o
 
 namespace crgpu {
 
-// subset: optional list of read indices to align (device reads/offsets cover ALL reads); when
-// null all n_total reads are aligned.  recs/strings are indexed by ORIGINAL read index.
-int align_core(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_reads, const int64_t *d_offsets,
-               const int64_t *h_offsets, const int32_t *subset, int64_t nsub, const int32_t *d_out_index, int rc_out,
-               double gapopen, double gapextend, crgpu_aln_rec *d_recs, uint8_t *d_ref, uint8_t *d_mark, uint8_t *d_qry,
-               int64_t slot, int64_t *n_cells)
+// ---------------------------------------------------------------------------------------------
+// build_plan: bucket the reads (all n, or `d_subset`) by length on the device, pair consecutive
+// reads of a bucket, encode the pair codes.  The plan depends only on the reads, so the amplicon
+// pass and the HDR-amplicon pass share it.  Only the length histogram (8 KB) visits the host.
+// ---------------------------------------------------------------------------------------------
+int build_plan(crgpu_ctx *ctx, const uint8_t *d_reads, const int64_t *d_offsets, const int32_t *d_subset, int64_t nsub)
 {
+    PairPlan &pl = ctx->plan;
+    pl = PairPlan();
+    pl.nsub = nsub;
+    if (nsub <= 0) return CRGPU_OK;
+    cudaStream_t s = ctx->stream;
+    const int NB = CRGPU_MAX_READ + 1;
+    CK(ctx->plan_hist.reserve((size_t)NB * 4 * 2 + 16));          // hist + cursor + err
+    int *d_hist = ctx->plan_hist.as<int>(), *d_cursor = d_hist + NB, *d_err = d_cursor + NB;
+    CK(cudaMemsetAsync(d_hist, 0, (size_t)NB * 4 * 2 + 16, s));
+    span_begin(ctx, T_ENCODE);
+    CK(launch_len_hist(d_offsets, d_subset, nsub, CRGPU_MIN_LEN, CRGPU_MAX_READ, d_hist, d_err, s));
+    span_end(ctx);
+    std::vector<int> hist((size_t)NB + 0);
+    int h_err = 0;
+    CK(cudaMemcpyAsync(hist.data(), d_hist, (size_t)NB * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (h_err & 2)
+        return fail(ctx, CRGPU_E_ALIGN, "a read has a length outside [%d, %d]", CRGPU_MIN_LEN, CRGPU_MAX_READ);
+    std::vector<int64_t> read_start((size_t)NB, 0);
+    int64_t rs = 0, ps = 0, pcs = 0;
+    for (int l = 0; l < NB; ++l) {
+        read_start[(size_t)l] = rs;
+        const int c = hist[(size_t)l];
+        if (c > 0) {
+            HostSeg sg;
+            sg.len = l; sg.cnt = c; sg.read_start = rs; sg.pair_start = ps; sg.pc_start = pcs;
+            pl.segs.push_back(sg);
+            const int64_t npair = ((int64_t)c + 1) / 2;
+            rs += c; ps += npair; pcs += npair * l;
+            pl.maxlen = l;
+            if (pl.minlen == 0) pl.minlen = l;
+            pl.sum_len += (int64_t)c * l;
+        }
+    }
+    if (ps >= ((int64_t)1 << 31)) return fail(ctx, CRGPU_E_ARG, "too many read pairs");
+    pl.np = (int)ps;
+    pl.total_pc = pcs;
+    const int nseg = (int)pl.segs.size();
+    CK(ctx->plan_tab.reserve((size_t)NB * 8 + (size_t)nseg * sizeof(HostSeg)));
+    int64_t *d_read_start = ctx->plan_tab.as<int64_t>();
+    HostSeg *d_segs = reinterpret_cast<HostSeg *>(d_read_start + NB);
+    CK(cudaMemcpyAsync(d_read_start, read_start.data(), (size_t)NB * 8, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(d_segs, pl.segs.data(), (size_t)nseg * sizeof(HostSeg), cudaMemcpyHostToDevice, s));
+    CK(ctx->order.reserve((size_t)nsub * 4));
+    CK(ctx->pc.reserve((size_t)std::max<int64_t>(pcs, 1)));
+    CK(ctx->pc_off.reserve((size_t)(pl.np + 1) * 8));
+    CK(ctx->plen.reserve((size_t)pl.np * 4));
+    CK(ctx->pair_lo.reserve((size_t)pl.np * 4));
+    CK(ctx->pair_hi.reserve((size_t)pl.np * 4));
+    span_begin(ctx, T_ENCODE);
+    CK(launch_scatter_order(d_offsets, d_subset, nsub, d_read_start, d_cursor, ctx->order.as<int32_t>(), s));
+    CK(launch_build_pairs(d_segs, nseg, pl.np, ctx->order.as<int32_t>(), ctx->pair_lo.as<int32_t>(), ctx->pair_hi.as<int32_t>(),
+                          ctx->plen.as<int32_t>(), ctx->pc_off.as<int64_t>(), pcs, s));
+    CK(launch_encode(d_reads, d_offsets, ctx->pair_lo.as<int32_t>(), ctx->pair_hi.as<int32_t>(), ctx->pc_off.as<int64_t>(), pl.np,
+                     ctx->pc.as<uint8_t>(), d_err, ctx->num_sms, s));
+    span_end(ctx);
+    CK(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));    // read_start / segs are locals of this frame
+    if (h_err & 1) return fail(ctx, CRGPU_E_ALIGN, "a read contains a base outside ACGTN(U)");
+    return CRGPU_OK;
+}
+
+// pc_off of pair p, from the per-length segments (host)
+static int64_t plan_pc_off(const PairPlan &pl, int64_t p)
+{
+    if (p >= pl.np) return pl.total_pc;
+    size_t lo = 0, hi = pl.segs.size() - 1;
+    while (lo < hi) {
+        const size_t mid = (lo + hi + 1) / 2;
+        if (pl.segs[mid].pair_start <= p) lo = mid; else hi = mid - 1;
+    }
+    return pl.segs[lo].pc_start + (p - pl.segs[lo].pair_start) * pl.segs[lo].len;
+}
+
+// ---------------------------------------------------------------------------------------------
+// run_plan: align every pair of the current plan to `amplicon`.  recs / rows are indexed by read
+// (or by d_out_index[read]).  Batches are bounded by the traceback budget.
+// ---------------------------------------------------------------------------------------------
+int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_reads, const int64_t *d_offsets,
+             const int32_t *d_out_index, int rc_out, double gapopen, double gapextend, crgpu_aln_rec *d_recs,
+             uint8_t *d_ref, uint8_t *d_mark, uint8_t *d_qry, int64_t slot, int64_t *n_cells, uint32_t *d_ops,
+             int64_t ops_stride)
+{
+    const PairPlan &pl = ctx->plan;
     if (La < CRGPU_MIN_LEN || La > CRGPU_MAX_AMPLICON)
         return fail(ctx, CRGPU_E_ALIGN, "amplicon length %d outside [%d, %d]", La, CRGPU_MIN_LEN, CRGPU_MAX_AMPLICON);
     int scale, open_s, ext_s;
@@ -160,81 +257,49 @@ int align_core(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_re
         if (acode[i] < 0) return fail(ctx, CRGPU_E_ALIGN, "amplicon has a base outside ACGTN at %d", i);
         amp_up[i] = amplicon[i];
     }
+    if (pl.np == 0) return CRGPU_OK;
     int G, K;
     if (!choose_tile(La, &G, &K)) return fail(ctx, CRGPU_E_ALIGN, "no kernel tile for amplicon length %d", La);
     const int GK = G * K, P = GK - La;
-
-    // ---- pair reads of equal length (host) ----
-    int maxlen = 0;
-    std::vector<int32_t> order((size_t)nsub);
-    {
-        std::vector<int64_t> cnt(CRGPU_MAX_READ + 2, 0);
-        for (int64_t i = 0; i < nsub; ++i) {
-            const int64_t r = subset ? subset[i] : i;
-            const int64_t len = h_offsets[r + 1] - h_offsets[r];
-            if (len < CRGPU_MIN_LEN || len > CRGPU_MAX_READ)
-                return fail(ctx, CRGPU_E_ALIGN, "read %lld has length %lld outside [%d, %d]", (long long)r, (long long)len,
-                            CRGPU_MIN_LEN, CRGPU_MAX_READ);
-            cnt[len + 1]++;
-            if (len > maxlen) maxlen = (int)len;
-        }
-        for (int l = 1; l <= CRGPU_MAX_READ + 1; ++l) cnt[l] += cnt[l - 1];
-        for (int64_t i = 0; i < nsub; ++i) {
-            const int64_t r = subset ? subset[i] : i;
-            const int64_t len = h_offsets[r + 1] - h_offsets[r];
-            order[(size_t)cnt[len]++] = (int32_t)r;
-        }
-    }
+    const int maxlen = pl.maxlen;
     if ((int64_t)scale * 5 * std::min(La, maxlen) + 64 >= MAX_ABS_SCORE ||
         (int64_t)2 * open_s + (int64_t)ext_s * (La + maxlen) + 8 * scale + 64 >= MAX_ABS_SCORE)
         return fail(ctx, CRGPU_E_ALIGN, "scores would leave the exact int16 range (scale %d, lengths %d/%d)", scale, La, maxlen);
     if (slot < (int64_t)La + maxlen && d_ref) return fail(ctx, CRGPU_E_ARG, "slot %lld < amplicon + longest read %d", (long long)slot, La + maxlen);
+    if (n_cells) *n_cells += (int64_t)La * pl.sum_len;
 
-    std::vector<int32_t> pair_lo, pair_hi, plen;
-    std::vector<int64_t> pc_off(1, 0);
-    pair_lo.reserve((size_t)nsub / 2 + 1); pair_hi.reserve((size_t)nsub / 2 + 1); plen.reserve((size_t)nsub / 2 + 1);
-    pc_off.reserve((size_t)nsub / 2 + 2);
-    int64_t cells = 0;
-    for (int64_t i = 0; i < nsub;) {
-        const int32_t r0 = order[(size_t)i];
-        const int len0 = (int)(h_offsets[r0 + 1] - h_offsets[r0]);
-        int32_t r1 = r0;
-        int64_t step = 1;
-        if (i + 1 < nsub) {
-            const int32_t c = order[(size_t)i + 1];
-            if ((int)(h_offsets[c + 1] - h_offsets[c]) == len0) { r1 = c; step = 2; }
-        }
-        pair_lo.push_back(r0); pair_hi.push_back(r1); plen.push_back(len0);
-        pc_off.push_back(pc_off.back() + len0);
-        cells += step * (int64_t)La * len0;
-        i += step;
-    }
-    if (n_cells) *n_cells += cells;
-    const int np = (int)plen.size();
-    if (np == 0) return CRGPU_OK;
-
-    // ---- batches bounded by the traceback budget ----
-    std::vector<int64_t> tb_off((size_t)np);
+    // ---- batches bounded by the traceback budget (pairs are ordered by length) ----
     std::vector<int> batch_start(1, 0);
+    int64_t max_tb_words = 0, max_lr = 0;
+    int max_bp = 0;
     {
         const int64_t words_per_col = GK / 2;
-        int64_t acc = 0;
         const int64_t budget_words = (int64_t)(ctx->tb_budget / 4);
-        for (int p = 0; p < np; ++p) {
-            const int64_t w = (int64_t)plen[p] * words_per_col;
-            if (acc > 0 && acc + w > budget_words) { batch_start.push_back(p); acc = 0; }
-            tb_off[(size_t)p] = acc;
-            acc += w;
+        int64_t acc = 0, acc_lr = 0;
+        int p_begin = 0;
+        auto close = [&](int p_end) {
+            max_tb_words = std::max(max_tb_words, acc);
+            max_lr = std::max(max_lr, acc_lr);
+            max_bp = std::max(max_bp, p_end - p_begin);
+            batch_start.push_back(p_end);
+            p_begin = p_end; acc = 0; acc_lr = 0;
+        };
+        for (const HostSeg &sg : pl.segs) {
+            const int64_t w = (int64_t)sg.len * words_per_col;
+            int64_t left = ((int64_t)sg.cnt + 1) / 2;
+            int64_t p = sg.pair_start;
+            while (left > 0) {
+                int64_t fit = (budget_words - acc) / w;
+                if (fit <= 0) {
+                    if (acc > 0) { close((int)p); continue; }
+                    fit = 1;                                   // a single pair always runs
+                }
+                const int64_t take = std::min(fit, left);
+                acc += take * w; acc_lr += take * sg.len; p += take; left -= take;
+                if (left > 0) close((int)p);
+            }
         }
-        batch_start.push_back(np);
-    }
-    int64_t max_tb_words = 0, max_lr = 0; int max_bp = 0;
-    for (size_t b = 0; b + 1 < batch_start.size(); ++b) {
-        const int p0 = batch_start[b], p1 = batch_start[b + 1];
-        const int64_t w = tb_off[(size_t)p1 - 1] + (int64_t)plen[(size_t)p1 - 1] * (GK / 2);
-        max_tb_words = std::max(max_tb_words, w);
-        max_lr = std::max(max_lr, pc_off[(size_t)p1] - pc_off[(size_t)p0]);
-        max_bp = std::max(max_bp, p1 - p0);
+        if (acc > 0) close(pl.np);
     }
 
     // ---- profile table ----
@@ -248,68 +313,64 @@ int align_core(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_re
             prof[(size_t)cp * PS + (r / K) * SS + (r % K)] = shi * 65536 + slo;
         }
     }
-
-    // ---- uploads ----
     cudaStream_t s = ctx->stream;
     CK(ctx->amp.reserve((size_t)La));
     CK(ctx->prof.reserve(prof.size() * 4));
-    CK(ctx->pc.reserve((size_t)pc_off.back()));
-    CK(ctx->pc_off.reserve(pc_off.size() * 8));
-    CK(ctx->plen.reserve((size_t)np * 4));
-    CK(ctx->pair_lo.reserve((size_t)np * 4));
-    CK(ctx->pair_hi.reserve((size_t)np * 4));
-    CK(ctx->tb_off.reserve((size_t)np * 8));
+    const bool two = batch_start.size() > 2 && !getenv("CRGPU_NO_OVERLAP");     // double-buffer only when there is a second batch to overlap with
     CK(ctx->tb.reserve((size_t)max_tb_words * 4));
-    CK(ctx->lastrow.reserve((size_t)max_lr * 12));
-    CK(ctx->lastcol.reserve((size_t)max_bp * GK * 12));
-    CK(ctx->errflag.reserve(4));
+    CK(ctx->lastrow.reserve((size_t)max_bp * 12));
+    CK(ctx->lastcol.reserve((size_t)max_bp * G * 12));
+    if (two) {
+        CK(ctx->tb2.reserve((size_t)max_tb_words * 4));
+        CK(ctx->lastrow2.reserve((size_t)max_bp * 12));
+        CK(ctx->lastcol2.reserve((size_t)max_bp * G * 12));
+    }
     CK(cudaMemcpyAsync(ctx->amp.p, amp_up.data(), (size_t)La, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(ctx->prof.p, prof.data(), prof.size() * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->pc_off.p, pc_off.data(), pc_off.size() * 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->plen.p, plen.data(), (size_t)np * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->pair_lo.p, pair_lo.data(), (size_t)np * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->pair_hi.p, pair_hi.data(), (size_t)np * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->tb_off.p, tb_off.data(), (size_t)np * 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMemsetAsync(ctx->errflag.p, 0, 4, s));
+    CK(cudaStreamSynchronize(s));      // amp_up / prof are locals of this frame
 
-    span_begin(ctx, T_ENCODE);
-    CK(launch_encode(d_reads, d_offsets, ctx->pair_lo.as<int32_t>(), ctx->pair_hi.as<int32_t>(), ctx->pc_off.as<int64_t>(), np,
-                     ctx->pc.as<uint8_t>(), ctx->errflag.as<int>(), ctx->num_sms, s));
-    span_end(ctx);
-    int h_err = 0;
-    CK(cudaMemcpyAsync(&h_err, ctx->errflag.p, 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));   // also keeps the host vectors above alive until the copies are done
-    if (h_err) return fail(ctx, CRGPU_E_ALIGN, "a read contains a base outside ACGTN(U)");
-
+    // Fill kernels run back to back on the main stream; the traceback walk of batch b runs on the
+    // second stream, overlapped with the fill of batch b+1 (the walk is DRAM-latency bound, the fill
+    // integer-issue bound).  Two sets of traceback scratch alternate.
+    cudaStream_t s2 = two ? ctx->stream2 : ctx->stream;
+    bool used[2] = {false, false};
     for (size_t b = 0; b + 1 < batch_start.size(); ++b) {
+        const int cur = two ? (int)(b & 1) : 0;
         FillArgs fa;
         fa.prof = ctx->prof.as<int32_t>();
         fa.pc = ctx->pc.as<uint8_t>();
         fa.pc_off = ctx->pc_off.as<int64_t>();
         fa.plen = ctx->plen.as<int32_t>();
-        fa.tb_off = ctx->tb_off.as<int64_t>();
-        fa.tb = ctx->tb.as<uint32_t>();
-        fa.lastrow = ctx->lastrow.as<uint32_t>();
-        fa.lastcol = ctx->lastcol.as<uint32_t>();
+        fa.tb = (cur ? ctx->tb2 : ctx->tb).as<uint32_t>();
+        fa.lastrow = (cur ? ctx->lastrow2 : ctx->lastrow).as<uint32_t>();
+        fa.lastcol = (cur ? ctx->lastcol2 : ctx->lastcol).as<uint32_t>();
         fa.p0 = batch_start[b]; fa.p1 = batch_start[b + 1];
-        fa.open = open_s; fa.ext = ext_s;
-        span_begin(ctx, T_FILL);
+        fa.open = open_s; fa.ext = ext_s; fa.La = La;
+        if (used[cur]) CK(cudaStreamWaitEvent(s, ctx->walk_done[cur], 0));     // scratch `cur` is free again
+        span_begin(ctx, T_FILL, s);
         CK(launch_fill(G, K, fa, ctx->num_sms, s));
         span_end(ctx);
+        CK(cudaEventRecord(ctx->fill_done[cur], s));
 
         WalkArgs wa;
-        wa.tb = fa.tb; wa.tb_off = fa.tb_off; wa.lastrow = fa.lastrow; wa.lastcol = fa.lastcol;
+        wa.tb = fa.tb; wa.lastrow = fa.lastrow; wa.lastcol = fa.lastcol;
         wa.pc_off = fa.pc_off; wa.plen = fa.plen;
         wa.pair_lo = ctx->pair_lo.as<int32_t>(); wa.pair_hi = ctx->pair_hi.as<int32_t>();
         wa.reads = d_reads; wa.offsets = d_offsets; wa.amplicon = ctx->amp.as<uint8_t>();
-        wa.La = La; wa.GK = GK; wa.P = P; wa.p0 = fa.p0; wa.p1 = fa.p1;
+        wa.La = La; wa.GK = GK; wa.P = P; wa.G = G; wa.K = K; wa.p0 = fa.p0; wa.p1 = fa.p1;
         wa.open = open_s; wa.ext = ext_s; wa.scale = scale;
         wa.recs = d_recs; wa.ref_out = d_ref; wa.mark_out = d_mark; wa.qry_out = d_qry; wa.slot = slot;
-        wa.out_index = d_out_index; wa.rc_out = rc_out;
-        span_begin(ctx, T_WALK);
-        CK(launch_walk(wa, s));
+        wa.out_index = d_out_index; wa.rc_out = rc_out; wa.ops_out = d_ops; wa.ops_stride = ops_stride;
+        CK(cudaStreamWaitEvent(s2, ctx->fill_done[cur], 0));
+        span_begin(ctx, T_WALK, s2);
+        CK(launch_walk(wa, s2));
         span_end(ctx);
+        CK(cudaEventRecord(ctx->walk_done[cur], s2));
+        used[cur] = true;
     }
+    // everything queued later on the main stream (next pass, quantification, copies) sees the walks' results
+    for (int i = 0; i < 2; ++i) if (used[i]) CK(cudaStreamWaitEvent(s, ctx->walk_done[i], 0));
+    (void)plan_pc_off;
     return CRGPU_OK;
 }
 
@@ -333,16 +394,9 @@ int crgpu_align(crgpu_ctx *ctx, int mem, const char *amplicon, int amplicon_len,
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
 
-    std::vector<int64_t> h_off_copy;
-    const int64_t *h_off = offsets;
     const uint8_t *d_reads = reads; const int64_t *d_off = offsets;
     crgpu_aln_rec *d_recs = recs; uint8_t *d_ref = ref_out, *d_mark = mark_out, *d_qry = qry_out;
-    if (mem == CRGPU_MEM_DEVICE) {
-        h_off_copy.resize((size_t)n + 1);
-        CK(cudaMemcpyAsync(h_off_copy.data(), offsets, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        h_off = h_off_copy.data();
-    } else {
+    if (mem == CRGPU_MEM_HOST) {
         const int64_t total = offsets[n];
         CK(ctx->reads.reserve((size_t)std::max<int64_t>(total, 1)));
         CK(ctx->offsets.reserve((size_t)(n + 1) * 8));
@@ -357,8 +411,10 @@ int crgpu_align(crgpu_ctx *ctx, int mem, const char *amplicon, int amplicon_len,
             d_ref = ctx->sref.as<uint8_t>(); d_mark = ctx->smark.as<uint8_t>(); d_qry = ctx->sqry.as<uint8_t>();
         }
     }
-    int rc = align_core(ctx, amplicon, amplicon_len, d_reads, d_off, h_off, nullptr, n, nullptr, 0, gapopen, gapextend, d_recs,
-                        d_ref, d_mark, d_qry, slot, nullptr);
+    int rc = build_plan(ctx, d_reads, d_off, nullptr, n);
+    if (rc == CRGPU_OK)
+        rc = run_plan(ctx, amplicon, amplicon_len, d_reads, d_off, nullptr, 0, gapopen, gapextend, d_recs, d_ref, d_mark, d_qry,
+                      slot, nullptr);
     if (rc != CRGPU_OK) { cudaStreamSynchronize(s); return rc; }
     if (mem == CRGPU_MEM_HOST) {
         CK(cudaMemcpyAsync(recs, d_recs, (size_t)n * sizeof(crgpu_aln_rec), cudaMemcpyDeviceToHost, s));

@@ -39,17 +39,16 @@ struct FillArgs {
     const uint8_t *pc;        // pair codes, pc[pc_off[p] + x]
     const int64_t *pc_off;    // [npairs+1] prefix sum of pair lengths
     const int32_t *plen;      // [npairs]
-    const int64_t *tb_off;    // [npairs]  offset (in uint32 words) of pair p inside tb, batch-relative
-    uint32_t *tb;             // traceback flags of this batch
-    uint32_t *lastrow;        // [(pc_off[p]-pc_off[p0]) + x][3]  (m,ix,iy) of amplicon row La-1
-    uint32_t *lastcol;        // [(p-p0)*G*K + r][3]              (m,ix,iy) of read column Lb-1
+    uint32_t *tb;             // traceback flags of this batch; pair p starts at word (pc_off[p]-pc_off[p0]) * G*K/2
+    uint32_t *lastrow;        // [p-p0][3]        (best max3, first column lo, hi) of amplicon row La-1
+    uint32_t *lastcol;        // [(p-p0)*G + t][3] (best max3, first slot lo, hi) of lane t's rows in read column Lb-1
+    int La;                   // amplicon length (padding rows = G*K - La)
     int p0, p1;               // pair range of this batch
     int open, ext;            // gap open / extend, scaled (positive)
 };
 
 struct WalkArgs {
     const uint32_t *tb;
-    const int64_t *tb_off;
     const uint32_t *lastrow;
     const uint32_t *lastcol;
     const int64_t *pc_off;
@@ -59,13 +58,15 @@ struct WalkArgs {
     const uint8_t *reads;     // original read bytes (device)
     const int64_t *offsets;   // [n+1]
     const uint8_t *amplicon;  // La bytes (upper-cased by the host)
-    int La, GK, P;            // rows, padded rows, pad rows on top (P = GK - La)
+    int La, GK, P, G, K;      // rows, padded rows, pad rows on top (P = GK - La), tile
     int p0, p1;
     int open, ext, scale;
     // outputs, indexed by read
     void *recs;               // crgpu_aln_rec*
     uint8_t *ref_out, *mark_out, *qry_out;   // may be null
     int64_t slot;
+    uint32_t *ops_out;        // optional: 2-bit op per column in walk order, row stride ops_stride words
+    int64_t ops_stride;
     const int32_t *out_index; // optional: output row of read r (null: row r)
     int rc_out;               // 1: the amplicon is a reverse complement; emit rows flipped back to the
                               // forward strand (CORE:1982-1990), left-aligned in the slot

@@ -33,15 +33,32 @@ struct DBuf {
 
 struct TimedSpan { int family; cudaEvent_t a, b; };
 
+// One length bucket of the pairing plan (same layout as crgpu::LenSeg in traceback_walk.cu).
+struct HostSeg { int len; int cnt; int64_t read_start; int64_t pair_start; int64_t pc_start; };
+
+// Pairing plan of the current read set (device arrays live in the context's scratch buffers).
+struct PairPlan {
+    int64_t nsub = 0;         // reads covered
+    int np = 0;               // pairs
+    int maxlen = 0, minlen = 0;
+    int64_t sum_len = 0;      // sum of read lengths (DP cells = La * sum_len)
+    int64_t total_pc = 0;     // sum of pair lengths
+    std::vector<HostSeg> segs;
+};
+
 struct crgpu_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;      // traceback walks run here, overlapped with the next batch's fill
+    cudaStream_t span_stream = nullptr;
+    cudaEvent_t fill_done[2] = {nullptr, nullptr}, walk_done[2] = {nullptr, nullptr};
     size_t tb_budget = (size_t)8 << 30;
     std::string err;
     // device scratch
-    DBuf reads, offsets, amp, prof, pc, pc_off, plen, pair_lo, pair_hi, tb_off, tb, lastrow, lastcol, errflag;
-    DBuf recs, sref, smark, sqry;
+    DBuf reads, offsets, amp, prof, pc, pc_off, plen, pair_lo, pair_hi, order, plan_hist, plan_tab, tb, lastrow, lastcol, tb2, lastrow2, lastcol2, errflag;
+    PairPlan plan;
+    DBuf recs, sref, smark, sqry, ops, ops_rc;
     DBuf q_in[8], q_out[4];
     DBuf aux[8];
     // timing
@@ -80,15 +97,17 @@ inline cudaEvent_t next_event(crgpu_ctx *c)
     }
     return c->ev_pool[c->ev_used++];
 }
-inline void span_begin(crgpu_ctx *c, int family)
+inline void span_begin(crgpu_ctx *c, int family, cudaStream_t st = nullptr)
 {
+    if (!st) st = c->stream;
+    c->span_stream = st;
     TimedSpan s{family, next_event(c), next_event(c)};
-    cudaEventRecord(s.a, c->stream);
+    cudaEventRecord(s.a, st);
     c->spans.push_back(s);
 }
 inline void span_end(crgpu_ctx *c)
 {
-    cudaEventRecord(c->spans.back().b, c->stream);
+    cudaEventRecord(c->spans.back().b, c->span_stream);
     c->launches[c->spans.back().family]++;
 }
 inline void timing_reset(crgpu_ctx *c)
@@ -119,9 +138,16 @@ cudaError_t launch_walk(const WalkArgs &a, cudaStream_t s);
 cudaError_t launch_qualfilter(const uint8_t *qual, const int64_t *offsets, int64_t n, int q, int sq, uint8_t *keep,
                               int num_sms, cudaStream_t s);
 cudaError_t launch_int_peak(int which, int num_sms, int iters, unsigned *sink, cudaStream_t s, double *lane_ops);
-// alignment core (crgpu_api.cu): device pointers; h_offsets = host copy of the offsets
-int align_core(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_reads, const int64_t *d_offsets,
-               const int64_t *h_offsets, const int32_t *subset, int64_t nsub, const int32_t *d_out_index, int rc_out,
-               double gapopen, double gapextend, crgpu_aln_rec *d_recs, uint8_t *d_ref, uint8_t *d_mark, uint8_t *d_qry,
-               int64_t slot, int64_t *n_cells);
+cudaError_t launch_len_hist(const int64_t *offsets, const int32_t *subset, int64_t n, int min_len, int max_len, int *hist,
+                            int *err, cudaStream_t s);
+cudaError_t launch_scatter_order(const int64_t *offsets, const int32_t *subset, int64_t n, const int64_t *read_start,
+                                 int *cursor, int32_t *order, cudaStream_t s);
+cudaError_t launch_build_pairs(const void *segs, int nseg, int np, const int32_t *order, int32_t *pair_lo, int32_t *pair_hi,
+                               int32_t *plen, int64_t *pc_off, int64_t total_pc, cudaStream_t s);
+// alignment core (crgpu_api.cu): device pointers only
+int build_plan(crgpu_ctx *ctx, const uint8_t *d_reads, const int64_t *d_offsets, const int32_t *d_subset, int64_t nsub);
+int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_reads, const int64_t *d_offsets,
+             const int32_t *d_out_index, int rc_out, double gapopen, double gapextend, crgpu_aln_rec *d_recs,
+             uint8_t *d_ref, uint8_t *d_mark, uint8_t *d_qry, int64_t slot, int64_t *n_cells,
+             uint32_t *d_ops = nullptr, int64_t ops_stride = 0);
 }  // namespace crgpu

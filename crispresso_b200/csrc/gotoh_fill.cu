@@ -17,8 +17,9 @@
 //     (25 read-code pairs x padded rows, one LDS.128 per 4 rows), loaded once per CTA with a
 //     TMA bulk copy (cp.async.bulk -> UBLKCP);
 //   * per cell 5 "not equal" flag bits (crgpu_common.cuh) are packed into one byte and written
-//     with 16-byte vector stores; the last amplicon row and the last read column are written as
-//     values for the traceback's start-cell scan.
+//     with 16-byte vector stores; needle's start-cell scan over the last amplicon row and the last
+//     read column is folded into the sweep (running first-maximum per lane), so only 12 bytes per
+//     pair and per lane leave the kernel for it.
 // The kernel is persistent: grid = SMs x resident CTAs, groups stride over the batch's pairs.
 #include "crgpu_common.cuh"
 
@@ -59,7 +60,8 @@ __device__ __forceinline__ void column_step(Strip<K> &st, const int32_t *__restr
                                             const uint32_t nopen16, const uint32_t ext32,
                                             const uint32_t nopen16_last, const uint32_t ext32_last,
                                             const bool lastLane, const bool isFirstCol, const bool isLastCol,
-                                            uint32_t *__restrict__ tbw, uint32_t *__restrict__ lastcol,
+                                            uint32_t *__restrict__ tbw, const int firstRealSlot,
+                                            uint32_t &colBest, int &colPosLo, int &colPosHi,
                                             uint32_t &botH3, uint32_t &botIY, uint32_t &botM)
 {
     uint32_t words[K / 2];
@@ -106,7 +108,15 @@ __device__ __forceinline__ void column_step(Strip<K> &st, const int32_t *__restr
         if (k & 1) words[k >> 1] = ceven + (c << 8);
         else ceven = c;
         if (EDGE) {
-            if (isLastCol) { lastcol[3 * k] = m; lastcol[3 * k + 1] = ix; lastcol[3 * k + 2] = iy; }
+            // start-cell scan down the last read column (App. A.4): first row whose max(m,ix,iy) is
+            // strictly greater than everything above it; padded rows are not part of the matrix
+            if (isLastCol && k >= firstRealSlot) {
+                const uint32_t nb = vmax2(colBest, h3);
+                const uint32_t d = nb ^ colBest;
+                if (d & 0xffffu) colPosLo = k;
+                if (d >> 16) colPosHi = k;
+                colBest = nb;
+            }
         }
         st.H3[k] = h3;
         st.IX[k] = ix;
@@ -186,9 +196,10 @@ __global__ void __maxnreg__(fill_maxnreg<K>()) k_gotoh_fill(const FillArgs a)
         const int steps = __reduce_max_sync(0xffffffffu, Lb) + G - 1;
         const int64_t pco = valid ? a.pc_off[p] : 0;
         const uint8_t *pcp = a.pc + pco;
-        uint32_t *tbp = a.tb + (valid ? a.tb_off[p] : 0) + t * (K / 2);
-        uint32_t *lrp = a.lastrow + (pco - a.pc_off[a.p0]) * 3;
-        uint32_t *lcp = a.lastcol + ((int64_t)(p - a.p0) * GK + t * K) * 3;
+        uint32_t *tbp = a.tb + (valid ? (pco - a.pc_off[a.p0]) * (GK / 2) : 0) + t * (K / 2);
+        uint32_t *lrp = a.lastrow + (int64_t)(p - a.p0) * 3;             // (best, x_lo, x_hi) of amplicon row La-1
+        uint32_t *lcp = a.lastcol + ((int64_t)(p - a.p0) * G + t) * 3;   // (best, slot_lo, slot_hi) of this lane's rows, column Lb-1
+        const int firstRealSlot = (GK - a.La) - t * K;                   // slots below it are padding rows
 
         Strip<K> st;
 #pragma unroll
@@ -196,6 +207,8 @@ __global__ void __maxnreg__(fill_maxnreg<K>()) k_gotoh_fill(const FillArgs a)
         st.mlast = Z;
         uint32_t botH3 = Z, botIY = NOPEN_ST, botM = Z;
         uint32_t hd0 = Z;
+        uint32_t rowBest = 0, colBest = 0;                               // stored scores are > 0: 0 is -infinity
+        int rowPosLo = 0, rowPosHi = 0, colPosLo = 0, colPosHi = 0;
         int cp_next = (t == 0 && Lb > 0) ? pcp[0] : 0;
 
         for (int s = 0; s < steps; ++s) {
@@ -214,14 +227,25 @@ __global__ void __maxnreg__(fill_maxnreg<K>()) k_gotoh_fill(const FillArgs a)
                 uint32_t *tbw = tbp + (int64_t)x * (GK / 2);
                 if (edge)
                     column_step<K, true>(st, prow, rH3, rIY, rM, hd0, nopen16, ext32, nopen16_last, ext32_last,
-                                         lastLane, firstCol, lastCol, tbw, lcp, botH3, botIY, botM);
+                                         lastLane, firstCol, lastCol, tbw, firstRealSlot, colBest, colPosLo, colPosHi,
+                                         botH3, botIY, botM);
                 else
                     column_step<K, false>(st, prow, rH3, rIY, rM, hd0, nopen16, ext32, nopen16_last, ext32_last,
-                                          lastLane, false, false, tbw, lcp, botH3, botIY, botM);
+                                          lastLane, false, false, tbw, firstRealSlot, colBest, colPosLo, colPosHi,
+                                          botH3, botIY, botM);
                 hd0 = rH3;                                            // max3[row above, x] for column x+1
-                if (lastLane) {
-                    uint32_t *lr = lrp + (int64_t)x * 3;
-                    lr[0] = botM; lr[1] = st.IX[K - 1]; lr[2] = botIY;
+                // start-cell scan along the last amplicon row (meaningful in the last lane only): first
+                // column whose max(m,ix,iy) is strictly greater than all columns before it
+                {
+                    const uint32_t nb = vmax2(rowBest, botH3);
+                    const uint32_t d = nb ^ rowBest;
+                    if (d & 0xffffu) rowPosLo = x;
+                    if (d >> 16) rowPosHi = x;
+                    rowBest = nb;
+                }
+                if (lastCol) {
+                    lcp[0] = colBest; lcp[1] = (uint32_t)colPosLo; lcp[2] = (uint32_t)colPosHi;
+                    if (lastLane) { lrp[0] = rowBest; lrp[1] = (uint32_t)rowPosLo; lrp[2] = (uint32_t)rowPosHi; }
                 }
             }
         }

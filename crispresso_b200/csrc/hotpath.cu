@@ -7,6 +7,8 @@
 namespace crgpu {
 
 cudaError_t launch_quantify(const QuantArgs &a, cudaStream_t s);
+cudaError_t launch_rows_to_ops(const uint8_t *ref, const uint8_t *mark, const uint8_t *qry, int64_t slot, const int32_t *aln_off,
+                               const int32_t *alnlen, int64_t n, uint32_t *ops, int64_t ops_stride, cudaStream_t s);
 cudaError_t launch_prepare_rows(const crgpu_aln_rec *ref, const crgpu_aln_rec *rep, int64_t n, double min_identity,
                                 int32_t *tenths_ref, int32_t *tenths_rep, int32_t *aln_off, int32_t *alnlen, uint8_t *unmod,
                                 uint8_t *flags_out, cudaStream_t s);
@@ -112,9 +114,11 @@ int crgpu_quantify(crgpu_ctx *ctx, int mem, const crgpu_quant_params *params,
     if (rc) return rc;
     QuantArgs qa{};
     fill_quant_args(&qa, params, acc, d_bits, W, hist_zero);
-    qa.slot = slot; qa.n = n; qa.active = nullptr; qa.active_bit = 0;
+    qa.n = n; qa.active = nullptr; qa.active_bit = 0;
+    const uint8_t *d_r = ref_rows, *d_m = mark_rows, *d_q = qry_rows;
+    const int32_t *d_aoff = aln_off;
     if (mem == CRGPU_MEM_DEVICE) {
-        qa.ref = ref_rows; qa.mark = mark_rows; qa.qry = qry_rows; qa.aln_off = aln_off; qa.alnlen = alnlen;
+        qa.alnlen = alnlen;
         qa.tenths_ref = tenths_ref; qa.tenths_rep = tenths_rep; qa.unmod_in = unmodified_in; qa.recs = out_recs;
     } else if (n > 0) {
         const size_t rb = (size_t)n * slot;
@@ -130,11 +134,24 @@ int crgpu_quantify(crgpu_ctx *ctx, int mem, const crgpu_quant_params *params,
         CK(cudaMemcpyAsync(ctx->q_in[3].p, tenths_ref, (size_t)n * 4, cudaMemcpyHostToDevice, s));
         if (tenths_rep) CK(cudaMemcpyAsync(ctx->q_in[4].p, tenths_rep, (size_t)n * 4, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(ctx->q_in[5].p, unmodified_in, (size_t)n, cudaMemcpyHostToDevice, s));
-        qa.ref = ctx->sref.as<uint8_t>(); qa.mark = ctx->smark.as<uint8_t>(); qa.qry = ctx->sqry.as<uint8_t>();
-        qa.aln_off = aln_off ? ctx->q_in[1].as<int32_t>() : nullptr; qa.alnlen = ctx->q_in[2].as<int32_t>();
+        d_r = ctx->sref.as<uint8_t>(); d_m = ctx->smark.as<uint8_t>(); d_q = ctx->sqry.as<uint8_t>();
+        d_aoff = aln_off ? ctx->q_in[1].as<int32_t>() : nullptr; qa.alnlen = ctx->q_in[2].as<int32_t>();
         qa.tenths_ref = ctx->q_in[3].as<int32_t>(); qa.tenths_rep = tenths_rep ? ctx->q_in[4].as<int32_t>() : nullptr;
         qa.unmod_in = ctx->q_in[5].as<uint8_t>(); qa.recs = ctx->q_out[1].as<crgpu_read_rec>();
     }
+    // the three text rows -> 2-bit ops (the caller's markup is already N-masked, CORE:2052 runs before
+    // process_df_chunk; the amplicon is therefore not consulted: all-'A' placeholder)
+    const int64_t ops_stride = (slot + 15) / 16;
+    if (n > 0) {
+        CK(ctx->ops.reserve((size_t)n * ops_stride * 4));
+        CK(ctx->amp.reserve((size_t)params->amplicon_len));
+        CK(cudaMemsetAsync(ctx->amp.p, 'A', (size_t)params->amplicon_len, s));
+        span_begin(ctx, T_OTHER);
+        CK(launch_rows_to_ops(d_r, d_m, d_q, slot, d_aoff, qa.alnlen, n, ctx->ops.as<uint32_t>(), ops_stride, s));
+        span_end(ctx);
+    }
+    qa.ops = ctx->ops.as<uint32_t>(); qa.ops_stride = ops_stride; qa.ops_reversed = 0; qa.amp = ctx->amp.as<uint8_t>();
+    qa.flags &= ~CRGPU_Q_MASK_N;
     span_begin(ctx, T_QUANT);
     CK(launch_quantify(qa, s));
     span_end(ctx);
@@ -187,16 +204,9 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
     cudaStream_t s = ctx->stream;
     const bool host = mem == CRGPU_MEM_HOST;
 
-    // ---- inputs on the device, offsets on the host ----
-    std::vector<int64_t> h_off_copy;
-    const int64_t *h_off = offsets;
+    // ---- inputs on the device ----
     const uint8_t *d_reads = reads; const int64_t *d_off = offsets;
-    if (!host) {
-        h_off_copy.resize((size_t)n + 1);
-        CK(cudaMemcpyAsync(h_off_copy.data(), offsets, (size_t)(n + 1) * 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        h_off = h_off_copy.data();
-    } else {
+    if (host) {
         const int64_t total = offsets[n];
         CK(ctx->reads.reserve((size_t)std::max<int64_t>(total, 1)));
         CK(ctx->offsets.reserve((size_t)(n + 1) * 8));
@@ -204,8 +214,10 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
         CK(cudaMemcpyAsync(ctx->offsets.p, offsets, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s));
         d_reads = ctx->reads.as<uint8_t>(); d_off = ctx->offsets.as<int64_t>();
     }
-    int maxlen = 0;
-    for (int64_t i = 0; i < n; ++i) maxlen = std::max<int64_t>(maxlen, h_off[i + 1] - h_off[i]);
+    // pairing plan of the whole read set: shared by the amplicon and the HDR-amplicon pass
+    int rc = build_plan(ctx, d_reads, d_off, nullptr, n);
+    if (rc) { cudaStreamSynchronize(s); return rc; }
+    const int maxlen = ctx->plan.maxlen;
     const int max_amp = std::max(amplicon_len, has_hdr ? path->hdr_amplicon_len : 0);
     // rows are always produced on the device (the quantifier reads them); slot = caller's or minimal
     int64_t slot = out->slot > 0 ? out->slot : (int64_t)max_amp + maxlen;
@@ -224,24 +236,29 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
         if (out->tenths_rep) d_trep = out->tenths_rep;
         else { CK(ctx->q_in[4].reserve((size_t)n * 4)); d_trep = ctx->q_in[4].as<int32_t>(); }
     }
+    // text rows only when the caller wants them; the quantifier reads the walker's 2-bit ops
+    d_ref = d_mark = d_qry = nullptr;
     if (!host && want_rows) { d_ref = out->ref_rows; d_mark = out->mark_rows; d_qry = out->qry_rows; }
-    else {
+    else if (want_rows) {
         const size_t rb = (size_t)n * slot;
         CK(ctx->sref.reserve(rb)); CK(ctx->smark.reserve(rb)); CK(ctx->sqry.reserve(rb));
         d_ref = ctx->sref.as<uint8_t>(); d_mark = ctx->smark.as<uint8_t>(); d_qry = ctx->sqry.as<uint8_t>();
     }
+    const int64_t ops_stride = (slot + 15) / 16;
+    CK(ctx->ops.reserve((size_t)n * ops_stride * 4));
+    uint32_t *d_ops = ctx->ops.as<uint32_t>();
 
     // ---- 1. forward alignments ----
     int64_t cells = 0;
-    int rc = align_core(ctx, amplicon, amplicon_len, d_reads, d_off, h_off, nullptr, n, nullptr, 0, path->gapopen,
-                        path->gapextend, d_aln, d_ref, d_mark, d_qry, slot, &cells);
+    rc = run_plan(ctx, amplicon, amplicon_len, d_reads, d_off, nullptr, 0, path->gapopen, path->gapextend, d_aln, d_ref, d_mark,
+                  d_qry, slot, &cells, d_ops, ops_stride);
     if (rc) { cudaStreamSynchronize(s); return rc; }
     crgpu_aln_rec *d_aln_hdr = nullptr;
     if (has_hdr) {
         CK(ctx->aux[1].reserve((size_t)n * sizeof(crgpu_aln_rec)));
         d_aln_hdr = ctx->aux[1].as<crgpu_aln_rec>();
-        rc = align_core(ctx, path->hdr_amplicon, path->hdr_amplicon_len, d_reads, d_off, h_off, nullptr, n, nullptr, 0,
-                        path->gapopen, path->gapextend, d_aln_hdr, nullptr, nullptr, nullptr, slot, &cells);
+        rc = run_plan(ctx, path->hdr_amplicon, path->hdr_amplicon_len, d_reads, d_off, nullptr, 0, path->gapopen,
+                      path->gapextend, d_aln_hdr, nullptr, nullptr, nullptr, slot, &cells);
         if (rc) { cudaStreamSynchronize(s); return rc; }
     }
 
@@ -272,7 +289,15 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
     if (rc) return rc;
     QuantArgs qa{};
     fill_quant_args(&qa, quant, acc, d_bits, W, out->hist_zero);
-    qa.ref = d_ref; qa.mark = d_mark; qa.qry = d_qry; qa.slot = slot; qa.aln_off = d_aln_off; qa.alnlen = d_alnlen;
+    // forward amplicon, upper case, for the N mask (run_plan leaves the amplicon of its LAST pass in ctx->amp)
+    CK(ctx->aux[6].reserve((size_t)amplicon_len));
+    {
+        std::string up(amplicon, amplicon + amplicon_len);
+        for (auto &ch : up) if (ch >= 'a' && ch <= 'z') ch = (char)(ch - 32);
+        CK(cudaMemcpyAsync(ctx->aux[6].p, up.data(), (size_t)amplicon_len, cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    qa.ops = d_ops; qa.ops_stride = ops_stride; qa.ops_reversed = 1; qa.amp = ctx->aux[6].as<uint8_t>(); qa.alnlen = d_alnlen;
     qa.tenths_ref = d_tref; qa.tenths_rep = has_hdr ? d_trep : nullptr; qa.unmod_in = d_unmod;
     qa.active = d_kept; qa.active_bit = 1; qa.n = n; qa.recs = d_recs;
     if (amplicon_len > 0) {
@@ -303,12 +328,16 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
         if (!host && out->rc_recs) d_rc_recs = out->rc_recs;
         else { CK(ctx->aux[5].reserve((size_t)nrc * sizeof(crgpu_read_rec))); d_rc_recs = ctx->aux[5].as<crgpu_read_rec>(); }
         if (!host && want_rc_rows) { d_rc_ref = out->rc_ref_rows; d_rc_mark = out->rc_mark_rows; d_rc_qry = out->rc_qry_rows; }
-        else {
+        else if (want_rc_rows) {
             CK(ctx->q_out[2].reserve(rb * 3));
             d_rc_ref = ctx->q_out[2].as<uint8_t>(); d_rc_mark = d_rc_ref + rb; d_rc_qry = d_rc_mark + rb;
         }
-        rc = align_core(ctx, amp_rc.data(), amplicon_len, d_reads, d_off, h_off, rc_read.data(), nrc, ctx->aux[2].as<int32_t>(), 1,
-                        path->gapopen, path->gapextend, d_rc_aln, d_rc_ref, d_rc_mark, d_rc_qry, slot, &cells);
+        CK(ctx->ops_rc.reserve((size_t)nrc * ops_stride * 4));
+        rc = build_plan(ctx, d_reads, d_off, ctx->aux[3].as<int32_t>(), nrc);
+        if (rc == CRGPU_OK)
+            rc = run_plan(ctx, amp_rc.data(), amplicon_len, d_reads, d_off, ctx->aux[2].as<int32_t>(), 1, path->gapopen,
+                          path->gapextend, d_rc_aln, d_rc_ref, d_rc_mark, d_rc_qry, slot, &cells, ctx->ops_rc.as<uint32_t>(),
+                          ops_stride);
         if (rc) { cudaStreamSynchronize(s); return rc; }
         // per-row SoA for the quantifier (separate scratch: the forward views are still in use by the stream)
         CK(ctx->q_out[3].reserve((size_t)nrc * 14));
@@ -320,7 +349,7 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
                                   r_unmod, r_active, d_kept, s));
         span_end(ctx);
         QuantArgs qr = qa;
-        qr.ref = d_rc_ref; qr.mark = d_rc_mark; qr.qry = d_rc_qry; qr.aln_off = r_off; qr.alnlen = r_len;
+        qr.ops = ctx->ops_rc.as<uint32_t>(); qr.ops_reversed = 0; qr.alnlen = r_len;    // RC rows are walked in forward-strand order
         qr.tenths_ref = r_tref; qr.tenths_rep = nullptr; qr.unmod_in = r_unmod; qr.active = r_active; qr.active_bit = 1;
         qr.n = nrc; qr.recs = d_rc_recs;
         CK(cudaMemsetAsync(d_rc_recs, 0, (size_t)nrc * sizeof(crgpu_read_rec), s));

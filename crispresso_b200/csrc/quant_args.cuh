@@ -4,9 +4,13 @@
 #include <cuda_runtime.h>
 namespace crgpu {
 struct QuantArgs {
-    const uint8_t *ref, *mark, *qry;   // rows; row i at X + i*slot + aln_off[i]
-    int64_t slot;
-    const int32_t *aln_off;            // may be null (all zero)
+    // per-column alignment ops, 2 bits each (0 match, 1 mismatch, 2 gap in the amplicon row = insertion,
+    // 3 gap in the read row = deletion), 16 per word, row i at ops + i*ops_stride.  k_traceback_walk
+    // emits them in walk order: ops_reversed = 1 means entry 0 is the LAST alignment column.
+    const uint32_t *ops;
+    int64_t ops_stride;
+    int ops_reversed;
+    const uint8_t *amp;                // amplicon (forward strand, upper case): N positions for CRGPU_Q_MASK_N
     const int32_t *alnlen;
     const int32_t *tenths_ref, *tenths_rep;   // tenths_rep may be null (no HDR -> NaN)
     const uint8_t *unmod_in;           // UNMODIFIED column on entry

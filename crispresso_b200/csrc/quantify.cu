@@ -3,7 +3,9 @@
 // (CRISPResso/CRISPRessoCORE.py:428-753) together with the per-row preparation that feeds it
 // (ignore_n_in_alignment CORE:2040-2052, compute_ref_positions CORE:2055-2067).
 //
-// One thread per aligned read.  The read's substitution / deletion / insertion-flank position
+// One thread per aligned read, fed with 2 bits per alignment column (match / mismatch / insertion /
+// deletion) -- written by k_traceback_walk, or derived from the three text rows by k_rows_to_ops
+// when the caller comes through crgpu_quantify.  The read's substitution / deletion / insertion-flank position
 // sets are kept as amplicon-length bitmaps (<= 32 words each) in local memory, which makes the
 // reference's set semantics -- INCLUDE_IDXS.intersection(...), numpy's buffered fancy-index
 // `vec[list] += 1` that increments a duplicated index once, negative flank indices wrapping
@@ -20,8 +22,35 @@ namespace crgpu {
 constexpr int MAXW = CRGPU_MAX_AMPLICON / 32;
 
 
-// CORE:2059: only upper-case A,T,C,G,N advance the amplicon index
+// CORE:2059: only upper-case A,T,C,G,N advance the amplicon index (everything else in the amplicon
+// row is a gap column); CORE:504/518: '-' runs are the indels; CORE:491: '.' is a substitution
 __device__ __forceinline__ bool is_ref_base(uint8_t c) { return c == 'A' || c == 'T' || c == 'C' || c == 'G' || c == 'N'; }
+
+// rows (as parse_needle_output delivers them) -> 2-bit ops, forward order
+__global__ void k_rows_to_ops(const uint8_t *__restrict__ ref, const uint8_t *__restrict__ mark, const uint8_t *__restrict__ qry,
+                              int64_t slot, const int32_t *__restrict__ aln_off, const int32_t *__restrict__ alnlen, int64_t n,
+                              uint32_t *__restrict__ ops, int64_t ops_stride)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t base = i * slot + (aln_off ? aln_off[i] : 0);
+    const int len = alnlen[i];
+    uint32_t w = 0;
+    for (int c = 0; c < len; ++c) {
+        const uint32_t op = !is_ref_base(ref[base + c]) ? 2u : (qry[base + c] == '-' ? 3u : (mark[base + c] == '.' ? 1u : 0u));
+        w |= op << ((c & 15) * 2);
+        if ((c & 15) == 15) { ops[i * ops_stride + (c >> 4)] = w; w = 0; }
+    }
+    if (len & 15) ops[i * ops_stride + (len >> 4)] = w;
+}
+
+cudaError_t launch_rows_to_ops(const uint8_t *ref, const uint8_t *mark, const uint8_t *qry, int64_t slot, const int32_t *aln_off,
+                               const int32_t *alnlen, int64_t n, uint32_t *ops, int64_t ops_stride, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    k_rows_to_ops<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(ref, mark, qry, slot, aln_off, alnlen, n, ops, ops_stride);
+    return cudaGetLastError();
+}
 
 __device__ __forceinline__ void set_bit(uint32_t *bits, int v) { bits[v >> 5] |= 1u << (v & 31); }
 __device__ __forceinline__ bool get_bit(const uint32_t *bits, int v) { return (bits[v >> 5] >> (v & 31)) & 1u; }
@@ -38,15 +67,27 @@ __device__ __forceinline__ void add_bits(unsigned long long *vec, const uint32_t
     }
 }
 
+struct OpReader {
+    const uint32_t *w;
+    int n;
+    bool rev;
+    __device__ __forceinline__ int at(int c) const
+    {
+        const int j = rev ? n - 1 - c : c;
+        return (int)((__ldg(w + (j >> 4)) >> ((j & 15) * 2)) & 3u);
+    }
+};
+constexpr int OP_MATCH = 0, OP_MISMATCH = 1, OP_INS = 2, OP_DEL = 3;
+
 __global__ void __launch_bounds__(128) k_quantify(const QuantArgs a)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
     if (a.active && !(a.active[i] & a.active_bit)) return;
     const int L = a.L, W = a.W, flags = a.flags;
-    const int64_t base = i * a.slot + (a.aln_off ? a.aln_off[i] : 0);
-    const uint8_t *R = a.ref + base, *M = a.mark + base, *Q = a.qry + base;
     const int n = a.alnlen[i];
+    const OpReader ops{a.ops + i * a.ops_stride, n, a.ops_reversed != 0};
+    const uint8_t *amp = a.amp;
     const bool maskN = flags & CRGPU_Q_MASK_N;
     crgpu_read_rec rec;
     rec.cls = 0; rec.pad[0] = rec.pad[1] = rec.pad[2] = 0;
@@ -56,11 +97,19 @@ __global__ void __launch_bounds__(128) k_quantify(const QuantArgs a)
     if (maskN && !unmod) {
         // ignore_n_in_alignment (CORE:2040-2048): markup -> '|' where the amplicon row has N; a
         // markup made of ONE distinct character (whatever it is) marks the read UNMODIFIED.
+        // markup classes: 0 '|', 1 '.', 2 ' '
+        int idx = 0, first = -1;
         bool uniform = n > 0;
-        const uint8_t first = n > 0 ? (R[0] == 'N' ? (uint8_t)'|' : M[0]) : 0;
-        for (int c = 1; c < n && uniform; ++c) {
-            const uint8_t ch = R[c] == 'N' ? (uint8_t)'|' : M[c];
-            uniform = ch == first;
+        for (int c = 0; c < n && uniform; ++c) {
+            const int op = ops.at(c);
+            int cl;
+            if (op == OP_INS) cl = 2;
+            else {
+                cl = amp[idx] == 'N' ? 0 : (op == OP_MATCH ? 0 : op == OP_MISMATCH ? 1 : 2);
+                ++idx;
+            }
+            if (first < 0) first = cl;
+            else uniform = cl == first;
         }
         if (uniform) unmod = true;
     }
@@ -82,11 +131,11 @@ __global__ void __launch_bounds__(128) k_quantify(const QuantArgs a)
         int idx = 0;              // amplicon bases consumed so far == ref_positions of the next base column
         int c = 0;
         while (c < n) {
-            const uint8_t rc_ = R[c];
-            if (!is_ref_base(rc_)) {
+            const int op = ops.at(c);
+            if (op == OP_INS) {
                 // maximal '-' run in the amplicon row: an insertion [st, en)
                 const int st = c;
-                while (c < n && !is_ref_base(R[c])) ++c;
+                while (c < n && ops.at(c) == OP_INS) ++c;
                 if (doI) {
                     const int fl = st == 0 ? -1 : idx - 1;                       // ref_positions[max(0, st-1)]
                     const int fr = c < n ? idx : (idx == 0 ? -1 : -idx);         // ref_positions[min(n-1, en)]
@@ -97,8 +146,8 @@ __global__ void __launch_bounds__(128) k_quantify(const QuantArgs a)
                 }
                 continue;
             }
-            if (Q[c] == '-') { if (doD) set_bit(D, idx); }
-            else if (doS && M[c] == '.' && !(maskN && rc_ == 'N')) set_bit(S, idx);
+            if (op == OP_DEL) { if (doD) set_bit(D, idx); }
+            else if (doS && op == OP_MISMATCH && !(maskN && amp[idx] == 'N')) set_bit(S, idx);
             ++idx; ++c;
         }
         for (int w = 0; w < W; ++w) if ((S[w] | D[w]) & a.inc[w]) inc_hit = true;
@@ -149,9 +198,10 @@ __global__ void __launch_bounds__(128) k_quantify(const QuantArgs a)
     {
         int idx = 0, c = 0;
         while (c < n) {
-            if (!is_ref_base(R[c])) {
+            const int op = ops.at(c);
+            if (op == OP_INS) {
                 const int st = c;
-                while (c < n && !is_ref_base(R[c])) ++c;
+                while (c < n && ops.at(c) == OP_INS) ++c;
                 if (doI) {
                     const int size = c - st;
                     const int fl = st == 0 ? -1 : idx - 1;
@@ -170,9 +220,9 @@ __global__ void __launch_bounds__(128) k_quantify(const QuantArgs a)
                 }
                 continue;
             }
-            if (Q[c] == '-' && doD) {
+            if (op == OP_DEL && doD) {
                 const int st = c, p0 = idx;
-                while (c < n && Q[c] == '-') { ++c; ++idx; }      // amplicon has bases under a deletion run
+                while (c < n && ops.at(c) == OP_DEL) { ++c; ++idx; }   // amplicon has bases under a deletion run
                 const int size = c - st;
                 bool keep = true;
                 if (windowed) {

@@ -92,25 +92,16 @@ __global__ void __launch_bounds__(128) k_traceback_walk(const WalkArgs a)
     const int La = a.La, Lb = a.plen[p];
     const uint8_t *b = a.reads + a.offsets[r];
     const uint8_t *amp = a.amplicon;
-    const uint32_t *lr = a.lastrow + (a.pc_off[p] - a.pc_off[a.p0]) * 3;
-    const uint32_t *lc = a.lastcol + ((int64_t)(p - a.p0) * a.GK + a.P) * 3;
+    const uint32_t *lr = a.lastrow + (int64_t)(p - a.p0) * 3;
+    const uint32_t *lc = a.lastcol + (int64_t)(p - a.p0) * a.G * 3;
 
-    // ---- start cell (App. A.4): last row left to right, then last column top to bottom,
-    //      (m, ix, iy) in that order, strict '>' so the first maximum wins.
-    int best = -1, s1 = La - 1, s2 = Lb - 1;
-    for (int x = 0; x < Lb; ++x) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int v = half16(lr[3 * x + k], h);
-            if (v > best) { best = v; s2 = x; }
-        }
-    }
-    for (int y = 0; y < La; ++y) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const int v = half16(lc[3 * y + k], h);
-            if (v > best) { best = v; s1 = y; s2 = Lb - 1; }
-        }
+    // ---- start cell (App. A.4): the fill kernel already scanned the last amplicon row left to right
+    //      and, per lane, the last read column top to bottom ((m, ix, iy) in that order, strict '>':
+    //      the first maximum wins).  Combine: the column only wins with a strictly greater value.
+    int best = half16(lr[0], h), s1 = La - 1, s2 = (int)lr[1 + h];
+    for (int t = 0; t < a.G; ++t) {
+        const int v = half16(lc[3 * t], h);
+        if (v > best) { best = v; s1 = t * a.K + (int)lc[3 * t + 1 + h] - a.P; s2 = Lb - 1; }
     }
 
     const bool want = a.ref_out != nullptr;
@@ -126,22 +117,35 @@ __global__ void __launch_bounds__(128) k_traceback_walk(const WalkArgs a)
     uint8_t *qo = want ? a.qry_out + orow * slot + first : nullptr;
     const bool rc = a.rc_out != 0;
     int n = 0, ident = 0;
+    // 2-bit op per column for k_quantify, in walk order (entry 0 = last column of the forward strand)
+    uint32_t *opo = a.ops_out ? a.ops_out + orow * a.ops_stride : nullptr;
+    uint32_t opw = 0;
+#define EMIT_OP(op) do { opw |= (uint32_t)(op) << ((n & 15) * 2); if ((n & 15) == 15) { if (opo) opo[n >> 4] = opw; opw = 0; } } while (0)
 #define OUTC(c) (rc ? comp_upper(c) : (c))
-#define EMIT_GAP_A(cb) do { if (want) { ro[dirn * n] = '-'; mo[dirn * n] = ' '; qo[dirn * n] = OUTC(cb); } ++n; } while (0)
-#define EMIT_GAP_B(ca) do { if (want) { ro[dirn * n] = OUTC(ca); mo[dirn * n] = ' '; qo[dirn * n] = '-'; } ++n; } while (0)
+#define EMIT_GAP_A(cb) do { if (want) { ro[dirn * n] = '-'; mo[dirn * n] = ' '; qo[dirn * n] = OUTC(cb); } EMIT_OP(2); ++n; } while (0)
+#define EMIT_GAP_B(ca) do { if (want) { ro[dirn * n] = OUTC(ca); mo[dirn * n] = ' '; qo[dirn * n] = '-'; } EMIT_OP(3); ++n; } while (0)
 
     // ---- walk (App. A.5): trailing end gaps first (the strings are built right to left)
     for (int x = Lb - 1; x > s2; --x) EMIT_GAP_A(b[x]);
     for (int y = La - 1; y > s1; --y) EMIT_GAP_B(amp[y]);
 
-    const uint8_t *tb = reinterpret_cast<const uint8_t *>(a.tb + a.tb_off[p]);
+    const uint8_t *tb = reinterpret_cast<const uint8_t *>(a.tb + (a.pc_off[p] - a.pc_off[a.p0]) * (a.GK / 2));
     const int64_t colbytes = (int64_t)a.GK * 2;
+    const int P = a.P;
     int y = s1, x = s2, prev = 0;
     bool contL = false, contD = false;
     const int ca0 = base_code(amp[0]);
+    // The walk is a chain of dependent one-byte loads.  Paths are diagonal almost everywhere, so the
+    // flags of the next PF cells down the diagonal are loaded ahead of time (pf[k] = cell (y-k, x-k));
+    // a LEFT / DOWN step invalidates the window and refills it with PF independent loads.
+    constexpr int PF = 8;
+    uint8_t pf[PF];
+#define TB_AT(yy, xx) tb[(xx) * colbytes + ((((yy) + P) >> 1) << 2) + (h << 1) + (((yy) + P) & 1)]
+#define PF_LOAD(k) pf[k] = (y - (k) >= 0 && x - (k) >= 0) ? TB_AT(y - (k), x - (k)) : (uint8_t)0
+#pragma unroll
+    for (int k = 0; k < PF; ++k) PF_LOAD(k);
     while (x >= 0 && y >= 0) {
-        const int rr = y + a.P;
-        const int f = tb[x * colbytes + ((rr >> 1) << 2) + (h << 1) + (rr & 1)];
+        const int f = pf[0];
         int dir;
         if (prev == 1 && contL) dir = 1;
         else if (prev == 2 && contD) dir = 2;
@@ -157,7 +161,11 @@ __global__ void __launch_bounds__(128) k_traceback_walk(const WalkArgs a)
             const bool same = base_code(ca) == base_code(cb);
             ident += same;
             if (want) { ro[dirn * n] = OUTC(ca); mo[dirn * n] = same ? '|' : '.'; qo[dirn * n] = OUTC(cb); }
+            EMIT_OP(same ? 0 : 1);
             ++n; --x; --y;
+#pragma unroll
+            for (int k = 0; k < PF - 1; ++k) pf[k] = pf[k + 1];
+            PF_LOAD(PF - 1);
         } else if (dir == 1) {
             // the next cell (y, x-1) continues LEFT iff ix[y,x-1] - gex(y) == ix[y,x].  The fill
             // kernel evaluates that with gex = gapextend except on amplicon row La-1; needle uses
@@ -168,18 +176,26 @@ __global__ void __launch_bounds__(128) k_traceback_walk(const WalkArgs a)
                 contL = !(f & F_NFX);
             EMIT_GAP_A(b[x]);
             --x;
+#pragma unroll
+            for (int k = 0; k < PF; ++k) PF_LOAD(k);
         } else {
             contD = !(f & F_NFY);
             EMIT_GAP_B(amp[y]);
             --y;
+#pragma unroll
+            for (int k = 0; k < PF; ++k) PF_LOAD(k);
         }
         prev = dir;
     }
+#undef PF_LOAD
+#undef TB_AT
     for (; x >= 0; --x) EMIT_GAP_A(b[x]);
     for (; y >= 0; --y) EMIT_GAP_B(amp[y]);
 #undef EMIT_GAP_A
 #undef EMIT_GAP_B
 #undef OUTC
+#undef EMIT_OP
+    if (opo && (n & 15)) opo[n >> 4] = opw;
 
     crgpu_aln_rec rec;
     rec.score = (float)(best - BIAS) / (float)a.scale;
@@ -220,6 +236,90 @@ __global__ void k_qualfilter(const uint8_t *__restrict__ qual, const int64_t *__
         }
         if (lane == 0) keep[i] = (len > 0 && sum >= (long long)min_mean_q * len && mn >= min_single_q) ? 1 : 0;
     }
+}
+
+
+// ---- pairing plan, built on the device (crgpu_api.cu: build_plan) ---------------------------
+// Reads are bucketed by length; consecutive reads of a bucket form the lo/hi halves of a pair.
+// Only the 2049-bin length histogram visits the host.
+__global__ void k_len_hist(const int64_t *__restrict__ offsets, const int32_t *__restrict__ subset, int64_t n,
+                           int min_len, int max_len, int *__restrict__ hist, int *err)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = i < n;
+    int len = -1;
+    if (in) {
+        const int64_t r = subset ? subset[i] : i;
+        const int64_t l = offsets[r + 1] - offsets[r];
+        if (l < min_len || l > max_len) atomicOr(err, 2);
+        else len = (int)l;
+    }
+    // warp-aggregated increment: one atomic per distinct length per warp
+    const unsigned peers = __match_any_sync(0xffffffffu, len);
+    if (len >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(hist + len, __popc(peers));
+}
+
+__global__ void k_scatter_order(const int64_t *__restrict__ offsets, const int32_t *__restrict__ subset, int64_t n,
+                                const int64_t *__restrict__ read_start /* [max_len+1] */, int *__restrict__ cursor,
+                                int32_t *__restrict__ order)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = i < n;
+    int len = -1;
+    int64_t r = 0;
+    if (in) { r = subset ? subset[i] : i; len = (int)(offsets[r + 1] - offsets[r]); }
+    const unsigned peers = __match_any_sync(0xffffffffu, len);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    int base = 0;
+    if (in && lane == leader) base = atomicAdd(cursor + len, __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (in) order[read_start[len] + base + __popc(peers & ((1u << lane) - 1))] = (int32_t)r;
+}
+
+struct LenSeg { int len; int cnt; int64_t read_start; int64_t pair_start; int64_t pc_start; };
+
+__global__ void k_build_pairs(const LenSeg *__restrict__ segs, int nseg, int np, const int32_t *__restrict__ order,
+                              int32_t *__restrict__ pair_lo, int32_t *__restrict__ pair_hi, int32_t *__restrict__ plen,
+                              int64_t *__restrict__ pc_off, int64_t total_pc)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == np) pc_off[np] = total_pc;
+    if (p >= np) return;
+    int lo = 0, hi = nseg - 1;
+    while (lo < hi) {                       // last segment with pair_start <= p
+        const int mid = (lo + hi + 1) >> 1;
+        if (segs[mid].pair_start <= p) lo = mid; else hi = mid - 1;
+    }
+    const LenSeg sg = segs[lo];
+    const int64_t j = p - sg.pair_start;
+    const int32_t a = order[sg.read_start + 2 * j];
+    const int32_t b = (2 * j + 1 < sg.cnt) ? order[sg.read_start + 2 * j + 1] : a;
+    pair_lo[p] = a; pair_hi[p] = b; plen[p] = sg.len;
+    pc_off[p] = sg.pc_start + j * sg.len;
+}
+
+cudaError_t launch_len_hist(const int64_t *offsets, const int32_t *subset, int64_t n, int min_len, int max_len, int *hist,
+                            int *err, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    k_len_hist<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(offsets, subset, n, min_len, max_len, hist, err);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scatter_order(const int64_t *offsets, const int32_t *subset, int64_t n, const int64_t *read_start,
+                                 int *cursor, int32_t *order, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    k_scatter_order<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(offsets, subset, n, read_start, cursor, order);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_build_pairs(const void *segs, int nseg, int np, const int32_t *order, int32_t *pair_lo, int32_t *pair_hi,
+                               int32_t *plen, int64_t *pc_off, int64_t total_pc, cudaStream_t s)
+{
+    k_build_pairs<<<(unsigned)((np + 1 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const LenSeg *>(segs), nseg, np, order,
+                                                                   pair_lo, pair_hi, plen, pc_off, total_pc);
+    return cudaGetLastError();
 }
 
 // ---- launch wrappers (called from crgpu_api.cu) -------------------------------------------
