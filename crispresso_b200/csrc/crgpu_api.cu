@@ -345,7 +345,7 @@ int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_read
         fa.lastrow = (cur ? ctx->lastrow2 : ctx->lastrow).as<uint32_t>();
         fa.lastcol = (cur ? ctx->lastcol2 : ctx->lastcol).as<uint32_t>();
         fa.p0 = batch_start[b]; fa.p1 = batch_start[b + 1];
-        fa.open = open_s; fa.ext = ext_s; fa.La = La;
+        fa.open = open_s; fa.ext = ext_s; fa.La = La; fa.one = 1;
         if (used[cur]) CK(cudaStreamWaitEvent(s, ctx->walk_done[cur], 0));     // scratch `cur` is free again
         span_begin(ctx, T_FILL, s);
         CK(launch_fill(G, K, fa, ctx->num_sms, s));

@@ -45,6 +45,7 @@ struct FillArgs {
     int La;                   // amplicon length (padding rows = G*K - La)
     int p0, p1;               // pair range of this batch
     int open, ext;            // gap open / extend, scaled (positive)
+    int one;                  // always 1 (an opaque multiplier, see fma_add in gotoh_fill.cu)
 };
 
 struct WalkArgs {

@@ -22,6 +22,8 @@
 //     pair and per lane leave the kernel for it.
 // The kernel is persistent: grid = SMs x resident CTAs, groups stride over the batch's pairs.
 #include "crgpu_common.cuh"
+#include <cstdio>
+#include <cstdlib>
 
 namespace crgpu {
 
@@ -30,6 +32,16 @@ __device__ __forceinline__ uint32_t vmin2(uint32_t a, uint32_t b) { return __vmi
 __device__ __forceinline__ uint32_t vaddmax2(uint32_t a, uint32_t b, uint32_t c)                   // VIADDMNMX.S16x2
 {
     return __viaddmax_s16x2(a, b, c);
+}
+
+// a + b issued on the FMA pipe (IMAD): `one` is a register holding 1 that ptxas cannot see through,
+// so the multiply-add is not turned back into an IADD3.  Used to take plain adds off the integer-ALU
+// pipe, which also has to run every VIMNMX / VIADDMNMX of the cell (profiles/r01_notes.md).
+__device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t b, uint32_t one)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+    return d;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -59,7 +71,7 @@ __device__ __forceinline__ void column_step(Strip<K> &st, const int32_t *__restr
                                             uint32_t upH3, uint32_t upIY, uint32_t upM, uint32_t hd,
                                             const uint32_t nopen16, const uint32_t ext32,
                                             const uint32_t nopen16_last, const uint32_t ext32_last,
-                                            const bool lastLane, const bool isFirstCol, const bool isLastCol,
+                                            const bool lastLane, const bool isFirstCol, const bool isLastCol, const uint32_t one,
                                             uint32_t *__restrict__ tbw, const int firstRealSlot,
                                             uint32_t &colBest, int &colPosLo, int &colPosHi,
                                             uint32_t &botH3, uint32_t &botIY, uint32_t &botM)
@@ -67,6 +79,8 @@ __device__ __forceinline__ void column_step(Strip<K> &st, const int32_t *__restr
     uint32_t words[K / 2];
     uint32_t ceven = 0;
     int32_t S4[4];
+    // the profile row is read 4 rows ahead (LDS latency ~30 cycles would otherwise sit on the m chain)
+    int4 Snext = *reinterpret_cast<const int4 *>(prow);
     // per-lane vertical-gap parameters of this column (EDGE only)
     const uint32_t nopen16_v = (EDGE && isLastCol) ? 0u : nopen16;
     const uint32_t ext32_v = (EDGE && isLastCol) ? 0u : ext32;
@@ -74,8 +88,8 @@ __device__ __forceinline__ void column_step(Strip<K> &st, const int32_t *__restr
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         if ((k & 3) == 0) {
-            const int4 v = *reinterpret_cast<const int4 *>(prow + k);
-            S4[0] = v.x; S4[1] = v.y; S4[2] = v.z; S4[3] = v.w;
+            S4[0] = Snext.x; S4[1] = Snext.y; S4[2] = Snext.z; S4[3] = Snext.w;
+            if (k + 4 < K) Snext = *reinterpret_cast<const int4 *>(prow + k + 4);
         }
         const uint32_t S = (uint32_t)S4[k & 3];
         const uint32_t h0 = st.H3[k], ix0 = st.IX[k];
@@ -86,7 +100,11 @@ __device__ __forceinline__ void column_step(Strip<K> &st, const int32_t *__restr
             t_ = ix0 - ext32_last;
             ix = vaddmax2(src, nopen16_last, t_);
         } else {
+#if defined(FILL_FMA_ADDS) && FILL_FMA_ADDS >= 2
+            t_ = fma_add(ix0, 0u - ext32, one);
+#else
             t_ = ix0 - ext32;
+#endif
             ix = vaddmax2(h0, nopen16, t_);
         }
         uint32_t iy, nFY;
@@ -95,7 +113,11 @@ __device__ __forceinline__ void column_step(Strip<K> &st, const int32_t *__restr
             iy = vaddmax2(src, nopen16_v, upIY - ext32_v);
             nFY = vmin2(iy ^ (upIY - ext32_f), ONE2);
         } else {
+#ifdef FILL_FMA_ADDS
+            const uint32_t u_ = fma_add(upIY, 0u - ext32, one);
+#else
             const uint32_t u_ = upIY - ext32;
+#endif
             iy = vaddmax2(upH3, nopen16, u_);
             nFY = vmin2(iy - u_, ONE2);
         }
@@ -139,10 +161,11 @@ __device__ __forceinline__ void column_step(Strip<K> &st, const int32_t *__restr
 // The register cap per strip height was swept on a B200 (profiles/r01_notes.md): K = 32 runs
 // 2007 GCUPS at 136 registers vs 1845 at ptxas' own choice (133) and 1513 at 128 (4 CTAs/SM but
 // spills + extra moves); one 12-warp CTA per SM under __launch_bounds__(384) is 25 % slower.
+// K = 40: 1605 GCUPS at 144 registers (3 CTAs/SM), 1855 at 184 (2 CTAs/SM): ILP beats occupancy here.
 #ifdef FILL_MAXNREG
 template <int K> constexpr int fill_maxnreg() { return FILL_MAXNREG; }
 #else
-template <int K> constexpr int fill_maxnreg() { return K >= 36 ? 144 : (K >= 32 ? 136 : 128); }
+template <int K> constexpr int fill_maxnreg() { return K >= 36 ? 184 : (K >= 32 ? 136 : 128); }
 #endif
 
 template <int G, int K>
@@ -188,6 +211,7 @@ __global__ void __maxnreg__(fill_maxnreg<K>()) k_gotoh_fill(const FillArgs a)
     const uint32_t ext32 = (uint32_t)a.ext * 0x10001u;
     const uint32_t nopen16_last = lastLane ? 0u : nopen16;                // amplicon row La-1: zero end-gap penalties
     const uint32_t ext32_last = lastLane ? 0u : ext32;
+    const uint32_t one = (uint32_t)a.one;
 
     for (int base = a.p0 + warp_global * GPW; base < a.p1; base += nwarps * GPW) {
         const int p = base + gl;
@@ -227,11 +251,11 @@ __global__ void __maxnreg__(fill_maxnreg<K>()) k_gotoh_fill(const FillArgs a)
                 uint32_t *tbw = tbp + (int64_t)x * (GK / 2);
                 if (edge)
                     column_step<K, true>(st, prow, rH3, rIY, rM, hd0, nopen16, ext32, nopen16_last, ext32_last,
-                                         lastLane, firstCol, lastCol, tbw, firstRealSlot, colBest, colPosLo, colPosHi,
+                                         lastLane, firstCol, lastCol, one, tbw, firstRealSlot, colBest, colPosLo, colPosHi,
                                          botH3, botIY, botM);
                 else
                     column_step<K, false>(st, prow, rH3, rIY, rM, hd0, nopen16, ext32, nopen16_last, ext32_last,
-                                          lastLane, false, false, tbw, firstRealSlot, colBest, colPosLo, colPosHi,
+                                          lastLane, false, false, one, tbw, firstRealSlot, colBest, colPosLo, colPosHi,
                                           botH3, botIY, botM);
                 hd0 = rH3;                                            // max3[row above, x] for column x+1
                 // start-cell scan along the last amplicon row (meaningful in the last lane only): first
@@ -282,10 +306,12 @@ static cudaError_t launch_tile(const FillArgs &a, int num_sms, cudaStream_t stre
 // Smallest padded tile G*K >= La from the compiled menu.
 bool choose_tile(int La, int *G, int *K)
 {
+    // strip heights with K % 8 == 0 only: the 8-byte-store variants (K = 20, 28, 36) measured 2.2x
+    // slower per cell on B200 (profiles/r01_notes.md)
     static const Tile menu[] = {
-        {4, 16}, {4, 24}, {4, 32}, {8, 20}, {8, 24}, {8, 28}, {8, 32}, {8, 36}, {8, 40},
-        {16, 24}, {16, 28}, {16, 32}, {16, 36}, {16, 40}, {32, 24}, {32, 28}, {32, 32},
+        {4, 16}, {4, 24}, {4, 32}, {4, 40}, {8, 24}, {8, 32}, {8, 40}, {16, 24}, {16, 32}, {16, 40}, {32, 24}, {32, 32},
     };
+    if (getenv("CRGPU_TILE")) { int g, k; if (sscanf(getenv("CRGPU_TILE"), "%d,%d", &g, &k) == 2 && g * k >= La) { *G = g; *K = k; return true; } }
     int best = -1, bestgk = 1 << 30;
     for (unsigned i = 0; i < sizeof(menu) / sizeof(menu[0]); ++i) {
         const int gk = menu[i].G * menu[i].K;
@@ -299,10 +325,8 @@ bool choose_tile(int La, int *G, int *K)
 cudaError_t launch_fill(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream)
 {
 #define CASE(g, k) if (G == g && K == k) return launch_tile<g, k>(a, num_sms, stream);
-    CASE(4, 16) CASE(4, 24) CASE(4, 32)
-    CASE(8, 20) CASE(8, 24) CASE(8, 28) CASE(8, 32) CASE(8, 36) CASE(8, 40)
-    CASE(16, 24) CASE(16, 28) CASE(16, 32) CASE(16, 36) CASE(16, 40)
-    CASE(32, 24) CASE(32, 28) CASE(32, 32)
+    CASE(4, 16) CASE(4, 24) CASE(4, 32) CASE(4, 40) CASE(8, 16) CASE(8, 24) CASE(8, 32) CASE(8, 40)
+    CASE(16, 16) CASE(16, 24) CASE(16, 32) CASE(16, 40) CASE(32, 24) CASE(32, 32)
 #undef CASE
     return cudaErrorInvalidValue;
 }
