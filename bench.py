@@ -241,6 +241,18 @@ def main():
     barrier()
     t_wall1 = time.time()
     dev_ms = ev0.elapsed_time(ev1)
+    # one extra, untimed step with the walk/fill overlap off: per-kernel times without a co-running kernel
+    iso_ms = {k: 0.0 for k in Context.TIMING_NAMES}
+    iso_ln = {k: 0 for k in Context.TIMING_NAMES}
+    ctx.set_overlap(False)
+    hotpath.run_hot_path(ctx, amp, None, hdr_amplicon=hdr, flags=flags, inc=inc, red=hotpath.Reductions(L),
+                         device_inputs=(d_buf.data_ptr(), d_off.data_ptr(), n, READ_LEN, dev_ptrs))
+    ms_, ln_ = ctx.last_timing()
+    for k in ms_:
+        iso_ms[k] += ms_[k]
+        iso_ln[k] += ln_[k]
+    ctx.set_overlap(True)
+    torch.cuda.synchronize()
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -346,7 +358,13 @@ def main():
                      "peak_source": "measured live: crgpu_int_peak, best of IADD3+IMAD.IADD 1:1 and VIMNMX.S16x2+IMAD 1:1 "
                                     "(single-pipe rate is half of it)",
                      "peak_theoretical": 148 * 128 * 1.965e9 / 1e12,
-                     "frac_of_theoretical": achieved / (148 * 128 * 1.965e9 / 1e12)},
+                     "frac_of_theoretical": achieved / (148 * 128 * 1.965e9 / 1e12),
+                     "note": "timed region runs the traceback walks concurrently with the next batch's fill; "
+                             "`isolated` = the same launches in one extra step with that overlap switched off",
+                     "isolated": {"ms_per_launch": iso_ms["fill"] / max(1, iso_ln["fill"]),
+                                  "achieved": cells_per_launch * OPS_PER_CELL / (iso_ms["fill"] / max(1, iso_ln["fill"]) * 1e-3) / 1e12,
+                                  "frac": cells_per_launch * OPS_PER_CELL / (iso_ms["fill"] / max(1, iso_ln["fill"]) * 1e-3) / 1e12 / peak if peak else None,
+                                  "kernel_ms_per_step": iso_ms}},
         "roofline_hbm": {"bound": "hbm", "kernel": "k_gotoh_fill<8,32>", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": hbm_achieved / hbm_peak, "bytes_per_cell": tb_bytes_per_cell,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else "fallback"},

@@ -72,6 +72,7 @@ def load():
     lib.crgpu_last_error.restype = ctypes.c_char_p
     lib.crgpu_set_traceback_budget.argtypes = [vp, ctypes.c_size_t]
     lib.crgpu_last_timing.argtypes = [vp, vp, vp]
+    lib.crgpu_set_overlap.argtypes = [vp, i32]
     lib.crgpu_sync.argtypes = [vp]
     lib.crgpu_stream.argtypes = [vp]
     lib.crgpu_stream.restype = vp
@@ -82,7 +83,7 @@ def load():
     lib.crgpu_align_quantify.argtypes = [vp, i32, ctypes.c_char_p, i32, ctypes.POINTER(PathParams),
                                          ctypes.POINTER(QuantParams), vp, vp, i64, ctypes.POINTER(PathOut)]
     lib.crgpu_int_peak.argtypes = [vp, i32, ctypes.POINTER(dbl)]
-    for name in ("crgpu_create", "crgpu_set_traceback_budget", "crgpu_last_timing", "crgpu_sync", "crgpu_qualfilter",
+    for name in ("crgpu_create", "crgpu_set_overlap", "crgpu_set_traceback_budget", "crgpu_last_timing", "crgpu_sync", "crgpu_qualfilter",
                  "crgpu_align", "crgpu_quantify", "crgpu_align_quantify", "crgpu_int_peak"):
         getattr(lib, name).restype = i32
     _lib = lib
@@ -133,6 +134,9 @@ class Context:
 
     def set_traceback_budget(self, nbytes):
         self.check(self.lib.crgpu_set_traceback_budget(self.handle, int(nbytes)))
+
+    def set_overlap(self, on):
+        self.check(self.lib.crgpu_set_overlap(self.handle, 1 if on else 0))
 
     def last_timing(self):
         ms = (ctypes.c_float * 6)()

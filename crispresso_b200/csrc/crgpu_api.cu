@@ -62,6 +62,13 @@ int crgpu_set_traceback_budget(crgpu_ctx *c, size_t bytes)
     return CRGPU_OK;
 }
 
+int crgpu_set_overlap(crgpu_ctx *c, int on)
+{
+    if (!c) return CRGPU_E_ARG;
+    c->overlap = on != 0;
+    return CRGPU_OK;
+}
+
 int crgpu_last_timing(const crgpu_ctx *c, float out_ms[6], int64_t out_launches[6])
 {
     if (!c) return CRGPU_E_ARG;
@@ -316,7 +323,7 @@ int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_read
     cudaStream_t s = ctx->stream;
     CK(ctx->amp.reserve((size_t)La));
     CK(ctx->prof.reserve(prof.size() * 4));
-    const bool two = batch_start.size() > 2 && !getenv("CRGPU_NO_OVERLAP");     // double-buffer only when there is a second batch to overlap with
+    const bool two = batch_start.size() > 2 && ctx->overlap && !getenv("CRGPU_NO_OVERLAP");     // double-buffer only when there is a second batch to overlap with
     CK(ctx->tb.reserve((size_t)max_tb_words * 4));
     CK(ctx->lastrow.reserve((size_t)max_bp * 12));
     CK(ctx->lastcol.reserve((size_t)max_bp * G * 12));

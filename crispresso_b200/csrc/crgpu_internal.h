@@ -54,6 +54,7 @@ struct crgpu_ctx {
     cudaStream_t span_stream = nullptr;
     cudaEvent_t fill_done[2] = {nullptr, nullptr}, walk_done[2] = {nullptr, nullptr};
     size_t tb_budget = (size_t)8 << 30;
+    bool overlap = true;
     std::string err;
     // device scratch
     DBuf reads, offsets, amp, prof, pc, pc_off, plen, pair_lo, pair_hi, order, plan_hist, plan_tab, tb, lastrow, lastcol, tb2, lastrow2, lastcol2, errflag;

@@ -60,6 +60,9 @@ const char *crgpu_last_error(const crgpu_ctx *ctx);
 /* Cap on the traceback scratch held in HBM per batch (bytes; default 8 GiB).  Reads are
  * processed in batches sized to this cap; results do not depend on it. */
 int crgpu_set_traceback_budget(crgpu_ctx *ctx, size_t bytes);
+/* Traceback walks of batch b normally run on a second stream, overlapped with the fill of batch b+1
+ * (default on).  Turning it off serialises the kernels, which is what per-kernel timing wants. */
+int crgpu_set_overlap(crgpu_ctx *ctx, int on);
 /* Device time (ms, CUDA events on the context's stream) spent in each kernel family during
  * the LAST call on this context, and launch counts.  out_ms[0..5] = encode, fill, walk,
  * quantify, qualfilter, other;  out_launches likewise. */
