@@ -165,7 +165,7 @@ __device__ __forceinline__ void column_step(Strip<K> &st, const int32_t *__restr
 #ifdef FILL_MAXNREG
 template <int K> constexpr int fill_maxnreg() { return FILL_MAXNREG; }
 #else
-template <int K> constexpr int fill_maxnreg() { return K >= 36 ? 184 : (K >= 32 ? 136 : 128); }
+template <int K> constexpr int fill_maxnreg() { return K >= 48 ? 255 : (K >= 36 ? 184 : (K >= 32 ? 136 : 128)); }
 #endif
 
 template <int G, int K>
@@ -309,7 +309,7 @@ bool choose_tile(int La, int *G, int *K)
     // strip heights with K % 8 == 0 only: the 8-byte-store variants (K = 20, 28, 36) measured 2.2x
     // slower per cell on B200 (profiles/r01_notes.md)
     static const Tile menu[] = {
-        {4, 16}, {4, 24}, {4, 32}, {4, 40}, {8, 24}, {8, 32}, {8, 40}, {16, 24}, {16, 32}, {16, 40}, {32, 24}, {32, 32},
+        {4, 16}, {4, 24}, {4, 32}, {4, 40}, {4, 48}, {8, 32}, {8, 40}, {8, 48}, {16, 32}, {16, 40}, {32, 24}, {32, 32},
     };
     if (getenv("CRGPU_TILE")) { int g, k; if (sscanf(getenv("CRGPU_TILE"), "%d,%d", &g, &k) == 2 && g * k >= La) { *G = g; *K = k; return true; } }
     int best = -1, bestgk = 1 << 30;
@@ -326,7 +326,7 @@ cudaError_t launch_fill(int G, int K, const FillArgs &a, int num_sms, cudaStream
 {
 #define CASE(g, k) if (G == g && K == k) return launch_tile<g, k>(a, num_sms, stream);
     CASE(4, 16) CASE(4, 24) CASE(4, 32) CASE(4, 40) CASE(8, 16) CASE(8, 24) CASE(8, 32) CASE(8, 40)
-    CASE(16, 16) CASE(16, 24) CASE(16, 32) CASE(16, 40) CASE(32, 24) CASE(32, 32)
+    CASE(16, 16) CASE(16, 24) CASE(16, 32) CASE(16, 40) CASE(32, 24) CASE(32, 32) CASE(4, 48) CASE(8, 48) CASE(16, 48)
 #undef CASE
     return cudaErrorInvalidValue;
 }
