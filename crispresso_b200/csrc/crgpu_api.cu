@@ -26,6 +26,8 @@ int crgpu_create(crgpu_ctx **out, int device)
     if (!getenv("CRGPU_NO_L2_HINT")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return CRGPU_E_CUDA; }
     if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete c; return CRGPU_E_CUDA; }
+    if (cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking) != cudaSuccess) { delete c; return CRGPU_E_CUDA; }
+    cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming);
     for (int i = 0; i < 2; ++i) {
         cudaEventCreateWithFlags(&c->fill_done[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&c->walk_done[i], cudaEventDisableTiming);
@@ -40,6 +42,7 @@ void crgpu_destroy(crgpu_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->stream2);
+    cudaStreamSynchronize(c->stream3);
     DBuf *all[] = {&c->reads, &c->offsets, &c->amp, &c->prof, &c->pc, &c->pc_off, &c->plen, &c->pair_lo, &c->pair_hi,
                    &c->order, &c->plan_hist, &c->plan_tab, &c->tb2, &c->lastrow2, &c->lastcol2, &c->tb, &c->lastrow, &c->lastcol, &c->errflag, &c->recs, &c->sref, &c->smark, &c->sqry, &c->ops, &c->ops_rc};
     for (DBuf *b : all) b->release();
@@ -48,6 +51,8 @@ void crgpu_destroy(crgpu_ctx *c)
     for (auto &b : c->aux) b.release();
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->fill_done[i]); cudaEventDestroy(c->walk_done[i]); }
+    cudaEventDestroy(c->ready);
+    cudaStreamDestroy(c->stream3);
     cudaStreamDestroy(c->stream2);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -336,10 +341,17 @@ int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_read
     CK(cudaMemcpyAsync(ctx->prof.p, prof.data(), prof.size() * 4, cudaMemcpyHostToDevice, s));
     CK(cudaStreamSynchronize(s));      // amp_up / prof are locals of this frame
 
-    // Fill kernels run back to back on the main stream; the traceback walk of batch b runs on the
-    // second stream, overlapped with the fill of batch b+1 (the walk is DRAM-latency bound, the fill
-    // integer-issue bound).  Two sets of traceback scratch alternate.
+    // Even fill batches run on the main stream, odd ones on a third stream, so that the persistent CTAs
+    // of batch b+1 back-fill the SMs that the tail of batch b vacates (a fill launch is ~9 waves; its
+    // last partial wave would otherwise leave most of the chip idle for one pair-time).  The traceback
+    // walk of batch b runs on the second stream, overlapped with the fill of batch b+1 (the walk is
+    // DRAM-latency bound, the fill integer-issue bound).  Two sets of traceback scratch alternate.
     cudaStream_t s2 = two ? ctx->stream2 : ctx->stream;
+    cudaStream_t sf[2] = {s, two ? ctx->stream3 : s};
+    if (two) {
+        CK(cudaEventRecord(ctx->ready, s));                   // plan, profile, amplicon are in place
+        CK(cudaStreamWaitEvent(sf[1], ctx->ready, 0));
+    }
     bool used[2] = {false, false};
     for (size_t b = 0; b + 1 < batch_start.size(); ++b) {
         const int cur = two ? (int)(b & 1) : 0;
@@ -353,11 +365,11 @@ int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_read
         fa.lastcol = (cur ? ctx->lastcol2 : ctx->lastcol).as<uint32_t>();
         fa.p0 = batch_start[b]; fa.p1 = batch_start[b + 1];
         fa.open = open_s; fa.ext = ext_s; fa.La = La; fa.one = 1;
-        if (used[cur]) CK(cudaStreamWaitEvent(s, ctx->walk_done[cur], 0));     // scratch `cur` is free again
-        span_begin(ctx, T_FILL, s);
-        CK(launch_fill(G, K, fa, ctx->num_sms, s));
+        if (used[cur]) CK(cudaStreamWaitEvent(sf[cur], ctx->walk_done[cur], 0));     // scratch `cur` is free again
+        span_begin(ctx, T_FILL, sf[cur]);
+        CK(launch_fill(G, K, fa, ctx->num_sms, sf[cur]));
         span_end(ctx);
-        CK(cudaEventRecord(ctx->fill_done[cur], s));
+        CK(cudaEventRecord(ctx->fill_done[cur], sf[cur]));
 
         WalkArgs wa;
         wa.tb = fa.tb; wa.lastrow = fa.lastrow; wa.lastcol = fa.lastcol;

@@ -51,6 +51,8 @@ struct crgpu_ctx {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;      // traceback walks run here, overlapped with the next batch's fill
+    cudaStream_t stream3 = nullptr;      // odd fill batches: their CTAs back-fill the SMs the previous fill's tail vacates
+    cudaEvent_t ready = nullptr;
     cudaStream_t span_stream = nullptr;
     cudaEvent_t fill_done[2] = {nullptr, nullptr}, walk_done[2] = {nullptr, nullptr};
     size_t tb_budget = (size_t)8 << 30;
