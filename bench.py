@@ -196,6 +196,7 @@ def main():
         "tenths_rep": torch.zeros(n, dtype=torch.int32, device="cuda"),
     }
     dev_ptrs = {k: v.data_ptr() for k, v in dev_out.items()}
+    torch.cuda.synchronize()          # torch initialises these on its own stream; the library uses another
 
     def allreduce(red):
         if world > 1:
