@@ -42,7 +42,9 @@ class PathOut(ctypes.Structure):
                 ("rc_mark_rows", ctypes.c_void_p), ("rc_qry_rows", ctypes.c_void_p),
                 ("vectors", ctypes.c_void_p), ("hist_inframe", ctypes.c_void_p), ("hist_frameshift", ctypes.c_void_p),
                 ("hist_len", ctypes.c_int32), ("hist_zero", ctypes.c_int32), ("counters", ctypes.c_void_p),
-                ("class_counts", ctypes.c_int64 * 4), ("n_total", ctypes.c_int64), ("n_cells", ctypes.c_int64)]
+                ("class_counts", ctypes.c_int64 * 4), ("n_total", ctypes.c_int64), ("n_cells", ctypes.c_int64),
+                ("allele_cap", ctypes.c_int64), ("allele_n", ctypes.c_int64), ("allele_row", ctypes.c_void_p),
+                ("allele_count", ctypes.c_void_p)]
 
 
 class CrgpuError(RuntimeError):

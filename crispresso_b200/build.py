@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["gotoh_fill.cu", "traceback_walk.cu", "quantify.cu", "int_peak.cu", "crgpu_api.cu", "hotpath.cu"]
+SOURCES = ["gotoh_fill.cu", "traceback_walk.cu", "quantify.cu", "int_peak.cu", "crgpu_api.cu", "hotpath.cu", "alleles.cu"]
 LIB = os.path.join(HERE, "libcrgpu.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared"]

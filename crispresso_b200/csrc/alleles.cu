@@ -1,0 +1,182 @@
+// alleles.cu -- device side of the allele table.
+//
+// The reference groups df_needle_alignment by (align_seq, ref_seq, NHEJ, UNMODIFIED, HDR, n_deleted,
+// n_inserted, n_mutated) and counts the rows (CRISPResso/CRISPRessoCORE.py:2923-2946).  For a fixed
+// amplicon that key is a function of the read's bases as they appear in align_seq, the alignment's
+// gap / mismatch pattern (the walker's 2-bit ops) and the four record fields, so rows are hashed over
+// exactly those, radix-sorted (cub), run-length encoded and ordered by count.  Only one
+// representative row per allele has to be materialised as text afterwards.
+// A second, independent hash guards the grouping: rows that collide in the 64-bit sort key but differ
+// in the check hash make the call fail instead of merging two alleles.
+#include <cub/cub.cuh>
+
+#include "crgpu_common.cuh"
+#include "../../include/crgpu.h"
+
+namespace crgpu {
+
+__device__ __forceinline__ uint64_t mix64(uint64_t h, uint64_t v, uint64_t mul)
+{
+    h ^= v;
+    h *= mul;
+    h ^= h >> 29;
+    return h;
+}
+
+__device__ __forceinline__ uint8_t comp_up(uint8_t c)
+{
+    switch (c) {
+    case 'A': case 'a': return 'T';
+    case 'C': case 'c': return 'G';
+    case 'G': case 'g': return 'C';
+    case 'T': case 't': case 'U': case 'u': return 'A';
+    case 'N': case 'n': return 'N';
+    default: return c;
+    }
+}
+
+// rows [0, n): forward row of read i (valid iff kept[i] & 1); rows [n, n + nrc): RC row j of read
+// rc_read[j] (valid iff kept[rc_read[j]] & 2).  Invalid rows get key = ~0 and sort last.
+__global__ void k_hash_rows(const uint8_t *__restrict__ reads, const int64_t *__restrict__ offsets, int64_t n,
+                            const uint8_t *__restrict__ kept, const int32_t *__restrict__ rc_read, int64_t nrc,
+                            const uint32_t *__restrict__ ops_fw, const uint32_t *__restrict__ ops_rc, int64_t ops_stride,
+                            const crgpu_aln_rec *__restrict__ aln_fw, const crgpu_aln_rec *__restrict__ aln_rc,
+                            const crgpu_read_rec *__restrict__ rec_fw, const crgpu_read_rec *__restrict__ rec_rc,
+                            uint64_t *__restrict__ keys, uint64_t *__restrict__ chk, int32_t *__restrict__ rows)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n + nrc) return;
+    rows[r] = (int32_t)r;
+    const bool rc = r >= n;
+    const int64_t read = rc ? rc_read[r - n] : r;
+    const bool valid = rc ? (kept[read] & 2) != 0 : (kept[read] & 1) != 0;
+    if (!valid) { keys[r] = ~0ull; chk[r] = 0; return; }
+    const uint8_t *b = reads + offsets[read];
+    const int len = (int)(offsets[read + 1] - offsets[read]);
+    uint64_t h1 = 0x9e3779b97f4a7c15ull, h2 = 0xc2b2ae3d27d4eb4full;
+    // bases as they appear in align_seq: raw for forward rows, upper-cased reverse complement for RC rows
+    for (int i = 0; i < len; ++i) {
+        const uint8_t c = rc ? comp_up(b[len - 1 - i]) : b[i];
+        h1 = mix64(h1, c, 0xff51afd7ed558ccdull);
+        h2 = mix64(h2, c + 0x100u * (uint32_t)(i & 255), 0xc4ceb9fe1a85ec53ull);
+    }
+    const crgpu_aln_rec a = rc ? aln_rc[r - n] : aln_fw[read];
+    const uint32_t *ops = rc ? ops_rc + (r - n) * ops_stride : ops_fw + read * ops_stride;
+    // ops are stored in walk order: reversed for forward rows, forward for RC rows; hash them in
+    // FORWARD column order so that a forward row and an RC row with the same text rows agree
+    const int ncol = a.alnlen;
+    uint64_t acc = 0;
+    for (int c = 0; c < ncol; ++c) {
+        const int j = rc ? c : ncol - 1 - c;
+        const uint64_t op = (ops[j >> 4] >> ((j & 15) * 2)) & 3u;
+        acc = (acc << 2) | op;
+        if ((c & 31) == 31) { h1 = mix64(h1, acc, 0xff51afd7ed558ccdull); h2 = mix64(h2, ~acc, 0xc4ceb9fe1a85ec53ull); acc = 0; }
+    }
+    h1 = mix64(h1, acc ^ ((uint64_t)ncol << 40), 0xff51afd7ed558ccdull);
+    h2 = mix64(h2, acc + ncol, 0xc4ceb9fe1a85ec53ull);
+    const crgpu_read_rec q = rc ? rec_rc[r - n] : rec_fw[read];
+    const uint64_t f = (uint64_t)q.cls | ((uint64_t)(uint32_t)q.n_mutated << 8) | ((uint64_t)(uint32_t)q.n_inserted << 24) |
+                       ((uint64_t)(uint32_t)q.n_deleted << 44);
+    h1 = mix64(h1, f, 0xff51afd7ed558ccdull);
+    h2 = mix64(h2, f, 0xc4ceb9fe1a85ec53ull);
+    if (h1 == ~0ull) h1 = 0x5bd1e995u;
+    keys[r] = h1;
+    chk[r] = h2;
+}
+
+// sorted order: rows with equal key must carry equal check hashes
+__global__ void k_check_groups(const uint64_t *__restrict__ skeys, const int32_t *__restrict__ srows,
+                               const uint64_t *__restrict__ chk, int64_t m, int *err)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < 1 || p >= m) return;
+    if (skeys[p] != ~0ull && skeys[p] == skeys[p - 1] && chk[srows[p]] != chk[srows[p - 1]]) atomicOr(err, 1);
+}
+
+// representative (first sorted row) of every run; the run of invalid rows gets count 0; slots past
+// the last run are neutral (count 0 from the memset, representative -1)
+__global__ void k_group_reps(const uint64_t *__restrict__ ukeys, const int32_t *__restrict__ starts, const int32_t *__restrict__ srows,
+                             int32_t *__restrict__ counts, const int *__restrict__ nruns, int32_t *__restrict__ rep,
+                             int32_t *__restrict__ gid, int64_t m)
+{
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= m) return;
+    gid[g] = (int32_t)g;
+    if (g >= *nruns) { rep[g] = -1; return; }
+    rep[g] = srows[starts[g]];
+    if (ukeys[g] == ~0ull) counts[g] = 0;
+}
+
+__global__ void k_gather_i32(const int32_t *__restrict__ src, const int32_t *__restrict__ idx, int32_t *__restrict__ out, int64_t m)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) out[i] = src[idx[i]];
+}
+
+// Group the rows; returns the number of alleles (runs with a non-zero count) and, sorted by count
+// descending, up to `cap` (representative row, count) pairs in host arrays.
+// tmp: caller-provided scratch allocator callback is avoided: all scratch comes in through `scratch`
+// (bytes >= allele_scratch_bytes(m)).
+size_t allele_scratch_bytes(int64_t m)
+{
+    size_t a = 0, b = 0, c = 0, d = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (uint64_t *)nullptr, (uint64_t *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr, (int)m);
+    cub::DeviceRunLengthEncode::Encode(nullptr, b, (uint64_t *)nullptr, (uint64_t *)nullptr, (int32_t *)nullptr, (int *)nullptr, (int)m);
+    cub::DeviceScan::ExclusiveSum(nullptr, c, (int32_t *)nullptr, (int32_t *)nullptr, (int)m);
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, d, (int32_t *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr, (int)m);
+    size_t t = a;
+    if (b > t) t = b;
+    if (c > t) t = c;
+    if (d > t) t = d;
+    t = (t + 255) & ~(size_t)255;
+    // keys, chk, skeys, ukeys (8 B) + rows, srows, counts, starts, rep, gid, scounts, sgid (4 B) + nruns/err
+    return t + (size_t)m * (4 * 8 + 8 * 4) + 1024;
+}
+
+cudaError_t allele_groups(const uint8_t *reads, const int64_t *offsets, int64_t n, const uint8_t *kept, const int32_t *rc_read,
+                          int64_t nrc, const uint32_t *ops_fw, const uint32_t *ops_rc, int64_t ops_stride,
+                          const crgpu_aln_rec *aln_fw, const crgpu_aln_rec *aln_rc, const crgpu_read_rec *rec_fw,
+                          const crgpu_read_rec *rec_rc, void *scratch, size_t scratch_bytes, cudaStream_t s,
+                          int32_t **d_rep_sorted, int32_t **d_count_sorted, int **d_nruns, int **d_err)
+{
+    const int64_t m = n + nrc;
+    size_t tmp_bytes = scratch_bytes - ((size_t)m * (4 * 8 + 8 * 4) + 1024);
+    uint8_t *p = reinterpret_cast<uint8_t *>(scratch);
+    void *tmp = p; p += tmp_bytes;
+    uint64_t *keys = reinterpret_cast<uint64_t *>(p); p += m * 8;
+    uint64_t *chk = reinterpret_cast<uint64_t *>(p); p += m * 8;
+    uint64_t *skeys = reinterpret_cast<uint64_t *>(p); p += m * 8;
+    uint64_t *ukeys = reinterpret_cast<uint64_t *>(p); p += m * 8;
+    int32_t *rows = reinterpret_cast<int32_t *>(p); p += m * 4;
+    int32_t *srows = reinterpret_cast<int32_t *>(p); p += m * 4;
+    int32_t *counts = reinterpret_cast<int32_t *>(p); p += m * 4;
+    int32_t *starts = reinterpret_cast<int32_t *>(p); p += m * 4;
+    int32_t *rep = reinterpret_cast<int32_t *>(p); p += m * 4;
+    int32_t *gid = reinterpret_cast<int32_t *>(p); p += m * 4;
+    int32_t *scounts = reinterpret_cast<int32_t *>(p); p += m * 4;
+    int32_t *sgid = reinterpret_cast<int32_t *>(p); p += m * 4;
+    int *nruns = reinterpret_cast<int *>(p); int *err = nruns + 1;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(nruns, 0, 8, s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(counts, 0, (size_t)m * 4, s)) != cudaSuccess) return e;
+    const unsigned grid = (unsigned)((m + 127) / 128);
+    k_hash_rows<<<grid, 128, 0, s>>>(reads, offsets, n, kept, rc_read, nrc, ops_fw, ops_rc, ops_stride, aln_fw, aln_rc, rec_fw,
+                                     rec_rc, keys, chk, rows);
+    size_t tb = tmp_bytes;
+    if ((e = cub::DeviceRadixSort::SortPairs(tmp, tb, keys, skeys, rows, srows, (int)m, 0, 64, s)) != cudaSuccess) return e;
+    k_check_groups<<<grid, 128, 0, s>>>(skeys, srows, chk, m, err);
+    tb = tmp_bytes;
+    if ((e = cub::DeviceRunLengthEncode::Encode(tmp, tb, skeys, ukeys, counts, nruns, (int)m, s)) != cudaSuccess) return e;
+    tb = tmp_bytes;
+    if ((e = cub::DeviceScan::ExclusiveSum(tmp, tb, counts, starts, (int)m, s)) != cudaSuccess) return e;
+    k_group_reps<<<grid, 128, 0, s>>>(ukeys, starts, srows, counts, nruns, rep, gid, m);
+    tb = tmp_bytes;
+    // all m slots are sorted (slots past the number of runs hold count 0 and sort last)
+    if ((e = cub::DeviceRadixSort::SortPairsDescending(tmp, tb, counts, scounts, gid, sgid, (int)m, 0, 32, s)) != cudaSuccess) return e;
+    // representatives in the sorted order (the exclusive-sum buffer is free again)
+    k_gather_i32<<<grid, 128, 0, s>>>(rep, sgid, starts, m);
+    *d_rep_sorted = starts; *d_count_sorted = scounts; *d_nruns = nruns; *d_err = err;
+    return cudaGetLastError();
+}
+
+}  // namespace crgpu

@@ -44,7 +44,7 @@ void crgpu_destroy(crgpu_ctx *c)
     cudaStreamSynchronize(c->stream2);
     cudaStreamSynchronize(c->stream3);
     DBuf *all[] = {&c->reads, &c->offsets, &c->amp, &c->prof, &c->pc, &c->pc_off, &c->plen, &c->pair_lo, &c->pair_hi,
-                   &c->order, &c->plan_hist, &c->plan_tab, &c->tb2, &c->lastrow2, &c->lastcol2, &c->tb, &c->lastrow, &c->lastcol, &c->errflag, &c->recs, &c->sref, &c->smark, &c->sqry, &c->ops, &c->ops_rc};
+                   &c->order, &c->plan_hist, &c->plan_tab, &c->tb2, &c->lastrow2, &c->lastcol2, &c->tb, &c->lastrow, &c->lastcol, &c->errflag, &c->recs, &c->sref, &c->smark, &c->sqry, &c->ops, &c->ops_rc, &c->alleles};
     for (DBuf *b : all) b->release();
     for (auto &b : c->q_in) b.release();
     for (auto &b : c->q_out) b.release();

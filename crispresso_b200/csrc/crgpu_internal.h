@@ -61,7 +61,7 @@ struct crgpu_ctx {
     // device scratch
     DBuf reads, offsets, amp, prof, pc, pc_off, plen, pair_lo, pair_hi, order, plan_hist, plan_tab, tb, lastrow, lastcol, tb2, lastrow2, lastcol2, errflag;
     PairPlan plan;
-    DBuf recs, sref, smark, sqry, ops, ops_rc;
+    DBuf recs, sref, smark, sqry, ops, ops_rc, alleles;
     DBuf q_in[8], q_out[4];
     DBuf aux[8];
     // timing
@@ -147,6 +147,12 @@ cudaError_t launch_scatter_order(const int64_t *offsets, const int32_t *subset, 
                                  int *cursor, int32_t *order, cudaStream_t s);
 cudaError_t launch_build_pairs(const void *segs, int nseg, int np, const int32_t *order, int32_t *pair_lo, int32_t *pair_hi,
                                int32_t *plen, int64_t *pc_off, int64_t total_pc, cudaStream_t s);
+size_t allele_scratch_bytes(int64_t m);
+cudaError_t allele_groups(const uint8_t *reads, const int64_t *offsets, int64_t n, const uint8_t *kept, const int32_t *rc_read,
+                          int64_t nrc, const uint32_t *ops_fw, const uint32_t *ops_rc, int64_t ops_stride,
+                          const crgpu_aln_rec *aln_fw, const crgpu_aln_rec *aln_rc, const crgpu_read_rec *rec_fw,
+                          const crgpu_read_rec *rec_rc, void *scratch, size_t scratch_bytes, cudaStream_t s,
+                          int32_t **d_rep_sorted, int32_t **d_count_sorted, int **d_nruns, int **d_err);
 // alignment core (crgpu_api.cu): device pointers only
 int build_plan(crgpu_ctx *ctx, const uint8_t *d_reads, const int64_t *d_offsets, const int32_t *d_subset, int64_t nsub);
 int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_reads, const int64_t *d_offsets,

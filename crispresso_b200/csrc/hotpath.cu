@@ -358,6 +358,45 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
         span_end(ctx);
     }
 
+    // ---- 4b. allele table: group the kept rows on the device (CORE:2923-2946) ----
+    if (out->allele_cap > 0) {
+        if (!out->allele_row || !out->allele_count) return fail(ctx, CRGPU_E_ARG, "allele_row / allele_count are required with allele_cap > 0");
+        const int64_t m = n + nrc;
+        const size_t sb = allele_scratch_bytes(m);
+        CK(ctx->alleles.reserve(sb));
+        int32_t *d_rep, *d_cnt; int *d_nruns, *d_aerr;
+        span_begin(ctx, T_OTHER);
+        CK(allele_groups(d_reads, d_off, n, d_kept, nrc ? ctx->aux[3].as<int32_t>() : nullptr, nrc, d_ops,
+                         nrc ? ctx->ops_rc.as<uint32_t>() : nullptr, ops_stride, d_aln, d_rc_aln, d_recs, d_rc_recs,
+                         ctx->alleles.p, sb, s, &d_rep, &d_cnt, &d_nruns, &d_aerr));
+        span_end(ctx);
+        int h2[2] = {0, 0};
+        CK(cudaMemcpyAsync(h2, d_nruns, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (h2[1]) return fail(ctx, CRGPU_E_CUDA, "allele grouping: 64-bit hash collision between different alleles");
+        const int64_t take = std::min<int64_t>(out->allele_cap, h2[0]);
+        std::vector<int32_t> hrep((size_t)take), hcnt((size_t)take);
+        if (take > 0) {
+            CK(cudaMemcpyAsync(hrep.data(), d_rep, (size_t)take * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(hcnt.data(), d_cnt, (size_t)take * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+        }
+        int64_t na = 0;
+        for (int64_t i = 0; i < take; ++i) {
+            if (hcnt[(size_t)i] <= 0) break;
+            out->allele_row[na] = hrep[(size_t)i];
+            out->allele_count[na] = hcnt[(size_t)i];
+            ++na;
+        }
+        // runs = alleles (+ 1 run of rows that were not kept, which sorts last with count 0)
+        int32_t last_count = 1;
+        if (h2[0] > 0) {
+            CK(cudaMemcpyAsync(&last_count, d_cnt + (h2[0] - 1), 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+        }
+        out->allele_n = (int64_t)h2[0] - (last_count == 0 ? 1 : 0);
+    }
+
     // ---- 5. results ----
     if (host) {
         CK(cudaMemcpyAsync(out->kept, d_kept, (size_t)n, cudaMemcpyDeviceToHost, s));

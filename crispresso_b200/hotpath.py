@@ -257,12 +257,13 @@ def process_df_chunk(chunk_input, ctx, INCLUDE_IDXS, LEN_AMPLICON, EXON_POSITION
 
 
 HotPathResult = namedtuple("HotPathResult", [
-    "kept", "aln", "tenths_rep", "recs", "rows", "slot", "rc_read", "rc_aln", "rc_recs", "rc_rows", "red"])
+    "kept", "aln", "tenths_rep", "recs", "rows", "slot", "rc_read", "rc_aln", "rc_recs", "rc_rows", "red",
+    "allele_row", "allele_count", "allele_n"], defaults=(None, None, 0))
 
 
 def run_hot_path(ctx, amplicon, reads, gapopen=10.0, gapextend=0.5, min_identity_score=60.0, hdr_amplicon=None,
                  flags=None, hdr_thr=98.0, inc=None, exon=None, splice=None, want_rows=False, rc_rescue=True,
-                 red=None, device_inputs=None):
+                 red=None, device_inputs=None, alleles=0):
     """CORE:1791-2072 + 2773-2869 for one amplicon through crgpu_align_quantify.
 
     reads: (uint8 buffer, int64 offsets) host arrays, or with ``device_inputs=(ptr_reads,
@@ -291,6 +292,11 @@ def run_hot_path(ctx, amplicon, reads, gapopen=10.0, gapextend=0.5, min_identity
     po.hist_frameshift = red.hist_frameshift.ctypes.data
     po.hist_len, po.hist_zero = HIST_LEN, HIST_ZERO
     po.counters = red.counters.ctypes.data
+    allele_row = allele_count = None
+    if alleles:
+        allele_row = np.zeros(int(alleles), np.int32)
+        allele_count = np.zeros(int(alleles), np.int64)
+        po.allele_cap, po.allele_row, po.allele_count = int(alleles), allele_row.ctypes.data, allele_count.ctypes.data
 
     if device_inputs is not None:
         d_reads, d_off, n, _maxlen, dev_out = device_inputs
@@ -300,7 +306,9 @@ def run_hot_path(ctx, amplicon, reads, gapopen=10.0, gapextend=0.5, min_identity
         po.rc_cap = 0
         ctx.check(ctx.lib.crgpu_align_quantify(ctx.handle, _lib.MEM_DEVICE, amp, L, ctypes.byref(pp), ctypes.byref(qp),
                                                d_reads, d_off, n, ctypes.byref(po)))
-        res = HotPathResult(None, None, None, None, None, 0, None, None, None, None, red)
+        na = min(int(po.allele_n), int(alleles)) if alleles else 0
+        res = HotPathResult(None, None, None, None, None, 0, None, None, None, None, red,
+                            allele_row[:na] if alleles else None, allele_count[:na] if alleles else None, int(po.allele_n))
     else:
         buf, offsets = reads
         n = len(offsets) - 1
@@ -332,7 +340,9 @@ def run_hot_path(ctx, amplicon, reads, gapopen=10.0, gapextend=0.5, min_identity
         if want_rows:
             # RC rows come back already flipped to the forward strand, left-aligned in their slot
             rc_rows = [[b[j, :rc_aln["alnlen"][j]].tobytes().decode() for j in range(nrc)] for b in rc_bufs]
-        res = HotPathResult(kept, aln, trep, recs, rows, slot, rc_read[:nrc], rc_aln[:nrc], rc_recs[:nrc], rc_rows, red)
+        na = min(int(po.allele_n), int(alleles)) if alleles else 0
+        res = HotPathResult(kept, aln, trep, recs, rows, slot, rc_read[:nrc], rc_aln[:nrc], rc_recs[:nrc], rc_rows, red,
+                            allele_row[:na] if alleles else None, allele_count[:na] if alleles else None, int(po.allele_n))
     red.class_counts += np.array(list(po.class_counts), np.int64)
     red.n_total += int(po.n_total)
     red.n_cells += int(po.n_cells)
@@ -382,4 +392,65 @@ def build_dataframe(res, read_names, has_hdr=False, amplicon=None):
             ids = [names[res.rc_read[j]] + "_RC" for j in sel]
             df_rc = frame(ids, res.rc_aln[sel], None, res.rc_recs[sel], rr[0], rr[1], rr[2], True)
             df = pd.concat([df, df_rc])
+    return df
+
+
+def allele_table(ctx, res, amplicon, reads, gapopen=10.0, gapextend=0.5):
+    """df_alleles (CORE:2923-2946) from the device-side grouping of run_hot_path(..., alleles=K): one
+    row per allele, most frequent first, columns Aligned_Sequence, Reference_Sequence, NHEJ,
+    UNMODIFIED, HDR, n_deleted, n_inserted, n_mutated, #Reads, %Reads.  Only the representatives'
+    text rows are materialised (a second, small alignment call when run_hot_path did not keep rows)."""
+    import pandas as pd
+
+    from .aligner import needle_align
+    from .synth import revcomp
+    buf, offsets = reads
+    n = len(offsets) - 1
+    rows, counts = res.allele_row, res.allele_count
+    fw = [(k, int(r)) for k, r in enumerate(rows) if r < n]
+    rc = [(k, int(r) - n) for k, r in enumerate(rows) if r >= n]
+    aligned = [None] * len(rows)
+    refseq = [None] * len(rows)
+    recs = [None] * len(rows)
+
+    def sub(idx):
+        lens = (offsets[1:] - offsets[:-1])[idx]
+        off = np.zeros(len(idx) + 1, np.int64)
+        off[1:] = np.cumsum(lens)
+        out = np.empty(int(off[-1]), np.uint8)
+        for j, i in enumerate(idx):
+            out[off[j]:off[j + 1]] = buf[offsets[i]:offsets[i + 1]]
+        return out, off
+
+    if fw:
+        idx = np.array([r for _k, r in fw])
+        if res.rows is not None:
+            for (k, r) in fw:
+                o, ln = res.aln["aln_off"][r], res.aln["alnlen"][r]
+                refseq[k] = res.rows[0][r, o:o + ln].tobytes().decode()
+                aligned[k] = res.rows[2][r, o:o + ln].tobytes().decode()
+        else:
+            _r, a_ref, _m, a_qry = needle_align(ctx, amplicon.upper(), sub(idx), gapopen, gapextend)
+            for j, (k, _r2) in enumerate(fw):
+                refseq[k], aligned[k] = a_ref[j], a_qry[j]
+        for (k, r) in fw:
+            recs[k] = res.recs[r]
+    if rc:
+        reads_idx = np.array([int(res.rc_read[j]) for _k, j in rc])
+        if res.rc_rows is not None:
+            for (k, j) in rc:
+                refseq[k], aligned[k] = res.rc_rows[0][j], res.rc_rows[2][j]
+        else:
+            _r, a_ref, _m, a_qry = needle_align(ctx, revcomp(amplicon.upper()), sub(reads_idx), gapopen, gapextend)
+            for j2, (k, _j) in enumerate(rc):
+                refseq[k], aligned[k] = revcomp(a_ref[j2].upper()), revcomp(a_qry[j2].upper())
+        for (k, j) in rc:
+            recs[k] = res.rc_recs[j]
+    cls = np.array([r["cls"] for r in recs], np.uint8) if recs else np.zeros(0, np.uint8)
+    df = pd.DataFrame({
+        "Aligned_Sequence": aligned, "Reference_Sequence": refseq,
+        "NHEJ": (cls & _lib.C_NHEJ) != 0, "UNMODIFIED": (cls & _lib.C_UNMODIFIED) != 0, "HDR": (cls & _lib.C_HDR) != 0,
+        "n_deleted": [int(r["n_deleted"]) for r in recs], "n_inserted": [int(r["n_inserted"]) for r in recs],
+        "n_mutated": [int(r["n_mutated"]) for r in recs], "#Reads": counts.astype(np.int64)})
+    df["%Reads"] = df["#Reads"] / float(res.red.n_total) * 100.0
     return df

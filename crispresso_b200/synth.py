@@ -2,7 +2,7 @@
 import numpy as np
 
 _ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
-_COMP = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N"}
+_COMP = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N", "-": "-"}
 
 
 def random_seq(rng, n):

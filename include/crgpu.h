@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CRGPU_ABI_VERSION 1
+#define CRGPU_ABI_VERSION 2
 
 enum {
     CRGPU_OK = 0,
@@ -212,6 +212,13 @@ typedef struct {
     int64_t class_counts[4];               /* OUT (added): UNMODIFIED, NHEJ, HDR, MIXED rows (CORE:2866-2869) */
     int64_t n_total;                       /* OUT (added): rows kept = df_needle_alignment.shape[0] (CORE:2025) */
     int64_t n_cells;                       /* OUT (added): DP cells computed, for GCUPS */
+    /* allele table (CORE:2923-2946): kept rows grouped by (align_seq, ref_seq, class, n_deleted,
+     * n_inserted, n_mutated) on the device; HOST arrays, most frequent allele first */
+    int64_t allele_cap;                    /* capacity of the two arrays below; 0 = skip the grouping */
+    int64_t allele_n;                      /* OUT: distinct alleles among the kept rows (may exceed allele_cap) */
+    int32_t *allele_row;                   /* [allele_cap] a representative row: read index i for a forward row,
+                                              n + j for the RC row j */
+    int64_t *allele_count;                 /* [allele_cap] #Reads */
 } crgpu_path_out;
 
 int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int amplicon_len,
