@@ -224,7 +224,7 @@ int build_plan(crgpu_ctx *ctx, const uint8_t *d_reads, const int64_t *d_offsets,
                           ctx->plen.as<int32_t>(), ctx->pc_off.as<int64_t>(), pcs, s));
     CK(launch_encode(d_reads, d_offsets, ctx->pair_lo.as<int32_t>(), ctx->pair_hi.as<int32_t>(), ctx->pc_off.as<int64_t>(), pl.np,
                      ctx->pc.as<uint8_t>(), d_err, ctx->num_sms, s));
-    span_end(ctx);
+    span_end(ctx, 3);
     CK(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));    // read_start / segs are locals of this frame
     if (h_err & 1) return fail(ctx, CRGPU_E_ALIGN, "a read contains a base outside ACGTN(U)");

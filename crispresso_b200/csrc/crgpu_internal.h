@@ -108,10 +108,10 @@ inline void span_begin(crgpu_ctx *c, int family, cudaStream_t st = nullptr)
     cudaEventRecord(s.a, st);
     c->spans.push_back(s);
 }
-inline void span_end(crgpu_ctx *c)
+inline void span_end(crgpu_ctx *c, int kernels = 1)   // kernels launched inside the span
 {
     cudaEventRecord(c->spans.back().b, c->span_stream);
-    c->launches[c->spans.back().family]++;
+    c->launches[c->spans.back().family] += kernels;
 }
 inline void timing_reset(crgpu_ctx *c)
 {

@@ -369,7 +369,7 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
         CK(allele_groups(d_reads, d_off, n, d_kept, nrc ? ctx->aux[3].as<int32_t>() : nullptr, nrc, d_ops,
                          nrc ? ctx->ops_rc.as<uint32_t>() : nullptr, ops_stride, d_aln, d_rc_aln, d_recs, d_rc_recs,
                          ctx->alleles.p, sb, s, &d_rep, &d_cnt, &d_nruns, &d_aerr));
-        span_end(ctx);
+        span_end(ctx, 4);     // k_hash_rows, k_check_groups, k_group_reps, k_gather_i32 (+ cub's own kernels, not counted)
         int h2[2] = {0, 0};
         CK(cudaMemcpyAsync(h2, d_nruns, 8, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
