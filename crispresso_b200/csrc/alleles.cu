@@ -9,6 +9,7 @@
 // A second, independent hash guards the grouping: rows that collide in the 64-bit sort key but differ
 // in the check hash make the call fail instead of merging two alleles.
 #include <cub/cub.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include "crgpu_common.cuh"
 #include "../../include/crgpu.h"
@@ -177,6 +178,29 @@ cudaError_t allele_groups(const uint8_t *reads, const int64_t *offsets, int64_t 
     k_gather_i32<<<grid, 128, 0, s>>>(rep, sgid, starts, m);
     *d_rep_sorted = starts; *d_count_sorted = scounts; *d_nruns = nruns; *d_err = err;
     return cudaGetLastError();
+}
+
+
+// ---- stream compaction of the reads that go to the reverse-complement rescue (read order kept) ----
+struct FlagSet {
+    const uint8_t *flags;
+    int bit;
+    __device__ __forceinline__ bool operator()(const int32_t &i) const { return (flags[i] & bit) != 0; }
+};
+
+size_t select_scratch_bytes(int64_t n)
+{
+    size_t t = 0;
+    thrust::counting_iterator<int32_t> it(0);
+    cub::DeviceSelect::If(nullptr, t, it, (int32_t *)nullptr, (int *)nullptr, (int)n, FlagSet{nullptr, 0});
+    return t + 256;
+}
+
+cudaError_t select_flagged(const uint8_t *flags, int64_t n, int bit, int32_t *out_idx, int *d_count, void *tmp, size_t tmp_bytes,
+                           cudaStream_t s)
+{
+    thrust::counting_iterator<int32_t> it(0);
+    return cub::DeviceSelect::If(tmp, tmp_bytes, it, out_idx, d_count, (int)n, FlagSet{flags, bit}, s);
 }
 
 }  // namespace crgpu

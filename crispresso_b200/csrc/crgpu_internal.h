@@ -148,6 +148,9 @@ cudaError_t launch_scatter_order(const int64_t *offsets, const int32_t *subset, 
 cudaError_t launch_build_pairs(const void *segs, int nseg, int np, const int32_t *order, int32_t *pair_lo, int32_t *pair_hi,
                                int32_t *plen, int64_t *pc_off, int64_t total_pc, cudaStream_t s);
 size_t allele_scratch_bytes(int64_t m);
+size_t select_scratch_bytes(int64_t n);
+cudaError_t select_flagged(const uint8_t *flags, int64_t n, int bit, int32_t *out_idx, int *d_count, void *tmp, size_t tmp_bytes,
+                           cudaStream_t s);
 cudaError_t allele_groups(const uint8_t *reads, const int64_t *offsets, int64_t n, const uint8_t *kept, const int32_t *rc_read,
                           int64_t nrc, const uint32_t *ops_fw, const uint32_t *ops_rc, int64_t ops_stride,
                           const crgpu_aln_rec *aln_fw, const crgpu_aln_rec *aln_rc, const crgpu_read_rec *rec_fw,

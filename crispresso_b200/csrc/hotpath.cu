@@ -271,12 +271,24 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
     CK(launch_prepare_rows(d_aln, d_aln_hdr, n, path->min_identity_score, d_tref, d_trep, d_aln_off, d_alnlen, d_unmod, d_kept, s));
     span_end(ctx);
 
+    // reads with score_ref < min_identity, in read order: compacted on the device (cub::DeviceSelect),
+    // only their count and indices visit the host
     std::vector<int32_t> rc_read;
     if (path->rc_rescue) {
-        std::vector<uint8_t> h_flags((size_t)n);
-        CK(cudaMemcpyAsync(h_flags.data(), d_kept, (size_t)n, cudaMemcpyDeviceToHost, s));
+        const size_t sb = select_scratch_bytes(n);
+        CK(ctx->aux[3].reserve((size_t)n * 4 + 16));
+        CK(ctx->alleles.reserve(sb));
+        int32_t *d_sel = ctx->aux[3].as<int32_t>();
+        int *d_cnt = reinterpret_cast<int *>(d_sel + n);
+        CK(select_flagged(d_kept, n, 4, d_sel, d_cnt, ctx->alleles.p, sb, s));
+        int h_cnt = 0;
+        CK(cudaMemcpyAsync(&h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        for (int64_t i = 0; i < n; ++i) if (h_flags[(size_t)i] & 4) rc_read.push_back((int32_t)i);
+        if (h_cnt > 0) {
+            rc_read.resize((size_t)h_cnt);
+            CK(cudaMemcpyAsync(rc_read.data(), d_sel, (size_t)h_cnt * 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+        }
     }
     const int64_t nrc = (int64_t)rc_read.size();
     out->rc_n = nrc;
@@ -318,9 +330,8 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
         // out_index: read -> compact RC row
         std::vector<int32_t> out_index((size_t)n, -1);
         for (int64_t j = 0; j < nrc; ++j) out_index[(size_t)rc_read[(size_t)j]] = (int32_t)j;
-        CK(ctx->aux[2].reserve((size_t)n * 4)); CK(ctx->aux[3].reserve((size_t)nrc * 4));
+        CK(ctx->aux[2].reserve((size_t)n * 4));          // aux[3] already holds rc_read (device compaction above)
         CK(cudaMemcpyAsync(ctx->aux[2].p, out_index.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->aux[3].p, rc_read.data(), (size_t)nrc * 4, cudaMemcpyHostToDevice, s));
         CK(cudaStreamSynchronize(s));
         const size_t rb = (size_t)nrc * slot;
         if (!host && out->rc_aln) d_rc_aln = out->rc_aln;
