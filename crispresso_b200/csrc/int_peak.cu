@@ -4,6 +4,7 @@
 // one lane.  `cuobjdump -sass` of this file must show the unrolled body made of exactly the
 // named instruction (checked in profiles/r01_sass_notes.md).
 #include "crgpu_common.cuh"
+#include <cuda_fp16.h>
 
 namespace crgpu {
 
@@ -36,6 +37,11 @@ __global__ void __launch_bounds__(1024) k_int_peak(int iters, unsigned *sink, un
                 else if (WHICH == 5) a[j] = __vimax3_s16x2(a[j], o, c);                                             // VIMNMX3.S16x2
                 else if (WHICH == 6) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[j]) : "r"(o), "r"(c)); // LOP3
                 else if (WHICH == 7) a[j] = __vminu2(a[j] - o, 0x00010001u) + c;                                    // sub + VIMNMX imm + add
+                else if (WHICH == 8) a[j] = __hne2_mask(*reinterpret_cast<__half2 *>(&a[j]), *reinterpret_cast<const __half2 *>(&o)) ^ c;   // HSET2.NE + LOP3
+                else if (WHICH == 9) {                                                                              // HSET2.NE only (result kept live through a xor chain every 8th)
+                    const unsigned m_ = __hne2_mask(*reinterpret_cast<__half2 *>(&a[j]), *reinterpret_cast<const __half2 *>(&o));
+                    a[j] = m_;
+                }
             }
         }
     }
@@ -58,9 +64,11 @@ cudaError_t launch_int_peak(int which, int num_sms, int iters, unsigned *sink, c
     case 5: k_int_peak<5><<<grid, block, 0, s>>>(iters, sink, b, c); break;
     case 6: k_int_peak<6><<<grid, block, 0, s>>>(iters, sink, b, c); break;
     case 7: k_int_peak<7><<<grid, block, 0, s>>>(iters, sink, b, c); break;
+    case 8: k_int_peak<8><<<grid, block, 0, s>>>(iters, sink, b, c); break;
+    case 9: k_int_peak<9><<<grid, block, 0, s>>>(iters, sink, b, c); break;
     default: return cudaErrorInvalidValue;
     }
-    *lane_ops = (double)grid * block * (double)iters * PEAK_UNROLL * PEAK_CHAINS * (which == 7 ? 3.0 : 1.0);
+    *lane_ops = (double)grid * block * (double)iters * PEAK_UNROLL * PEAK_CHAINS * (which == 7 ? 3.0 : (which == 8 ? 2.0 : 1.0));
     return cudaGetLastError();
 }
 
