@@ -17,6 +17,14 @@ def pack_reads(reads):
     return buf, offsets
 
 
+def needle_id(fastq_header):
+    """The ID parse_needle_output ends up with for a FASTQ header line (without the leading '@'):
+    awk keeps the '@', sed turns every ':' into '_' (CORE:1796-1797), needle names the sequence after
+    the first whitespace-delimited token, and the parser turns every '_' back into ':' (CORE:1725) --
+    so underscores of the original name come back as colons too (lossy, as in the reference)."""
+    return ("@" + fastq_header.split()[0]).replace("_", ":")
+
+
 def parse_needle_options(options):
     """Pull -gapopen / -gapextend out of --needle_options_string (CORE:4226-4231).  Options the
     GPU aligner cannot honour are refused loudly instead of being ignored."""

@@ -392,6 +392,8 @@ def build_dataframe(res, read_names, has_hdr=False, amplicon=None):
             ids = [names[res.rc_read[j]] + "_RC" for j in sel]
             df_rc = frame(ids, res.rc_aln[sel], None, res.rc_recs[sel], rr[0], rr[1], rr[2], True)
             df = pd.concat([df, df_rc])
+    if df.shape[0] != df.index.unique().shape[0]:                      # CORE:2002-2010
+        raise ValueError("The .fastq file/s contain/s duplicate sequence IDs (DuplicateSequenceIdException)")
     return df
 
 

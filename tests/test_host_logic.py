@@ -40,6 +40,11 @@ def test_cut_points_and_exons():
     assert set(np.nonzero(splice)[0]) == {10, 11, 188, 189}
 
 
+def test_needle_ids_follow_the_sed_and_parser_round_trip():
+    assert aligner.needle_id("M06879:15:000000000-DFF22:1:1101:25894:23776 1:N:0:1") == "@M06879:15:000000000-DFF22:1:1101:25894:23776"
+    assert aligner.needle_id("read_7_x extra") == "@read:7:x"          # underscores come back as colons (CORE:1725)
+
+
 def test_needle_option_parsing():
     assert aligner.parse_needle_options("-gapopen=10 -gapextend=0.5  -awidth3=5000") == (10.0, 0.5)
     assert aligner.parse_needle_options("-gapextend=2 -gapopen=12") == (12.0, 2.0)
