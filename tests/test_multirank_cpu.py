@@ -41,16 +41,13 @@ def _worker(rank, world, port, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     amp, guide, cut, hdr = synth.make_case(21, 120)
     buf, off = synth.make_reads(amp, hdr, cut, 400, seed=21)
-    n = len(off) - 1
-    lo, hi = rank * n // world, (rank + 1) * n // world            # contiguous, equal-count shards
+    from crispresso_b200 import distributed
+    sbuf, soff = distributed.shard_reads(buf, off, rank, world)     # contiguous, equal-count shards
     inc = hotpath.include_mask(120, hotpath.cut_points_from_guides(amp, guide), 1, 15, 15)
-    res = quantify.hot_path(amp, (buf[off[lo]:off[hi]].copy(), (off[lo:hi + 1] - off[lo]).copy()), hdr_amplicon=hdr,
+    res = quantify.hot_path(amp, (sbuf.copy(), soff.copy()), hdr_amplicon=hdr,
                             opts=quantify.Opts(expected_hdr_amplicon_seq=hdr, coding_seq=amp[40:80]),
                             include=np.nonzero(inc)[0], exon=range(40, 80), splice=[38, 39, 80, 81], nthreads=1)
-    red = _to_reductions(res, 120)
-    t = torch.from_numpy(red.flat())
-    dist.all_reduce(t)
-    red.load_flat(t.numpy())
+    red = distributed.allreduce_reductions(_to_reductions(res, 120))
     if rank == 0:
         np.save(out, red.flat())
     dist.destroy_process_group()
