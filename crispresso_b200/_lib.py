@@ -44,7 +44,7 @@ class PathOut(ctypes.Structure):
                 ("hist_len", ctypes.c_int32), ("hist_zero", ctypes.c_int32), ("counters", ctypes.c_void_p),
                 ("class_counts", ctypes.c_int64 * 4), ("n_total", ctypes.c_int64), ("n_cells", ctypes.c_int64),
                 ("allele_cap", ctypes.c_int64), ("allele_n", ctypes.c_int64), ("allele_row", ctypes.c_void_p),
-                ("allele_count", ctypes.c_void_p)]
+                ("allele_count", ctypes.c_void_p), ("n_cells_computed", ctypes.c_int64)]
 
 
 class CrgpuError(RuntimeError):
@@ -75,6 +75,7 @@ def load():
     lib.crgpu_set_traceback_budget.argtypes = [vp, ctypes.c_size_t]
     lib.crgpu_last_timing.argtypes = [vp, vp, vp]
     lib.crgpu_set_overlap.argtypes = [vp, i32]
+    lib.crgpu_set_share_prefix.argtypes = [vp, i32]
     lib.crgpu_sync.argtypes = [vp]
     lib.crgpu_stream.argtypes = [vp]
     lib.crgpu_stream.restype = vp
@@ -85,7 +86,7 @@ def load():
     lib.crgpu_align_quantify.argtypes = [vp, i32, ctypes.c_char_p, i32, ctypes.POINTER(PathParams),
                                          ctypes.POINTER(QuantParams), vp, vp, i64, ctypes.POINTER(PathOut)]
     lib.crgpu_int_peak.argtypes = [vp, i32, ctypes.POINTER(dbl)]
-    for name in ("crgpu_create", "crgpu_set_overlap", "crgpu_set_traceback_budget", "crgpu_last_timing", "crgpu_sync", "crgpu_qualfilter",
+    for name in ("crgpu_create", "crgpu_set_overlap", "crgpu_set_share_prefix", "crgpu_set_traceback_budget", "crgpu_last_timing", "crgpu_sync", "crgpu_qualfilter",
                  "crgpu_align", "crgpu_quantify", "crgpu_align_quantify", "crgpu_int_peak"):
         getattr(lib, name).restype = i32
     _lib = lib
@@ -139,6 +140,9 @@ class Context:
 
     def set_overlap(self, on):
         self.check(self.lib.crgpu_set_overlap(self.handle, 1 if on else 0))
+
+    def set_share_prefix(self, on):
+        self.check(self.lib.crgpu_set_share_prefix(self.handle, 1 if on else 0))
 
     def last_timing(self):
         ms = (ctypes.c_float * 6)()

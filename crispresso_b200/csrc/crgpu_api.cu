@@ -44,7 +44,8 @@ void crgpu_destroy(crgpu_ctx *c)
     cudaStreamSynchronize(c->stream2);
     cudaStreamSynchronize(c->stream3);
     DBuf *all[] = {&c->reads, &c->offsets, &c->amp, &c->prof, &c->pc, &c->pc_off, &c->plen, &c->pair_lo, &c->pair_hi,
-                   &c->order, &c->plan_hist, &c->plan_tab, &c->tb2, &c->lastrow2, &c->lastcol2, &c->tb, &c->lastrow, &c->lastcol, &c->errflag, &c->recs, &c->sref, &c->smark, &c->sqry, &c->ops, &c->ops_rc, &c->alleles};
+                   &c->order, &c->plan_hist, &c->plan_tab, &c->tb2, &c->lastrow2, &c->lastcol2, &c->tb, &c->lastrow, &c->lastcol, &c->errflag, &c->recs, &c->sref, &c->smark, &c->sqry, &c->ops, &c->ops_rc, &c->alleles, &c->prof_h, &c->amp_h, &c->tbh, &c->tbh2,
+                   &c->top, &c->top2, &c->lastrow_h, &c->lastrow_h2, &c->lastcol_h, &c->lastcol_h2};
     for (DBuf *b : all) b->release();
     for (auto &b : c->q_in) b.release();
     for (auto &b : c->q_out) b.release();
@@ -71,6 +72,13 @@ int crgpu_set_overlap(crgpu_ctx *c, int on)
 {
     if (!c) return CRGPU_E_ARG;
     c->overlap = on != 0;
+    return CRGPU_OK;
+}
+
+int crgpu_set_share_prefix(crgpu_ctx *c, int on)
+{
+    if (!c) return CRGPU_E_ARG;
+    c->share_prefix = on != 0;
     return CRGPU_OK;
 }
 
@@ -365,6 +373,7 @@ int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_read
         fa.lastcol = (cur ? ctx->lastcol2 : ctx->lastcol).as<uint32_t>();
         fa.p0 = batch_start[b]; fa.p1 = batch_start[b + 1];
         fa.open = open_s; fa.ext = ext_s; fa.La = La; fa.one = 1;
+        fa.top_out = nullptr; fa.top_out_lane = -1; fa.top_in = nullptr;
         if (used[cur]) CK(cudaStreamWaitEvent(sf[cur], ctx->walk_done[cur], 0));     // scratch `cur` is free again
         span_begin(ctx, T_FILL, sf[cur]);
         CK(launch_fill(G, K, fa, ctx->num_sms, sf[cur]));
@@ -373,6 +382,7 @@ int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_read
 
         WalkArgs wa;
         wa.tb = fa.tb; wa.lastrow = fa.lastrow; wa.lastcol = fa.lastcol;
+        wa.tb_upper = nullptr; wa.lastcol_upper = nullptr; wa.G_upper = 0; wa.split_row = 0;
         wa.pc_off = fa.pc_off; wa.plen = fa.plen;
         wa.pair_lo = ctx->pair_lo.as<int32_t>(); wa.pair_hi = ctx->pair_hi.as<int32_t>();
         wa.reads = d_reads; wa.offsets = d_offsets; wa.amplicon = ctx->amp.as<uint8_t>();
@@ -390,6 +400,181 @@ int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_read
     // everything queued later on the main stream (next pass, quantification, copies) sees the walks' results
     for (int i = 0; i < 2; ++i) if (used[i]) CK(cudaStreamWaitEvent(s, ctx->walk_done[i], 0));
     (void)plan_pc_off;
+    return CRGPU_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// run_plan_dual: the amplicon pass and the HDR-amplicon pass of CORE:1791-1828 in one sweep.
+// DP row y depends only on amplicon rows <= y, so all rows above the first base where the two
+// amplicons differ are IDENTICAL in both matrices (values, flags, last-column summaries).  The
+// amplicon pass runs the full tile (G lanes) and saves what lane t0-1 hands down; the HDR pass runs
+// only the bottom Gh = G - t0 lanes (a compiled tile: Gh in {4,8,16,32}) with that saved row as its
+// top boundary, and its traceback walks into the amplicon pass's flags above the split.  Results are
+// bit-identical to two full passes (tests/test_gpu_hotpath.py, scripts/gpu_fuzz_hotpath.py).
+// ---------------------------------------------------------------------------------------------
+int run_plan_dual(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon, int La, const uint8_t *d_reads,
+                  const int64_t *d_offsets, double gapopen, double gapextend, crgpu_aln_rec *d_recs, crgpu_aln_rec *d_recs_hdr,
+                  uint8_t *d_ref, uint8_t *d_mark, uint8_t *d_qry, int64_t slot, int64_t *n_cells, int64_t *n_cells_computed,
+                  uint32_t *d_ops, int64_t ops_stride, bool *done)
+{
+    *done = false;
+    const PairPlan &pl = ctx->plan;
+    if (!ctx->share_prefix || getenv("CRGPU_NO_SHARE") || pl.np == 0) return CRGPU_OK;
+    if (La < CRGPU_MIN_LEN || La > CRGPU_MAX_AMPLICON) return CRGPU_OK;      // let run_plan report it
+    int scale, open_s, ext_s;
+    if (!scale_penalties(gapopen, gapextend, &scale, &open_s, &ext_s) || gapopen < 4.0 || gapextend < 0.0 || gapextend > gapopen)
+        return CRGPU_OK;
+    std::vector<int> acode(La), hcode(La);
+    std::string amp_up(La, 'N'), hdr_up(La, 'N');
+    int d = La;                                                            // first differing base
+    for (int i = 0; i < La; ++i) {
+        acode[i] = host_code(amplicon[i]); hcode[i] = host_code(hdr_amplicon[i]);
+        if (acode[i] < 0 || hcode[i] < 0) return CRGPU_OK;
+        amp_up[i] = amplicon[i]; hdr_up[i] = hdr_amplicon[i];
+        if (d == La && acode[i] != hcode[i]) d = i;
+    }
+    int G, K;
+    if (!choose_tile(La, &G, &K)) return CRGPU_OK;
+    const int GK = G * K, P = GK - La;
+    // smallest compiled lane count Gh < G whose rows all lie at or below the first difference
+    int Gh = 0;
+    for (int g = 4; g < G; g *= 2)
+        if (tile_available(g, K) && (G - g) * K - P <= d) { Gh = g; break; }
+    if (Gh == 0) return CRGPU_OK;
+    const int t0 = G - Gh, split = t0 * K, GKh = Gh * K;
+    const int maxlen = pl.maxlen;
+    if ((int64_t)scale * 5 * std::min(La, maxlen) + 64 >= MAX_ABS_SCORE ||
+        (int64_t)2 * open_s + (int64_t)ext_s * (La + maxlen) + 8 * scale + 64 >= MAX_ABS_SCORE)
+        return CRGPU_OK;
+    if (slot < (int64_t)La + maxlen && d_ref) return CRGPU_OK;
+    if (n_cells) *n_cells += 2 * (int64_t)La * pl.sum_len;
+    if (n_cells_computed) *n_cells_computed += ((int64_t)La + (int64_t)(La - (split - P))) * pl.sum_len;
+
+    // ---- batches: a pair needs Lb * (GK + GKh) / 2 traceback words ----
+    std::vector<int> batch_start(1, 0);
+    int64_t max_cols = 0;
+    int max_bp = 0;
+    {
+        const int64_t words_per_col = (GK + GKh) / 2;
+        const int64_t budget_words = (int64_t)(ctx->tb_budget / 4);
+        int64_t acc = 0, acc_cols = 0;
+        int p_begin = 0;
+        auto close = [&](int p_end) {
+            max_cols = std::max(max_cols, acc_cols);
+            max_bp = std::max(max_bp, p_end - p_begin);
+            batch_start.push_back(p_end);
+            p_begin = p_end; acc = 0; acc_cols = 0;
+        };
+        for (const HostSeg &sg : pl.segs) {
+            const int64_t w = (int64_t)sg.len * words_per_col;
+            int64_t left = ((int64_t)sg.cnt + 1) / 2;
+            int64_t p = sg.pair_start;
+            while (left > 0) {
+                int64_t fit = (budget_words - acc) / w;
+                if (fit <= 0) {
+                    if (acc > 0) { close((int)p); continue; }
+                    fit = 1;
+                }
+                const int64_t take = std::min(fit, left);
+                acc += take * w; acc_cols += take * sg.len; p += take; left -= take;
+                if (left > 0) close((int)p);
+            }
+        }
+        if (acc > 0) close(pl.np);
+    }
+
+    // ---- profiles: full frame for the amplicon, bottom Gh lanes for the HDR amplicon ----
+    auto build_prof = [&](const std::vector<int> &code, int g, int row0, std::vector<int32_t> &prof) {
+        const int PS = prof_stride(g, K), SS = strip_stride(K);
+        prof.assign((size_t)NPAIR * PS, 0);
+        for (int cp = 0; cp < NPAIR; ++cp) {
+            const int lo = cp % NCODE, hi = cp / NCODE;
+            for (int r = std::max(P, row0); r < GK; ++r) {
+                const int a = code[r - P];
+                const int32_t slo = scale * host_ednafull(a, lo), shi = scale * host_ednafull(a, hi);
+                const int rr = r - row0;
+                prof[(size_t)cp * PS + (rr / K) * SS + (rr % K)] = shi * 65536 + slo;
+            }
+        }
+    };
+    std::vector<int32_t> prof_a, prof_h;
+    build_prof(acode, G, 0, prof_a);
+    build_prof(hcode, Gh, split, prof_h);
+    cudaStream_t s = ctx->stream;
+    const bool two = batch_start.size() > 2 && ctx->overlap && !getenv("CRGPU_NO_OVERLAP");
+    CK(ctx->amp.reserve((size_t)La)); CK(ctx->amp_h.reserve((size_t)La));
+    CK(ctx->prof.reserve(prof_a.size() * 4)); CK(ctx->prof_h.reserve(prof_h.size() * 4));
+    DBuf *tbA[2] = {&ctx->tb, &ctx->tb2}, *tbH[2] = {&ctx->tbh, &ctx->tbh2}, *top[2] = {&ctx->top, &ctx->top2};
+    DBuf *lrA[2] = {&ctx->lastrow, &ctx->lastrow2}, *lcA[2] = {&ctx->lastcol, &ctx->lastcol2};
+    DBuf *lrH[2] = {&ctx->lastrow_h, &ctx->lastrow_h2}, *lcH[2] = {&ctx->lastcol_h, &ctx->lastcol_h2};
+    for (int i = 0; i < (two ? 2 : 1); ++i) {
+        CK(tbA[i]->reserve((size_t)max_cols * (GK / 2) * 4));
+        CK(tbH[i]->reserve((size_t)max_cols * (GKh / 2) * 4));
+        CK(top[i]->reserve((size_t)max_cols * 12));
+        CK(lrA[i]->reserve((size_t)max_bp * 12)); CK(lcA[i]->reserve((size_t)max_bp * G * 12));
+        CK(lrH[i]->reserve((size_t)max_bp * 12)); CK(lcH[i]->reserve((size_t)max_bp * Gh * 12));
+    }
+    CK(cudaMemcpyAsync(ctx->amp.p, amp_up.data(), (size_t)La, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->amp_h.p, hdr_up.data(), (size_t)La, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->prof.p, prof_a.data(), prof_a.size() * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->prof_h.p, prof_h.data(), prof_h.size() * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));      // the staging vectors are locals of this frame
+
+    cudaStream_t s2 = two ? ctx->stream2 : ctx->stream;
+    cudaStream_t sf[2] = {s, two ? ctx->stream3 : s};
+    if (two) {
+        CK(cudaEventRecord(ctx->ready, s));
+        CK(cudaStreamWaitEvent(sf[1], ctx->ready, 0));
+    }
+    bool used[2] = {false, false};
+    for (size_t b = 0; b + 1 < batch_start.size(); ++b) {
+        const int cur = two ? (int)(b & 1) : 0;
+        FillArgs fa;
+        fa.prof = ctx->prof.as<int32_t>();
+        fa.pc = ctx->pc.as<uint8_t>(); fa.pc_off = ctx->pc_off.as<int64_t>(); fa.plen = ctx->plen.as<int32_t>();
+        fa.tb = tbA[cur]->as<uint32_t>(); fa.lastrow = lrA[cur]->as<uint32_t>(); fa.lastcol = lcA[cur]->as<uint32_t>();
+        fa.p0 = batch_start[b]; fa.p1 = batch_start[b + 1];
+        fa.open = open_s; fa.ext = ext_s; fa.La = La; fa.one = 1;
+        fa.top_out = top[cur]->as<uint32_t>(); fa.top_out_lane = t0 - 1; fa.top_in = nullptr;
+        FillArgs fh = fa;                                               // HDR pass: bottom Gh lanes
+        fh.prof = ctx->prof_h.as<int32_t>();
+        fh.tb = tbH[cur]->as<uint32_t>(); fh.lastrow = lrH[cur]->as<uint32_t>(); fh.lastcol = lcH[cur]->as<uint32_t>();
+        fh.La = GKh;                                                    // no padding rows inside the sub-tile
+        fh.top_out = nullptr; fh.top_out_lane = -1; fh.top_in = top[cur]->as<uint32_t>();
+        if (used[cur]) CK(cudaStreamWaitEvent(sf[cur], ctx->walk_done[cur], 0));
+        span_begin(ctx, T_FILL, sf[cur]);
+        CK(launch_fill(G, K, fa, ctx->num_sms, sf[cur]));
+        CK(launch_fill(Gh, K, fh, ctx->num_sms, sf[cur]));
+        span_end(ctx, 2);
+        CK(cudaEventRecord(ctx->fill_done[cur], sf[cur]));
+
+        WalkArgs wa;
+        wa.tb = fa.tb; wa.lastrow = fa.lastrow; wa.lastcol = fa.lastcol;
+        wa.tb_upper = nullptr; wa.lastcol_upper = nullptr; wa.G_upper = 0; wa.split_row = 0;
+        wa.pc_off = fa.pc_off; wa.plen = fa.plen;
+        wa.pair_lo = ctx->pair_lo.as<int32_t>(); wa.pair_hi = ctx->pair_hi.as<int32_t>();
+        wa.reads = d_reads; wa.offsets = d_offsets; wa.amplicon = ctx->amp.as<uint8_t>();
+        wa.La = La; wa.GK = GK; wa.P = P; wa.G = G; wa.K = K; wa.p0 = fa.p0; wa.p1 = fa.p1;
+        wa.open = open_s; wa.ext = ext_s; wa.scale = scale;
+        wa.recs = d_recs; wa.ref_out = d_ref; wa.mark_out = d_mark; wa.qry_out = d_qry; wa.slot = slot;
+        wa.out_index = nullptr; wa.rc_out = 0; wa.ops_out = d_ops; wa.ops_stride = ops_stride;
+        WalkArgs wh = wa;                                               // HDR alignment: identity only
+        wh.tb = fh.tb; wh.lastrow = fh.lastrow; wh.lastcol = fh.lastcol;
+        wh.tb_upper = fa.tb; wh.lastcol_upper = fa.lastcol; wh.G_upper = G; wh.split_row = split;
+        wh.amplicon = ctx->amp_h.as<uint8_t>();
+        wh.GK = GKh; wh.G = Gh;
+        wh.recs = d_recs_hdr; wh.ref_out = wh.mark_out = wh.qry_out = nullptr; wh.ops_out = nullptr;
+        CK(cudaStreamWaitEvent(s2, ctx->fill_done[cur], 0));
+        span_begin(ctx, T_WALK, s2);
+        CK(launch_walk(wa, s2));
+        CK(launch_walk(wh, s2));
+        span_end(ctx, 2);
+        CK(cudaEventRecord(ctx->walk_done[cur], s2));
+        used[cur] = true;
+    }
+    for (int i = 0; i < 2; ++i) if (used[i]) CK(cudaStreamWaitEvent(s, ctx->walk_done[i], 0));
+    *done = true;
     return CRGPU_OK;
 }
 

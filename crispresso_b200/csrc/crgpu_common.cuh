@@ -46,10 +46,21 @@ struct FillArgs {
     int p0, p1;               // pair range of this batch
     int open, ext;            // gap open / extend, scaled (positive)
     int one;                  // always 1 (an opaque multiplier, see fma_add in gotoh_fill.cu)
+    // Shared DP prefix between the amplicon pass and the HDR-amplicon pass (crgpu_api.cu run_plan_dual):
+    // the amplicon pass saves what lane `top_out_lane` hands down ((max3, iy, m) of its bottom row) for
+    // every column; the HDR pass starts below that row and takes those values as its top boundary.
+    uint32_t *top_out;        // [(pc_off[p]-pc_off[p0]) + x][3] or null
+    int top_out_lane;
+    const uint32_t *top_in;   // same layout, or null (free end-gap boundary)
 };
 
 struct WalkArgs {
     const uint32_t *tb;
+    // optional upper part: padded rows below `split_row` were computed by another pass with tile
+    // (G_upper, K) -- the shared DP prefix of the HDR pass -- and are read from there
+    const uint32_t *tb_upper;
+    const uint32_t *lastcol_upper;
+    int G_upper, split_row;
     const uint32_t *lastrow;
     const uint32_t *lastcol;
     const int64_t *pc_off;

@@ -62,6 +62,8 @@ struct crgpu_ctx {
     DBuf reads, offsets, amp, prof, pc, pc_off, plen, pair_lo, pair_hi, order, plan_hist, plan_tab, tb, lastrow, lastcol, tb2, lastrow2, lastcol2, errflag;
     PairPlan plan;
     DBuf recs, sref, smark, sqry, ops, ops_rc, alleles;
+    DBuf prof_h, amp_h, tbh, tbh2, top, top2, lastrow_h, lastrow_h2, lastcol_h, lastcol_h2;   // HDR pass of run_plan_dual
+    bool share_prefix = true;
     DBuf q_in[8], q_out[4];
     DBuf aux[8];
     // timing
@@ -134,6 +136,7 @@ inline void timing_collect(crgpu_ctx *c)
 
 namespace crgpu {
 bool choose_tile(int La, int *G, int *K);
+bool tile_available(int G, int K);
 cudaError_t launch_fill(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream);
 cudaError_t launch_encode(const uint8_t *reads, const int64_t *offsets, const int32_t *pair_lo, const int32_t *pair_hi,
                           const int64_t *pc_off, int npairs, uint8_t *pc, int *err, int num_sms, cudaStream_t s);
@@ -162,4 +165,11 @@ int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_read
              const int32_t *d_out_index, int rc_out, double gapopen, double gapextend, crgpu_aln_rec *d_recs,
              uint8_t *d_ref, uint8_t *d_mark, uint8_t *d_qry, int64_t slot, int64_t *n_cells,
              uint32_t *d_ops = nullptr, int64_t ops_stride = 0);
+// amplicon + HDR amplicon in one sweep over the batches; the HDR pass reuses the DP rows it shares with
+// the amplicon pass.  Returns CRGPU_OK and *done = false when the two amplicons cannot share a prefix
+// (the caller then runs two plain passes).
+int run_plan_dual(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon, int La, const uint8_t *d_reads,
+                  const int64_t *d_offsets, double gapopen, double gapextend, crgpu_aln_rec *d_recs, crgpu_aln_rec *d_recs_hdr,
+                  uint8_t *d_ref, uint8_t *d_mark, uint8_t *d_qry, int64_t slot, int64_t *n_cells, int64_t *n_cells_computed,
+                  uint32_t *d_ops, int64_t ops_stride, bool *done);
 }  // namespace crgpu

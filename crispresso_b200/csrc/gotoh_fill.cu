@@ -234,13 +234,19 @@ __global__ void __maxnreg__(fill_maxnreg<K>()) k_gotoh_fill(const FillArgs a)
         uint32_t rowBest = 0, colBest = 0;                               // stored scores are > 0: 0 is -infinity
         int rowPosLo = 0, rowPosHi = 0, colPosLo = 0, colPosHi = 0;
         int cp_next = (t == 0 && Lb > 0) ? pcp[0] : 0;
+        // top boundary from the pass that owns the rows above (shared DP prefix), read one column ahead
+        const uint32_t *tin = a.top_in ? a.top_in + (pco - a.pc_off[a.p0]) * 3 : nullptr;
+        uint32_t *tout = (a.top_out && t == a.top_out_lane) ? a.top_out + (pco - a.pc_off[a.p0]) * 3 : nullptr;
+        uint32_t tn0 = Z, tn1 = NOPEN_ST, tn2 = Z;
+        if (tin && t == 0 && Lb > 0) { tn0 = tin[0]; tn1 = tin[1]; tn2 = tin[2]; }
 
         for (int s = 0; s < steps; ++s) {
             const int x = s - t;
             uint32_t rH3 = __shfl_up_sync(0xffffffffu, botH3, 1, G);
             uint32_t rIY = __shfl_up_sync(0xffffffffu, botIY, 1, G);
             uint32_t rM = __shfl_up_sync(0xffffffffu, botM, 1, G);
-            if (t == 0) { rH3 = Z; rIY = NOPEN_ST; rM = Z; }          // free boundary above the padded top
+            if (t == 0) { rH3 = tn0; rIY = tn1; rM = tn2; }           // free boundary above the padded top, or the saved row
+            if (tin && t == 0 && x + 1 >= 0 && x + 1 < Lb) { tn0 = tin[3 * (x + 1)]; tn1 = tin[3 * (x + 1) + 1]; tn2 = tin[3 * (x + 1) + 2]; }
             const bool active = (x >= 0) && (x < Lb);
             const bool firstCol = active && x == 0, lastCol = active && x == Lb - 1;
             const bool edge = __any_sync(0xffffffffu, firstCol || lastCol);   // warp-uniform
@@ -267,6 +273,7 @@ __global__ void __maxnreg__(fill_maxnreg<K>()) k_gotoh_fill(const FillArgs a)
                     if (d >> 16) rowPosHi = x;
                     rowBest = nb;
                 }
+                if (tout) { tout[3 * x] = botH3; tout[3 * x + 1] = botIY; tout[3 * x + 2] = botM; }
                 if (lastCol) {
                     lcp[0] = colBest; lcp[1] = (uint32_t)colPosLo; lcp[2] = (uint32_t)colPosHi;
                     if (lastLane) { lrp[0] = rowBest; lrp[1] = (uint32_t)rowPosLo; lrp[2] = (uint32_t)rowPosHi; }
@@ -320,6 +327,15 @@ bool choose_tile(int La, int *G, int *K)
     if (best < 0) return false;
     *G = menu[best].G; *K = menu[best].K;
     return true;
+}
+
+// is there a compiled kernel for this tile?
+bool tile_available(int G, int K)
+{
+    static const Tile all[] = {{4, 16}, {4, 24}, {4, 32}, {4, 40}, {4, 48}, {8, 16}, {8, 24}, {8, 32}, {8, 40}, {8, 48},
+                               {16, 16}, {16, 24}, {16, 32}, {16, 40}, {16, 48}, {32, 24}, {32, 32}};
+    for (const Tile &t : all) if (t.G == G && t.K == K) return true;
+    return false;
 }
 
 cudaError_t launch_fill(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream)

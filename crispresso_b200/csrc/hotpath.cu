@@ -248,18 +248,30 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
     CK(ctx->ops.reserve((size_t)n * ops_stride * 4));
     uint32_t *d_ops = ctx->ops.as<uint32_t>();
 
-    // ---- 1. forward alignments ----
-    int64_t cells = 0;
-    rc = run_plan(ctx, amplicon, amplicon_len, d_reads, d_off, nullptr, 0, path->gapopen, path->gapextend, d_aln, d_ref, d_mark,
-                  d_qry, slot, &cells, d_ops, ops_stride);
-    if (rc) { cudaStreamSynchronize(s); return rc; }
+    // ---- 1. forward alignments: amplicon (+ HDR amplicon, CORE:1810-1828) ----
+    int64_t cells = 0, cells_computed = 0;
     crgpu_aln_rec *d_aln_hdr = nullptr;
+    bool dual_done = false;
     if (has_hdr) {
         CK(ctx->aux[1].reserve((size_t)n * sizeof(crgpu_aln_rec)));
         d_aln_hdr = ctx->aux[1].as<crgpu_aln_rec>();
-        rc = run_plan(ctx, path->hdr_amplicon, path->hdr_amplicon_len, d_reads, d_off, nullptr, 0, path->gapopen,
-                      path->gapextend, d_aln_hdr, nullptr, nullptr, nullptr, slot, &cells);
+        if (path->hdr_amplicon_len == amplicon_len) {
+            rc = run_plan_dual(ctx, amplicon, path->hdr_amplicon, amplicon_len, d_reads, d_off, path->gapopen, path->gapextend,
+                               d_aln, d_aln_hdr, d_ref, d_mark, d_qry, slot, &cells, &cells_computed, d_ops, ops_stride, &dual_done);
+            if (rc) { cudaStreamSynchronize(s); return rc; }
+        }
+    }
+    if (!dual_done) {
+        int64_t c0 = 0;
+        rc = run_plan(ctx, amplicon, amplicon_len, d_reads, d_off, nullptr, 0, path->gapopen, path->gapextend, d_aln, d_ref, d_mark,
+                      d_qry, slot, &c0, d_ops, ops_stride);
         if (rc) { cudaStreamSynchronize(s); return rc; }
+        if (has_hdr) {
+            rc = run_plan(ctx, path->hdr_amplicon, path->hdr_amplicon_len, d_reads, d_off, nullptr, 0, path->gapopen,
+                          path->gapextend, d_aln_hdr, nullptr, nullptr, nullptr, slot, &c0);
+            if (rc) { cudaStreamSynchronize(s); return rc; }
+        }
+        cells += c0; cells_computed += c0;
     }
 
     // ---- 2. keep / rescue decision ----
@@ -344,11 +356,13 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
             d_rc_ref = ctx->q_out[2].as<uint8_t>(); d_rc_mark = d_rc_ref + rb; d_rc_qry = d_rc_mark + rb;
         }
         CK(ctx->ops_rc.reserve((size_t)nrc * ops_stride * 4));
+        int64_t c_rc = 0;
         rc = build_plan(ctx, d_reads, d_off, ctx->aux[3].as<int32_t>(), nrc);
         if (rc == CRGPU_OK)
             rc = run_plan(ctx, amp_rc.data(), amplicon_len, d_reads, d_off, ctx->aux[2].as<int32_t>(), 1, path->gapopen,
-                          path->gapextend, d_rc_aln, d_rc_ref, d_rc_mark, d_rc_qry, slot, &cells, ctx->ops_rc.as<uint32_t>(),
+                          path->gapextend, d_rc_aln, d_rc_ref, d_rc_mark, d_rc_qry, slot, &c_rc, ctx->ops_rc.as<uint32_t>(),
                           ops_stride);
+        cells += c_rc; cells_computed += c_rc;
         if (rc) { cudaStreamSynchronize(s); return rc; }
         // per-row SoA for the quantifier (separate scratch: the forward views are still in use by the stream)
         CK(ctx->q_out[3].reserve((size_t)nrc * 14));
@@ -439,6 +453,7 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
                        &out->n_total);
     if (rc) return rc;
     out->n_cells += cells;
+    out->n_cells_computed += cells_computed;
     timing_collect(ctx);
     return CRGPU_OK;
 }

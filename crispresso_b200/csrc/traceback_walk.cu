@@ -98,10 +98,19 @@ __global__ void __launch_bounds__(128) k_traceback_walk(const WalkArgs a)
     // ---- start cell (App. A.4): the fill kernel already scanned the last amplicon row left to right
     //      and, per lane, the last read column top to bottom ((m, ix, iy) in that order, strict '>':
     //      the first maximum wins).  Combine: the column only wins with a strictly greater value.
+    // With a shared prefix (tb_upper) the padded rows below split_row belong to the other pass: their
+    // column summaries come from that pass's G_upper lanes; rows are numbered in the full padded frame.
     int best = half16(lr[0], h), s1 = La - 1, s2 = (int)lr[1 + h];
+    if (a.tb_upper) {
+        const uint32_t *lcu = a.lastcol_upper + (int64_t)(p - a.p0) * a.G_upper * 3;
+        for (int t = 0; t < a.split_row / a.K; ++t) {
+            const int v = half16(lcu[3 * t], h);
+            if (v > best) { best = v; s1 = t * a.K + (int)lcu[3 * t + 1 + h] - a.P; s2 = Lb - 1; }
+        }
+    }
     for (int t = 0; t < a.G; ++t) {
         const int v = half16(lc[3 * t], h);
-        if (v > best) { best = v; s1 = t * a.K + (int)lc[3 * t + 1 + h] - a.P; s2 = Lb - 1; }
+        if (v > best) { best = v; s1 = a.split_row + t * a.K + (int)lc[3 * t + 1 + h] - a.P; s2 = Lb - 1; }
     }
 
     const bool want = a.ref_out != nullptr;
@@ -131,6 +140,9 @@ __global__ void __launch_bounds__(128) k_traceback_walk(const WalkArgs a)
 
     const uint8_t *tb = reinterpret_cast<const uint8_t *>(a.tb + (a.pc_off[p] - a.pc_off[a.p0]) * (a.GK / 2));
     const int64_t colbytes = (int64_t)a.GK * 2;
+    const uint8_t *tbu = a.tb_upper ? reinterpret_cast<const uint8_t *>(a.tb_upper + (a.pc_off[p] - a.pc_off[a.p0]) * (a.G_upper * a.K / 2)) : nullptr;
+    const int64_t colbytes_u = (int64_t)a.G_upper * a.K * 2;
+    const int split = a.tb_upper ? a.split_row : 0;
     const int P = a.P;
     int y = s1, x = s2, prev = 0;
     bool contL = false, contD = false;
@@ -140,7 +152,8 @@ __global__ void __launch_bounds__(128) k_traceback_walk(const WalkArgs a)
     // a LEFT / DOWN step invalidates the window and refills it with PF independent loads.
     constexpr int PF = 8;
     uint8_t pf[PF];
-#define TB_AT(yy, xx) tb[(xx) * colbytes + ((((yy) + P) >> 1) << 2) + (h << 1) + (((yy) + P) & 1)]
+#define TB_AT(yy, xx) (((yy) + P) < split ? tbu[(xx) * colbytes_u + ((((yy) + P) >> 1) << 2) + (h << 1) + (((yy) + P) & 1)] \
+                                        : tb[(xx) * colbytes + ((((yy) + P - split) >> 1) << 2) + (h << 1) + (((yy) + P - split) & 1)])
 #define PF_LOAD(k) pf[k] = (y - (k) >= 0 && x - (k) >= 0) ? TB_AT(y - (k), x - (k)) : (uint8_t)0
 #pragma unroll
     for (int k = 0; k < PF; ++k) PF_LOAD(k);

@@ -129,12 +129,13 @@ class Reductions:
         self.counters = np.zeros(_lib.NUM_COUNTERS, np.int64)
         self.class_counts = np.zeros(4, np.int64)      # UNMODIFIED, NHEJ, HDR, MIXED
         self.n_total = 0
-        self.n_cells = 0
+        self.n_cells = 0             # La x Lb summed over every alignment made (the GCUPS numerator)
+        self.n_cells_computed = 0    # cells actually evaluated (less when the HDR pass shares a DP prefix)
 
     def flat(self):
         """One int64 vector (for the multi-GPU all-reduce)."""
         return np.concatenate([self.vectors.ravel(), self.hist_inframe, self.hist_frameshift, self.counters,
-                               self.class_counts, np.array([self.n_total, self.n_cells], np.int64)])
+                               self.class_counts, np.array([self.n_total, self.n_cells, self.n_cells_computed], np.int64)])
 
     def load_flat(self, v):
         v = np.asarray(v, dtype=np.int64)
@@ -144,7 +145,7 @@ class Reductions:
             k = int(np.prod(shape))
             setattr(self, name, v[o:o + k].reshape(shape).copy())
             o += k
-        self.n_total, self.n_cells = int(v[o]), int(v[o + 1])
+        self.n_total, self.n_cells, self.n_cells_computed = int(v[o]), int(v[o + 1]), int(v[o + 2])
 
     def vector(self, name):
         return self.vectors[VECTOR_NAMES.index(name)]
@@ -346,6 +347,7 @@ def run_hot_path(ctx, amplicon, reads, gapopen=10.0, gapextend=0.5, min_identity
     red.class_counts += np.array(list(po.class_counts), np.int64)
     red.n_total += int(po.n_total)
     red.n_cells += int(po.n_cells)
+    red.n_cells_computed += int(po.n_cells_computed)
     return res
 
 

@@ -63,6 +63,9 @@ int crgpu_set_traceback_budget(crgpu_ctx *ctx, size_t bytes);
 /* Traceback walks of batch b normally run on a second stream, overlapped with the fill of batch b+1
  * (default on).  Turning it off serialises the kernels, which is what per-kernel timing wants. */
 int crgpu_set_overlap(crgpu_ctx *ctx, int on);
+/* The HDR-amplicon pass normally reuses the DP rows it shares with the amplicon pass (bit-identical
+ * results, fewer cells evaluated; default on).  Off = two full passes. */
+int crgpu_set_share_prefix(crgpu_ctx *ctx, int on);
 /* Device time (ms, CUDA events on the context's stream) spent in each kernel family during
  * the LAST call on this context, and launch counts.  out_ms[0..5] = encode, fill, walk,
  * quantify, qualfilter, other;  out_launches likewise. */
@@ -219,6 +222,9 @@ typedef struct {
     int32_t *allele_row;                   /* [allele_cap] a representative row: read index i for a forward row,
                                               n + j for the RC row j */
     int64_t *allele_count;                 /* [allele_cap] #Reads */
+    int64_t n_cells_computed;              /* OUT (added): DP cells actually evaluated.  Less than n_cells when the HDR
+                                              pass reuses the DP rows it shares with the amplicon pass (same-length HDR
+                                              amplicon: all rows above the first differing base are identical) */
 } crgpu_path_out;
 
 int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int amplicon_len,

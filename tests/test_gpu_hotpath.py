@@ -106,3 +106,36 @@ def test_reductions_do_not_depend_on_sharding(ctx):
     hotpath.run_hot_path(ctx, amp, (buf[:off[h]].copy(), off[:h + 1].copy()), hdr_amplicon=hdr, flags=flags, inc=inc, red=red)
     hotpath.run_hot_path(ctx, amp, (buf[off[h]:].copy(), (off[h:] - off[h]).copy()), hdr_amplicon=hdr, flags=flags, inc=inc, red=red)
     assert np.array_equal(whole.flat(), red.flat())
+
+
+def test_shared_dp_prefix_of_the_hdr_pass_changes_nothing(ctx):
+    """Same-length HDR amplicon: the HDR pass reuses the DP rows above the first differing base.  Every
+    output must equal the two-full-passes result; only the number of evaluated cells drops."""
+    from crispresso_b200 import Context
+    for La, seed in ((250, 71), (300, 72), (500, 73), (120, 74)):
+        amp, guide, cut, hdr = synth.make_case(seed, La)
+        packed = synth.make_reads(amp, hdr, cut, 1500, seed=seed, rc_frac=0.05)
+        flags = hotpath.quant_flags(hdr)
+        other = Context(0)
+        try:
+            other.set_traceback_budget(32 << 20)
+            a = hotpath.run_hot_path(other, amp, packed, hdr_amplicon=hdr, flags=flags, want_rows=True)
+            other.set_share_prefix(False)
+            b = hotpath.run_hot_path(other, amp, packed, hdr_amplicon=hdr, flags=flags, want_rows=True)
+        finally:
+            other.close()
+        assert b.red.n_cells_computed == b.red.n_cells == a.red.n_cells
+        if La in (250, 500):
+            assert a.red.n_cells_computed < 0.8 * a.red.n_cells           # the edit sits mid-amplicon: ~half of the HDR rows are shared
+        a.red.n_cells_computed = b.red.n_cells_computed
+        assert np.array_equal(a.red.flat(), b.red.flat())
+        assert np.array_equal(a.aln, b.aln) and np.array_equal(a.recs, b.recs) and np.array_equal(a.kept, b.kept)
+        assert np.array_equal(a.tenths_rep, b.tenths_rep)
+        for k in range(3):
+            assert np.array_equal(a.rows[k], b.rows[k])
+    # an HDR amplicon that differs in the first bases shares nothing and silently takes two full passes
+    amp, guide, cut, _ = synth.make_case(75, 200, hdr=False)
+    hdr2 = "T" + amp[1:] if amp[0] != "T" else "G" + amp[1:]
+    packed = synth.make_reads(amp, hdr2, cut, 500, seed=75)
+    r = hotpath.run_hot_path(ctx, amp, packed, hdr_amplicon=hdr2, flags=hotpath.quant_flags(hdr2))
+    assert r.red.n_cells_computed == r.red.n_cells
