@@ -47,6 +47,18 @@ class PathOut(ctypes.Structure):
                 ("allele_count", ctypes.c_void_p), ("n_cells_computed", ctypes.c_int64)]
 
 
+class MergeParams(ctypes.Structure):
+    _fields_ = [("min_overlap", ctypes.c_int32), ("max_overlap", ctypes.c_int32),
+                ("max_mismatch_density", ctypes.c_float), ("allow_outies", ctypes.c_int32)]
+
+
+class MergeOut(ctypes.Structure):
+    _fields_ = [("pos", ctypes.c_void_p), ("kind", ctypes.c_void_p), ("cap_bytes", ctypes.c_int64),
+                ("cap_reads", ctypes.c_int64), ("seq", ctypes.c_void_p), ("qual", ctypes.c_void_p),
+                ("offsets", ctypes.c_void_p), ("index", ctypes.c_void_p), ("n_merged", ctypes.c_int64),
+                ("n_innie", ctypes.c_int64), ("n_outie", ctypes.c_int64), ("bytes", ctypes.c_int64)]
+
+
 class CrgpuError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("libcrgpu error %d: %s" % (code, msg))
@@ -86,8 +98,10 @@ def load():
     lib.crgpu_align_quantify.argtypes = [vp, i32, ctypes.c_char_p, i32, ctypes.POINTER(PathParams),
                                          ctypes.POINTER(QuantParams), vp, vp, i64, ctypes.POINTER(PathOut)]
     lib.crgpu_int_peak.argtypes = [vp, i32, ctypes.POINTER(dbl)]
+    lib.crgpu_flash_merge.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i64, ctypes.POINTER(MergeParams),
+                                      ctypes.POINTER(MergeOut)]
     for name in ("crgpu_create", "crgpu_set_overlap", "crgpu_set_share_prefix", "crgpu_set_traceback_budget", "crgpu_last_timing", "crgpu_sync", "crgpu_qualfilter",
-                 "crgpu_align", "crgpu_quantify", "crgpu_align_quantify", "crgpu_int_peak"):
+                 "crgpu_align", "crgpu_quantify", "crgpu_align_quantify", "crgpu_int_peak", "crgpu_flash_merge"):
         getattr(lib, name).restype = i32
     _lib = lib
     return lib

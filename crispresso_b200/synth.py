@@ -102,3 +102,59 @@ def make_reads_fast(amp, hdr_amp, cut, n, seed=1234, read_len=None, **kw):
         idx = np.repeat(starts - offsets[:-1], lens) + np.arange(int(offsets[-1]))
         out[:] = buf[idx]
     return np.ascontiguousarray(out), offsets
+
+
+def make_pairs(amp, n, read_len=150, seed=1234, sub_rate=0.01, n_rate=0.002, short_frac=0.08, junk_frac=0.03,
+               low_complexity_frac=0.0, coarse_quals=False):
+    """Paired-end reads of one amplicon (the input of the FLASH step, CORE:1655-1664): read 1 = the first
+    read_len bases of the fragment, read 2 = reverse complement of its last read_len bases; sequencing
+    errors and N calls grow towards the 3' ends, where qualities drop.  short_frac of the fragments are
+    shorter than a read (the mates then run into the adapter on both sides: an "outie"), junk_frac of the
+    pairs are unrelated sequences.  coarse_quals draws qualities from 4 bins (as current instruments
+    do), which makes equal-quality and equal-density ties common.  Returns lists (s1, q1, s2, q2) of str."""
+    rng = np.random.default_rng(seed)
+    a = np.frombuffer(amp.encode(), dtype=np.uint8)
+    adapter1, adapter2 = _ACGT[rng.integers(0, 4, size=read_len)], _ACGT[rng.integers(0, 4, size=read_len)]
+    bins = np.array([2, 12, 23, 37])
+    s1, q1, s2, q2 = [], [], [], []
+
+    def sequence(frag, adapter, L):
+        r = np.concatenate([frag, adapter])[:L].copy()
+        ramp = np.linspace(0.3, 3.0, len(r))
+        m = rng.random(len(r)) < sub_rate * ramp
+        r[m] = _ACGT[rng.integers(0, 4, size=int(m.sum()))]
+        m2 = rng.random(len(r)) < n_rate * ramp
+        r[m2] = ord("N")
+        q = np.clip(np.round(rng.normal(36, 3, size=len(r)) - 6 * ramp * rng.random()), 2, 41).astype(np.int64)
+        q[m] = np.minimum(q[m], rng.integers(2, 30, size=int(m.sum())))
+        q[m2] = 2
+        if coarse_quals:
+            q = bins[np.abs(q[:, None] - bins[None, :]).argmin(axis=1)]
+        return r.tobytes().decode(), "".join(chr(int(v) + 33) for v in q)
+
+    for _ in range(n):
+        u = rng.random()
+        L1 = read_len if rng.random() < 0.9 else int(rng.integers(max(1, read_len // 3), read_len + 1))
+        L2 = read_len if rng.random() < 0.9 else int(rng.integers(max(1, read_len // 3), read_len + 1))
+        if u < junk_frac:
+            f1, f2 = _ACGT[rng.integers(0, 4, size=L1)], _ACGT[rng.integers(0, 4, size=L2)]
+            r1, qa = sequence(f1, adapter1, L1)
+            r2, qb = sequence(f2, adapter2, L2)
+        else:
+            if u < junk_frac + low_complexity_frac:
+                unit = _ACGT[rng.integers(0, 4, size=int(rng.integers(1, 4)))]
+                frag = np.tile(unit, 2 * read_len)[:int(rng.integers(read_len, 2 * read_len))]
+            elif u < junk_frac + low_complexity_frac + short_frac:
+                lo = int(rng.integers(0, len(a) // 2))
+                frag = a[lo:lo + int(rng.integers(max(8, read_len // 4), read_len))]
+            else:
+                frag = a
+                if rng.random() < 0.2:                           # an indel somewhere in the middle
+                    pos, size = int(rng.integers(len(a) // 3, 2 * len(a) // 3)), int(min(40, rng.geometric(0.2)))
+                    frag = np.concatenate([a[:pos], a[pos + size:]]) if rng.random() < 0.5 else \
+                        np.concatenate([a[:pos], _ACGT[rng.integers(0, 4, size=size)], a[pos:]])
+            r1, qa = sequence(frag, adapter1, L1)
+            rc = np.frombuffer(revcomp(frag.tobytes().decode()).encode(), dtype=np.uint8)
+            r2, qb = sequence(rc, adapter2, L2)
+        s1.append(r1); q1.append(qa); s2.append(r2); q2.append(qb)
+    return s1, q1, s2, q2

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CRGPU_ABI_VERSION 2
+#define CRGPU_ABI_VERSION 3
 
 enum {
     CRGPU_OK = 0,
@@ -230,6 +230,41 @@ typedef struct {
 int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int amplicon_len,
                          const crgpu_path_params *path, const crgpu_quant_params *quant,
                          const uint8_t *reads, const int64_t *offsets, int64_t n, crgpu_path_out *out);
+
+/* ---- S0: paired-end merge -- the `flash` subprocess of CORE:1655-1664 -------------- *
+ * `flash R1 R2 --allow-outies --max-overlap M --min-overlap m` (FLASH 1.2.11; default maximum mismatch
+ * density 0.25).  Mate i of file 1 is bytes seq1/qual1[off1[i]..off1[i+1]) (phred+33 qualities share the
+ * sequence offsets), likewise file 2.  Read 2 is reverse-complemented; the best overlap is the first
+ * lexicographic minimum of (mismatch density, mismatch quality score) in FLASH's scan order (innies by
+ * increasing start in read 1, then -- with allow_outies -- outies); a pair whose best density exceeds
+ * max_mismatch_density stays uncombined.  Bases must be ACGTN, mates at most 1024 long (CRGPU_E_ALIGN). */
+typedef struct {
+    int32_t min_overlap;           /* args.min_paired_end_reads_overlap (CORE:4147), flash -m */
+    int32_t max_overlap;           /* args.max_paired_end_reads_overlap (CORE:4140), flash -M */
+    float max_mismatch_density;    /* flash -x, default 0.25 (CRISPResso never changes it) */
+    int32_t allow_outies;          /* flash -O (CORE:1659 always passes it) */
+} crgpu_merge_params;
+
+typedef struct {
+    /* per pair; follow `mem` */
+    int32_t *pos;                  /* [n] start of the overlap in the left read (read 1 for an innie,
+                                      revcomp(read 2) for an outie); -1 = not combined */
+    uint8_t *kind;                 /* [n] 0 = not combined (out.notCombined_*), 1 = innie, 2 = outie */
+    /* merged reads (out.extendedFrags), compact and in pair order; follow `mem` */
+    int64_t cap_bytes, cap_reads;  /* capacities of seq/qual and of offsets(-1)/index; sum of all mate
+                                      lengths and n always suffice */
+    uint8_t *seq, *qual;           /* [cap_bytes] merged bases / phred+33 qualities */
+    int64_t *offsets;              /* [cap_reads + 1] merged read j is bytes offsets[j]..offsets[j+1]: the
+                                      (reads, offsets) pair crgpu_align / crgpu_align_quantify consume */
+    int32_t *index;                /* [cap_reads] pair index of merged read j */
+    int64_t n_merged;              /* OUT */
+    int64_t n_innie, n_outie;      /* OUT (reserved; the shim counts `kind`) */
+    int64_t bytes;                 /* OUT: offsets[n_merged] */
+} crgpu_merge_out;
+
+int crgpu_flash_merge(crgpu_ctx *ctx, int mem, const uint8_t *seq1, const uint8_t *qual1, const int64_t *off1,
+                      const uint8_t *seq2, const uint8_t *qual2, const int64_t *off2, int64_t n,
+                      const crgpu_merge_params *params, crgpu_merge_out *out);
 
 /* ---- measurement helper ---------------------------------------------------------------- *
  * Integer issue-rate micro-benchmark ("measure it"): dependency-free chains of ONE
