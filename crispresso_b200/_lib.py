@@ -59,6 +59,13 @@ class MergeOut(ctypes.Structure):
                 ("n_innie", ctypes.c_int64), ("n_outie", ctypes.c_int64), ("bytes", ctypes.c_int64)]
 
 
+class FastqOut(ctypes.Structure):
+    _fields_ = [("n_records", ctypes.c_int64), ("consumed", ctypes.c_int64), ("seq_bytes", ctypes.c_int64),
+                ("cap_records", ctypes.c_int64), ("cap_bytes", ctypes.c_int64), ("seq", ctypes.c_void_p),
+                ("qual", ctypes.c_void_p), ("offsets", ctypes.c_void_p), ("name_start", ctypes.c_void_p),
+                ("name_len", ctypes.c_void_p)]
+
+
 class CrgpuError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("libcrgpu error %d: %s" % (code, msg))
@@ -98,10 +105,11 @@ def load():
     lib.crgpu_align_quantify.argtypes = [vp, i32, ctypes.c_char_p, i32, ctypes.POINTER(PathParams),
                                          ctypes.POINTER(QuantParams), vp, vp, i64, ctypes.POINTER(PathOut)]
     lib.crgpu_int_peak.argtypes = [vp, i32, ctypes.POINTER(dbl)]
+    lib.crgpu_fastq_index.argtypes = [vp, i32, vp, i64, i32, ctypes.POINTER(FastqOut)]
     lib.crgpu_flash_merge.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i64, ctypes.POINTER(MergeParams),
                                       ctypes.POINTER(MergeOut)]
     for name in ("crgpu_create", "crgpu_set_overlap", "crgpu_set_share_prefix", "crgpu_set_traceback_budget", "crgpu_last_timing", "crgpu_sync", "crgpu_qualfilter",
-                 "crgpu_align", "crgpu_quantify", "crgpu_align_quantify", "crgpu_int_peak", "crgpu_flash_merge"):
+                 "crgpu_align", "crgpu_quantify", "crgpu_align_quantify", "crgpu_int_peak", "crgpu_flash_merge", "crgpu_fastq_index"):
         getattr(lib, name).restype = i32
     _lib = lib
     return lib

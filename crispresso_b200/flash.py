@@ -13,7 +13,7 @@ import numpy as np
 
 from . import _lib
 from .aligner import pack_reads
-from .fastq import read_fastq
+from .fastq import read_fastq_packed
 
 
 class MergeResult:
@@ -81,18 +81,22 @@ def flash_merge_files(ctx, fastq_r1, fastq_r2, output_directory, min_overlap=4, 
                       max_mismatch_density=0.25):
     """Drop-in for `flash R1 R2 --allow-outies --max-overlap M --min-overlap m -z -d DIR` (CORE:1657-1664).
     Returns (extendedFrags path, notCombined_1 path, notCombined_2 path, MergeResult)."""
-    h1, s1, q1 = read_fastq(fastq_r1)
-    h2, s2, q2 = read_fastq(fastq_r2)
-    res = merge_pairs(ctx, s1, q1, s2, q2, min_overlap=min_overlap, max_overlap=max_overlap,
-                      max_mismatch_density=max_mismatch_density, allow_outies=allow_outies)
+    h1, s1, q1, o1 = read_fastq_packed(ctx, fastq_r1)
+    h2, s2, q2, o2 = read_fastq_packed(ctx, fastq_r2)
+    res = merge_packed(ctx, s1, q1, o1, s2, q2, o2, min_overlap=min_overlap, max_overlap=max_overlap,
+                       max_mismatch_density=max_mismatch_density, allow_outies=allow_outies)
     ext = os.path.join(output_directory, "out.extendedFrags.fastq.gz")
     nc1 = os.path.join(output_directory, "out.notCombined_1.fastq.gz")
     nc2 = os.path.join(output_directory, "out.notCombined_2.fastq.gz")
     with gzip.open(ext, "wt") as f:
         for p, s, q in zip(res.index, res.reads(), res.quals()):
             f.write("@%s\n%s\n+\n%s\n" % (combined_tag(h1[p], h2[p]), s, q))
+
+    def rec(h, s, q, o, p):
+        return "@%s\n%s\n+\n%s\n" % (h[p], s[o[p]:o[p + 1]].tobytes().decode(), q[o[p]:o[p + 1]].tobytes().decode())
+
     with gzip.open(nc1, "wt") as f1, gzip.open(nc2, "wt") as f2:
         for p in np.nonzero(res.kind == 0)[0]:
-            f1.write("@%s\n%s\n+\n%s\n" % (h1[p], s1[p], q1[p]))
-            f2.write("@%s\n%s\n+\n%s\n" % (h2[p], s2[p], q2[p]))
+            f1.write(rec(h1, s1, q1, o1, p))
+            f2.write(rec(h2, s2, q2, o2, p))
     return ext, nc1, nc2, res

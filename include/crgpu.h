@@ -266,6 +266,31 @@ int crgpu_flash_merge(crgpu_ctx *ctx, int mem, const uint8_t *seq1, const uint8_
                       const uint8_t *seq2, const uint8_t *qual2, const int64_t *off2, int64_t n,
                       const crgpu_merge_params *params, crgpu_merge_out *out);
 
+/* ---- FASTQ record splitting ------------------------------------------------------ *
+ * Indexes inflated FASTQ text: what `gunzip | awk 'NR%4==1 {...} NR%4==2 {...}'` (CORE:1793-1797), `wc -l`
+ * (get_n_reads_fastq, CORE:335-348), the read-length awk (get_average_read_length_fastq, CORE:313-332)
+ * and the Biopython record iterator of the quality filter (CORE:176-190) do on the host today.
+ * text[0..nbytes) holds 4-line records ('\n' or '\r\n' line ends).  With final_chunk = 0 the text may
+ * end inside a record: n_records complete records are indexed and `consumed` says where the incomplete
+ * tail starts (prepend it to the next chunk).  With final_chunk = 1 a missing last newline is accepted and
+ * a line count that is not a multiple of 4 is an error.  A record whose line 1 does not start with '@',
+ * line 3 with '+', or whose bases and qualities differ in length fails the call (CRGPU_E_ARG).
+ * Pass seq = qual = offsets = NULL to get the three counts only (then size the buffers exactly). */
+typedef struct {
+    int64_t n_records;             /* OUT: complete records = get_n_reads_fastq */
+    int64_t consumed;              /* OUT: bytes of text those records occupy */
+    int64_t seq_bytes;             /* OUT: sum of read lengths; seq_bytes / n_records (integer) =
+                                      get_average_read_length_fastq */
+    int64_t cap_records, cap_bytes;/* capacities of the arrays below */
+    uint8_t *seq, *qual;           /* [cap_bytes] packed bases / phred+33 qualities; follow `mem` */
+    int64_t *offsets;              /* [cap_records + 1]; follow `mem` */
+    int64_t *name_start;           /* [cap_records] offset of the record's '@' in text, or NULL; follow `mem` */
+    int32_t *name_len;             /* [cap_records] length of the header line incl. '@', or NULL */
+} crgpu_fastq_out;
+
+int crgpu_fastq_index(crgpu_ctx *ctx, int mem, const uint8_t *text, int64_t nbytes, int final_chunk,
+                      crgpu_fastq_out *out);
+
 /* ---- measurement helper ---------------------------------------------------------------- *
  * Integer issue-rate micro-benchmark ("measure it"): dependency-free chains of ONE
  * instruction kind on every SM.  Returns lane-ops per second (one SASS instruction on one lane).
