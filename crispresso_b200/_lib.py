@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcrgpu.so")
+LIB_PATH = os.environ.get("CRGPU_LIB") or os.path.join(HERE, "libcrgpu.so")     # CRGPU_LIB: experiment builds (scripts/)
 
 MEM_HOST, MEM_DEVICE = 0, 1
 E_CUDA, E_ARG, E_ALIGN, E_NOMEM = 1, 2, 3, 4
@@ -95,6 +95,8 @@ def load():
     lib.crgpu_last_timing.argtypes = [vp, vp, vp]
     lib.crgpu_set_overlap.argtypes = [vp, i32]
     lib.crgpu_set_share_prefix.argtypes = [vp, i32]
+    lib.crgpu_set_band.argtypes = [vp, i32]
+    lib.crgpu_last_escaped.argtypes = [vp, ctypes.POINTER(ctypes.c_int * 2)]
     lib.crgpu_sync.argtypes = [vp]
     lib.crgpu_stream.argtypes = [vp]
     lib.crgpu_stream.restype = vp
@@ -108,7 +110,7 @@ def load():
     lib.crgpu_fastq_index.argtypes = [vp, i32, vp, i64, i32, ctypes.POINTER(FastqOut)]
     lib.crgpu_flash_merge.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i64, ctypes.POINTER(MergeParams),
                                       ctypes.POINTER(MergeOut)]
-    for name in ("crgpu_create", "crgpu_set_overlap", "crgpu_set_share_prefix", "crgpu_set_traceback_budget", "crgpu_last_timing", "crgpu_sync", "crgpu_qualfilter",
+    for name in ("crgpu_create", "crgpu_set_overlap", "crgpu_set_share_prefix", "crgpu_set_band", "crgpu_last_escaped", "crgpu_set_traceback_budget", "crgpu_last_timing", "crgpu_sync", "crgpu_qualfilter",
                  "crgpu_align", "crgpu_quantify", "crgpu_align_quantify", "crgpu_int_peak", "crgpu_flash_merge", "crgpu_fastq_index"):
         getattr(lib, name).restype = i32
     _lib = lib
@@ -165,6 +167,16 @@ class Context:
 
     def set_share_prefix(self, on):
         self.check(self.lib.crgpu_set_share_prefix(self.handle, 1 if on else 0))
+
+    def set_band(self, half_width):
+        """Half-width (read columns) of the banded two-pass fill; 0 = single-pass fill."""
+        self.check(self.lib.crgpu_set_band(self.handle, int(half_width)))
+
+    def last_escaped(self):
+        """(amplicon pass, HDR pass) reads of the last fused call that left the band and were re-aligned."""
+        out = (ctypes.c_int * 2)()
+        self.check(self.lib.crgpu_last_escaped(self.handle, ctypes.byref(out)))
+        return int(out[0]), int(out[1])
 
     def last_timing(self):
         ms = (ctypes.c_float * 6)()

@@ -45,7 +45,8 @@ void crgpu_destroy(crgpu_ctx *c)
     cudaStreamSynchronize(c->stream3);
     DBuf *all[] = {&c->reads, &c->offsets, &c->amp, &c->prof, &c->pc, &c->pc_off, &c->plen, &c->pair_lo, &c->pair_hi,
                    &c->order, &c->plan_hist, &c->plan_tab, &c->tb2, &c->lastrow2, &c->lastcol2, &c->tb, &c->lastrow, &c->lastcol, &c->errflag, &c->recs, &c->sref, &c->smark, &c->sqry, &c->ops, &c->ops_rc, &c->alleles, &c->prof_h, &c->amp_h, &c->tbh, &c->tbh2,
-                   &c->top, &c->top2, &c->lastrow_h, &c->lastrow_h2, &c->lastcol_h, &c->lastcol_h2};
+                   &c->top, &c->top2, &c->lastrow_h, &c->lastrow_h2, &c->lastcol_h, &c->lastcol_h2,
+                   &c->btops[0], &c->btops[1], &c->bleft[0], &c->bleft[1], &c->btops_h[0], &c->btops_h[1], &c->bleft_h[0], &c->bleft_h[1], &c->escaped};
     for (DBuf *b : all) b->release();
     for (auto &b : c->q_in) b.release();
     for (auto &b : c->q_out) b.release();
@@ -79,6 +80,20 @@ int crgpu_set_share_prefix(crgpu_ctx *c, int on)
 {
     if (!c) return CRGPU_E_ARG;
     c->share_prefix = on != 0;
+    return CRGPU_OK;
+}
+
+int crgpu_set_band(crgpu_ctx *c, int half_width)
+{
+    if (!c || half_width < 0 || half_width > 512) return CRGPU_E_ARG;
+    c->band_B = half_width;
+    return CRGPU_OK;
+}
+
+int crgpu_last_escaped(const crgpu_ctx *c, int out[2])
+{
+    if (!c || !out) return CRGPU_E_ARG;
+    out[0] = c->n_escaped[0]; out[1] = c->n_escaped[1];
     return CRGPU_OK;
 }
 
@@ -374,6 +389,7 @@ int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_read
         fa.p0 = batch_start[b]; fa.p1 = batch_start[b + 1];
         fa.open = open_s; fa.ext = ext_s; fa.La = La; fa.one = 1;
         fa.top_out = nullptr; fa.top_out_lane = -1; fa.top_in = nullptr;
+        fa.band_B = 0; fa.band_W = 0; fa.band_row0 = 0; fa.band_tops = nullptr; fa.band_left = nullptr; fa.band_tb = nullptr;
         if (used[cur]) CK(cudaStreamWaitEvent(sf[cur], ctx->walk_done[cur], 0));     // scratch `cur` is free again
         span_begin(ctx, T_FILL, sf[cur]);
         CK(launch_fill(G, K, fa, ctx->num_sms, sf[cur]));
@@ -383,6 +399,7 @@ int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_read
         WalkArgs wa;
         wa.tb = fa.tb; wa.lastrow = fa.lastrow; wa.lastcol = fa.lastcol;
         wa.tb_upper = nullptr; wa.lastcol_upper = nullptr; wa.G_upper = 0; wa.split_row = 0;
+        wa.band_B = 0; wa.band_W = 0; wa.kdiv_magic = 0; wa.escaped = nullptr; wa.escape_bit = 0;
         wa.pc_off = fa.pc_off; wa.plen = fa.plen;
         wa.pair_lo = ctx->pair_lo.as<int32_t>(); wa.pair_hi = ctx->pair_hi.as<int32_t>();
         wa.reads = d_reads; wa.offsets = d_offsets; wa.amplicon = ctx->amp.as<uint8_t>();
@@ -511,7 +528,7 @@ int run_plan_dual(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     for (int i = 0; i < (two ? 2 : 1); ++i) {
         CK(tbA[i]->reserve((size_t)max_cols * (GK / 2) * 4));
         CK(tbH[i]->reserve((size_t)max_cols * (GKh / 2) * 4));
-        CK(top[i]->reserve((size_t)max_cols * 12));
+        CK(top[i]->reserve((size_t)(max_cols + max_bp + 2) * 16));
         CK(lrA[i]->reserve((size_t)max_bp * 12)); CK(lcA[i]->reserve((size_t)max_bp * G * 12));
         CK(lrH[i]->reserve((size_t)max_bp * 12)); CK(lcH[i]->reserve((size_t)max_bp * Gh * 12));
     }
@@ -537,6 +554,7 @@ int run_plan_dual(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         fa.p0 = batch_start[b]; fa.p1 = batch_start[b + 1];
         fa.open = open_s; fa.ext = ext_s; fa.La = La; fa.one = 1;
         fa.top_out = top[cur]->as<uint32_t>(); fa.top_out_lane = t0 - 1; fa.top_in = nullptr;
+        fa.band_B = 0; fa.band_W = 0; fa.band_row0 = 0; fa.band_tops = nullptr; fa.band_left = nullptr; fa.band_tb = nullptr;
         FillArgs fh = fa;                                               // HDR pass: bottom Gh lanes
         fh.prof = ctx->prof_h.as<int32_t>();
         fh.tb = tbH[cur]->as<uint32_t>(); fh.lastrow = lrH[cur]->as<uint32_t>(); fh.lastcol = lcH[cur]->as<uint32_t>();
@@ -552,6 +570,7 @@ int run_plan_dual(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         WalkArgs wa;
         wa.tb = fa.tb; wa.lastrow = fa.lastrow; wa.lastcol = fa.lastcol;
         wa.tb_upper = nullptr; wa.lastcol_upper = nullptr; wa.G_upper = 0; wa.split_row = 0;
+        wa.band_B = 0; wa.band_W = 0; wa.kdiv_magic = 0; wa.escaped = nullptr; wa.escape_bit = 0;
         wa.pc_off = fa.pc_off; wa.plen = fa.plen;
         wa.pair_lo = ctx->pair_lo.as<int32_t>(); wa.pair_hi = ctx->pair_hi.as<int32_t>();
         wa.reads = d_reads; wa.offsets = d_offsets; wa.amplicon = ctx->amp.as<uint8_t>();
@@ -570,6 +589,202 @@ int run_plan_dual(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         CK(launch_walk(wa, s2));
         CK(launch_walk(wh, s2));
         span_end(ctx, 2);
+        CK(cudaEventRecord(ctx->walk_done[cur], s2));
+        used[cur] = true;
+    }
+    for (int i = 0; i < 2; ++i) if (used[i]) CK(cudaStreamWaitEvent(s, ctx->walk_done[i], 0));
+    *done = true;
+    return CRGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// run_plan_band: the forward alignment pass(es) with the banded two-pass fill (gotoh_fill.cu).
+//   hdr_amplicon == nullptr : one amplicon.
+//   hdr_amplicon != nullptr : amplicon + HDR amplicon sharing the DP prefix (as run_plan_dual); returns
+//                             *done = false when the two cannot share rows (the caller then makes two
+//                             single-amplicon calls).
+// Reads whose traceback leaves the band get d_escaped[read] |= escape bit (1: amplicon pass, 2: HDR pass)
+// and are re-aligned by the caller with the full fill.  Returns *done = false (nothing launched) when the
+// band would not pay (reads not much longer than the band).
+// ---------------------------------------------------------------------------------------------
+int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon, int La, const uint8_t *d_reads,
+                  const int64_t *d_offsets, double gapopen, double gapextend, crgpu_aln_rec *d_recs, crgpu_aln_rec *d_recs_hdr,
+                  uint8_t *d_ref, uint8_t *d_mark, uint8_t *d_qry, int64_t slot, int64_t *n_cells, int64_t *n_cells_computed,
+                  uint32_t *d_ops, int64_t ops_stride, uint8_t *d_escaped, int escape_bit, bool *done)
+{
+    *done = false;
+    const PairPlan &pl = ctx->plan;
+    const int B = ctx->band_B;
+    if (B <= 0 || getenv("CRGPU_NO_BAND") || pl.np == 0 || pl.nsub == 0) return CRGPU_OK;
+    if (La < CRGPU_MIN_LEN || La > CRGPU_MAX_AMPLICON) return CRGPU_OK;      // let run_plan report it
+    int scale, open_s, ext_s;
+    if (!scale_penalties(gapopen, gapextend, &scale, &open_s, &ext_s) || gapopen < 4.0 || gapextend < 0.0 || gapextend > gapopen)
+        return CRGPU_OK;
+    const bool dual = hdr_amplicon != nullptr;
+    std::vector<int> acode(La), hcode(La);
+    std::string amp_up(La, 'N'), hdr_up(La, 'N');
+    int d = La;                                                            // first differing base
+    for (int i = 0; i < La; ++i) {
+        acode[i] = host_code(amplicon[i]);
+        if (acode[i] < 0) return CRGPU_OK;
+        amp_up[i] = amplicon[i];
+        if (dual) {
+            hcode[i] = host_code(hdr_amplicon[i]);
+            if (hcode[i] < 0) return CRGPU_OK;
+            hdr_up[i] = hdr_amplicon[i];
+            if (d == La && acode[i] != hcode[i]) d = i;
+        }
+    }
+    int G, K;
+    if (!choose_tile(La, &G, &K)) return CRGPU_OK;
+    const int GK = G * K, P = GK - La;
+    const int W = K + 2 * B + 1;
+    // the band pays when it is well below the read length (score pass ~0.4x + band pass ~W/Lb of a full fill)
+    if ((int64_t)W * 5 * pl.nsub > 3 * pl.sum_len) return CRGPU_OK;
+    int Gh = 0;
+    if (dual) {
+        if (!ctx->share_prefix || getenv("CRGPU_NO_SHARE")) return CRGPU_OK;
+        for (int g = 4; g < G; g *= 2)
+            if (tile_available(g, K) && (G - g) * K - P <= d) { Gh = g; break; }
+        if (Gh == 0) return CRGPU_OK;
+    }
+    const int t0 = G - Gh, split = dual ? t0 * K : 0, GKh = Gh * K;
+    const int maxlen = pl.maxlen;
+    if ((int64_t)scale * 5 * std::min(La, maxlen) + 64 >= MAX_ABS_SCORE ||
+        (int64_t)2 * open_s + (int64_t)ext_s * (La + maxlen) + 8 * scale + 64 >= MAX_ABS_SCORE)
+        return CRGPU_OK;
+    if (slot < (int64_t)La + maxlen && d_ref) return CRGPU_OK;
+
+    // ---- batches: fixed scratch per pair and lane (tops, left edge, band flags) ----
+    const int TOPW = band_topw(W), LEFTW = band_leftw(K);
+    const size_t lane_bytes = (size_t)TOPW * 16 + (size_t)LEFTW * 4 + (size_t)W * K * 2;
+    const size_t pair_bytes = lane_bytes * (size_t)(G + Gh) + (dual ? (size_t)(maxlen + 2) * 16 : 0);
+    int64_t bp = (int64_t)(ctx->tb_budget / pair_bytes);
+    bp = std::max<int64_t>(1, std::min<int64_t>(bp, std::max<int64_t>(((int64_t)pl.np + 7) / 8, 16384)));
+    std::vector<int> batch_start;
+    for (int64_t p = 0; p < pl.np; p += bp) batch_start.push_back((int)p);
+    batch_start.push_back(pl.np);
+    const int max_bp = (int)std::min<int64_t>(bp, pl.np);
+    int64_t max_cols = 0;
+    for (size_t b = 0; b + 1 < batch_start.size(); ++b)
+        max_cols = std::max(max_cols, plan_pc_off(pl, batch_start[b + 1]) - plan_pc_off(pl, batch_start[b]));
+    if (n_cells) *n_cells += (dual ? 2 : 1) * (int64_t)La * pl.sum_len;
+    if (n_cells_computed) {
+        // score pass: every cell (HDR: the rows below the split); band pass: at most W columns per lane
+        const int64_t band_cols = std::min<int64_t>((int64_t)W * pl.nsub, pl.sum_len);
+        *n_cells_computed += (int64_t)La * pl.sum_len + (int64_t)GK * band_cols;
+        if (dual) *n_cells_computed += (int64_t)(La - (split - P)) * pl.sum_len + (int64_t)GKh * band_cols;
+    }
+
+    // ---- profiles ----
+    auto build_prof = [&](const std::vector<int> &code, int g, int row0, std::vector<int32_t> &prof) {
+        const int PS = prof_stride(g, K), SS = strip_stride(K);
+        prof.assign((size_t)NPAIR * PS, 0);
+        for (int cp = 0; cp < NPAIR; ++cp) {
+            const int lo = cp % NCODE, hi = cp / NCODE;
+            for (int r = std::max(P, row0); r < GK; ++r) {
+                const int a = code[r - P];
+                const int32_t slo = scale * host_ednafull(a, lo), shi = scale * host_ednafull(a, hi);
+                const int rr = r - row0;
+                prof[(size_t)cp * PS + (rr / K) * SS + (rr % K)] = shi * 65536 + slo;
+            }
+        }
+    };
+    std::vector<int32_t> prof_a, prof_h;
+    build_prof(acode, G, 0, prof_a);
+    if (dual) build_prof(hcode, Gh, split, prof_h);
+    cudaStream_t s = ctx->stream;
+    const bool two = batch_start.size() > 2 && ctx->overlap && !getenv("CRGPU_NO_OVERLAP");
+    CK(ctx->amp.reserve((size_t)La)); CK(ctx->prof.reserve(prof_a.size() * 4));
+    if (dual) { CK(ctx->amp_h.reserve((size_t)La)); CK(ctx->prof_h.reserve(prof_h.size() * 4)); }
+    DBuf *tbA[2] = {&ctx->tb, &ctx->tb2}, *tbH[2] = {&ctx->tbh, &ctx->tbh2}, *top[2] = {&ctx->top, &ctx->top2};
+    DBuf *lrA[2] = {&ctx->lastrow, &ctx->lastrow2}, *lcA[2] = {&ctx->lastcol, &ctx->lastcol2};
+    DBuf *lrH[2] = {&ctx->lastrow_h, &ctx->lastrow_h2}, *lcH[2] = {&ctx->lastcol_h, &ctx->lastcol_h2};
+    for (int i = 0; i < (two ? 2 : 1); ++i) {
+        CK(tbA[i]->reserve((size_t)max_bp * G * W * K * 2));
+        CK(ctx->btops[i].reserve((size_t)max_bp * G * TOPW * 16));
+        CK(ctx->bleft[i].reserve((size_t)max_bp * G * LEFTW * 4));
+        CK(lrA[i]->reserve((size_t)max_bp * 12)); CK(lcA[i]->reserve((size_t)max_bp * G * 12));
+        if (dual) {
+            CK(tbH[i]->reserve((size_t)max_bp * Gh * W * K * 2));
+            CK(ctx->btops_h[i].reserve((size_t)max_bp * Gh * TOPW * 16));
+            CK(ctx->bleft_h[i].reserve((size_t)max_bp * Gh * LEFTW * 4));
+            CK(top[i]->reserve((size_t)(max_cols + max_bp + 2) * 16));
+            CK(lrH[i]->reserve((size_t)max_bp * 12)); CK(lcH[i]->reserve((size_t)max_bp * Gh * 12));
+        }
+    }
+    CK(cudaMemcpyAsync(ctx->amp.p, amp_up.data(), (size_t)La, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->prof.p, prof_a.data(), prof_a.size() * 4, cudaMemcpyHostToDevice, s));
+    if (dual) {
+        CK(cudaMemcpyAsync(ctx->amp_h.p, hdr_up.data(), (size_t)La, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->prof_h.p, prof_h.data(), prof_h.size() * 4, cudaMemcpyHostToDevice, s));
+    }
+    CK(cudaStreamSynchronize(s));      // the staging vectors are locals of this frame
+
+    cudaStream_t s2 = two ? ctx->stream2 : ctx->stream;
+    cudaStream_t sf[2] = {s, two ? ctx->stream3 : s};
+    if (two) {
+        CK(cudaEventRecord(ctx->ready, s));
+        CK(cudaStreamWaitEvent(sf[1], ctx->ready, 0));
+    }
+    const uint32_t magic = (uint32_t)((((uint64_t)1 << 32) + K - 1) / K);
+    bool used[2] = {false, false};
+    for (size_t b = 0; b + 1 < batch_start.size(); ++b) {
+        const int cur = two ? (int)(b & 1) : 0;
+        FillArgs fa;
+        fa.prof = ctx->prof.as<int32_t>();
+        fa.pc = ctx->pc.as<uint8_t>(); fa.pc_off = ctx->pc_off.as<int64_t>(); fa.plen = ctx->plen.as<int32_t>();
+        fa.tb = nullptr; fa.lastrow = lrA[cur]->as<uint32_t>(); fa.lastcol = lcA[cur]->as<uint32_t>();
+        fa.p0 = batch_start[b]; fa.p1 = batch_start[b + 1];
+        fa.open = open_s; fa.ext = ext_s; fa.La = La; fa.one = 1;
+        fa.top_out = dual ? top[cur]->as<uint32_t>() : nullptr; fa.top_out_lane = dual ? t0 - 1 : -1; fa.top_in = nullptr;
+        fa.band_B = B; fa.band_W = W; fa.band_row0 = -P;
+        fa.band_tops = ctx->btops[cur].as<uint32_t>(); fa.band_left = ctx->bleft[cur].as<uint32_t>();
+        fa.band_tb = tbA[cur]->as<uint32_t>();
+        FillArgs fh = fa;                                               // HDR pass: bottom Gh lanes
+        if (dual) {
+            fh.prof = ctx->prof_h.as<int32_t>();
+            fh.lastrow = lrH[cur]->as<uint32_t>(); fh.lastcol = lcH[cur]->as<uint32_t>();
+            fh.La = GKh;                                                // no padding rows inside the sub-tile
+            fh.top_out = nullptr; fh.top_out_lane = -1; fh.top_in = top[cur]->as<uint32_t>();
+            fh.band_row0 = split - P;
+            fh.band_tops = ctx->btops_h[cur].as<uint32_t>(); fh.band_left = ctx->bleft_h[cur].as<uint32_t>();
+            fh.band_tb = tbH[cur]->as<uint32_t>();
+        }
+        if (used[cur]) CK(cudaStreamWaitEvent(sf[cur], ctx->walk_done[cur], 0));
+        span_begin(ctx, T_FILL, sf[cur]);
+        CK(launch_fill(G, K, fa, ctx->num_sms, sf[cur], 1));
+        if (dual) CK(launch_fill(Gh, K, fh, ctx->num_sms, sf[cur], 1));
+        CK(launch_fill(G, K, fa, ctx->num_sms, sf[cur], 2));
+        if (dual) CK(launch_fill(Gh, K, fh, ctx->num_sms, sf[cur], 2));
+        span_end(ctx, dual ? 4 : 2);
+        CK(cudaEventRecord(ctx->fill_done[cur], sf[cur]));
+
+        WalkArgs wa;
+        wa.tb = fa.band_tb; wa.lastrow = fa.lastrow; wa.lastcol = fa.lastcol;
+        wa.tb_upper = nullptr; wa.lastcol_upper = nullptr; wa.G_upper = 0; wa.split_row = 0;
+        wa.band_B = B; wa.band_W = W; wa.kdiv_magic = magic; wa.escaped = d_escaped; wa.escape_bit = escape_bit;
+        wa.pc_off = fa.pc_off; wa.plen = fa.plen;
+        wa.pair_lo = ctx->pair_lo.as<int32_t>(); wa.pair_hi = ctx->pair_hi.as<int32_t>();
+        wa.reads = d_reads; wa.offsets = d_offsets; wa.amplicon = ctx->amp.as<uint8_t>();
+        wa.La = La; wa.GK = GK; wa.P = P; wa.G = G; wa.K = K; wa.p0 = fa.p0; wa.p1 = fa.p1;
+        wa.open = open_s; wa.ext = ext_s; wa.scale = scale;
+        wa.recs = d_recs; wa.ref_out = d_ref; wa.mark_out = d_mark; wa.qry_out = d_qry; wa.slot = slot;
+        wa.out_index = nullptr; wa.rc_out = 0; wa.ops_out = d_ops; wa.ops_stride = ops_stride;
+        CK(cudaStreamWaitEvent(s2, ctx->fill_done[cur], 0));
+        span_begin(ctx, T_WALK, s2);
+        CK(launch_walk(wa, s2));
+        if (dual) {
+            WalkArgs wh = wa;                                           // HDR alignment: identity only
+            wh.tb = fh.band_tb; wh.lastrow = fh.lastrow; wh.lastcol = fh.lastcol;
+            wh.tb_upper = fa.band_tb; wh.lastcol_upper = fa.lastcol; wh.G_upper = G; wh.split_row = split;
+            wh.amplicon = ctx->amp_h.as<uint8_t>();
+            wh.GK = GKh; wh.G = Gh;
+            wh.escape_bit = 2;
+            wh.recs = d_recs_hdr; wh.ref_out = wh.mark_out = wh.qry_out = nullptr; wh.ops_out = nullptr;
+            CK(launch_walk(wh, s2));
+        }
+        span_end(ctx, dual ? 2 : 1);
         CK(cudaEventRecord(ctx->walk_done[cur], s2));
         used[cur] = true;
     }

@@ -47,12 +47,23 @@ struct FillArgs {
     int open, ext;            // gap open / extend, scaled (positive)
     int one;                  // always 1 (an opaque multiplier, see fma_add in gotoh_fill.cu)
     // Shared DP prefix between the amplicon pass and the HDR-amplicon pass (crgpu_api.cu run_plan_dual):
-    // the amplicon pass saves what lane `top_out_lane` hands down ((max3, iy, m) of its bottom row) for
+    // the amplicon pass saves what lane `top_out_lane` hands down ((max3, iy, m, 0) of its bottom row) for
     // every column; the HDR pass starts below that row and takes those values as its top boundary.
-    uint32_t *top_out;        // [(pc_off[p]-pc_off[p0]) + x][3] or null
+    uint32_t *top_out;        // [(pc_off[p]-pc_off[p0]) + x][4] or null
     int top_out_lane;
     const uint32_t *top_in;   // same layout, or null (free end-gap boundary)
+    // Banded two-pass fill (DESIGN.md "Band"): k_gotoh_score evaluates every cell without flags and saves,
+    // per lane, the state k_gotoh_band needs to re-evaluate -- with flags -- only the band_W read columns
+    // around the main diagonal of the lane's K rows: x in [xlo, xlo + band_W), xlo = band_row0 + t*K - band_B.
+    int band_B, band_W;       // band_W = K + 2*band_B + 1; band_B = 0: not banded
+    int band_row0;            // amplicon row of lane 0's first slot (-P for a full tile, split - P for the HDR sub-tile)
+    uint32_t *band_tops;      // [(p-p0)*G + t][band_topw()][4]: what lane t receives from above at columns xlo-1 .. xlo+W-1
+    uint32_t *band_left;      // [(p-p0)*G + t][band_leftw(K)]: H3[K], IX[K], mlast of column xlo-1
+    uint32_t *band_tb;        // [(p-p0)*G + t][band_W][K/2]: flag words of the band columns
 };
+
+__host__ __device__ constexpr int band_topw(int W) { return (W + 2) & ~1; }          // columns, even
+__host__ __device__ constexpr int band_leftw(int K) { return 2 * K + 4; }           // words, 16-byte multiple
 
 struct WalkArgs {
     const uint32_t *tb;
@@ -61,6 +72,12 @@ struct WalkArgs {
     const uint32_t *tb_upper;
     const uint32_t *lastcol_upper;
     int G_upper, split_row;
+    // banded fill: tb / tb_upper are band_tb arrays ([pair][lane][band_W][K/2 words]); a cell outside the
+    // band of its lane raises escaped[read] (the caller re-aligns those reads with the full fill)
+    int band_B, band_W;
+    uint32_t kdiv_magic;      // ceil(2^32 / K): padded row / K by multiply-high
+    uint8_t *escaped;         // [n reads] |= escape_bit
+    int escape_bit;
     const uint32_t *lastrow;
     const uint32_t *lastcol;
     const int64_t *pc_off;

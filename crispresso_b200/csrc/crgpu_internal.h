@@ -64,6 +64,9 @@ struct crgpu_ctx {
     DBuf recs, sref, smark, sqry, ops, ops_rc, alleles;
     DBuf prof_h, amp_h, tbh, tbh2, top, top2, lastrow_h, lastrow_h2, lastcol_h, lastcol_h2;   // HDR pass of run_plan_dual
     bool share_prefix = true;
+    DBuf btops[2], bleft[2], btops_h[2], bleft_h[2], escaped;      // banded two-pass fill (run_plan_band)
+    int n_escaped[2] = {0, 0};                                     // reads re-aligned after the last banded call (amplicon, HDR)
+    int band_B = 24;                                               // band half-width in read columns; 0 = single-pass fill
     DBuf q_in[8], q_out[4];
     DBuf aux[8];
     // timing
@@ -137,7 +140,7 @@ inline void timing_collect(crgpu_ctx *c)
 namespace crgpu {
 bool choose_tile(int La, int *G, int *K);
 bool tile_available(int G, int K);
-cudaError_t launch_fill(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream);
+cudaError_t launch_fill(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream, int kind = 0);
 cudaError_t launch_encode(const uint8_t *reads, const int64_t *offsets, const int32_t *pair_lo, const int32_t *pair_hi,
                           const int64_t *pc_off, int npairs, uint8_t *pc, int *err, int num_sms, cudaStream_t s);
 cudaError_t launch_walk(const WalkArgs &a, cudaStream_t s);
@@ -172,4 +175,8 @@ int run_plan_dual(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
                   const int64_t *d_offsets, double gapopen, double gapextend, crgpu_aln_rec *d_recs, crgpu_aln_rec *d_recs_hdr,
                   uint8_t *d_ref, uint8_t *d_mark, uint8_t *d_qry, int64_t slot, int64_t *n_cells, int64_t *n_cells_computed,
                   uint32_t *d_ops, int64_t ops_stride, bool *done);
+int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon, int La, const uint8_t *d_reads,
+                  const int64_t *d_offsets, double gapopen, double gapextend, crgpu_aln_rec *d_recs, crgpu_aln_rec *d_recs_hdr,
+                  uint8_t *d_ref, uint8_t *d_mark, uint8_t *d_qry, int64_t slot, int64_t *n_cells, int64_t *n_cells_computed,
+                  uint32_t *d_ops, int64_t ops_stride, uint8_t *d_escaped, int escape_bit, bool *done);
 }  // namespace crgpu

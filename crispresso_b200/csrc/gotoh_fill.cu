@@ -21,9 +21,19 @@
 //     read column is folded into the sweep (running first-maximum per lane), so only 12 bytes per
 //     pair and per lane leave the kernel for it.
 // The kernel is persistent: grid = SMs x resident CTAs, groups stride over the batch's pairs.
+//
+// Banded two-pass variant (FillArgs.band_B > 0; DESIGN.md "Band"): 16 of the ~22 instructions per cell
+// pair produce the traceback flags, but a traceback only ever reads the cells on its path, and the path
+// of an amplicon read hugs the main diagonal.  k_gotoh_fill<G,K,SCORE> therefore evaluates every cell
+// WITHOUT flags (scores, start-cell scan) and saves, per lane, what it received from the lane above at
+// the columns of a diagonal band and its register state at the band's left edge; k_gotoh_band<G,K>
+// re-evaluates only the band columns of every lane with flags -- lanes are independent there, the top
+// boundary comes from memory.  The walker raises an escape flag for a read whose path leaves the band
+// and the host re-aligns those reads with the full single-pass kernel: results never depend on the band.
 #include "crgpu_common.cuh"
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 namespace crgpu {
 
@@ -66,7 +76,7 @@ struct Strip {
 //  iy rule / FY flag differ (App. A.2/A.3: the last column opens from m only with zero penalties;
 //  A.4: gey = 0 on both).  The whole warp then runs this body with per-lane sources/penalties, so
 //  the special columns cost no divergence.
-template <int K, bool EDGE>
+template <int K, bool EDGE, bool FLAGS, bool SCAN>
 __device__ __forceinline__ void column_step(Strip<K> &st, const int32_t *__restrict__ prow,
                                             uint32_t upH3, uint32_t upIY, uint32_t upM, uint32_t hd,
                                             const uint32_t nopen16, const uint32_t ext32,
@@ -107,11 +117,11 @@ __device__ __forceinline__ void column_step(Strip<K> &st, const int32_t *__restr
 #endif
             ix = vaddmax2(h0, nopen16, t_);
         }
-        uint32_t iy, nFY;
+        uint32_t iy, nFY = 0;
         if (EDGE) {
             const uint32_t src = isLastCol ? upM : upH3;
             iy = vaddmax2(src, nopen16_v, upIY - ext32_v);
-            nFY = vmin2(iy ^ (upIY - ext32_f), ONE2);
+            if (FLAGS) nFY = vmin2(iy ^ (upIY - ext32_f), ONE2);
         } else {
 #ifdef FILL_FMA_ADDS
             const uint32_t u_ = fma_add(upIY, 0u - ext32, one);
@@ -119,17 +129,19 @@ __device__ __forceinline__ void column_step(Strip<K> &st, const int32_t *__restr
             const uint32_t u_ = upIY - ext32;
 #endif
             iy = vaddmax2(upH3, nopen16, u_);
-            nFY = vmin2(iy - u_, ONE2);
+            if (FLAGS) nFY = vmin2(iy - u_, ONE2);
         }
         const uint32_t h3 = __vimax3_s16x2(m, ix, iy);
-        const uint32_t nM = vmin2(h3 - m, ONE2);
-        const uint32_t nX = vmin2(h3 - ix, ONE2);
-        const uint32_t nY = vmin2(h3 - iy, ONE2);
-        const uint32_t nFX = vmin2(ix - t_, ONE2);
-        const uint32_t c = nM + 2u * nX + 4u * nY + 8u * nFX + 16u * nFY;
-        if (k & 1) words[k >> 1] = ceven + (c << 8);
-        else ceven = c;
-        if (EDGE) {
+        if (FLAGS) {
+            const uint32_t nM = vmin2(h3 - m, ONE2);
+            const uint32_t nX = vmin2(h3 - ix, ONE2);
+            const uint32_t nY = vmin2(h3 - iy, ONE2);
+            const uint32_t nFX = vmin2(ix - t_, ONE2);
+            const uint32_t c = nM + 2u * nX + 4u * nY + 8u * nFX + 16u * nFY;
+            if (k & 1) words[k >> 1] = ceven + (c << 8);
+            else ceven = c;
+        }
+        if (EDGE && SCAN) {
             // start-cell scan down the last read column (App. A.4): first row whose max(m,ix,iy) is
             // strictly greater than everything above it; padded rows are not part of the matrix
             if (isLastCol && k >= firstRealSlot) {
@@ -146,6 +158,7 @@ __device__ __forceinline__ void column_step(Strip<K> &st, const int32_t *__restr
         upH3 = h3; upIY = iy; upM = m; hd = h0;
     }
     botH3 = upH3; botIY = upIY; botM = upM;
+    if constexpr (!FLAGS) return;
     if constexpr ((K % 8) == 0) {
 #pragma unroll
         for (int j = 0; j < K / 8; ++j)
@@ -168,34 +181,49 @@ template <int K> constexpr int fill_maxnreg() { return FILL_MAXNREG; }
 template <int K> constexpr int fill_maxnreg() { return K >= 48 ? 255 : (K >= 36 ? 184 : (K >= 32 ? 136 : 128)); }
 #endif
 
-template <int G, int K>
-__global__ void __maxnreg__(fill_maxnreg<K>()) k_gotoh_fill(const FillArgs a)
-{
-    static_assert(K % 4 == 0 && (32 % G) == 0, "bad tile");
-    constexpr int PS = prof_stride(G, K);
-    constexpr int GK = G * K;
-    extern __shared__ __align__(128) int32_t sprof[];
-    __shared__ __align__(8) uint64_t mbar;
+enum { FILL_FULL = 0, FILL_SCORE = 1 };
 
-    // ---- stage the pair profile with one TMA bulk copy -------------------------------------
-    const uint32_t prof_bytes = NPAIR * PS * 4;
+// stage the pair profile with one TMA bulk copy (all threads of the CTA call this)
+__device__ __forceinline__ void stage_profile(int32_t *sprof, uint64_t *mbar, const int32_t *prof, uint32_t prof_bytes)
+{
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&mbar)), "r"(prof_bytes) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(prof_bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(sprof)), "l"(a.prof), "r"(prof_bytes), "r"(smem_u32(&mbar)) : "memory");
+                     ::"r"(smem_u32(sprof)), "l"(prof), "r"(prof_bytes), "r"(smem_u32(mbar)) : "memory");
     }
-    {
-        uint32_t done = 0;
-        while (!done) {
-            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                         : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0u) : "memory");
-        }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(smem_u32(mbar)), "r"(0u) : "memory");
     }
+}
+
+// Boundary rows in memory are 16 bytes per column, (max3, iy, m, 0).  A lane writes consecutive columns on
+// consecutive steps, so the two halves of a 32-byte sector meet in L2 long before the sector is evicted (a
+// half-written sector would cost HBM a read-modify-write: measured 2.6x on the whole kernel when every lane
+// leaves its sectors half-written).  First column of pair p in a per-pair array: even, and the ranges of
+// consecutive pairs do not overlap.
+__device__ __forceinline__ int64_t top_base_col(int64_t pco_rel, int pair_rel) { return (pco_rel + pair_rel + 1) & ~(int64_t)1; }
+
+// the score pass keeps a few more values live across the column and has no flag words: 168 registers still
+// leave 3 CTAs of 128 threads per SM
+template <int K, int MODE> constexpr int fill_maxnreg_mode() { return (MODE == FILL_SCORE && K <= 32) ? 168 : fill_maxnreg<K>(); }
+
+template <int G, int K, int MODE>
+__global__ void __maxnreg__((fill_maxnreg_mode<K, MODE>())) k_gotoh_fill(const FillArgs a)
+{
+    static_assert(K % 4 == 0 && (32 % G) == 0, "bad tile");
+    constexpr int PS = prof_stride(G, K);
+    constexpr int GK = G * K;
+    constexpr bool FLAGS = MODE == FILL_FULL;
+    extern __shared__ __align__(128) int32_t sprof[];
+    __shared__ __align__(8) uint64_t mbar;
+    stage_profile(sprof, &mbar, a.prof, NPAIR * PS * 4);
 
     const int lane = threadIdx.x & 31;
     const int t = lane % G;
@@ -212,6 +240,7 @@ __global__ void __maxnreg__(fill_maxnreg<K>()) k_gotoh_fill(const FillArgs a)
     const uint32_t nopen16_last = lastLane ? 0u : nopen16;                // amplicon row La-1: zero end-gap penalties
     const uint32_t ext32_last = lastLane ? 0u : ext32;
     const uint32_t one = (uint32_t)a.one;
+    const int xlo1 = a.band_row0 + t * K - a.band_B - 1;                  // SCORE: the band's columns are xlo1+1 .. xlo1+W
 
     for (int base = a.p0 + warp_global * GPW; base < a.p1; base += nwarps * GPW) {
         const int p = base + gl;
@@ -219,8 +248,9 @@ __global__ void __maxnreg__(fill_maxnreg<K>()) k_gotoh_fill(const FillArgs a)
         const int Lb = valid ? a.plen[p] : 0;
         const int steps = __reduce_max_sync(0xffffffffu, Lb) + G - 1;
         const int64_t pco = valid ? a.pc_off[p] : 0;
+        const int64_t pco_rel = valid ? pco - a.pc_off[a.p0] : 0;
         const uint8_t *pcp = a.pc + pco;
-        uint32_t *tbp = a.tb + (valid ? (pco - a.pc_off[a.p0]) * (GK / 2) : 0) + t * (K / 2);
+        uint32_t *tbp = FLAGS ? a.tb + pco_rel * (GK / 2) + t * (K / 2) : nullptr;
         uint32_t *lrp = a.lastrow + (int64_t)(p - a.p0) * 3;             // (best, x_lo, x_hi) of amplicon row La-1
         uint32_t *lcp = a.lastcol + ((int64_t)(p - a.p0) * G + t) * 3;   // (best, slot_lo, slot_hi) of this lane's rows, column Lb-1
         const int firstRealSlot = (GK - a.La) - t * K;                   // slots below it are padding rows
@@ -235,34 +265,49 @@ __global__ void __maxnreg__(fill_maxnreg<K>()) k_gotoh_fill(const FillArgs a)
         int rowPosLo = 0, rowPosHi = 0, colPosLo = 0, colPosHi = 0;
         int cp_next = (t == 0 && Lb > 0) ? pcp[0] : 0;
         // top boundary from the pass that owns the rows above (shared DP prefix), read one column ahead
-        const uint32_t *tin = a.top_in ? a.top_in + (pco - a.pc_off[a.p0]) * 3 : nullptr;
-        uint32_t *tout = (a.top_out && t == a.top_out_lane) ? a.top_out + (pco - a.pc_off[a.p0]) * 3 : nullptr;
-        uint32_t tn0 = Z, tn1 = NOPEN_ST, tn2 = Z;
-        if (tin && t == 0 && Lb > 0) { tn0 = tin[0]; tn1 = tin[1]; tn2 = tin[2]; }
+        const int64_t tcol = top_base_col(pco_rel, p - a.p0);
+        const uint4 *tin = (a.top_in && valid) ? reinterpret_cast<const uint4 *>(a.top_in) + tcol : nullptr;
+        uint4 *tout = (a.top_out && valid && t == a.top_out_lane) ? reinterpret_cast<uint4 *>(a.top_out) + tcol : nullptr;
+        uint4 tn = make_uint4(Z, NOPEN_ST, Z, 0u);
+        if (tin && t == 0 && Lb > 0) tn = tin[0];
+        // SCORE: what this lane receives at its band columns, and its registers at the band's left edge
+        uint4 *bandw = nullptr;                                          // indexed by column x
+        uint32_t *leftp = nullptr;
+        if (MODE == FILL_SCORE && valid && a.band_tops) {
+            const int64_t lane_id = (int64_t)(p - a.p0) * G + t;
+            if (t > 0) bandw = reinterpret_cast<uint4 *>(a.band_tops) + lane_id * band_topw(a.band_W) - xlo1;
+            leftp = a.band_left + lane_id * band_leftw(K);
+        }
 
-        for (int s = 0; s < steps; ++s) {
+        // One systolic step.  STEADY = every lane of the warp is on an interior column of its read (no lane
+        // idle, none on a first or last column): the votes, the activity branch and the edge body drop out.
+        auto step = [&](auto steady_tag, const int s) {
+            constexpr bool STEADY = decltype(steady_tag)::value;
             const int x = s - t;
             uint32_t rH3 = __shfl_up_sync(0xffffffffu, botH3, 1, G);
             uint32_t rIY = __shfl_up_sync(0xffffffffu, botIY, 1, G);
             uint32_t rM = __shfl_up_sync(0xffffffffu, botM, 1, G);
-            if (t == 0) { rH3 = tn0; rIY = tn1; rM = tn2; }           // free boundary above the padded top, or the saved row
-            if (tin && t == 0 && x + 1 >= 0 && x + 1 < Lb) { tn0 = tin[3 * (x + 1)]; tn1 = tin[3 * (x + 1) + 1]; tn2 = tin[3 * (x + 1) + 2]; }
-            const bool active = (x >= 0) && (x < Lb);
-            const bool firstCol = active && x == 0, lastCol = active && x == Lb - 1;
-            const bool edge = __any_sync(0xffffffffu, firstCol || lastCol);   // warp-uniform
+            if (t == 0) { rH3 = tn.x; rIY = tn.y; rM = tn.z; }        // free boundary above the padded top, or the saved row
+            if (tin && t == 0 && x + 1 >= 0 && x + 1 < Lb) tn = tin[x + 1];
+            const bool active = STEADY || ((x >= 0) && (x < Lb));
+            const bool firstCol = !STEADY && active && x == 0, lastCol = !STEADY && active && x == Lb - 1;
+            const bool edge = !STEADY && __any_sync(0xffffffffu, firstCol || lastCol);   // warp-uniform
             const int cp = cp_next;
-            if (x + 1 >= 0 && x + 1 < Lb) cp_next = pcp[x + 1];
+            if (STEADY || (x + 1 >= 0 && x + 1 < Lb)) cp_next = pcp[x + 1];
             if (active) {
                 const int32_t *prow = sprof + cp * PS + t * strip_stride(K);
-                uint32_t *tbw = tbp + (int64_t)x * (GK / 2);
+                uint32_t *tbw = FLAGS ? tbp + (int64_t)x * (GK / 2) : nullptr;
+                if (MODE == FILL_SCORE) {
+                    if (bandw && (unsigned)(x - xlo1) <= (unsigned)a.band_W) bandw[x] = make_uint4(rH3, rIY, rM, 0u);
+                }
                 if (edge)
-                    column_step<K, true>(st, prow, rH3, rIY, rM, hd0, nopen16, ext32, nopen16_last, ext32_last,
-                                         lastLane, firstCol, lastCol, one, tbw, firstRealSlot, colBest, colPosLo, colPosHi,
-                                         botH3, botIY, botM);
+                    column_step<K, true, FLAGS, true>(st, prow, rH3, rIY, rM, hd0, nopen16, ext32, nopen16_last, ext32_last,
+                                                      lastLane, firstCol, lastCol, one, tbw, firstRealSlot, colBest, colPosLo, colPosHi,
+                                                      botH3, botIY, botM);
                 else
-                    column_step<K, false>(st, prow, rH3, rIY, rM, hd0, nopen16, ext32, nopen16_last, ext32_last,
-                                          lastLane, false, false, one, tbw, firstRealSlot, colBest, colPosLo, colPosHi,
-                                          botH3, botIY, botM);
+                    column_step<K, false, FLAGS, true>(st, prow, rH3, rIY, rM, hd0, nopen16, ext32, nopen16_last, ext32_last,
+                                                       lastLane, false, false, one, tbw, firstRealSlot, colBest, colPosLo, colPosHi,
+                                                       botH3, botIY, botM);
                 hd0 = rH3;                                            // max3[row above, x] for column x+1
                 // start-cell scan along the last amplicon row (meaningful in the last lane only): first
                 // column whose max(m,ix,iy) is strictly greater than all columns before it
@@ -273,11 +318,120 @@ __global__ void __maxnreg__(fill_maxnreg<K>()) k_gotoh_fill(const FillArgs a)
                     if (d >> 16) rowPosHi = x;
                     rowBest = nb;
                 }
-                if (tout) { tout[3 * x] = botH3; tout[3 * x + 1] = botIY; tout[3 * x + 2] = botM; }
+                if (tout) tout[x] = make_uint4(botH3, botIY, botM, 0u);
+                if (MODE == FILL_SCORE) {
+                    if (leftp && x == xlo1) {                             // registers after column xlo-1: the band pass starts from them
+                        // (scalar stores on purpose: vector stores would make ptxas shuffle 2K registers into aligned
+                        // quads on EVERY step, outside this once-per-pair branch)
+#pragma unroll
+                        for (int k = 0; k < K; ++k) { leftp[k] = st.H3[k]; leftp[K + k] = st.IX[k]; }
+                        leftp[2 * K] = st.mlast;
+                    }
+                }
                 if (lastCol) {
                     lcp[0] = colBest; lcp[1] = (uint32_t)colPosLo; lcp[2] = (uint32_t)colPosHi;
                     if (lastLane) { lrp[0] = rowBest; lrp[1] = (uint32_t)rowPosLo; lrp[2] = (uint32_t)rowPosHi; }
                 }
+            }
+        };
+        // steps G .. Lmin-2 are steady for the whole warp (lane t is on column s - t)
+        const int Lmin = __reduce_min_sync(0xffffffffu, Lb);
+        const int steady_end = max(min(Lmin - 1, steps), min(G, steps));      // first non-steady step after the steady run
+        int s = 0;
+        for (; s < min(G, steps); ++s) step(std::false_type{}, s);
+        for (; s < steady_end; ++s) step(std::true_type{}, s);
+        for (; s < steps; ++s) step(std::false_type{}, s);
+    }
+}
+
+// Second pass of the banded fill: lane t re-evaluates columns xlo .. xlo+W-1 of its K rows with flags.
+// Lanes are independent (top boundary from band_tops / top_in / the free boundary, left edge from
+// band_left), so there are no shuffles and every lane of a warp runs the same W iterations.
+template <int G, int K>
+__global__ void __maxnreg__(fill_maxnreg<K>()) k_gotoh_band(const FillArgs a)
+{
+    constexpr int PS = prof_stride(G, K);
+    extern __shared__ __align__(128) int32_t sprof[];
+    __shared__ __align__(8) uint64_t mbar;
+    stage_profile(sprof, &mbar, a.prof, NPAIR * PS * 4);
+
+    const int lane = threadIdx.x & 31;
+    const int t = lane % G;
+    const int gl = lane / G;
+    constexpr int GPW = 32 / G;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const bool lastLane = (t == G - 1);
+    const uint32_t Z = BIAS2;
+    const uint32_t NOPEN_ST = BIAS2 - (uint32_t)a.open * 0x10001u;
+    const uint32_t nopen16 = ((uint32_t)(-a.open) & 0xffffu) * 0x10001u;
+    const uint32_t ext32 = (uint32_t)a.ext * 0x10001u;
+    const uint32_t nopen16_last = lastLane ? 0u : nopen16;
+    const uint32_t ext32_last = lastLane ? 0u : ext32;
+    const uint32_t one = (uint32_t)a.one;
+    const int W = a.band_W;
+    const int xlo = a.band_row0 + t * K - a.band_B;
+    const uint4 FREE = make_uint4(Z, NOPEN_ST, Z, 0u);
+
+    for (int base = a.p0 + warp_global * GPW; base < a.p1; base += nwarps * GPW) {
+        const int p = base + gl;
+        const bool valid = p < a.p1;
+        const int Lb = valid ? a.plen[p] : 0;
+        const int64_t pco = valid ? a.pc_off[p] : 0;
+        const int64_t pco_rel = valid ? pco - a.pc_off[a.p0] : 0;
+        const uint8_t *pcp = a.pc + pco;
+        const int64_t lane_id = (int64_t)(valid ? p - a.p0 : 0) * G + t;
+        const int x0 = max(xlo, 0), x1 = min(xlo + W - 1, Lb - 1);       // this lane's columns; empty when x0 > x1
+        // source of the top boundary: the lane above (saved by the score pass), the pass that owns the rows
+        // above the sub-tile, or the free boundary.  Indexed so that src[x] is column x.
+        const uint4 *src = nullptr;
+        if (t > 0) src = reinterpret_cast<const uint4 *>(a.band_tops) + lane_id * band_topw(W) - (xlo - 1);
+        else if (a.top_in) src = reinterpret_cast<const uint4 *>(a.top_in) + top_base_col(pco_rel, valid ? p - a.p0 : 0);
+        uint32_t *tbl = a.band_tb + lane_id * W * (K / 2);
+
+        Strip<K> st;
+        uint32_t hd0 = Z;
+        if (x0 > 0 && x0 <= x1) {
+            const uint4 *lp = reinterpret_cast<const uint4 *>(a.band_left + lane_id * band_leftw(K));
+#pragma unroll
+            for (int j = 0; j < K / 4; ++j) {
+                const uint4 v = lp[j], w = lp[K / 4 + j];
+                st.H3[4 * j] = v.x; st.H3[4 * j + 1] = v.y; st.H3[4 * j + 2] = v.z; st.H3[4 * j + 3] = v.w;
+                st.IX[4 * j] = w.x; st.IX[4 * j + 1] = w.y; st.IX[4 * j + 2] = w.z; st.IX[4 * j + 3] = w.w;
+            }
+            st.mlast = lp[K / 2].x;
+            if (src) hd0 = src[x0 - 1].x;
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) { st.H3[k] = Z; st.IX[k] = NOPEN_ST; }
+            st.mlast = Z;
+        }
+        uint32_t botH3, botIY, botM, colBest = 0;
+        int colPosLo = 0, colPosHi = 0;
+        uint4 rn = FREE;
+        int cp_next = 0;
+        if (x0 <= x1) { if (src) rn = src[x0]; cp_next = pcp[x0]; }
+
+        for (int i = 0; i < W; ++i) {
+            const int x = xlo + i;
+            const bool active = x >= x0 && x <= x1;
+            const uint4 r = rn;
+            const int cp = cp_next;
+            if (x + 1 >= x0 && x + 1 <= x1) { if (src) rn = src[x + 1]; cp_next = pcp[x + 1]; }
+            const bool firstCol = active && x == 0, lastCol = active && x == Lb - 1;
+            const bool edge = __any_sync(0xffffffffu, firstCol || lastCol);   // warp-uniform
+            if (active) {
+                const int32_t *prow = sprof + cp * PS + t * strip_stride(K);
+                uint32_t *tbw = tbl + (int64_t)i * (K / 2);
+                if (edge)
+                    column_step<K, true, true, false>(st, prow, r.x, r.y, r.z, hd0, nopen16, ext32, nopen16_last, ext32_last,
+                                                      lastLane, firstCol, lastCol, one, tbw, 0, colBest, colPosLo, colPosHi,
+                                                      botH3, botIY, botM);
+                else
+                    column_step<K, false, true, false>(st, prow, r.x, r.y, r.z, hd0, nopen16, ext32, nopen16_last, ext32_last,
+                                                       lastLane, false, false, one, tbw, 0, colBest, colPosLo, colPosHi,
+                                                       botH3, botIY, botM);
+                hd0 = r.x;
             }
         }
     }
@@ -287,26 +441,29 @@ __global__ void __maxnreg__(fill_maxnreg<K>()) k_gotoh_fill(const FillArgs a)
 struct Tile { int G, K; };
 
 template <int G, int K>
-static cudaError_t launch_tile(const FillArgs &a, int num_sms, cudaStream_t stream)
+static cudaError_t launch_tile(const FillArgs &a, int num_sms, cudaStream_t stream, int kind)
 {
     const size_t smem = (size_t)NPAIR * prof_stride(G, K) * 4;
     static bool configured = false;
-    static int blocks_per_sm = 1;
+    static int blocks_per_sm[3] = {1, 1, 1};
+    void (*kern[3])(const FillArgs) = {k_gotoh_fill<G, K, FILL_FULL>, k_gotoh_fill<G, K, FILL_SCORE>, k_gotoh_band<G, K>};
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_gotoh_fill<G, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_gotoh_fill<G, K>, 128, smem);
-        if (e != cudaSuccess) return e;
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
+        for (int i = 0; i < 3; ++i) {
+            cudaError_t e = cudaFuncSetAttribute(kern[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[i], kern[i], 128, smem);
+            if (e != cudaSuccess) return e;
+            if (blocks_per_sm[i] < 1) blocks_per_sm[i] = 1;
+        }
         configured = true;
     }
     const int npairs = a.p1 - a.p0;
     const int groups_per_block = 4 * (32 / G);
     int grid = (npairs + groups_per_block - 1) / groups_per_block;
-    const int cap = num_sms * blocks_per_sm;      // persistent: a multiple of the SM count
+    const int cap = num_sms * blocks_per_sm[kind];      // persistent: a multiple of the SM count
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    k_gotoh_fill<G, K><<<grid, 128, smem, stream>>>(a);
+    kern[kind]<<<grid, 128, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -338,9 +495,11 @@ bool tile_available(int G, int K)
     return false;
 }
 
-cudaError_t launch_fill(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream)
+// kind: 0 = full single pass (flags for every cell), 1 = score pass of the banded fill, 2 = band pass
+cudaError_t launch_fill(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream, int kind)
 {
-#define CASE(g, k) if (G == g && K == k) return launch_tile<g, k>(a, num_sms, stream);
+    if (kind < 0 || kind > 2) return cudaErrorInvalidValue;
+#define CASE(g, k) if (G == g && K == k) return launch_tile<g, k>(a, num_sms, stream, kind);
     CASE(4, 16) CASE(4, 24) CASE(4, 32) CASE(4, 40) CASE(8, 16) CASE(8, 24) CASE(8, 32) CASE(8, 40)
     CASE(16, 16) CASE(16, 24) CASE(16, 32) CASE(16, 40) CASE(32, 24) CASE(32, 32) CASE(4, 48) CASE(8, 48) CASE(16, 48)
 #undef CASE

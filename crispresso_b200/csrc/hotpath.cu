@@ -197,6 +197,7 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
     const bool has_hdr = path->hdr_amplicon != nullptr && path->hdr_amplicon_len > 0;
     if (has_hdr != ((quant->flags & CRGPU_Q_HAS_HDR) != 0)) return fail(ctx, CRGPU_E_ARG, "CRGPU_Q_HAS_HDR must match path->hdr_amplicon");
     timing_reset(ctx);
+    ctx->n_escaped[0] = ctx->n_escaped[1] = 0;
     out->rc_n = 0;
     if (n == 0) return CRGPU_OK;
     if (!out->kept || !out->aln || !out->recs) return fail(ctx, CRGPU_E_ARG, "kept/aln/recs are required");
@@ -251,27 +252,88 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
     // ---- 1. forward alignments: amplicon (+ HDR amplicon, CORE:1810-1828) ----
     int64_t cells = 0, cells_computed = 0;
     crgpu_aln_rec *d_aln_hdr = nullptr;
-    bool dual_done = false;
+    bool amp_done = false, hdr_done = !has_hdr, banded = false;
+    uint8_t *d_esc = nullptr;
     if (has_hdr) {
         CK(ctx->aux[1].reserve((size_t)n * sizeof(crgpu_aln_rec)));
         d_aln_hdr = ctx->aux[1].as<crgpu_aln_rec>();
-        if (path->hdr_amplicon_len == amplicon_len) {
-            rc = run_plan_dual(ctx, amplicon, path->hdr_amplicon, amplicon_len, d_reads, d_off, path->gapopen, path->gapextend,
-                               d_aln, d_aln_hdr, d_ref, d_mark, d_qry, slot, &cells, &cells_computed, d_ops, ops_stride, &dual_done);
+    }
+    if (ctx->band_B > 0) {
+        // banded two-pass fill; reads whose traceback leaves the band are flagged in d_esc and re-aligned below
+        CK(ctx->escaped.reserve((size_t)n));
+        d_esc = ctx->escaped.as<uint8_t>();
+        CK(cudaMemsetAsync(d_esc, 0, (size_t)n, s));
+        bool done = false;
+        if (has_hdr && path->hdr_amplicon_len == amplicon_len) {
+            rc = run_plan_band(ctx, amplicon, path->hdr_amplicon, amplicon_len, d_reads, d_off, path->gapopen, path->gapextend,
+                               d_aln, d_aln_hdr, d_ref, d_mark, d_qry, slot, &cells, &cells_computed, d_ops, ops_stride, d_esc, 1, &done);
             if (rc) { cudaStreamSynchronize(s); return rc; }
+            if (done) amp_done = hdr_done = banded = true;
+        }
+        if (!amp_done) {
+            rc = run_plan_band(ctx, amplicon, nullptr, amplicon_len, d_reads, d_off, path->gapopen, path->gapextend,
+                               d_aln, nullptr, d_ref, d_mark, d_qry, slot, &cells, &cells_computed, d_ops, ops_stride, d_esc, 1, &done);
+            if (rc) { cudaStreamSynchronize(s); return rc; }
+            if (done) {
+                amp_done = banded = true;
+                if (has_hdr) {
+                    rc = run_plan_band(ctx, path->hdr_amplicon, nullptr, path->hdr_amplicon_len, d_reads, d_off, path->gapopen,
+                                       path->gapextend, d_aln_hdr, nullptr, nullptr, nullptr, nullptr, slot, &cells, &cells_computed,
+                                       nullptr, 0, d_esc, 2, &done);
+                    if (rc) { cudaStreamSynchronize(s); return rc; }
+                    hdr_done = done;
+                }
+            }
         }
     }
-    if (!dual_done) {
+    if (!amp_done && has_hdr && path->hdr_amplicon_len == amplicon_len) {
+        bool dual_done = false;
+        rc = run_plan_dual(ctx, amplicon, path->hdr_amplicon, amplicon_len, d_reads, d_off, path->gapopen, path->gapextend,
+                           d_aln, d_aln_hdr, d_ref, d_mark, d_qry, slot, &cells, &cells_computed, d_ops, ops_stride, &dual_done);
+        if (rc) { cudaStreamSynchronize(s); return rc; }
+        if (dual_done) amp_done = hdr_done = true;
+    }
+    if (!amp_done) {
         int64_t c0 = 0;
         rc = run_plan(ctx, amplicon, amplicon_len, d_reads, d_off, nullptr, 0, path->gapopen, path->gapextend, d_aln, d_ref, d_mark,
                       d_qry, slot, &c0, d_ops, ops_stride);
         if (rc) { cudaStreamSynchronize(s); return rc; }
-        if (has_hdr) {
-            rc = run_plan(ctx, path->hdr_amplicon, path->hdr_amplicon_len, d_reads, d_off, nullptr, 0, path->gapopen,
-                          path->gapextend, d_aln_hdr, nullptr, nullptr, nullptr, slot, &c0);
-            if (rc) { cudaStreamSynchronize(s); return rc; }
-        }
         cells += c0; cells_computed += c0;
+    }
+    if (!hdr_done) {
+        int64_t c0 = 0;
+        rc = run_plan(ctx, path->hdr_amplicon, path->hdr_amplicon_len, d_reads, d_off, nullptr, 0, path->gapopen,
+                      path->gapextend, d_aln_hdr, nullptr, nullptr, nullptr, slot, &c0);
+        if (rc) { cudaStreamSynchronize(s); return rc; }
+        cells += c0; cells_computed += c0;
+    }
+    if (banded) {
+        // reads that escaped the band: compacted on the device, re-aligned with the single-pass fill
+        const size_t sb = select_scratch_bytes(n);
+        CK(ctx->aux[3].reserve((size_t)n * 4 + 16));
+        CK(ctx->alleles.reserve(sb));
+        int32_t *d_sel = ctx->aux[3].as<int32_t>();
+        int *d_cnt = reinterpret_cast<int *>(d_sel + n);
+        for (int bit = 1; bit <= (has_hdr ? 2 : 1); bit <<= 1) {
+            CK(select_flagged(d_esc, n, bit, d_sel, d_cnt, ctx->alleles.p, sb, s));
+            int h_cnt = 0;
+            CK(cudaMemcpyAsync(&h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            ctx->n_escaped[bit - 1] = h_cnt;
+            if (h_cnt == 0) continue;
+            int64_t c0 = 0;
+            rc = build_plan(ctx, d_reads, d_off, d_sel, h_cnt);
+            if (rc == CRGPU_OK) {
+                if (bit == 1)
+                    rc = run_plan(ctx, amplicon, amplicon_len, d_reads, d_off, nullptr, 0, path->gapopen, path->gapextend, d_aln, d_ref,
+                                  d_mark, d_qry, slot, &c0, d_ops, ops_stride);
+                else
+                    rc = run_plan(ctx, path->hdr_amplicon, path->hdr_amplicon_len, d_reads, d_off, nullptr, 0, path->gapopen,
+                                  path->gapextend, d_aln_hdr, nullptr, nullptr, nullptr, slot, &c0);
+            }
+            if (rc) { cudaStreamSynchronize(s); return rc; }
+            cells_computed += c0;
+        }
     }
 
     // ---- 2. keep / rescue decision ----

@@ -138,12 +138,33 @@ __global__ void __launch_bounds__(128) k_traceback_walk(const WalkArgs a)
     for (int x = Lb - 1; x > s2; --x) EMIT_GAP_A(b[x]);
     for (int y = La - 1; y > s1; --y) EMIT_GAP_B(amp[y]);
 
-    const uint8_t *tb = reinterpret_cast<const uint8_t *>(a.tb + (a.pc_off[p] - a.pc_off[a.p0]) * (a.GK / 2));
+    const bool band = a.band_W > 0;
+    const int64_t pair_rel = p - a.p0;
+    const uint8_t *tb = band ? reinterpret_cast<const uint8_t *>(a.tb) + pair_rel * a.G * a.band_W * a.K * 2
+                             : reinterpret_cast<const uint8_t *>(a.tb + (a.pc_off[p] - a.pc_off[a.p0]) * (a.GK / 2));
     const int64_t colbytes = (int64_t)a.GK * 2;
-    const uint8_t *tbu = a.tb_upper ? reinterpret_cast<const uint8_t *>(a.tb_upper + (a.pc_off[p] - a.pc_off[a.p0]) * (a.G_upper * a.K / 2)) : nullptr;
+    const uint8_t *tbu = !a.tb_upper ? nullptr
+                         : band ? reinterpret_cast<const uint8_t *>(a.tb_upper) + pair_rel * a.G_upper * a.band_W * a.K * 2
+                                : reinterpret_cast<const uint8_t *>(a.tb_upper + (a.pc_off[p] - a.pc_off[a.p0]) * (a.G_upper * a.K / 2));
     const int64_t colbytes_u = (int64_t)a.G_upper * a.K * 2;
     const int split = a.tb_upper ? a.split_row : 0;
     const int P = a.P;
+    // flag byte of cell (yy, xx).  Banded fill: lane t = padded row / K holds columns [t*K - P - B, +W) only;
+    // anything else reads as 0xff (never a flag byte), which ends the walk with an escape when it is consumed.
+    auto tb_at = [&](int yy, int xx) -> uint8_t {
+        const int v = yy + P;
+        if (band) {
+            const int tf = (int)__umulhi((unsigned)v, a.kdiv_magic);
+            const int rr = v - tf * a.K;
+            const int xr = xx - (tf * a.K - P - a.band_B);
+            if ((unsigned)xr >= (unsigned)a.band_W) return (uint8_t)0xff;
+            const uint8_t *q = v < split ? tbu + ((int64_t)tf * a.band_W + xr) * (a.K * 2)
+                                         : tb + ((int64_t)(tf - split / a.K) * a.band_W + xr) * (a.K * 2);
+            return q[((rr >> 1) << 2) + (h << 1) + (rr & 1)];
+        }
+        return v < split ? tbu[xx * colbytes_u + ((v >> 1) << 2) + (h << 1) + (v & 1)]
+                         : tb[xx * colbytes + (((v - split) >> 1) << 2) + (h << 1) + ((v - split) & 1)];
+    };
     int y = s1, x = s2, prev = 0;
     bool contL = false, contD = false;
     const int ca0 = base_code(amp[0]);
@@ -152,13 +173,15 @@ __global__ void __launch_bounds__(128) k_traceback_walk(const WalkArgs a)
     // a LEFT / DOWN step invalidates the window and refills it with PF independent loads.
     constexpr int PF = 8;
     uint8_t pf[PF];
-#define TB_AT(yy, xx) (((yy) + P) < split ? tbu[(xx) * colbytes_u + ((((yy) + P) >> 1) << 2) + (h << 1) + (((yy) + P) & 1)] \
-                                        : tb[(xx) * colbytes + ((((yy) + P - split) >> 1) << 2) + (h << 1) + (((yy) + P - split) & 1)])
-#define PF_LOAD(k) pf[k] = (y - (k) >= 0 && x - (k) >= 0) ? TB_AT(y - (k), x - (k)) : (uint8_t)0
+#define PF_LOAD(k) pf[k] = (y - (k) >= 0 && x - (k) >= 0) ? tb_at(y - (k), x - (k)) : (uint8_t)0
 #pragma unroll
     for (int k = 0; k < PF; ++k) PF_LOAD(k);
     while (x >= 0 && y >= 0) {
         const int f = pf[0];
+        if (f == 0xff) {                               // the path left the band: this read is re-aligned with the full fill
+            a.escaped[r] |= (uint8_t)a.escape_bit;
+            return;
+        }
         int dir;
         if (prev == 1 && contL) dir = 1;
         else if (prev == 2 && contD) dir = 2;
@@ -201,7 +224,6 @@ __global__ void __launch_bounds__(128) k_traceback_walk(const WalkArgs a)
         prev = dir;
     }
 #undef PF_LOAD
-#undef TB_AT
     for (; x >= 0; --x) EMIT_GAP_A(b[x]);
     for (; y >= 0; --y) EMIT_GAP_B(amp[y]);
 #undef EMIT_GAP_A

@@ -66,6 +66,14 @@ int crgpu_set_overlap(crgpu_ctx *ctx, int on);
 /* The HDR-amplicon pass normally reuses the DP rows it shares with the amplicon pass (bit-identical
  * results, fewer cells evaluated; default on).  Off = two full passes. */
 int crgpu_set_share_prefix(crgpu_ctx *ctx, int on);
+/* Banded two-pass fill (default half-width 24 read columns; 0 = single-pass fill with flags for every
+ * cell).  The first pass evaluates every DP cell without traceback flags, the second re-evaluates, with
+ * flags, only the columns within half_width of the main diagonal of each lane's rows; a read whose
+ * traceback leaves the band is re-aligned with the single-pass fill, so results never depend on this. */
+int crgpu_set_band(crgpu_ctx *ctx, int half_width);
+/* Reads the last crgpu_align_quantify call re-aligned with the single-pass fill because their traceback
+ * left the band: out[0] amplicon pass, out[1] HDR-amplicon pass. */
+int crgpu_last_escaped(const crgpu_ctx *ctx, int out[2]);
 /* Device time (ms, CUDA events on the context's stream) spent in each kernel family during
  * the LAST call on this context, and launch counts.  out_ms[0..5] = encode, fill, walk,
  * quantify, qualfilter, other;  out_launches likewise. */

@@ -119,6 +119,7 @@ def test_shared_dp_prefix_of_the_hdr_pass_changes_nothing(ctx):
         other = Context(0)
         try:
             other.set_traceback_budget(32 << 20)
+            other.set_band(0)                             # single-pass fill: evaluated cells are exactly the DP cells
             a = hotpath.run_hot_path(other, amp, packed, hdr_amplicon=hdr, flags=flags, want_rows=True)
             other.set_share_prefix(False)
             b = hotpath.run_hot_path(other, amp, packed, hdr_amplicon=hdr, flags=flags, want_rows=True)
@@ -137,5 +138,44 @@ def test_shared_dp_prefix_of_the_hdr_pass_changes_nothing(ctx):
     amp, guide, cut, _ = synth.make_case(75, 200, hdr=False)
     hdr2 = "T" + amp[1:] if amp[0] != "T" else "G" + amp[1:]
     packed = synth.make_reads(amp, hdr2, cut, 500, seed=75)
-    r = hotpath.run_hot_path(ctx, amp, packed, hdr_amplicon=hdr2, flags=hotpath.quant_flags(hdr2))
+    ctx.set_band(0)
+    try:
+        r = hotpath.run_hot_path(ctx, amp, packed, hdr_amplicon=hdr2, flags=hotpath.quant_flags(hdr2))
+    finally:
+        ctx.set_band(24)
     assert r.red.n_cells_computed == r.red.n_cells
+
+
+@pytest.mark.parametrize("La,read_len,sigma,hdr_on", [(250, 250, 0.0, True), (300, 300, 8.0, False), (600, 600, 0.0, True),
+                                                      (250, None, 0.0, True), (180, 400, 10.0, False), (700, 700, 0.0, True)])
+def test_banded_two_pass_fill_changes_nothing(La, read_len, sigma, hdr_on):
+    """The banded fill (score pass + band pass + re-alignment of reads whose traceback leaves the band) must
+    give exactly what the single-pass fill gives, for every band width -- including widths so small that
+    most edited reads escape -- with and without the shared HDR prefix."""
+    from crispresso_b200 import Context
+    seed = 500 + La
+    amp, guide, cut, hdr = synth.make_case(seed, La, hdr=hdr_on)
+    packed = synth.make_reads(amp, hdr, cut, 1200, seed=seed, read_len=read_len, len_sigma=sigma, rc_frac=0.04, n_rate=0.002)
+    flags = hotpath.quant_flags(hdr or "")
+    c = Context(0)
+    try:
+        c.set_traceback_budget(24 << 20)
+        c.set_band(0)
+        ref = hotpath.run_hot_path(c, amp, packed, hdr_amplicon=hdr, flags=flags, want_rows=True)
+        assert c.last_escaped() == (0, 0)
+        seen_escape = False
+        for B, share in ((24, True), (2, True), (40, False), (9, True)):
+            c.set_band(B)
+            c.set_share_prefix(share)
+            got = hotpath.run_hot_path(c, amp, packed, hdr_amplicon=hdr, flags=flags, want_rows=True)
+            seen_escape |= c.last_escaped()[0] > 0
+            got.red.n_cells_computed = ref.red.n_cells_computed
+            assert np.array_equal(got.red.flat(), ref.red.flat()), (B, share)
+            assert np.array_equal(got.aln, ref.aln) and np.array_equal(got.recs, ref.recs) and np.array_equal(got.kept, ref.kept)
+            assert np.array_equal(got.tenths_rep, ref.tenths_rep)
+            for k in range(3):
+                assert np.array_equal(got.rows[k], ref.rows[k])
+        if La >= 250:
+            assert seen_escape                   # the 2-column band cannot hold a read with an indel
+    finally:
+        c.close()
