@@ -27,7 +27,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-OPS_PER_CELL = 13          # algorithmic integer ops per DP cell
+OPS_PER_CELL = 13          # scalar integer ops per DP cell (continuity figure)
+ALU_INSTR_PER_CELL = 1.5   # integer-ALU-pipe lane-instructions per DP cell that no formulation avoids
 AMPLICON_LEN = 250
 READ_LEN = 250
 SEED = 1234
@@ -182,9 +183,11 @@ def main():
     flags = hotpath.quant_flags(hdr)
     h2d_bytes = int(buf.nbytes + off.nbytes)
 
-    # integer issue peak, measured live: dependency-free IADD chains that ptxas splits 1:1
-    # over the alu (IADD3) and fma (IMAD.IADD) pipes, and a VIMNMX.S16x2 + IMAD 1:1 mix; best of both
+    # integer issue peaks, measured live: (i) both integer pipes -- dependency-free IADD chains that
+    # ptxas splits 1:1 over the alu (IADD3) and fma (IMAD.IADD) pipes, and a VIMNMX.S16x2 + IMAD 1:1 mix; (ii) the
+    # integer-ALU pipe alone -- VIMNMX / VIADDMNMX / VIMNMX3 .S16x2 issue nowhere else (profiles/r01_notes.md)
     int_peak = max(ctx.int_peak(0), ctx.int_peak(4))
+    alu_peak = max(ctx.int_peak(2), ctx.int_peak(3), ctx.int_peak(5))
 
     # ---- device-resident arm ------------------------------------------------------------------
     d_buf = torch.from_numpy(buf).cuda()
@@ -249,6 +252,7 @@ def main():
     hotpath.run_hot_path(ctx, amp, None, hdr_amplicon=hdr, flags=flags, inc=inc, red=iso_red,
                          device_inputs=(d_buf.data_ptr(), d_off.data_ptr(), n, READ_LEN, dev_ptrs))
     ms_, ln_ = ctx.last_timing()
+    iso_kinds = ctx.last_fill_breakdown()
     for k in ms_:
         iso_ms[k] += ms_[k]
         iso_ln[k] += ln_[k]
@@ -324,30 +328,45 @@ def main():
     value = total_reads / (dev_ms * 1e-3)
     e2e_value = total_reads / (e2e_ms * 1e-3)
     cells_per_rank_step = 2.0 * L * float(off[-1])          # amplicon + HDR amplicon, full DP matrices (RC rescue cells are extra)
-    # cells the fill launches of one step actually evaluate (the HDR pass reuses the DP rows it shares with the
-    # amplicon pass; RC-rescue fills included) -- the numerator of the kernel roofline
+    # cells the fill launches of one step actually evaluate (score pass: every cell once, the HDR pass only the rows
+    # below the shared prefix; band pass: the band columns again, with flags; escapes and the RC rescue: single-pass
+    # fill) -- the numerators of the kernel rooflines
     computed_per_step = float(iso_red.n_cells_computed)
-    cells_per_launch = computed_per_step / max(1, iso_ln["fill"])
     peak = int_peak / 1e12
-    # (1) the kernel by itself: one extra step right after the timed region with the stream overlap
-    #     switched off, so every k_gotoh_fill launch runs alone and its CUDA-event duration is its own
-    iso_fill_ms = iso_ms["fill"] / max(1, iso_ln["fill"])
-    achieved = cells_per_launch * OPS_PER_CELL / (iso_fill_ms * 1e-3) / 1e12
-    fill_ms = iso_fill_ms
-    # (2) inside the timed region the launches overlap each other (tail back-fill) and the walks, so
-    #     their individual durations are not additive; the whole step's effective rate is reported instead
-    conc_fill_ms = fam_ms["fill"] / max(1, fam_launch["fill"])
-    step_effective = computed_per_step * OPS_PER_CELL / (dev_ms / args.steps * 1e-3) / 1e12
-    tb_bytes_per_cell = 1.0
+    alu_pk = alu_peak / 1e12
+    # Roofline model: per packed cell pair the recurrences need 1 add + 2 VIADDMNMX.S16x2 + 1
+    # VIMNMX3.S16x2; the three min/max instructions issue only on the integer-ALU pipe => 1.5 ALU lane-instructions
+    # per cell, peak = the measured single-pipe rate.  Per-kernel durations come from one extra step right after the
+    # timed region (same data) with the stream overlap off, so every launch runs alone between its CUDA events.
+    kinds = {}
+    for kname, label in (("score", "k_gotoh_score<G,K> (score pass, drift coordinates, no flags)"),
+                         ("band", "k_gotoh_band<G,K> (band pass, flags)"),
+                         ("full", "k_gotoh_fill<G,K> (single pass with flags: band escapes + RC rescue)")):
+        ms_k, ln_k, cells_k = iso_kinds[kname]
+        if ln_k == 0 or ms_k <= 0:
+            continue
+        tc = cells_k / (ms_k * 1e-3) / 1e12
+        kinds[kname] = {"kernel": label, "launches_per_step": ln_k, "ms_per_step": ms_k, "ms_per_launch": ms_k / ln_k,
+                        "cells_per_step": cells_k, "cells_per_launch": cells_k / ln_k, "tcups": tc,
+                        "achieved": tc * ALU_INSTR_PER_CELL, "frac": tc * ALU_INSTR_PER_CELL / alu_pk,
+                        "survey_13ops_tiops": tc * OPS_PER_CELL, "survey_13ops_frac_of_dual_pipe_peak": tc * OPS_PER_CELL / peak}
+    dom = max(kinds, key=lambda k: kinds[k]["ms_per_step"])
+    iso_fill_total = sum(v["ms_per_step"] for v in kinds.values())
+    blended_tcups = computed_per_step / (iso_fill_total * 1e-3) / 1e12
+    # inside the timed region the launches overlap each other (tail back-fill) and the walks, so their individual
+    # durations are not additive; the whole step's effective rate is reported instead
+    step_tcups_evaluated = computed_per_step / (dev_ms / args.steps * 1e-3) / 1e12
+    step_tcups_useful = cells_per_rank_step / (dev_ms / args.steps * 1e-3) / 1e12
     hbm_peak = None
     try:
         hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         hbm_peak = 6650.0
-    hbm_achieved = cells_per_launch * tb_bytes_per_cell / (fill_ms * 1e-3) / 1e9
     traffic = None
+    traffic_all = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "fill_traffic.json")))["dram_bytes_per_cell"] * cells_per_launch
+        traffic_all = json.load(open(os.path.join(ROOT, "profiles", "fill_traffic.json")))
+        traffic = traffic_all[dom]["dram_bytes_per_cell"] * kinds[dom]["cells_per_launch"]
     except Exception:
         pass
     line = {
@@ -356,7 +375,8 @@ def main():
         "vs_baseline": None, "dtype": "int16x2", "data": "synthetic",
         "gcups": (cells_per_rank_step * world * args.steps) / (dev_ms * 1e-3) / 1e9,
         "gcups_note": "La x Lb of every alignment made (2 per read) / time; `gcups_evaluated` counts only the DP cells the "
-                      "kernels evaluate (the HDR pass reuses the rows it shares with the amplicon pass, bit-identical results)",
+                      "kernels evaluate (the HDR pass reuses the rows it shares with the amplicon pass; the band pass evaluates the "
+                      "band columns a second time, with flags; bit-identical results)",
         "gcups_evaluated": (computed_per_step * world * args.steps) / (dev_ms * 1e-3) / 1e9,
         "config": {"workload": "cfg2: %d single-end %d-bp reads per GPU vs %d-bp amplicon + HDR amplicon (needle "
                                "gapopen 10 / gapextend 0.5), RC rescue, classification + histograms" % (n, READ_LEN, L),
@@ -366,26 +386,36 @@ def main():
                 "ms_per_step": e2e_ms / args.steps, "results_equal_device_arm": same},
         "gpu_launches": int(sum(fam_launch.values())),
         "kernel_ms_per_step": {k: fam_ms[k] / args.steps for k in fam_ms},
-        "roofline": {"bound": "int_alu", "kernel": "k_gotoh_fill<8,32> (amplicon pass) + k_gotoh_fill<4,32> (HDR pass below the shared rows)", "achieved": achieved, "peak": peak, "unit": "Tiop/s",
-                     "frac": achieved / peak if peak else None, "traffic": traffic,
-                     "ops_per_cell": OPS_PER_CELL, "cells_per_launch": cells_per_launch, "ms_per_launch": fill_ms,
-                     "cells_evaluated_per_step": computed_per_step, "fill_launches_per_step": iso_ln["fill"],
-                     "tcups": cells_per_launch / (fill_ms * 1e-3) / 1e12,
-                     "peak_source": "measured live: crgpu_int_peak, best of IADD3+IMAD.IADD 1:1 and VIMNMX.S16x2+IMAD 1:1 "
-                                    "(single-pipe rate is half of it)",
-                     "peak_theoretical": 148 * 128 * 1.965e9 / 1e12,
-                     "frac_of_theoretical": achieved / (148 * 128 * 1.965e9 / 1e12),
-                     "note": "achieved/frac: k_gotoh_fill launches timed with CUDA events in one extra step (same data, right "
-                             "after the timed region) in which launches are serialised; in the timed region consecutive "
-                             "fill launches and the traceback walks overlap on three streams, so per-launch durations there "
-                             "are not additive (`in_timed_region`); `step_effective` = all DP cells of a step x 13 / step time",
-                     "in_timed_region": {"ms_per_launch_concurrent": conc_fill_ms,
-                                         "step_effective_tiops": step_effective,
-                                         "step_effective_frac": step_effective / peak if peak else None},
+        "roofline": {"bound": "int_alu", "kernel": kinds[dom]["kernel"], "achieved": kinds[dom]["achieved"], "peak": alu_pk,
+                     "unit": "T lane-instr/s on the integer-ALU pipe", "frac": kinds[dom]["frac"], "traffic": traffic,
+                     "alu_instr_per_cell": ALU_INSTR_PER_CELL, "cells_per_launch": kinds[dom]["cells_per_launch"],
+                     "ms_per_launch": kinds[dom]["ms_per_launch"], "tcups": kinds[dom]["tcups"],
+                     "peak_source": "measured live: crgpu_int_peak, best of the VIMNMX / VIADDMNMX / VIMNMX3 .S16x2 probes (one "
+                                    "pipe; the dual-pipe IADD3+IMAD rate is %.2f)" % peak,
+                     "peak_tcups": alu_pk / ALU_INSTR_PER_CELL,
+                     "model": "per packed cell pair: 1 add (m) + 2 VIADDMNMX.S16x2 (ix, iy; the gap extension is carried as a "
+                              "coordinate drift) + 1 VIMNMX3.S16x2; the 3 min/max instructions issue only on the integer-ALU "
+                              "pipe => 1.5 ALU lane-instructions per DP cell; flags, boundary hand-over and the walk are overhead",
+                     "by_kernel": kinds,
+                     "fill_blended": {"tcups": blended_tcups, "frac": blended_tcups * ALU_INSTR_PER_CELL / alu_pk,
+                                      "cells_evaluated_per_step": computed_per_step, "ms_per_step": iso_fill_total},
+                     "survey_8d": {"ops_per_cell": OPS_PER_CELL, "peak_tiops": peak, "peak_theoretical_tiops": 148 * 128 * 1.965e9 / 1e12,
+                                   "achieved_tiops": blended_tcups * OPS_PER_CELL, "frac": blended_tcups * OPS_PER_CELL / peak,
+                                   "note": "SURVEY 8(d)'s accounting (13 scalar ops per cell against the 32-bit lane-op rate of both "
+                                           "pipes): one packed .S16x2 lane-instruction serves two cells and VIADDMNMX / VIMNMX3 fuse two "
+                                           "scalar ops each, so this ratio can exceed 1 and is kept only for continuity with the round-1 "
+                                           "lines; `frac` above is the bound that holds"},
+                     "in_timed_region": {"note": "fill launches of consecutive batches and the traceback walks overlap on three streams; "
+                                                 "per-launch durations there are not additive",
+                                         "fill_ms_per_step_concurrent": fam_ms["fill"] / args.steps,
+                                         "step_tcups_evaluated": step_tcups_evaluated, "step_tcups_useful": step_tcups_useful,
+                                         "step_frac_evaluated": step_tcups_evaluated * ALU_INSTR_PER_CELL / alu_pk},
                      "isolated_kernel_ms_per_step": iso_ms},
-        "roofline_hbm": {"bound": "hbm", "kernel": "k_gotoh_fill<8,32>", "achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": hbm_achieved / hbm_peak, "bytes_per_cell": tb_bytes_per_cell,
+        "roofline_hbm": {"bound": "hbm", "kernel": "k_gotoh_band<G,K> (1 flag byte per band cell)",
+                         "achieved": (kinds["band"]["tcups"] * 1e3 if "band" in kinds else None), "peak": hbm_peak, "unit": "GB/s",
+                         "frac": (kinds["band"]["tcups"] * 1e3 / hbm_peak if "band" in kinds else None), "bytes_per_cell": 1.0,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else "fallback"},
+        "band": {"half_width": ctx.band(), "escaped_amplicon_hdr": list(ctx.last_escaped())},
         "clocks": clocks,
         "classes": {"n_total": int(n_total), "unmodified": int(red.class_counts[0]), "nhej": int(red.class_counts[1]),
                     "hdr": int(red.class_counts[2]), "mixed": int(red.class_counts[3])},

@@ -93,9 +93,12 @@ def load():
     lib.crgpu_last_error.restype = ctypes.c_char_p
     lib.crgpu_set_traceback_budget.argtypes = [vp, ctypes.c_size_t]
     lib.crgpu_last_timing.argtypes = [vp, vp, vp]
+    lib.crgpu_last_fill_breakdown.argtypes = [vp, vp, vp, vp]
     lib.crgpu_set_overlap.argtypes = [vp, i32]
     lib.crgpu_set_share_prefix.argtypes = [vp, i32]
     lib.crgpu_set_band.argtypes = [vp, i32]
+    lib.crgpu_get_band.argtypes = [vp]
+    lib.crgpu_get_band.restype = i32
     lib.crgpu_last_escaped.argtypes = [vp, ctypes.POINTER(ctypes.c_int * 2)]
     lib.crgpu_sync.argtypes = [vp]
     lib.crgpu_stream.argtypes = [vp]
@@ -110,7 +113,7 @@ def load():
     lib.crgpu_fastq_index.argtypes = [vp, i32, vp, i64, i32, ctypes.POINTER(FastqOut)]
     lib.crgpu_flash_merge.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i64, ctypes.POINTER(MergeParams),
                                       ctypes.POINTER(MergeOut)]
-    for name in ("crgpu_create", "crgpu_set_overlap", "crgpu_set_share_prefix", "crgpu_set_band", "crgpu_last_escaped", "crgpu_set_traceback_budget", "crgpu_last_timing", "crgpu_sync", "crgpu_qualfilter",
+    for name in ("crgpu_create", "crgpu_set_overlap", "crgpu_set_share_prefix", "crgpu_set_band", "crgpu_last_escaped", "crgpu_set_traceback_budget", "crgpu_last_timing", "crgpu_last_fill_breakdown", "crgpu_sync", "crgpu_qualfilter",
                  "crgpu_align", "crgpu_quantify", "crgpu_align_quantify", "crgpu_int_peak", "crgpu_flash_merge", "crgpu_fastq_index"):
         getattr(lib, name).restype = i32
     _lib = lib
@@ -172,11 +175,22 @@ class Context:
         """Half-width (read columns) of the banded two-pass fill; 0 = single-pass fill."""
         self.check(self.lib.crgpu_set_band(self.handle, int(half_width)))
 
+    def band(self):
+        return int(self.lib.crgpu_get_band(self.handle))
+
     def last_escaped(self):
         """(amplicon pass, HDR pass) reads of the last fused call that left the band and were re-aligned."""
         out = (ctypes.c_int * 2)()
         self.check(self.lib.crgpu_last_escaped(self.handle, ctypes.byref(out)))
         return int(out[0]), int(out[1])
+
+    def last_fill_breakdown(self):
+        """{'full' | 'score' | 'band': (ms, launches, DP cells evaluated)} of the last call's fill kernels."""
+        ms = (ctypes.c_double * 3)()
+        ln = (ctypes.c_int64 * 3)()
+        cells = (ctypes.c_int64 * 3)()
+        self.check(self.lib.crgpu_last_fill_breakdown(self.handle, ms, ln, cells))
+        return {k: (float(ms[i]), int(ln[i]), int(cells[i])) for i, k in enumerate(("full", "score", "band"))}
 
     def last_timing(self):
         ms = (ctypes.c_float * 6)()

@@ -46,7 +46,7 @@ void crgpu_destroy(crgpu_ctx *c)
     DBuf *all[] = {&c->reads, &c->offsets, &c->amp, &c->prof, &c->pc, &c->pc_off, &c->plen, &c->pair_lo, &c->pair_hi,
                    &c->order, &c->plan_hist, &c->plan_tab, &c->tb2, &c->lastrow2, &c->lastcol2, &c->tb, &c->lastrow, &c->lastcol, &c->errflag, &c->recs, &c->sref, &c->smark, &c->sqry, &c->ops, &c->ops_rc, &c->alleles, &c->prof_h, &c->amp_h, &c->tbh, &c->tbh2,
                    &c->top, &c->top2, &c->lastrow_h, &c->lastrow_h2, &c->lastcol_h, &c->lastcol_h2,
-                   &c->btops[0], &c->btops[1], &c->bleft[0], &c->bleft[1], &c->btops_h[0], &c->btops_h[1], &c->bleft_h[0], &c->bleft_h[1], &c->escaped};
+                   &c->prof_s, &c->prof_hs, &c->btops[0], &c->btops[1], &c->bleft[0], &c->bleft[1], &c->btops_h[0], &c->btops_h[1], &c->bleft_h[0], &c->bleft_h[1], &c->escaped};
     for (DBuf *b : all) b->release();
     for (auto &b : c->q_in) b.release();
     for (auto &b : c->q_out) b.release();
@@ -90,6 +90,8 @@ int crgpu_set_band(crgpu_ctx *c, int half_width)
     return CRGPU_OK;
 }
 
+int crgpu_get_band(const crgpu_ctx *c) { return c ? c->band_B : -1; }
+
 int crgpu_last_escaped(const crgpu_ctx *c, int out[2])
 {
     if (!c || !out) return CRGPU_E_ARG;
@@ -100,9 +102,23 @@ int crgpu_last_escaped(const crgpu_ctx *c, int out[2])
 int crgpu_last_timing(const crgpu_ctx *c, float out_ms[6], int64_t out_launches[6])
 {
     if (!c) return CRGPU_E_ARG;
-    for (int i = 0; i < T_N; ++i) {
+    for (int i = 0; i <= T_OTHER; ++i) {
         if (out_ms) out_ms[i] = c->ms[i];
         if (out_launches) out_launches[i] = c->launches[i];
+    }
+    if (out_ms) out_ms[T_FILL] += c->ms[T_SCORE] + c->ms[T_BAND];
+    if (out_launches) out_launches[T_FILL] += c->launches[T_SCORE] + c->launches[T_BAND];
+    return CRGPU_OK;
+}
+
+int crgpu_last_fill_breakdown(const crgpu_ctx *c, double out_ms[3], int64_t out_launches[3], int64_t out_cells[3])
+{
+    if (!c) return CRGPU_E_ARG;
+    const int fam[3] = {T_FILL, T_SCORE, T_BAND};
+    for (int i = 0; i < 3; ++i) {
+        if (out_ms) out_ms[i] = c->ms[fam[i]];
+        if (out_launches) out_launches[i] = c->launches[fam[i]];
+        if (out_cells) out_cells[i] = c->cells_kind[i];
     }
     return CRGPU_OK;
 }
@@ -302,6 +318,7 @@ int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_read
         return fail(ctx, CRGPU_E_ALIGN, "scores would leave the exact int16 range (scale %d, lengths %d/%d)", scale, La, maxlen);
     if (slot < (int64_t)La + maxlen && d_ref) return fail(ctx, CRGPU_E_ARG, "slot %lld < amplicon + longest read %d", (long long)slot, La + maxlen);
     if (n_cells) *n_cells += (int64_t)La * pl.sum_len;
+    ctx->cells_kind[0] += (int64_t)La * pl.sum_len;
 
     // ---- batches bounded by the traceback budget (pairs are ordered by length) ----
     std::vector<int> batch_start(1, 0);
@@ -461,12 +478,14 @@ int run_plan_dual(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     if (Gh == 0) return CRGPU_OK;
     const int t0 = G - Gh, split = t0 * K, GKh = Gh * K;
     const int maxlen = pl.maxlen;
-    if ((int64_t)scale * 5 * std::min(La, maxlen) + 64 >= MAX_ABS_SCORE ||
-        (int64_t)2 * open_s + (int64_t)ext_s * (La + maxlen) + 8 * scale + 64 >= MAX_ABS_SCORE)
+    // the score pass adds a drift of up to ext * (rows + columns) to every value (gotoh_score.cu)
+    if ((int64_t)scale * 5 * std::min(La, maxlen) + (int64_t)ext_s * (GK + maxlen + 2) + 64 >= MAX_ABS_SCORE ||
+        (int64_t)2 * open_s + (int64_t)ext_s * (La + maxlen + 2) + 8 * scale + 64 >= MAX_ABS_SCORE)
         return CRGPU_OK;
     if (slot < (int64_t)La + maxlen && d_ref) return CRGPU_OK;
     if (n_cells) *n_cells += 2 * (int64_t)La * pl.sum_len;
     if (n_cells_computed) *n_cells_computed += ((int64_t)La + (int64_t)(La - (split - P))) * pl.sum_len;
+    ctx->cells_kind[0] += ((int64_t)La + (int64_t)(La - (split - P))) * pl.sum_len;
 
     // ---- batches: a pair needs Lb * (GK + GKh) / 2 traceback words ----
     std::vector<int> batch_start(1, 0);
@@ -650,8 +669,9 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     }
     const int t0 = G - Gh, split = dual ? t0 * K : 0, GKh = Gh * K;
     const int maxlen = pl.maxlen;
-    if ((int64_t)scale * 5 * std::min(La, maxlen) + 64 >= MAX_ABS_SCORE ||
-        (int64_t)2 * open_s + (int64_t)ext_s * (La + maxlen) + 8 * scale + 64 >= MAX_ABS_SCORE)
+    // the score pass adds a drift of up to ext * (rows + columns) to every value (gotoh_score.cu)
+    if ((int64_t)scale * 5 * std::min(La, maxlen) + (int64_t)ext_s * (GK + maxlen + 2) + 64 >= MAX_ABS_SCORE ||
+        (int64_t)2 * open_s + (int64_t)ext_s * (La + maxlen + 2) + 8 * scale + 64 >= MAX_ABS_SCORE)
         return CRGPU_OK;
     if (slot < (int64_t)La + maxlen && d_ref) return CRGPU_OK;
 
@@ -669,34 +689,44 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     for (size_t b = 0; b + 1 < batch_start.size(); ++b)
         max_cols = std::max(max_cols, plan_pc_off(pl, batch_start[b + 1]) - plan_pc_off(pl, batch_start[b]));
     if (n_cells) *n_cells += (dual ? 2 : 1) * (int64_t)La * pl.sum_len;
-    if (n_cells_computed) {
+    {
         // score pass: every cell (HDR: the rows below the split); band pass: at most W columns per lane
         const int64_t band_cols = std::min<int64_t>((int64_t)W * pl.nsub, pl.sum_len);
-        *n_cells_computed += (int64_t)La * pl.sum_len + (int64_t)GK * band_cols;
-        if (dual) *n_cells_computed += (int64_t)(La - (split - P)) * pl.sum_len + (int64_t)GKh * band_cols;
+        const int64_t score_cells = ((int64_t)La + (dual ? (int64_t)(La - (split - P)) : 0)) * pl.sum_len;
+        const int64_t band_cells = ((int64_t)GK + (dual ? (int64_t)GKh : 0)) * band_cols;
+        if (n_cells_computed) *n_cells_computed += score_cells + band_cells;
+        ctx->cells_kind[1] += score_cells;
+        ctx->cells_kind[2] += band_cells;
     }
 
     // ---- profiles ----
-    auto build_prof = [&](const std::vector<int> &code, int g, int row0, std::vector<int32_t> &prof) {
+    // `add` = 2 ext for the score pass, which works in drift coordinates (gotoh_score.cu); padding rows score 0 (+ add)
+    auto build_prof = [&](const std::vector<int> &code, int g, int row0, int add, std::vector<int32_t> &prof) {
         const int PS = prof_stride(g, K), SS = strip_stride(K);
         prof.assign((size_t)NPAIR * PS, 0);
         for (int cp = 0; cp < NPAIR; ++cp) {
             const int lo = cp % NCODE, hi = cp / NCODE;
-            for (int r = std::max(P, row0); r < GK; ++r) {
-                const int a = code[r - P];
-                const int32_t slo = scale * host_ednafull(a, lo), shi = scale * host_ednafull(a, hi);
+            for (int r = row0; r < GK; ++r) {
+                int32_t slo = add, shi = add;
+                if (r >= P) {
+                    const int a = code[r - P];
+                    slo += scale * host_ednafull(a, lo); shi += scale * host_ednafull(a, hi);
+                }
                 const int rr = r - row0;
                 prof[(size_t)cp * PS + (rr / K) * SS + (rr % K)] = shi * 65536 + slo;
             }
         }
     };
-    std::vector<int32_t> prof_a, prof_h;
-    build_prof(acode, G, 0, prof_a);
-    if (dual) build_prof(hcode, Gh, split, prof_h);
+    std::vector<int32_t> prof_a, prof_h, prof_as, prof_hs;
+    build_prof(acode, G, 0, 0, prof_a);
+    build_prof(acode, G, 0, 2 * ext_s, prof_as);
+    if (dual) { build_prof(hcode, Gh, split, 0, prof_h); build_prof(hcode, Gh, split, 2 * ext_s, prof_hs); }
     cudaStream_t s = ctx->stream;
     const bool two = batch_start.size() > 2 && ctx->overlap && !getenv("CRGPU_NO_OVERLAP");
     CK(ctx->amp.reserve((size_t)La)); CK(ctx->prof.reserve(prof_a.size() * 4));
     if (dual) { CK(ctx->amp_h.reserve((size_t)La)); CK(ctx->prof_h.reserve(prof_h.size() * 4)); }
+    CK(ctx->prof_s.reserve(prof_as.size() * 4));
+    if (dual) CK(ctx->prof_hs.reserve(prof_hs.size() * 4));
     DBuf *tbA[2] = {&ctx->tb, &ctx->tb2}, *tbH[2] = {&ctx->tbh, &ctx->tbh2}, *top[2] = {&ctx->top, &ctx->top2};
     DBuf *lrA[2] = {&ctx->lastrow, &ctx->lastrow2}, *lcA[2] = {&ctx->lastcol, &ctx->lastcol2};
     DBuf *lrH[2] = {&ctx->lastrow_h, &ctx->lastrow_h2}, *lcH[2] = {&ctx->lastcol_h, &ctx->lastcol_h2};
@@ -718,7 +748,9 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     if (dual) {
         CK(cudaMemcpyAsync(ctx->amp_h.p, hdr_up.data(), (size_t)La, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(ctx->prof_h.p, prof_h.data(), prof_h.size() * 4, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->prof_hs.p, prof_hs.data(), prof_hs.size() * 4, cudaMemcpyHostToDevice, s));
     }
+    CK(cudaMemcpyAsync(ctx->prof_s.p, prof_as.data(), prof_as.size() * 4, cudaMemcpyHostToDevice, s));
     CK(cudaStreamSynchronize(s));      // the staging vectors are locals of this frame
 
     cudaStream_t s2 = two ? ctx->stream2 : ctx->stream;
@@ -752,12 +784,16 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
             fh.band_tb = tbH[cur]->as<uint32_t>();
         }
         if (used[cur]) CK(cudaStreamWaitEvent(sf[cur], ctx->walk_done[cur], 0));
-        span_begin(ctx, T_FILL, sf[cur]);
-        CK(launch_fill(G, K, fa, ctx->num_sms, sf[cur], 1));
-        if (dual) CK(launch_fill(Gh, K, fh, ctx->num_sms, sf[cur], 1));
+        FillArgs fas = fa, fhs = fh;                                    // score pass: drifted profiles
+        fas.prof = ctx->prof_s.as<int32_t>(); fhs.prof = ctx->prof_hs.as<int32_t>();
+        span_begin(ctx, T_SCORE, sf[cur]);
+        CK(launch_fill(G, K, fas, ctx->num_sms, sf[cur], 1));
+        if (dual) CK(launch_fill(Gh, K, fhs, ctx->num_sms, sf[cur], 1));
+        span_end(ctx, dual ? 2 : 1);
+        span_begin(ctx, T_BAND, sf[cur]);
         CK(launch_fill(G, K, fa, ctx->num_sms, sf[cur], 2));
         if (dual) CK(launch_fill(Gh, K, fh, ctx->num_sms, sf[cur], 2));
-        span_end(ctx, dual ? 4 : 2);
+        span_end(ctx, dual ? 2 : 1);
         CK(cudaEventRecord(ctx->fill_done[cur], sf[cur]));
 
         WalkArgs wa;

@@ -11,7 +11,9 @@
 #include <string>
 #include <vector>
 
-enum { T_ENCODE = 0, T_FILL, T_WALK, T_QUANT, T_QUAL, T_OTHER, T_N };
+// T_SCORE / T_BAND: the two passes of the banded fill; crgpu_last_timing folds them into the fill slot and
+// crgpu_last_fill_breakdown reports them (with the DP cells each kind evaluated) separately
+enum { T_ENCODE = 0, T_FILL, T_WALK, T_QUANT, T_QUAL, T_OTHER, T_SCORE, T_BAND, T_N };
 
 struct DBuf {
     void *p = nullptr;
@@ -64,6 +66,7 @@ struct crgpu_ctx {
     DBuf recs, sref, smark, sqry, ops, ops_rc, alleles;
     DBuf prof_h, amp_h, tbh, tbh2, top, top2, lastrow_h, lastrow_h2, lastcol_h, lastcol_h2;   // HDR pass of run_plan_dual
     bool share_prefix = true;
+    DBuf prof_s, prof_hs;                                           // drifted profiles of the score pass
     DBuf btops[2], bleft[2], btops_h[2], bleft_h[2], escaped;      // banded two-pass fill (run_plan_band)
     int n_escaped[2] = {0, 0};                                     // reads re-aligned after the last banded call (amplicon, HDR)
     int band_B = 24;                                               // band half-width in read columns; 0 = single-pass fill
@@ -75,6 +78,7 @@ struct crgpu_ctx {
     std::vector<TimedSpan> spans;
     float ms[T_N] = {0};
     int64_t launches[T_N] = {0};
+    int64_t cells_kind[3] = {0, 0, 0};                             // DP cells evaluated: single-pass fill, score pass, band pass
 };
 
 inline int crgpu_fail(crgpu_ctx *c, int code, const char *fmt, ...)
@@ -123,6 +127,7 @@ inline void timing_reset(crgpu_ctx *c)
     c->ev_used = 0;
     c->spans.clear();
     for (int i = 0; i < T_N; ++i) { c->ms[i] = 0; c->launches[i] = 0; }
+    for (int i = 0; i < 3; ++i) c->cells_kind[i] = 0;
 }
 inline void timing_collect(crgpu_ctx *c)
 {

@@ -30,38 +30,12 @@
 // re-evaluates only the band columns of every lane with flags -- lanes are independent there, the top
 // boundary comes from memory.  The walker raises an escape flag for a read whose path leaves the band
 // and the host re-aligns those reads with the full single-pass kernel: results never depend on the band.
-#include "crgpu_common.cuh"
+#include "gotoh_tile.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
 namespace crgpu {
-
-__device__ __forceinline__ uint32_t vmax2(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }      // VIMNMX.U16x2
-__device__ __forceinline__ uint32_t vmin2(uint32_t a, uint32_t b) { return __vminu2(a, b); }
-__device__ __forceinline__ uint32_t vaddmax2(uint32_t a, uint32_t b, uint32_t c)                   // VIADDMNMX.S16x2
-{
-    return __viaddmax_s16x2(a, b, c);
-}
-
-// a + b issued on the FMA pipe (IMAD): `one` is a register holding 1 that ptxas cannot see through,
-// so the multiply-add is not turned back into an IADD3.  Used to take plain adds off the integer-ALU
-// pipe, which also has to run every VIMNMX / VIADDMNMX of the cell (profiles/r01_notes.md).
-__device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t b, uint32_t one)
-{
-    uint32_t d;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
-    return d;
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-template <int K>
-struct Strip {
-    uint32_t H3[K];   // max(m,ix,iy)[row, x-1]
-    uint32_t IX[K];   // ix[row, x-1]
-    uint32_t mlast;   // m[row K-1, x-1]; only meaningful in the lane that owns amplicon row La-1
-};
 
 // One read column for the K rows of this lane.
 //
@@ -170,57 +144,13 @@ __device__ __forceinline__ void column_step(Strip<K> &st, const int32_t *__restr
     }
 }
 
-// 128-thread CTAs, as many per SM as registers / shared memory allow (3 for the K = 32 strips).
-// The register cap per strip height was swept on a B200 (profiles/r01_notes.md): K = 32 runs
-// 2007 GCUPS at 136 registers vs 1845 at ptxas' own choice (133) and 1513 at 128 (4 CTAs/SM but
-// spills + extra moves); one 12-warp CTA per SM under __launch_bounds__(384) is 25 % slower.
-// K = 40: 1605 GCUPS at 144 registers (3 CTAs/SM), 1855 at 184 (2 CTAs/SM): ILP beats occupancy here.
-#ifdef FILL_MAXNREG
-template <int K> constexpr int fill_maxnreg() { return FILL_MAXNREG; }
-#else
-template <int K> constexpr int fill_maxnreg() { return K >= 48 ? 255 : (K >= 36 ? 184 : (K >= 32 ? 136 : 128)); }
-#endif
-
-enum { FILL_FULL = 0, FILL_SCORE = 1 };
-
-// stage the pair profile with one TMA bulk copy (all threads of the CTA call this)
-__device__ __forceinline__ void stage_profile(int32_t *sprof, uint64_t *mbar, const int32_t *prof, uint32_t prof_bytes)
-{
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(prof_bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(sprof)), "l"(prof), "r"(prof_bytes), "r"(smem_u32(mbar)) : "memory");
-    }
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(smem_u32(mbar)), "r"(0u) : "memory");
-    }
-}
-
-// Boundary rows in memory are 16 bytes per column, (max3, iy, m, 0).  A lane writes consecutive columns on
-// consecutive steps, so the two halves of a 32-byte sector meet in L2 long before the sector is evicted (a
-// half-written sector would cost HBM a read-modify-write: measured 2.6x on the whole kernel when every lane
-// leaves its sectors half-written).  First column of pair p in a per-pair array: even, and the ranges of
-// consecutive pairs do not overlap.
-__device__ __forceinline__ int64_t top_base_col(int64_t pco_rel, int pair_rel) { return (pco_rel + pair_rel + 1) & ~(int64_t)1; }
-
-// the score pass keeps a few more values live across the column and has no flag words: 168 registers still
-// leave 3 CTAs of 128 threads per SM
-template <int K, int MODE> constexpr int fill_maxnreg_mode() { return (MODE == FILL_SCORE && K <= 32) ? 168 : fill_maxnreg<K>(); }
-
-template <int G, int K, int MODE>
-__global__ void __maxnreg__((fill_maxnreg_mode<K, MODE>())) k_gotoh_fill(const FillArgs a)
+template <int G, int K>
+__global__ void __maxnreg__(fill_maxnreg<K>()) k_gotoh_fill(const FillArgs a)
 {
     static_assert(K % 4 == 0 && (32 % G) == 0, "bad tile");
     constexpr int PS = prof_stride(G, K);
     constexpr int GK = G * K;
-    constexpr bool FLAGS = MODE == FILL_FULL;
+    constexpr bool FLAGS = true;
     extern __shared__ __align__(128) int32_t sprof[];
     __shared__ __align__(8) uint64_t mbar;
     stage_profile(sprof, &mbar, a.prof, NPAIR * PS * 4);
@@ -240,7 +170,6 @@ __global__ void __maxnreg__((fill_maxnreg_mode<K, MODE>())) k_gotoh_fill(const F
     const uint32_t nopen16_last = lastLane ? 0u : nopen16;                // amplicon row La-1: zero end-gap penalties
     const uint32_t ext32_last = lastLane ? 0u : ext32;
     const uint32_t one = (uint32_t)a.one;
-    const int xlo1 = a.band_row0 + t * K - a.band_B - 1;                  // SCORE: the band's columns are xlo1+1 .. xlo1+W
 
     for (int base = a.p0 + warp_global * GPW; base < a.p1; base += nwarps * GPW) {
         const int p = base + gl;
@@ -270,15 +199,6 @@ __global__ void __maxnreg__((fill_maxnreg_mode<K, MODE>())) k_gotoh_fill(const F
         uint4 *tout = (a.top_out && valid && t == a.top_out_lane) ? reinterpret_cast<uint4 *>(a.top_out) + tcol : nullptr;
         uint4 tn = make_uint4(Z, NOPEN_ST, Z, 0u);
         if (tin && t == 0 && Lb > 0) tn = tin[0];
-        // SCORE: what this lane receives at its band columns, and its registers at the band's left edge
-        uint4 *bandw = nullptr;                                          // indexed by column x
-        uint32_t *leftp = nullptr;
-        if (MODE == FILL_SCORE && valid && a.band_tops) {
-            const int64_t lane_id = (int64_t)(p - a.p0) * G + t;
-            if (t > 0) bandw = reinterpret_cast<uint4 *>(a.band_tops) + lane_id * band_topw(a.band_W) - xlo1;
-            leftp = a.band_left + lane_id * band_leftw(K);
-        }
-
         // One systolic step.  STEADY = every lane of the warp is on an interior column of its read (no lane
         // idle, none on a first or last column): the votes, the activity branch and the edge body drop out.
         auto step = [&](auto steady_tag, const int s) {
@@ -297,9 +217,6 @@ __global__ void __maxnreg__((fill_maxnreg_mode<K, MODE>())) k_gotoh_fill(const F
             if (active) {
                 const int32_t *prow = sprof + cp * PS + t * strip_stride(K);
                 uint32_t *tbw = FLAGS ? tbp + (int64_t)x * (GK / 2) : nullptr;
-                if (MODE == FILL_SCORE) {
-                    if (bandw && (unsigned)(x - xlo1) <= (unsigned)a.band_W) bandw[x] = make_uint4(rH3, rIY, rM, 0u);
-                }
                 if (edge)
                     column_step<K, true, FLAGS, true>(st, prow, rH3, rIY, rM, hd0, nopen16, ext32, nopen16_last, ext32_last,
                                                       lastLane, firstCol, lastCol, one, tbw, firstRealSlot, colBest, colPosLo, colPosHi,
@@ -319,15 +236,6 @@ __global__ void __maxnreg__((fill_maxnreg_mode<K, MODE>())) k_gotoh_fill(const F
                     rowBest = nb;
                 }
                 if (tout) tout[x] = make_uint4(botH3, botIY, botM, 0u);
-                if (MODE == FILL_SCORE) {
-                    if (leftp && x == xlo1) {                             // registers after column xlo-1: the band pass starts from them
-                        // (scalar stores on purpose: vector stores would make ptxas shuffle 2K registers into aligned
-                        // quads on EVERY step, outside this once-per-pair branch)
-#pragma unroll
-                        for (int k = 0; k < K; ++k) { leftp[k] = st.H3[k]; leftp[K + k] = st.IX[k]; }
-                        leftp[2 * K] = st.mlast;
-                    }
-                }
                 if (lastCol) {
                     lcp[0] = colBest; lcp[1] = (uint32_t)colPosLo; lcp[2] = (uint32_t)colPosHi;
                     if (lastLane) { lrp[0] = rowBest; lrp[1] = (uint32_t)rowPosLo; lrp[2] = (uint32_t)rowPosHi; }
@@ -446,9 +354,9 @@ static cudaError_t launch_tile(const FillArgs &a, int num_sms, cudaStream_t stre
     const size_t smem = (size_t)NPAIR * prof_stride(G, K) * 4;
     static bool configured = false;
     static int blocks_per_sm[3] = {1, 1, 1};
-    void (*kern[3])(const FillArgs) = {k_gotoh_fill<G, K, FILL_FULL>, k_gotoh_fill<G, K, FILL_SCORE>, k_gotoh_band<G, K>};
+    void (*kern[3])(const FillArgs) = {k_gotoh_fill<G, K>, nullptr, k_gotoh_band<G, K>};
     if (!configured) {
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < 3; i += 2) {
             cudaError_t e = cudaFuncSetAttribute(kern[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
             e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[i], kern[i], 128, smem);
@@ -499,6 +407,7 @@ bool tile_available(int G, int K)
 cudaError_t launch_fill(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream, int kind)
 {
     if (kind < 0 || kind > 2) return cudaErrorInvalidValue;
+    if (kind == 1) return launch_score(G, K, a, num_sms, stream);
 #define CASE(g, k) if (G == g && K == k) return launch_tile<g, k>(a, num_sms, stream, kind);
     CASE(4, 16) CASE(4, 24) CASE(4, 32) CASE(4, 40) CASE(8, 16) CASE(8, 24) CASE(8, 32) CASE(8, 40)
     CASE(16, 16) CASE(16, 24) CASE(16, 32) CASE(16, 40) CASE(32, 24) CASE(32, 32) CASE(4, 48) CASE(8, 48) CASE(16, 48)

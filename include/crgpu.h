@@ -71,6 +71,8 @@ int crgpu_set_share_prefix(crgpu_ctx *ctx, int on);
  * flags, only the columns within half_width of the main diagonal of each lane's rows; a read whose
  * traceback leaves the band is re-aligned with the single-pass fill, so results never depend on this. */
 int crgpu_set_band(crgpu_ctx *ctx, int half_width);
+/* The current half-width (-1: no context). */
+int crgpu_get_band(const crgpu_ctx *ctx);
 /* Reads the last crgpu_align_quantify call re-aligned with the single-pass fill because their traceback
  * left the band: out[0] amplicon pass, out[1] HDR-amplicon pass. */
 int crgpu_last_escaped(const crgpu_ctx *ctx, int out[2]);
@@ -78,6 +80,10 @@ int crgpu_last_escaped(const crgpu_ctx *ctx, int out[2]);
  * the LAST call on this context, and launch counts.  out_ms[0..5] = encode, fill, walk,
  * quantify, qualfilter, other;  out_launches likewise. */
 int crgpu_last_timing(const crgpu_ctx *ctx, float out_ms[6], int64_t out_launches[6]);
+/* The fill slot of crgpu_last_timing split by kernel kind: [0] single-pass fill (flags for every cell),
+ * [1] score pass and [2] band pass of the banded fill -- device time (ms), launches and the DP cells
+ * each kind evaluated during the LAST call (the numerators of the per-kernel rooflines). */
+int crgpu_last_fill_breakdown(const crgpu_ctx *ctx, double out_ms[3], int64_t out_launches[3], int64_t out_cells[3]);
 /* Synchronise the context's stream. */
 int crgpu_sync(crgpu_ctx *ctx);
 /* The context's cudaStream_t (as void*), so that a caller can bracket calls with its own CUDA
