@@ -66,7 +66,7 @@ int crgpu_set_overlap(crgpu_ctx *ctx, int on);
 /* The HDR-amplicon pass normally reuses the DP rows it shares with the amplicon pass (bit-identical
  * results, fewer cells evaluated; default on).  Off = two full passes. */
 int crgpu_set_share_prefix(crgpu_ctx *ctx, int on);
-/* Banded two-pass fill (default half-width 24 read columns; 0 = single-pass fill with flags for every
+/* Banded two-pass fill (default half-width 16 read columns; 0 = single-pass fill with flags for every
  * cell).  The first pass evaluates every DP cell without traceback flags, the second re-evaluates, with
  * flags, only the columns within half_width of the main diagonal of each lane's rows; a read whose
  * traceback leaves the band is re-aligned with the single-pass fill, so results never depend on this. */
