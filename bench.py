@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--reads", type=int, default=1 << 20, help="reads per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=200000, help="reads in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunk", type=int, default=1 << 18, help="reads per crgpu_align_quantify call of the end-to-end arm")
+    ap.add_argument("--e2e-contexts", type=int, default=2, help="contexts (host threads) the end-to-end arm alternates between")
     return ap.parse_args()
 
 
@@ -181,7 +183,7 @@ def main():
     amp, guide, cut, hdr, buf, off, inc = workload(n, rank)
     L = len(amp)
     flags = hotpath.quant_flags(hdr)
-    h2d_bytes = int(buf.nbytes + off.nbytes)
+    h2d_bytes = int(buf.nbytes + off.nbytes)          # + 8 bytes per chunk of the end-to-end arm (chunk-relative offsets)
 
     # integer issue peaks, measured live: (i) both integer pipes -- dependency-free IADD chains that
     # ptxas splits 1:1 over the alu (IADD3) and fma (IMAD.IADD) pipes, and a VIMNMX.S16x2 + IMAD 1:1 mix; (ii) the
@@ -266,39 +268,33 @@ def main():
     cells_step = red.n_cells if world == 1 else None
     n_total = red.n_total
 
-    # ---- end-to-end arm: pinned host buffers through the C ABI ----------------------------------
+    # ---- end-to-end arm: pinned HOST buffers through the public host API -------------------------
+    # hotpath.run_hot_path_pipelined = crgpu_align_quantify (C ABI, CRGPU_MEM_HOST) on read chunks that alternate
+    # between two contexts, each driven by its own host thread: H2D of the reads and D2H of the per-read records of
+    # one chunk overlap the kernels of the other; everything is inside the timed region.
     p_buf = torch.from_numpy(buf).pin_memory()
     p_off = torch.from_numpy(off).pin_memory()
-    h_kept = torch.zeros(n, dtype=torch.uint8).pin_memory()
-    h_aln = torch.zeros(n * _lib.ALN_REC.itemsize, dtype=torch.uint8).pin_memory()
-    h_recs = torch.zeros(n * _lib.READ_REC.itemsize, dtype=torch.uint8).pin_memory()
-    h_trep = torch.zeros(n, dtype=torch.int32).pin_memory()
-    import ctypes
-    keep = []
-    qp = hotpath._quant_params(L, flags, 98.0, inc, None, None, keep)
-    pp = _lib.PathParams()
-    pp.gapopen, pp.gapextend, pp.min_identity_score = 10.0, 0.5, 60.0
-    hdr_b = hdr.encode()
-    pp.hdr_amplicon, pp.hdr_amplicon_len, pp.rc_rescue = hdr_b, len(hdr_b), 1
-    rc_cap = n
-    h_rc_read = np.zeros(rc_cap, np.int32)
-    h_rc_aln = np.zeros(rc_cap, _lib.ALN_REC)
-    h_rc_recs = np.zeros(rc_cap, _lib.READ_REC)
+    n_chunks = (n + args.e2e_chunk - 1) // args.e2e_chunk
+    pinned = {
+        "kept": torch.zeros(n, dtype=torch.uint8).pin_memory(),
+        "aln": torch.zeros(n * _lib.ALN_REC.itemsize, dtype=torch.uint8).pin_memory(),
+        "recs": torch.zeros(n * _lib.READ_REC.itemsize, dtype=torch.uint8).pin_memory(),
+        "tenths_rep": torch.zeros(n, dtype=torch.int32).pin_memory(),
+        "rc_read": torch.zeros(n, dtype=torch.int32).pin_memory(),
+        "rc_aln": torch.zeros(n * _lib.ALN_REC.itemsize, dtype=torch.uint8).pin_memory(),
+        "rc_recs": torch.zeros(n * _lib.READ_REC.itemsize, dtype=torch.uint8).pin_memory(),
+        "offsets": torch.zeros(n + n_chunks, dtype=torch.int64).pin_memory(),
+    }
+    outs = {k: v.numpy() for k, v in pinned.items()}
+    for k, dt in (("aln", _lib.ALN_REC), ("rc_aln", _lib.ALN_REC), ("recs", _lib.READ_REC), ("rc_recs", _lib.READ_REC)):
+        outs[k] = outs[k].view(dt)
+    e2e_ctxs = [ctx] + [Context(local) for _ in range(args.e2e_contexts - 1)]
+    host_reads = (p_buf.numpy(), p_off.numpy())
 
     def step_host():
         red = hotpath.Reductions(L)
-        po = _lib.PathOut()
-        po.kept, po.aln, po.recs, po.tenths_rep = h_kept.data_ptr(), h_aln.data_ptr(), h_recs.data_ptr(), h_trep.data_ptr()
-        po.rc_cap = rc_cap
-        po.rc_read, po.rc_aln, po.rc_recs = h_rc_read.ctypes.data, h_rc_aln.ctypes.data, h_rc_recs.ctypes.data
-        po.vectors, po.hist_inframe, po.hist_frameshift = red.vectors.ctypes.data, red.hist_inframe.ctypes.data, red.hist_frameshift.ctypes.data
-        po.hist_len, po.hist_zero, po.counters = hotpath.HIST_LEN, hotpath.HIST_ZERO, red.counters.ctypes.data
-        ctx.check(ctx.lib.crgpu_align_quantify(ctx.handle, _lib.MEM_HOST, amp.encode(), L, ctypes.byref(pp), ctypes.byref(qp),
-                                               p_buf.data_ptr(), p_off.data_ptr(), n, ctypes.byref(po)))
-        red.class_counts += np.array(list(po.class_counts), np.int64)
-        red.n_total += int(po.n_total)
-        red.n_cells += int(po.n_cells)
-        red.n_cells_computed += int(po.n_cells_computed)
+        hotpath.run_hot_path_pipelined(e2e_ctxs, amp, host_reads, chunk_reads=args.e2e_chunk, hdr_amplicon=hdr, flags=flags,
+                                       inc=inc, red=red, out=outs)
         allreduce(red)
         return red
 
@@ -316,8 +312,8 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
-    d2h_bytes = int(n * (1 + _lib.ALN_REC.itemsize + _lib.READ_REC.itemsize + 4) + red_h.flat().nbytes)
-    same = bool(np.array_equal(red_h.flat(), red.flat()))
+    d2h_bytes = int(n * (1 + _lib.ALN_REC.itemsize + _lib.READ_REC.itemsize + 4) + red_h.flat().nbytes * n_chunks)
+    same = bool(np.array_equal(red_h.flat()[:-1], red.flat()[:-1]))     # every reduction (n_cells_computed aside: bookkeeping)
 
     if rank != 0:
         if world > 1:
@@ -383,7 +379,9 @@ def main():
                    "reads_per_gpu_per_step": n, "alignments_per_read": 2, "l2": "inputs and traceback exceed L2 (reads %d MB, "
                    "traceback scratch 8 GB per batch)" % (buf.nbytes >> 20), "parallelism": "reads sharded x%d" % world},
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "ms_per_step": e2e_ms / args.steps, "results_equal_device_arm": same},
+                "ms_per_step": e2e_ms / args.steps, "results_equal_device_arm": same,
+                "api": "hotpath.run_hot_path_pipelined: crgpu_align_quantify(CRGPU_MEM_HOST) on %d-read chunks alternating "
+                       "between %d contexts / host threads" % (args.e2e_chunk, args.e2e_contexts)},
         "gpu_launches": int(sum(fam_launch.values())),
         "kernel_ms_per_step": {k: fam_ms[k] / args.steps for k in fam_ms},
         "roofline": {"bound": "int_alu", "kernel": kinds[dom]["kernel"], "achieved": kinds[dom]["achieved"], "peak": alu_pk,

@@ -406,7 +406,7 @@ int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_read
         fa.p0 = batch_start[b]; fa.p1 = batch_start[b + 1];
         fa.open = open_s; fa.ext = ext_s; fa.La = La; fa.one = 1;
         fa.top_out = nullptr; fa.top_out_lane = -1; fa.top_in = nullptr;
-        fa.band_B = 0; fa.band_W = 0; fa.band_row0 = 0; fa.band_tops = nullptr; fa.band_left = nullptr; fa.band_tb = nullptr;
+        fa.band_B = 0; fa.band_W = 0; fa.band_K = 0; fa.band_row0 = 0; fa.band_tops = nullptr; fa.band_left = nullptr; fa.band_tb = nullptr;
         if (used[cur]) CK(cudaStreamWaitEvent(sf[cur], ctx->walk_done[cur], 0));     // scratch `cur` is free again
         span_begin(ctx, T_FILL, sf[cur]);
         CK(launch_fill(G, K, fa, ctx->num_sms, sf[cur]));
@@ -416,7 +416,7 @@ int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_read
         WalkArgs wa;
         wa.tb = fa.tb; wa.lastrow = fa.lastrow; wa.lastcol = fa.lastcol;
         wa.tb_upper = nullptr; wa.lastcol_upper = nullptr; wa.G_upper = 0; wa.split_row = 0;
-        wa.band_B = 0; wa.band_W = 0; wa.kdiv_magic = 0; wa.escaped = nullptr; wa.escape_bit = 0;
+        wa.band_B = 0; wa.band_W = 0; wa.band_K = 0; wa.kdiv_magic = 0; wa.escaped = nullptr; wa.escape_bit = 0;
         wa.pc_off = fa.pc_off; wa.plen = fa.plen;
         wa.pair_lo = ctx->pair_lo.as<int32_t>(); wa.pair_hi = ctx->pair_hi.as<int32_t>();
         wa.reads = d_reads; wa.offsets = d_offsets; wa.amplicon = ctx->amp.as<uint8_t>();
@@ -573,7 +573,7 @@ int run_plan_dual(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         fa.p0 = batch_start[b]; fa.p1 = batch_start[b + 1];
         fa.open = open_s; fa.ext = ext_s; fa.La = La; fa.one = 1;
         fa.top_out = top[cur]->as<uint32_t>(); fa.top_out_lane = t0 - 1; fa.top_in = nullptr;
-        fa.band_B = 0; fa.band_W = 0; fa.band_row0 = 0; fa.band_tops = nullptr; fa.band_left = nullptr; fa.band_tb = nullptr;
+        fa.band_B = 0; fa.band_W = 0; fa.band_K = 0; fa.band_row0 = 0; fa.band_tops = nullptr; fa.band_left = nullptr; fa.band_tb = nullptr;
         FillArgs fh = fa;                                               // HDR pass: bottom Gh lanes
         fh.prof = ctx->prof_h.as<int32_t>();
         fh.tb = tbH[cur]->as<uint32_t>(); fh.lastrow = lrH[cur]->as<uint32_t>(); fh.lastcol = lcH[cur]->as<uint32_t>();
@@ -589,7 +589,7 @@ int run_plan_dual(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         WalkArgs wa;
         wa.tb = fa.tb; wa.lastrow = fa.lastrow; wa.lastcol = fa.lastcol;
         wa.tb_upper = nullptr; wa.lastcol_upper = nullptr; wa.G_upper = 0; wa.split_row = 0;
-        wa.band_B = 0; wa.band_W = 0; wa.kdiv_magic = 0; wa.escaped = nullptr; wa.escape_bit = 0;
+        wa.band_B = 0; wa.band_W = 0; wa.band_K = 0; wa.kdiv_magic = 0; wa.escaped = nullptr; wa.escape_bit = 0;
         wa.pc_off = fa.pc_off; wa.plen = fa.plen;
         wa.pair_lo = ctx->pair_lo.as<int32_t>(); wa.pair_hi = ctx->pair_hi.as<int32_t>();
         wa.reads = d_reads; wa.offsets = d_offsets; wa.amplicon = ctx->amp.as<uint8_t>();
@@ -657,7 +657,10 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     int G, K;
     if (!choose_tile(La, &G, &K)) return CRGPU_OK;
     const int GK = G * K, P = GK - La;
-    const int W = K + 2 * B + 1;
+    // the band pass works on sub-strips of Kb rows: half a lane's strip when that keeps 16-byte flag stores
+    const int nsub = (K % 16 == 0 && !getenv("CRGPU_NO_SUBSTRIP")) ? 2 : 1;
+    const int Kb = K / nsub;
+    const int W = Kb + 2 * B + 1;
     // the band pays when it is well below the read length (score pass ~0.4x + band pass ~W/Lb of a full fill)
     if ((int64_t)W * 5 * pl.nsub > 3 * pl.sum_len) return CRGPU_OK;
     int Gh = 0;
@@ -676,9 +679,9 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     if (slot < (int64_t)La + maxlen && d_ref) return CRGPU_OK;
 
     // ---- batches: fixed scratch per pair and lane (tops, left edge, band flags) ----
-    const int TOPW = band_topw(W), LEFTW = band_leftw(K);
-    const size_t lane_bytes = (size_t)TOPW * 16 + (size_t)LEFTW * 4 + (size_t)W * K * 2;
-    const size_t pair_bytes = lane_bytes * (size_t)(G + Gh) + (dual ? (size_t)(maxlen + 2) * 16 : 0);
+    const int TOPW = band_topw(W), LEFTW = band_leftw(Kb);
+    const size_t sub_bytes = (size_t)TOPW * 16 + (size_t)LEFTW * 4 + (size_t)W * Kb * 2;      // per sub-strip
+    const size_t pair_bytes = sub_bytes * (size_t)(G + Gh) * nsub + (dual ? (size_t)(maxlen + 2) * 16 : 0);
     int64_t bp = (int64_t)(ctx->tb_budget / pair_bytes);
     bp = std::max<int64_t>(1, std::min<int64_t>(bp, std::max<int64_t>(((int64_t)pl.np + 7) / 8, 16384)));
     std::vector<int> batch_start;
@@ -732,13 +735,13 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     DBuf *lrH[2] = {&ctx->lastrow_h, &ctx->lastrow_h2}, *lcH[2] = {&ctx->lastcol_h, &ctx->lastcol_h2};
     for (int i = 0; i < (two ? 2 : 1); ++i) {
         CK(tbA[i]->reserve((size_t)max_bp * G * W * K * 2));
-        CK(ctx->btops[i].reserve((size_t)max_bp * G * TOPW * 16));
-        CK(ctx->bleft[i].reserve((size_t)max_bp * G * LEFTW * 4));
+        CK(ctx->btops[i].reserve((size_t)max_bp * G * nsub * TOPW * 16));
+        CK(ctx->bleft[i].reserve((size_t)max_bp * G * nsub * LEFTW * 4));
         CK(lrA[i]->reserve((size_t)max_bp * 12)); CK(lcA[i]->reserve((size_t)max_bp * G * 12));
         if (dual) {
             CK(tbH[i]->reserve((size_t)max_bp * Gh * W * K * 2));
-            CK(ctx->btops_h[i].reserve((size_t)max_bp * Gh * TOPW * 16));
-            CK(ctx->bleft_h[i].reserve((size_t)max_bp * Gh * LEFTW * 4));
+            CK(ctx->btops_h[i].reserve((size_t)max_bp * Gh * nsub * TOPW * 16));
+            CK(ctx->bleft_h[i].reserve((size_t)max_bp * Gh * nsub * LEFTW * 4));
             CK(top[i]->reserve((size_t)(max_cols + max_bp + 2) * 16));
             CK(lrH[i]->reserve((size_t)max_bp * 12)); CK(lcH[i]->reserve((size_t)max_bp * Gh * 12));
         }
@@ -759,7 +762,7 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         CK(cudaEventRecord(ctx->ready, s));
         CK(cudaStreamWaitEvent(sf[1], ctx->ready, 0));
     }
-    const uint32_t magic = (uint32_t)((((uint64_t)1 << 32) + K - 1) / K);
+    const uint32_t magic = (uint32_t)((((uint64_t)1 << 32) + Kb - 1) / Kb);
     bool used[2] = {false, false};
     for (size_t b = 0; b + 1 < batch_start.size(); ++b) {
         const int cur = two ? (int)(b & 1) : 0;
@@ -770,7 +773,7 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         fa.p0 = batch_start[b]; fa.p1 = batch_start[b + 1];
         fa.open = open_s; fa.ext = ext_s; fa.La = La; fa.one = 1;
         fa.top_out = dual ? top[cur]->as<uint32_t>() : nullptr; fa.top_out_lane = dual ? t0 - 1 : -1; fa.top_in = nullptr;
-        fa.band_B = B; fa.band_W = W; fa.band_row0 = -P;
+        fa.band_B = B; fa.band_W = W; fa.band_K = Kb; fa.band_row0 = -P;
         fa.band_tops = ctx->btops[cur].as<uint32_t>(); fa.band_left = ctx->bleft[cur].as<uint32_t>();
         fa.band_tb = tbA[cur]->as<uint32_t>();
         FillArgs fh = fa;                                               // HDR pass: bottom Gh lanes
@@ -799,7 +802,7 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         WalkArgs wa;
         wa.tb = fa.band_tb; wa.lastrow = fa.lastrow; wa.lastcol = fa.lastcol;
         wa.tb_upper = nullptr; wa.lastcol_upper = nullptr; wa.G_upper = 0; wa.split_row = 0;
-        wa.band_B = B; wa.band_W = W; wa.kdiv_magic = magic; wa.escaped = d_escaped; wa.escape_bit = escape_bit;
+        wa.band_B = B; wa.band_W = W; wa.band_K = Kb; wa.kdiv_magic = magic; wa.escaped = d_escaped; wa.escape_bit = escape_bit;
         wa.pc_off = fa.pc_off; wa.plen = fa.plen;
         wa.pair_lo = ctx->pair_lo.as<int32_t>(); wa.pair_hi = ctx->pair_hi.as<int32_t>();
         wa.reads = d_reads; wa.offsets = d_offsets; wa.amplicon = ctx->amp.as<uint8_t>();

@@ -52,14 +52,16 @@ struct FillArgs {
     uint32_t *top_out;        // [(pc_off[p]-pc_off[p0]) + x][4] or null
     int top_out_lane;
     const uint32_t *top_in;   // same layout, or null (free end-gap boundary)
-    // Banded two-pass fill (DESIGN.md "Band"): k_gotoh_score evaluates every cell without flags and saves,
-    // per lane, the state k_gotoh_band needs to re-evaluate -- with flags -- only the band_W read columns
-    // around the main diagonal of the lane's K rows: x in [xlo, xlo + band_W), xlo = band_row0 + t*K - band_B.
-    int band_B, band_W;       // band_W = K + 2*band_B + 1; band_B = 0: not banded
+    // Banded two-pass fill (DESIGN.md "Band"): k_gotoh_score evaluates every cell without flags and saves the state
+    // k_gotoh_band needs to re-evaluate -- with flags -- only a diagonal band.  The band pass works on SUB-STRIPS of
+    // band_K rows (band_K = K, or K/2 when that is a multiple of 8): sub-strip u = t*(K/band_K) + hh of a pair covers
+    // the band_W read columns x in [xlo, xlo + band_W), xlo = band_row0 + u*band_K - band_B.
+    int band_B, band_W;       // band_W = band_K + 2*band_B + 1; band_B = 0: not banded
+    int band_K;               // rows per sub-strip of the band pass
     int band_row0;            // amplicon row of lane 0's first slot (-P for a full tile, split - P for the HDR sub-tile)
-    uint32_t *band_tops;      // [(p-p0)*G + t][band_topw()][4]: what lane t receives from above at columns xlo-1 .. xlo+W-1
-    uint32_t *band_left;      // [(p-p0)*G + t][band_leftw(K)]: H3[K], IX[K], mlast of column xlo-1
-    uint32_t *band_tb;        // [(p-p0)*G + t][band_W][K/2]: flag words of the band columns
+    uint32_t *band_tops;      // [(p-p0)*G2 + u][band_topw()][4]: (max3, iy, m, 0) of the row above sub-strip u at columns xlo-1 .. xlo+W-1
+    uint32_t *band_left;      // [(p-p0)*G2 + u][band_leftw(band_K)]: H3[band_K], IX[band_K], mlast of column xlo-1
+    uint32_t *band_tb;        // [(p-p0)*G2 + u][band_W][band_K/2]: flag words of the band columns      (G2 = G*K/band_K)
 };
 
 __host__ __device__ constexpr int band_topw(int W) { return (W + 2) & ~1; }          // columns, even
@@ -72,10 +74,10 @@ struct WalkArgs {
     const uint32_t *tb_upper;
     const uint32_t *lastcol_upper;
     int G_upper, split_row;
-    // banded fill: tb / tb_upper are band_tb arrays ([pair][lane][band_W][K/2 words]); a cell outside the
-    // band of its lane raises escaped[read] (the caller re-aligns those reads with the full fill)
-    int band_B, band_W;
-    uint32_t kdiv_magic;      // ceil(2^32 / K): padded row / K by multiply-high
+    // banded fill: tb / tb_upper are band_tb arrays ([pair][sub-strip][band_W][band_K/2 words]); a cell outside the
+    // band of its sub-strip raises escaped[read] (the caller re-aligns those reads with the full fill)
+    int band_B, band_W, band_K;
+    uint32_t kdiv_magic;      // ceil(2^32 / band_K): padded row / band_K by multiply-high
     uint8_t *escaped;         // [n reads] |= escape_bit
     int escape_bit;
     const uint32_t *lastrow;

@@ -24,7 +24,7 @@
 //
 // Banded two-pass variant (FillArgs.band_B > 0; DESIGN.md "Band"): 16 of the ~22 instructions per cell
 // pair produce the traceback flags, but a traceback only ever reads the cells on its path, and the path
-// of an amplicon read hugs the main diagonal.  k_gotoh_fill<G,K,SCORE> therefore evaluates every cell
+// of an amplicon read hugs the main diagonal.  k_gotoh_score<G,K> (gotoh_score.cu) therefore evaluates every cell
 // WITHOUT flags (scores, start-cell scan) and saves, per lane, what it received from the lane above at
 // the columns of a diagonal band and its register state at the band's left edge; k_gotoh_band<G,K>
 // re-evaluates only the band columns of every lane with flags -- lanes are independent there, the top
@@ -252,66 +252,72 @@ __global__ void __maxnreg__(fill_maxnreg<K>()) k_gotoh_fill(const FillArgs a)
     }
 }
 
-// Second pass of the banded fill: lane t re-evaluates columns xlo .. xlo+W-1 of its K rows with flags.
-// Lanes are independent (top boundary from band_tops / top_in / the free boundary, left edge from
-// band_left), so there are no shuffles and every lane of a warp runs the same W iterations.
-template <int G, int K>
-__global__ void __maxnreg__(fill_maxnreg<K>()) k_gotoh_band(const FillArgs a)
+// Second pass of the banded fill: one thread re-evaluates, with flags, columns xlo .. xlo+W-1 of one SUB-STRIP of
+// Kb = K / NSUB rows (sub-strip u = t*NSUB + hh of lane t's strip).  Sub-strips are independent (top boundary from
+// band_tops / top_in / the free boundary, left edge from band_left), so there are no shuffles, threads map to
+// (pair, sub-strip) linearly and every thread of a warp runs the same W iterations.  Halving the strip height
+// (NSUB = 2) shrinks the rectangle that covers the diagonal band from K + 2B + 1 to K/2 + 2B + 1 columns.
+template <int G, int K, int NSUB>
+__global__ void __maxnreg__(fill_maxnreg<K / NSUB>()) k_gotoh_band(const FillArgs a)
 {
     constexpr int PS = prof_stride(G, K);
+    constexpr int Kb = K / NSUB, G2 = G * NSUB;
+    static_assert(Kb % 8 == 0 || NSUB == 1, "sub-strips store 16-byte flag pieces");
     extern __shared__ __align__(128) int32_t sprof[];
     __shared__ __align__(8) uint64_t mbar;
     stage_profile(sprof, &mbar, a.prof, NPAIR * PS * 4);
 
     const int lane = threadIdx.x & 31;
-    const int t = lane % G;
-    const int gl = lane / G;
-    constexpr int GPW = 32 / G;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
-    const bool lastLane = (t == G - 1);
     const uint32_t Z = BIAS2;
     const uint32_t NOPEN_ST = BIAS2 - (uint32_t)a.open * 0x10001u;
     const uint32_t nopen16 = ((uint32_t)(-a.open) & 0xffffu) * 0x10001u;
     const uint32_t ext32 = (uint32_t)a.ext * 0x10001u;
-    const uint32_t nopen16_last = lastLane ? 0u : nopen16;
-    const uint32_t ext32_last = lastLane ? 0u : ext32;
     const uint32_t one = (uint32_t)a.one;
     const int W = a.band_W;
-    const int xlo = a.band_row0 + t * K - a.band_B;
     const uint4 FREE = make_uint4(Z, NOPEN_ST, Z, 0u);
+    const int64_t total = (int64_t)(a.p1 - a.p0) * G2;
 
-    for (int base = a.p0 + warp_global * GPW; base < a.p1; base += nwarps * GPW) {
-        const int p = base + gl;
-        const bool valid = p < a.p1;
+    for (int64_t base = (int64_t)warp_global * 32; base < total; base += (int64_t)nwarps * 32) {
+        const int64_t sub_id = base + lane;                               // (pair - p0) * G2 + u
+        const bool valid = sub_id < total;
+        const int pr = valid ? (int)(sub_id / G2) : 0;
+        const int u = valid ? (int)(sub_id - (int64_t)pr * G2) : 0;
+        const int t = u / NSUB, hh = u - t * NSUB;
+        const bool lastLane = (u == G2 - 1);                              // owns amplicon row La-1 in its last slot
+        const uint32_t nopen16_last = lastLane ? 0u : nopen16;
+        const uint32_t ext32_last = lastLane ? 0u : ext32;
+        const int p = a.p0 + pr;
         const int Lb = valid ? a.plen[p] : 0;
         const int64_t pco = valid ? a.pc_off[p] : 0;
         const int64_t pco_rel = valid ? pco - a.pc_off[a.p0] : 0;
         const uint8_t *pcp = a.pc + pco;
-        const int64_t lane_id = (int64_t)(valid ? p - a.p0 : 0) * G + t;
-        const int x0 = max(xlo, 0), x1 = min(xlo + W - 1, Lb - 1);       // this lane's columns; empty when x0 > x1
-        // source of the top boundary: the lane above (saved by the score pass), the pass that owns the rows
-        // above the sub-tile, or the free boundary.  Indexed so that src[x] is column x.
+        const int xlo = a.band_row0 + u * Kb - a.band_B;
+        const int x0 = max(xlo, 0), x1 = min(xlo + W - 1, Lb - 1);       // this sub-strip's columns; empty when x0 > x1
+        // source of the top boundary: the row above (saved by the score pass), the pass that owns the rows above the
+        // sub-tile, or the free boundary.  Indexed so that src[x] is column x.
         const uint4 *src = nullptr;
-        if (t > 0) src = reinterpret_cast<const uint4 *>(a.band_tops) + lane_id * band_topw(W) - (xlo - 1);
-        else if (a.top_in) src = reinterpret_cast<const uint4 *>(a.top_in) + top_base_col(pco_rel, valid ? p - a.p0 : 0);
-        uint32_t *tbl = a.band_tb + lane_id * W * (K / 2);
+        if (u > 0) src = reinterpret_cast<const uint4 *>(a.band_tops) + (valid ? sub_id : 0) * band_topw(W) - (xlo - 1);
+        else if (a.top_in) src = reinterpret_cast<const uint4 *>(a.top_in) + top_base_col(pco_rel, pr);
+        uint32_t *tbl = a.band_tb + (valid ? sub_id : 0) * W * (Kb / 2);
+        const int32_t *pbase = sprof + t * strip_stride(K) + hh * Kb;
 
-        Strip<K> st;
+        Strip<Kb> st;
         uint32_t hd0 = Z;
         if (x0 > 0 && x0 <= x1) {
-            const uint4 *lp = reinterpret_cast<const uint4 *>(a.band_left + lane_id * band_leftw(K));
+            const uint4 *lp = reinterpret_cast<const uint4 *>(a.band_left + sub_id * band_leftw(Kb));
 #pragma unroll
-            for (int j = 0; j < K / 4; ++j) {
-                const uint4 v = lp[j], w = lp[K / 4 + j];
+            for (int j = 0; j < Kb / 4; ++j) {
+                const uint4 v = lp[j], w = lp[Kb / 4 + j];
                 st.H3[4 * j] = v.x; st.H3[4 * j + 1] = v.y; st.H3[4 * j + 2] = v.z; st.H3[4 * j + 3] = v.w;
                 st.IX[4 * j] = w.x; st.IX[4 * j + 1] = w.y; st.IX[4 * j + 2] = w.z; st.IX[4 * j + 3] = w.w;
             }
-            st.mlast = lp[K / 2].x;
+            st.mlast = lp[Kb / 2].x;
             if (src) hd0 = src[x0 - 1].x;
         } else {
 #pragma unroll
-            for (int k = 0; k < K; ++k) { st.H3[k] = Z; st.IX[k] = NOPEN_ST; }
+            for (int k = 0; k < Kb; ++k) { st.H3[k] = Z; st.IX[k] = NOPEN_ST; }
             st.mlast = Z;
         }
         uint32_t botH3, botIY, botM, colBest = 0;
@@ -329,16 +335,16 @@ __global__ void __maxnreg__(fill_maxnreg<K>()) k_gotoh_band(const FillArgs a)
             const bool firstCol = active && x == 0, lastCol = active && x == Lb - 1;
             const bool edge = __any_sync(0xffffffffu, firstCol || lastCol);   // warp-uniform
             if (active) {
-                const int32_t *prow = sprof + cp * PS + t * strip_stride(K);
-                uint32_t *tbw = tbl + (int64_t)i * (K / 2);
+                const int32_t *prow = pbase + cp * PS;
+                uint32_t *tbw = tbl + (int64_t)i * (Kb / 2);
                 if (edge)
-                    column_step<K, true, true, false>(st, prow, r.x, r.y, r.z, hd0, nopen16, ext32, nopen16_last, ext32_last,
-                                                      lastLane, firstCol, lastCol, one, tbw, 0, colBest, colPosLo, colPosHi,
-                                                      botH3, botIY, botM);
-                else
-                    column_step<K, false, true, false>(st, prow, r.x, r.y, r.z, hd0, nopen16, ext32, nopen16_last, ext32_last,
-                                                       lastLane, false, false, one, tbw, 0, colBest, colPosLo, colPosHi,
+                    column_step<Kb, true, true, false>(st, prow, r.x, r.y, r.z, hd0, nopen16, ext32, nopen16_last, ext32_last,
+                                                       lastLane, firstCol, lastCol, one, tbw, 0, colBest, colPosLo, colPosHi,
                                                        botH3, botIY, botM);
+                else
+                    column_step<Kb, false, true, false>(st, prow, r.x, r.y, r.z, hd0, nopen16, ext32, nopen16_last, ext32_last,
+                                                        lastLane, false, false, one, tbw, 0, colBest, colPosLo, colPosHi,
+                                                        botH3, botIY, botM);
                 hd0 = r.x;
             }
         }
@@ -348,31 +354,48 @@ __global__ void __maxnreg__(fill_maxnreg<K>()) k_gotoh_band(const FillArgs a)
 // ---- host-side dispatch ----------------------------------------------------------------
 struct Tile { int G, K; };
 
+template <typename Kern>
+static cudaError_t launch_persistent(Kern kern, bool &configured, int &blocks_per_sm, size_t smem, int64_t blocks_wanted,
+                                     const FillArgs &a, int num_sms, cudaStream_t stream)
+{
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, 128, smem);
+        if (e != cudaSuccess) return e;
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+        configured = true;
+    }
+    int64_t grid = blocks_wanted;
+    const int cap = num_sms * blocks_per_sm;            // persistent: a multiple of the SM count
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    kern<<<(int)grid, 128, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+// kind 0: single pass with flags; kind 2: band pass on sub-strips of a.band_K rows (K, or K/2 when K % 16 == 0)
 template <int G, int K>
 static cudaError_t launch_tile(const FillArgs &a, int num_sms, cudaStream_t stream, int kind)
 {
     const size_t smem = (size_t)NPAIR * prof_stride(G, K) * 4;
-    static bool configured = false;
-    static int blocks_per_sm[3] = {1, 1, 1};
-    void (*kern[3])(const FillArgs) = {k_gotoh_fill<G, K>, nullptr, k_gotoh_band<G, K>};
-    if (!configured) {
-        for (int i = 0; i < 3; i += 2) {
-            cudaError_t e = cudaFuncSetAttribute(kern[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[i], kern[i], 128, smem);
-            if (e != cudaSuccess) return e;
-            if (blocks_per_sm[i] < 1) blocks_per_sm[i] = 1;
-        }
-        configured = true;
-    }
     const int npairs = a.p1 - a.p0;
-    const int groups_per_block = 4 * (32 / G);
-    int grid = (npairs + groups_per_block - 1) / groups_per_block;
-    const int cap = num_sms * blocks_per_sm[kind];      // persistent: a multiple of the SM count
-    if (grid > cap) grid = cap;
-    if (grid < 1) grid = 1;
-    kern[kind]<<<grid, 128, smem, stream>>>(a);
-    return cudaGetLastError();
+    if (kind == 0) {
+        static bool configured = false; static int bps = 1;
+        const int groups_per_block = 4 * (32 / G);
+        return launch_persistent(k_gotoh_fill<G, K>, configured, bps, smem, (npairs + groups_per_block - 1) / groups_per_block, a, num_sms, stream);
+    }
+    if (a.band_K == K) {
+        static bool configured = false; static int bps = 1;
+        return launch_persistent(k_gotoh_band<G, K, 1>, configured, bps, smem, ((int64_t)npairs * G + 127) / 128, a, num_sms, stream);
+    }
+    if constexpr (K % 16 == 0) {
+        if (2 * a.band_K == K) {
+            static bool configured = false; static int bps = 1;
+            return launch_persistent(k_gotoh_band<G, K, 2>, configured, bps, smem, ((int64_t)npairs * G * 2 + 127) / 128, a, num_sms, stream);
+        }
+    }
+    return cudaErrorInvalidValue;
 }
 
 // Smallest padded tile G*K >= La from the compiled menu.

@@ -33,14 +33,15 @@ namespace crgpu {
 //  EDGE = true: some lane of the warp is on its LAST read column (iy opens from m only, zero penalties:
 //  SURVEY App. A.2/A.3) -- the whole warp runs this body with per-lane parameters, no divergence.  The
 //  first column needs no special case here (only its FY flag differs, and there are no flags).
-template <int K, bool EDGE>
+template <int K, bool EDGE, int NSUB>
 __device__ __forceinline__ void score_column(Strip<K> &st, const int32_t *__restrict__ prow,
                                              uint32_t upH3, uint32_t upIY, uint32_t upM, uint32_t hd,
                                              const uint32_t cOpen, const uint32_t cA_last, const uint32_t cB_last,
                                              const uint32_t e32, const bool lastLane, const bool isLastCol,
                                              const int firstRealSlot, uint32_t drift0,
                                              uint32_t &colBest, int &colPosLo, int &colPosHi,
-                                             uint32_t &botH3, uint32_t &botIY, uint32_t &botM)
+                                             uint32_t &botH3, uint32_t &botIY, uint32_t &botM,
+                                             uint32_t &midH3, uint32_t &midIY, uint32_t &midM)
 {
 #if SCORE_HOIST_M
     // every m of the column first: m'[k] needs max3'[k-1, x-1], the value row k-1 is about to overwrite; with the
@@ -103,6 +104,7 @@ __device__ __forceinline__ void score_column(Strip<K> &st, const int32_t *__rest
         st.IX[k] = ix;
         if (k == K - 1) st.mlast = m;
         upH3 = h3; upIY = iy; upM = m; hd = h0;
+        if (NSUB == 2 && k == K / 2 - 1) { midH3 = h3; midIY = iy; midM = m; }   // top boundary of the lower sub-strip
     }
     botH3 = upH3; botIY = upIY; botM = upM;
 }
@@ -118,10 +120,11 @@ __device__ __forceinline__ void score_column(Strip<K> &st, const int32_t *__rest
 
 template <int K> constexpr int score_maxnreg() { return K <= 32 ? SCORE_MAXNREG : fill_maxnreg<K>(); }
 
-template <int G, int K>
+template <int G, int K, int NSUB>
 __global__ void __maxnreg__(score_maxnreg<K>()) k_gotoh_score(const FillArgs a)
 {
-    static_assert(K % 4 == 0 && (32 % G) == 0, "bad tile");
+    static_assert(K % 4 == 0 && (32 % G) == 0 && (NSUB == 1 || (NSUB == 2 && K % 16 == 0)), "bad tile");
+    constexpr int Kb = K / NSUB;                                          // rows per sub-strip of the band pass
     constexpr int PS = prof_stride(G, K);
     extern __shared__ __align__(128) int32_t sprof[];
     __shared__ __align__(8) uint64_t mbar;
@@ -142,7 +145,9 @@ __global__ void __maxnreg__(score_maxnreg<K>()) k_gotoh_score(const FillArgs a)
     const uint32_t cOpen = ((uint32_t)(a.ext - a.open) & 0xffffu) * 0x10001u;   // per-half two's complement of ext - open
     const uint32_t cA_last = lastLane ? e32 : cOpen;                      // amplicon row La-1: zero end-gap penalties
     const uint32_t cB_last = lastLane ? e32 : 0u;
-    const int xlo1 = a.band_row0 + t * K - a.band_B - 1;                  // the band's columns are xlo1+1 .. xlo1+W
+    // band columns of this lane's upper sub-strip: xlo1+1 .. xlo1+W; of its lower one (NSUB == 2): shifted by Kb
+    const int xlo1 = a.band_row0 + t * K - a.band_B - 1;
+    const uint32_t eKb = e32 * (uint32_t)Kb;
 
     for (int base = a.p0 + warp_global * GPW; base < a.p1; base += nwarps * GPW) {
         const int p = base + gl;
@@ -178,13 +183,15 @@ __global__ void __maxnreg__(score_maxnreg<K>()) k_gotoh_score(const FillArgs a)
         uint4 tn = make_uint4(Z, NOPEN_ST, Z, 0u);
         if (tin && t == 0 && Lb > 0) tn = tin[0];
         // what this lane receives at its band columns, and its registers at the band's left edge
-        uint4 *bandw = nullptr;                                          // indexed by column x
+        uint4 *bandw = nullptr, *midw = nullptr;                         // indexed by column x
         uint32_t *leftp = nullptr;
         if (valid && a.band_tops) {
-            const int64_t lane_id = (int64_t)(p - a.p0) * G + t;
-            if (t > 0) bandw = reinterpret_cast<uint4 *>(a.band_tops) + lane_id * band_topw(a.band_W) - xlo1;
-            leftp = a.band_left + lane_id * band_leftw(K);
+            const int64_t sub_id = ((int64_t)(p - a.p0) * G + t) * NSUB;   // this lane's upper sub-strip
+            if (t > 0) bandw = reinterpret_cast<uint4 *>(a.band_tops) + sub_id * band_topw(a.band_W) - xlo1;
+            if (NSUB == 2) midw = reinterpret_cast<uint4 *>(a.band_tops) + (sub_id + 1) * band_topw(a.band_W) - (xlo1 + Kb);
+            leftp = a.band_left + sub_id * band_leftw(Kb);
         }
+        uint32_t midH3 = Z, midIY = Z, midM = Z;
 
         // One systolic step.  STEADY = every lane of the warp is on an interior column of its read (no lane
         // idle, none on its last column): the votes, the activity branch and the edge body drop out.
@@ -206,11 +213,19 @@ __global__ void __maxnreg__(score_maxnreg<K>()) k_gotoh_score(const FillArgs a)
                 const int32_t *prow = sprof + cp * PS + t * strip_stride(K);
                 if (bandw && (unsigned)(x - xlo1) <= (unsigned)a.band_W) bandw[x] = make_uint4(rH3 - dTop, rIY - dTop, rM - dTop, 0u);
                 if (edge)
-                    score_column<K, true>(st, prow, rH3, rIY, rM, hd0, cOpen, cA_last, cB_last, e32, lastLane, lastCol,
-                                          firstRealSlot, dTop + e32, colBest, colPosLo, colPosHi, botH3, botIY, botM);
+                    score_column<K, true, NSUB>(st, prow, rH3, rIY, rM, hd0, cOpen, cA_last, cB_last, e32, lastLane, lastCol,
+                                                firstRealSlot, dTop + e32, colBest, colPosLo, colPosHi, botH3, botIY, botM,
+                                                midH3, midIY, midM);
                 else
-                    score_column<K, false>(st, prow, rH3, rIY, rM, hd0, cOpen, cA_last, cB_last, e32, lastLane, false,
-                                           firstRealSlot, 0u, colBest, colPosLo, colPosHi, botH3, botIY, botM);
+                    score_column<K, false, NSUB>(st, prow, rH3, rIY, rM, hd0, cOpen, cA_last, cB_last, e32, lastLane, false,
+                                                 firstRealSlot, 0u, colBest, colPosLo, colPosHi, botH3, botIY, botM,
+                                                 midH3, midIY, midM);
+                if (NSUB == 2) {
+                    if (midw && (unsigned)(x - xlo1 - Kb) <= (unsigned)a.band_W) {
+                        const uint32_t dMid = dTop + eKb;             // drift of (row t*K + Kb - 1, column x)
+                        midw[x] = make_uint4(midH3 - dMid, midIY - dMid, midM - dMid, 0u);
+                    }
+                }
                 hd0 = rH3;                                            // max3'[row above, x] for column x+1
                 // start-cell scan along the last amplicon row (meaningful in the last lane only), on plain
                 // values: first column whose max(m,ix,iy) is strictly greater than all columns before it
@@ -223,13 +238,23 @@ __global__ void __maxnreg__(score_maxnreg<K>()) k_gotoh_score(const FillArgs a)
                     rowBest = nb;
                 }
                 if (tout) tout[x] = make_uint4(botH3 - dBot, botIY - dBot, botM - dBot, 0u);
-                if (!STEADY && leftp && x == xlo1) {                  // registers after column xlo-1: the band pass starts from them
+                if (!STEADY && leftp) {
+                    // registers after column xlo-1 of a sub-strip: the band pass starts from them
                     // (scalar stores on purpose: vector stores would make ptxas shuffle 2K registers into aligned
                     // quads on EVERY step, outside this once-per-pair branch)
-                    uint32_t d = dTop;
+                    if (x == xlo1) {
+                        uint32_t d = dTop;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) { d += e32; leftp[k] = st.H3[k] - d; leftp[K + k] = st.IX[k] - d; }
-                    leftp[2 * K] = st.mlast - d;
+                        for (int k = 0; k < Kb; ++k) { d += e32; leftp[k] = st.H3[k] - d; leftp[Kb + k] = st.IX[k] - d; }
+                        if (NSUB == 1) leftp[2 * Kb] = st.mlast - d;
+                    }
+                    if (NSUB == 2 && x == xlo1 + Kb) {
+                        uint32_t *lp = leftp + band_leftw(Kb);
+                        uint32_t d = dTop + eKb;
+#pragma unroll
+                        for (int k = 0; k < Kb; ++k) { d += e32; lp[k] = st.H3[Kb + k] - d; lp[Kb + k] = st.IX[Kb + k] - d; }
+                        lp[2 * Kb] = st.mlast - d;
+                    }
                 }
                 if (lastCol) {
                     lcp[0] = colBest; lcp[1] = (uint32_t)colPosLo; lcp[2] = (uint32_t)colPosHi;
@@ -245,8 +270,9 @@ __global__ void __maxnreg__(score_maxnreg<K>()) k_gotoh_score(const FillArgs a)
         const int steady_end = min(Lmin - 1, steps);                          // first non-steady step after the steady run
         int s = 0;
         while (s < steps) {
-            const int d = xlo1 - (s - t);                                     // steps until this lane's save
-            if (s >= G && s + SCORE_UNROLL <= steady_end && !__any_sync(0xffffffffu, d >= 0 && d < SCORE_UNROLL)) {
+            const int d = xlo1 - (s - t);                                     // steps until this lane's (first) save
+            const bool saves = (d >= 0 && d < SCORE_UNROLL) || (NSUB == 2 && d + Kb >= 0 && d + Kb < SCORE_UNROLL);
+            if (s >= G && s + SCORE_UNROLL <= steady_end && !__any_sync(0xffffffffu, saves)) {
 #pragma unroll
                 for (int u = 0; u < SCORE_UNROLL; ++u) step(std::true_type{}, s + u);
                 s += SCORE_UNROLL;
@@ -258,16 +284,16 @@ __global__ void __maxnreg__(score_maxnreg<K>()) k_gotoh_score(const FillArgs a)
     }
 }
 
-template <int G, int K>
+template <int G, int K, int NSUB>
 static cudaError_t launch_score_tile(const FillArgs &a, int num_sms, cudaStream_t stream)
 {
     const size_t smem = (size_t)NPAIR * prof_stride(G, K) * 4;
     static bool configured = false;
     static int blocks_per_sm = 1;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_gotoh_score<G, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_gotoh_score<G, K, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_gotoh_score<G, K>, 128, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_gotoh_score<G, K, NSUB>, 128, smem);
         if (e != cudaSuccess) return e;
         if (blocks_per_sm < 1) blocks_per_sm = 1;
         configured = true;
@@ -278,13 +304,22 @@ static cudaError_t launch_score_tile(const FillArgs &a, int num_sms, cudaStream_
     const int cap = num_sms * blocks_per_sm;            // persistent: a multiple of the SM count
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    k_gotoh_score<G, K><<<grid, 128, smem, stream>>>(a);
+    k_gotoh_score<G, K, NSUB><<<grid, 128, smem, stream>>>(a);
     return cudaGetLastError();
+}
+
+// the band pass works on sub-strips of a.band_K rows: K (one per lane) or K/2 (two per lane, K % 16 == 0)
+template <int G, int K>
+static cudaError_t launch_score_sub(const FillArgs &a, int num_sms, cudaStream_t stream)
+{
+    if (a.band_K == K) return launch_score_tile<G, K, 1>(a, num_sms, stream);
+    if constexpr (K % 16 == 0) { if (2 * a.band_K == K) return launch_score_tile<G, K, 2>(a, num_sms, stream); }
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_score(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream)
 {
-#define CASE(g, k) if (G == g && K == k) return launch_score_tile<g, k>(a, num_sms, stream);
+#define CASE(g, k) if (G == g && K == k) return launch_score_sub<g, k>(a, num_sms, stream);
     CASE(4, 16) CASE(4, 24) CASE(4, 32) CASE(4, 40) CASE(8, 16) CASE(8, 24) CASE(8, 32) CASE(8, 40)
     CASE(16, 16) CASE(16, 24) CASE(16, 32) CASE(16, 40) CASE(32, 24) CASE(32, 32) CASE(4, 48) CASE(8, 48) CASE(16, 48)
 #undef CASE

@@ -148,18 +148,19 @@ __global__ void __launch_bounds__(128) k_traceback_walk(const WalkArgs a)
                                 : reinterpret_cast<const uint8_t *>(a.tb_upper + (a.pc_off[p] - a.pc_off[a.p0]) * (a.G_upper * a.K / 2));
     const int64_t colbytes_u = (int64_t)a.G_upper * a.K * 2;
     const int split = a.tb_upper ? a.split_row : 0;
+    const int split_sub = band ? split / a.band_K : 0;
     const int P = a.P;
-    // flag byte of cell (yy, xx).  Banded fill: lane t = padded row / K holds columns [t*K - P - B, +W) only;
+    // flag byte of cell (yy, xx).  Banded fill: sub-strip u = padded row / band_K holds columns [u*band_K - P - B, +W) only;
     // anything else reads as 0xff (never a flag byte), which ends the walk with an escape when it is consumed.
     auto tb_at = [&](int yy, int xx) -> uint8_t {
         const int v = yy + P;
         if (band) {
-            const int tf = (int)__umulhi((unsigned)v, a.kdiv_magic);
-            const int rr = v - tf * a.K;
-            const int xr = xx - (tf * a.K - P - a.band_B);
+            const int tf = (int)__umulhi((unsigned)v, a.kdiv_magic);           // sub-strip
+            const int rr = v - tf * a.band_K;
+            const int xr = xx - (tf * a.band_K - P - a.band_B);
             if ((unsigned)xr >= (unsigned)a.band_W) return (uint8_t)0xff;
-            const uint8_t *q = v < split ? tbu + ((int64_t)tf * a.band_W + xr) * (a.K * 2)
-                                         : tb + ((int64_t)(tf - split / a.K) * a.band_W + xr) * (a.K * 2);
+            const uint8_t *q = v < split ? tbu + ((int64_t)tf * a.band_W + xr) * (a.band_K * 2)
+                                         : tb + ((int64_t)(tf - split_sub) * a.band_W + xr) * (a.band_K * 2);
             return q[((rr >> 1) << 2) + (h << 1) + (rr & 1)];
         }
         return v < split ? tbu[xx * colbytes_u + ((v >> 1) << 2) + (h << 1) + (v & 1)]

@@ -351,6 +351,100 @@ def run_hot_path(ctx, amplicon, reads, gapopen=10.0, gapextend=0.5, min_identity
     return res
 
 
+def run_hot_path_pipelined(ctxs, amplicon, reads, chunk_reads=1 << 18, gapopen=10.0, gapextend=0.5, min_identity_score=60.0,
+                           hdr_amplicon=None, flags=None, hdr_thr=98.0, inc=None, exon=None, splice=None, rc_rescue=True,
+                           red=None, out=None):
+    """run_hot_path for HOST-resident reads with the PCIe copies hidden behind the kernels.
+
+    The read set is cut into chunks of ``chunk_reads``; chunk c runs as one crgpu_align_quantify call on context
+    ``ctxs[c % len(ctxs)]``, each context driven by its own host thread (the call is synchronous and ctypes releases the
+    GIL), so the H2D / D2H copies of one chunk overlap the kernels of the others.  Every read is independent and the
+    reductions are sums, so the result equals one call over all reads (per-read outputs in read order, RC rows in read
+    order).  Text rows and the allele table need the single call.
+
+    out: optional dict of preallocated (e.g. pinned) arrays ``kept`` u8[n], ``aln`` ALN_REC[n], ``tenths_rep`` i32[n],
+    ``recs`` READ_REC[n], ``rc_read`` i32[n], ``rc_aln`` ALN_REC[n], ``rc_recs`` READ_REC[n], ``offsets`` i64[n + chunks]
+    (staging for the chunk-relative offsets)."""
+    from concurrent.futures import ThreadPoolExecutor
+    buf, offsets = reads
+    n = len(offsets) - 1
+    amp = amplicon.upper().encode()
+    L = len(amp)
+    red = red or Reductions(L)
+    if flags is None:
+        flags = quant_flags(expected_hdr_amplicon_seq=hdr_amplicon or "")
+    if inc is None:
+        inc = np.ones(L, np.uint8)
+    hdr_b = hdr_amplicon.upper().encode() if hdr_amplicon else None
+    bounds = [(lo, min(n, lo + chunk_reads)) for lo in range(0, n, chunk_reads)]
+    out = out or {}
+
+    def arr(name, dtype, size):
+        a = out.get(name)
+        return a if a is not None else np.zeros(size, dtype)
+
+    kept, aln, recs = arr("kept", np.uint8, n), arr("aln", _lib.ALN_REC, n), arr("recs", _lib.READ_REC, n)
+    trep = out.get("tenths_rep")
+    if trep is None:
+        trep = np.full(n, -1, np.int32)
+    rc_read, rc_aln, rc_recs = arr("rc_read", np.int32, n), arr("rc_aln", _lib.ALN_REC, n), arr("rc_recs", _lib.READ_REC, n)
+    off_stage = arr("offsets", np.int64, n + len(bounds))
+    buf_addr, isz_aln, isz_rec = _lib.ptr(buf), _lib.ALN_REC.itemsize, _lib.READ_REC.itemsize
+    addr = {k: _lib.ptr(v) for k, v in (("kept", kept), ("aln", aln), ("recs", recs), ("trep", trep), ("rc_read", rc_read),
+                                        ("rc_aln", rc_aln), ("rc_recs", rc_recs))}
+
+    def worker(w):
+        ctx = ctxs[w]
+        my = Reductions(L)
+        keep = []
+        qp = _quant_params(L, flags, hdr_thr, inc, exon, splice, keep)
+        pp = _lib.PathParams()
+        pp.gapopen, pp.gapextend, pp.min_identity_score = float(gapopen), float(gapextend), float(min_identity_score)
+        pp.hdr_amplicon, pp.hdr_amplicon_len, pp.rc_rescue = hdr_b, len(hdr_b) if hdr_b else 0, 1 if rc_rescue else 0
+        nrcs = {}
+        for c in range(w, len(bounds), len(ctxs)):
+            lo, hi = bounds[c]
+            m = hi - lo
+            offs = off_stage[lo + c:lo + c + m + 1]
+            np.subtract(offsets[lo:hi + 1], offsets[lo], out=offs)
+            po = _lib.PathOut()
+            po.vectors, po.hist_inframe, po.hist_frameshift = my.vectors.ctypes.data, my.hist_inframe.ctypes.data, my.hist_frameshift.ctypes.data
+            po.hist_len, po.hist_zero, po.counters = HIST_LEN, HIST_ZERO, my.counters.ctypes.data
+            po.kept, po.aln, po.recs = addr["kept"] + lo, addr["aln"] + lo * isz_aln, addr["recs"] + lo * isz_rec
+            po.tenths_rep = addr["trep"] + lo * 4
+            po.slot, po.rc_cap = 0, m
+            po.rc_read, po.rc_aln, po.rc_recs = addr["rc_read"] + lo * 4, addr["rc_aln"] + lo * isz_aln, addr["rc_recs"] + lo * isz_rec
+            ctx.check(ctx.lib.crgpu_align_quantify(ctx.handle, _lib.MEM_HOST, amp, L, ctypes.byref(pp), ctypes.byref(qp),
+                                                   buf_addr + int(offsets[lo]), _lib.ptr(offs), m, ctypes.byref(po)))
+            my.class_counts += np.array(list(po.class_counts), np.int64)
+            my.n_total += int(po.n_total)
+            my.n_cells += int(po.n_cells)
+            my.n_cells_computed += int(po.n_cells_computed)
+            nrcs[c] = int(po.rc_n)
+        return my, nrcs
+
+    if len(ctxs) == 1:
+        results = [worker(0)]
+    else:
+        with ThreadPoolExecutor(max_workers=len(ctxs)) as ex:
+            results = list(ex.map(worker, range(len(ctxs))))
+    nrc_of = {}
+    for my, nrcs in results:
+        red.load_flat(red.flat() + my.flat())
+        nrc_of.update(nrcs)
+    # RC rows: each chunk left its own compact, read-ordered list at [lo, lo + nrc); close the gaps
+    pos = 0
+    for c, (lo, hi) in enumerate(bounds):
+        k = nrc_of.get(c, 0)
+        if k:
+            rc_read[pos:pos + k] = rc_read[lo:lo + k] + lo
+            if pos != lo:
+                rc_aln[pos:pos + k] = rc_aln[lo:lo + k]
+                rc_recs[pos:pos + k] = rc_recs[lo:lo + k]
+            pos += k
+    return HotPathResult(kept, aln, trep, recs, None, 0, rc_read[:pos], rc_aln[:pos], rc_recs[:pos], None, red)
+
+
 def build_dataframe(res, read_names, has_hdr=False, amplicon=None):
     """df_needle_alignment as run_crispresso holds it after CORE:2072 and the quantification
     (CORE:2864): index ID, columns score_ref [score_repaired score_diff] length ref_seq align_str

@@ -179,3 +179,30 @@ def test_banded_two_pass_fill_changes_nothing(La, read_len, sigma, hdr_on):
             assert seen_escape                   # the 2-column band cannot hold a read with an indel
     finally:
         c.close()
+
+
+def test_pipelined_chunks_on_two_contexts_equal_one_call(ctx):
+    """run_hot_path_pipelined (read chunks alternating between two contexts, each on its own host thread, so that
+    one chunk's PCIe copies overlap the other's kernels) must return what one call over all reads returns: per-read
+    records in read order, the RC-rescue list in read order, every reduction."""
+    from crispresso_b200 import Context
+    amp, guide, cut, hdr = synth.make_case(31, 210)
+    packed = synth.make_reads(amp, hdr, cut, 1500, seed=32, read_len=210, rc_frac=0.07, len_sigma=5.0)
+    inc = hotpath.include_mask(len(amp), hotpath.cut_points_from_guides(amp, guide), 1, 15, 15)
+    flags = hotpath.quant_flags(hdr)
+    one = hotpath.run_hot_path(ctx, amp, packed, hdr_amplicon=hdr, flags=flags, inc=inc)
+    other = Context(0)
+    try:
+        for ctxs, chunk in (([ctx, other], 400), ([ctx], 700), ([ctx, other], 4096)):
+            pip = hotpath.run_hot_path_pipelined(ctxs, amp, packed, chunk_reads=chunk, hdr_amplicon=hdr, flags=flags, inc=inc)
+            assert np.array_equal(pip.kept, one.kept)
+            assert pip.aln.tobytes() == one.aln.tobytes()
+            assert np.array_equal(pip.tenths_rep, one.tenths_rep)
+            assert pip.recs.tobytes() == one.recs.tobytes()
+            assert len(one.rc_read) > 0 and np.array_equal(pip.rc_read, one.rc_read)
+            assert pip.rc_aln.tobytes() == one.rc_aln.tobytes()
+            assert pip.rc_recs.tobytes() == one.rc_recs.tobytes()
+            a, b = pip.red.flat(), one.red.flat()
+            assert np.array_equal(a[:-1], b[:-1])          # all but n_cells_computed (the band decision is per chunk)
+    finally:
+        other.close()
