@@ -43,7 +43,8 @@ def parse():
     ap.add_argument("--reads", type=int, default=1 << 20, help="reads per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=200000, help="reads in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-chunk", type=int, default=1 << 18, help="reads per crgpu_align_quantify call of the end-to-end arm")
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="reads per crgpu_align_quantify call of the end-to-end arm "
+                                                               "(default: reads / contexts, measured best: t9 sweep in profiles/r01c_notes.md)")
     ap.add_argument("--e2e-contexts", type=int, default=2, help="contexts (host threads) the end-to-end arm alternates between")
     return ap.parse_args()
 
@@ -274,6 +275,8 @@ def main():
     # one chunk overlap the kernels of the other; everything is inside the timed region.
     p_buf = torch.from_numpy(buf).pin_memory()
     p_off = torch.from_numpy(off).pin_memory()
+    if args.e2e_chunk <= 0:
+        args.e2e_chunk = (n + args.e2e_contexts - 1) // args.e2e_contexts
     n_chunks = (n + args.e2e_chunk - 1) // args.e2e_chunk
     pinned = {
         "kept": torch.zeros(n, dtype=torch.uint8).pin_memory(),

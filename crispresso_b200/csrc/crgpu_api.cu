@@ -682,8 +682,18 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     const int TOPW = band_topw(W), LEFTW = band_leftw(Kb);
     const size_t sub_bytes = (size_t)TOPW * 16 + (size_t)LEFTW * 4 + (size_t)W * Kb * 2;      // per sub-strip
     const size_t pair_bytes = sub_bytes * (size_t)(G + Gh) * nsub + (dual ? (size_t)(maxlen + 2) * 16 : 0);
+    // ~8 batches per call (the walks of one batch overlap the fills of the next), each a whole number of WAVES of the
+    // persistent score kernels: a warp of k_gotoh_score owns pairs w, w + wave, ..., so a batch of 9.2 waves costs 10
     int64_t bp = (int64_t)(ctx->tb_budget / pair_bytes);
-    bp = std::max<int64_t>(1, std::min<int64_t>(bp, std::max<int64_t>(((int64_t)pl.np + 7) / 8, 16384)));
+    {
+        const int64_t wave = getenv("CRGPU_NO_WAVE_ALIGN") ? 1 : std::max<int64_t>(1, score_wave_pairs(dual ? Gh : G, K, nsub, ctx->num_sms));
+        int64_t want = std::max<int64_t>(((int64_t)pl.np + 7) / 8, 16384);
+        if (want >= 4 * wave) {                   // (small calls, e.g. the chunks of a pipelined run, measured better unaligned)
+            want = (want + wave - 1) / wave * wave;
+            if (bp >= wave) bp = bp / wave * wave;
+        }
+        bp = std::max<int64_t>(1, std::min<int64_t>(bp, want));
+    }
     std::vector<int> batch_start;
     for (int64_t p = 0; p < pl.np; p += bp) batch_start.push_back((int)p);
     batch_start.push_back(pl.np);

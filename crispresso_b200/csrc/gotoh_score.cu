@@ -21,6 +21,7 @@
 // memory holds plain values and the band pass / the walker are unaffected.  Exact integer arithmetic: the
 // host checks that value + drift stays inside the 15-bit range (run_plan_band).
 #include "gotoh_tile.cuh"
+#include <algorithm>
 #include <type_traits>
 
 #ifndef SCORE_HOIST_M
@@ -315,6 +316,25 @@ static cudaError_t launch_score_sub(const FillArgs &a, int num_sms, cudaStream_t
     if (a.band_K == K) return launch_score_tile<G, K, 1>(a, num_sms, stream);
     if constexpr (K % 16 == 0) { if (2 * a.band_K == K) return launch_score_tile<G, K, 2>(a, num_sms, stream); }
     return cudaErrorInvalidValue;
+}
+
+template <int G, int K, int NSUB>
+static int64_t wave_pairs_tile(int num_sms)
+{
+    const size_t smem = (size_t)NPAIR * prof_stride(G, K) * 4;
+    int bps = 0;
+    if (cudaFuncSetAttribute(k_gotoh_score<G, K, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_gotoh_score<G, K, NSUB>, 128, smem) != cudaSuccess) return 0;
+    return (int64_t)num_sms * std::max(bps, 1) * 4 * (32 / G);
+}
+
+int64_t score_wave_pairs(int G, int K, int nsub, int num_sms)
+{
+#define CASE(g, k) if (G == g && K == k) { if (nsub == 1) return wave_pairs_tile<g, k, 1>(num_sms); if constexpr (k % 16 == 0) { if (nsub == 2) return wave_pairs_tile<g, k, 2>(num_sms); } return 0; }
+    CASE(4, 16) CASE(4, 24) CASE(4, 32) CASE(4, 40) CASE(8, 16) CASE(8, 24) CASE(8, 32) CASE(8, 40)
+    CASE(16, 16) CASE(16, 24) CASE(16, 32) CASE(16, 40) CASE(32, 24) CASE(32, 32) CASE(4, 48) CASE(8, 48) CASE(16, 48)
+#undef CASE
+    return 0;
 }
 
 cudaError_t launch_score(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream)

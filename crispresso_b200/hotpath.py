@@ -360,7 +360,8 @@ def run_hot_path_pipelined(ctxs, amplicon, reads, chunk_reads=1 << 18, gapopen=1
     ``ctxs[c % len(ctxs)]``, each context driven by its own host thread (the call is synchronous and ctypes releases the
     GIL), so the H2D / D2H copies of one chunk overlap the kernels of the others.  Every read is independent and the
     reductions are sums, so the result equals one call over all reads (per-read outputs in read order, RC rows in read
-    order).  Text rows and the allele table need the single call.
+    order; `aln_off`, which positions a text row inside its call's slot, is per chunk).  Text rows and the allele
+    table need the single call.
 
     out: optional dict of preallocated (e.g. pinned) arrays ``kept`` u8[n], ``aln`` ALN_REC[n], ``tenths_rep`` i32[n],
     ``recs`` READ_REC[n], ``rc_read`` i32[n], ``rc_aln`` ALN_REC[n], ``rc_recs`` READ_REC[n], ``offsets`` i64[n + chunks]

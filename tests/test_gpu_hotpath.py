@@ -142,7 +142,7 @@ def test_shared_dp_prefix_of_the_hdr_pass_changes_nothing(ctx):
     try:
         r = hotpath.run_hot_path(ctx, amp, packed, hdr_amplicon=hdr2, flags=hotpath.quant_flags(hdr2))
     finally:
-        ctx.set_band(24)
+        ctx.set_band(16)
     assert r.red.n_cells_computed == r.red.n_cells
 
 
@@ -164,13 +164,21 @@ def test_banded_two_pass_fill_changes_nothing(La, read_len, sigma, hdr_on):
         ref = hotpath.run_hot_path(c, amp, packed, hdr_amplicon=hdr, flags=flags, want_rows=True)
         assert c.last_escaped() == (0, 0)
         seen_escape = False
-        for B, share in ((24, True), (2, True), (40, False), (9, True)):
+        import os
+        for B, share, whole_strips in ((24, True, False), (2, True, False), (40, False, False), (9, True, False), (16, True, True)):
             c.set_band(B)
             c.set_share_prefix(share)
-            got = hotpath.run_hot_path(c, amp, packed, hdr_amplicon=hdr, flags=flags, want_rows=True)
+            # the band pass works on half-height sub-strips where the tile allows it; CRGPU_NO_SUBSTRIP keeps whole strips
+            os.environ.pop("CRGPU_NO_SUBSTRIP", None)
+            if whole_strips:
+                os.environ["CRGPU_NO_SUBSTRIP"] = "1"
+            try:
+                got = hotpath.run_hot_path(c, amp, packed, hdr_amplicon=hdr, flags=flags, want_rows=True)
+            finally:
+                os.environ.pop("CRGPU_NO_SUBSTRIP", None)
             seen_escape |= c.last_escaped()[0] > 0
             got.red.n_cells_computed = ref.red.n_cells_computed
-            assert np.array_equal(got.red.flat(), ref.red.flat()), (B, share)
+            assert np.array_equal(got.red.flat(), ref.red.flat()), (B, share, whole_strips)
             assert np.array_equal(got.aln, ref.aln) and np.array_equal(got.recs, ref.recs) and np.array_equal(got.kept, ref.kept)
             assert np.array_equal(got.tenths_rep, ref.tenths_rep)
             for k in range(3):
@@ -196,11 +204,14 @@ def test_pipelined_chunks_on_two_contexts_equal_one_call(ctx):
         for ctxs, chunk in (([ctx, other], 400), ([ctx], 700), ([ctx, other], 4096)):
             pip = hotpath.run_hot_path_pipelined(ctxs, amp, packed, chunk_reads=chunk, hdr_amplicon=hdr, flags=flags, inc=inc)
             assert np.array_equal(pip.kept, one.kept)
-            assert pip.aln.tobytes() == one.aln.tobytes()
+            fields = [f for f in _lib.ALN_REC.names if f != "aln_off"]      # aln_off positions a text row in its call's slot
+            for f in fields:
+                assert np.array_equal(pip.aln[f], one.aln[f]), f
             assert np.array_equal(pip.tenths_rep, one.tenths_rep)
             assert pip.recs.tobytes() == one.recs.tobytes()
             assert len(one.rc_read) > 0 and np.array_equal(pip.rc_read, one.rc_read)
-            assert pip.rc_aln.tobytes() == one.rc_aln.tobytes()
+            for f in fields:
+                assert np.array_equal(pip.rc_aln[f], one.rc_aln[f]), f
             assert pip.rc_recs.tobytes() == one.rc_recs.tobytes()
             a, b = pip.red.flat(), one.red.flat()
             assert np.array_equal(a[:-1], b[:-1])          # all but n_cells_computed (the band decision is per chunk)
