@@ -87,6 +87,7 @@ int crgpu_set_band(crgpu_ctx *c, int half_width)
 {
     if (!c || half_width < 0 || half_width > 512) return CRGPU_E_ARG;
     c->band_B = half_width;
+    c->band_holdoff = 0;
     return CRGPU_OK;
 }
 

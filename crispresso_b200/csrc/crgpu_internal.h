@@ -69,6 +69,7 @@ struct crgpu_ctx {
     DBuf prof_s, prof_hs;                                           // drifted profiles of the score pass
     DBuf btops[2], bleft[2], btops_h[2], bleft_h[2], escaped;      // banded two-pass fill (run_plan_band)
     int n_escaped[2] = {0, 0};                                     // reads re-aligned after the last banded call (amplicon, HDR)
+    int band_holdoff = 0;                                          // calls left that skip the band (set when > 25 % of a call's reads escaped)
     int band_B = 16;                                               // band half-width in read columns; 0 = single-pass fill
     DBuf q_in[8], q_out[4];
     DBuf aux[8];

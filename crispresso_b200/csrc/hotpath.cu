@@ -258,7 +258,8 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
         CK(ctx->aux[1].reserve((size_t)n * sizeof(crgpu_aln_rec)));
         d_aln_hdr = ctx->aux[1].as<crgpu_aln_rec>();
     }
-    if (ctx->band_B > 0) {
+    if (ctx->band_B > 0 && ctx->band_holdoff > 0) --ctx->band_holdoff;          // recent calls escaped too often: single-pass fill
+    else if (ctx->band_B > 0) {
         // banded two-pass fill; reads whose traceback leaves the band are flagged in d_esc and re-aligned below
         CK(ctx->escaped.reserve((size_t)n));
         d_esc = ctx->escaped.as<uint8_t>();
@@ -320,6 +321,8 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
             CK(cudaMemcpyAsync(&h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
             ctx->n_escaped[bit - 1] = h_cnt;
+            // a read set whose tracebacks mostly leave the band pays for both fills: skip the band for the next 8 calls
+            if ((int64_t)h_cnt * 4 > n) ctx->band_holdoff = 8;
             if (h_cnt == 0) continue;
             int64_t c0 = 0;
             rc = build_plan(ctx, d_reads, d_off, d_sel, h_cnt);

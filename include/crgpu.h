@@ -69,7 +69,9 @@ int crgpu_set_share_prefix(crgpu_ctx *ctx, int on);
 /* Banded two-pass fill (default half-width 16 read columns; 0 = single-pass fill with flags for every
  * cell).  The first pass evaluates every DP cell without traceback flags, the second re-evaluates, with
  * flags, only the columns within half_width of the main diagonal of each lane's rows; a read whose
- * traceback leaves the band is re-aligned with the single-pass fill, so results never depend on this. */
+ * traceback leaves the band is re-aligned with the single-pass fill, so results never depend on this.  When
+ * more than a quarter of a call's reads leave the band, the next 8 fused calls on the context use the
+ * single-pass fill. */
 int crgpu_set_band(crgpu_ctx *ctx, int half_width);
 /* The current half-width (-1: no context). */
 int crgpu_get_band(const crgpu_ctx *ctx);

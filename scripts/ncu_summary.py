@@ -16,7 +16,11 @@ KEYS = [
 
 
 def main(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # an .ncu-rep, or the CSV of its raw page (`ncu -i x.ncu-rep --page raw --csv`)
+    if path.endswith(".csv"):
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     print("| kernel | " + " | ".join(k for k in KEYS if k in hdr) + " |")

@@ -15,4 +15,10 @@ ncu --set full --clock-control none --import-source on -k regex:"k_gotoh_score|k
 ncu --set full --clock-control none --import-source on -k regex:"k_quantify|k_gotoh_fill" \
     -c 3 -o $out/${tag}_kernels2 -f python bench.py --steps 1 --warmup 1 --reads 1048576 --no-cpu-baseline >> $out/${tag}_ncu_full.log 2>&1
 tail -2 $out/${tag}_ncu_full.log
+# gpurun copies back at most 64 MiB: keep the CSV pages, drop the reports
+for r in kernels kernels2; do
+    ncu -i $out/${tag}_$r.ncu-rep --page raw --csv > $out/${tag}_${r}_raw.csv 2>/dev/null
+    ncu -i $out/${tag}_$r.ncu-rep --page source --csv > $out/${tag}_${r}_source.csv 2>/dev/null
+    rm -f $out/${tag}_$r.ncu-rep
+done
 ls -la $out | grep ${tag}

@@ -147,7 +147,8 @@ def test_shared_dp_prefix_of_the_hdr_pass_changes_nothing(ctx):
 
 
 @pytest.mark.parametrize("La,read_len,sigma,hdr_on", [(250, 250, 0.0, True), (300, 300, 8.0, False), (600, 600, 0.0, True),
-                                                      (250, None, 0.0, True), (180, 400, 10.0, False), (700, 700, 0.0, True)])
+                                                      (250, None, 0.0, True), (180, 400, 10.0, False), (700, 700, 0.0, True),
+                                                      (60, 60, 2.0, True), (100, 100, 0.0, True)])
 def test_banded_two_pass_fill_changes_nothing(La, read_len, sigma, hdr_on):
     """The banded fill (score pass + band pass + re-alignment of reads whose traceback leaves the band) must
     give exactly what the single-pass fill gives, for every band width -- including widths so small that
@@ -217,3 +218,24 @@ def test_pipelined_chunks_on_two_contexts_equal_one_call(ctx):
             assert np.array_equal(a[:-1], b[:-1])          # all but n_cells_computed (the band decision is per chunk)
     finally:
         other.close()
+
+
+def test_band_holds_off_after_a_call_whose_reads_mostly_escape(ctx):
+    """More than a quarter of the reads leaving the band means the band costs more than it saves: the next calls run
+    the single-pass fill (same results, no escapes) until crgpu_set_band is called again."""
+    amp, guide, cut, hdr = synth.make_case(41, 250, hdr=False)
+    packed = synth.make_reads(amp, None, cut, 800, seed=42, read_len=250, p_exact=0.2, p_hdr=0.0)
+    flags = hotpath.quant_flags("")
+    ctx.set_band(1)
+    try:
+        first = hotpath.run_hot_path(ctx, amp, packed, flags=flags)
+        assert ctx.last_escaped()[0] * 4 > 800
+        second = hotpath.run_hot_path(ctx, amp, packed, flags=flags)
+        assert ctx.last_escaped() == (0, 0) and second.red.n_cells_computed == second.red.n_cells
+        assert np.array_equal(first.aln, second.aln) and np.array_equal(first.recs, second.recs)
+        assert np.array_equal(first.red.flat()[:-1], second.red.flat()[:-1])
+        ctx.set_band(1)                                   # a new setting is tried again
+        hotpath.run_hot_path(ctx, amp, packed, flags=flags)
+        assert ctx.last_escaped()[0] * 4 > 800
+    finally:
+        ctx.set_band(16)
