@@ -110,13 +110,13 @@ __device__ __forceinline__ void score_column(Strip<K> &st, const int32_t *__rest
     botH3 = upH3; botIY = upIY; botM = upM;
 }
 
-// no flag words and four instructions per cell pair: the registers ptxas wants stay below 168, which still
-// leaves 3 CTAs of 128 threads per SM for the K <= 32 strips
 #ifndef SCORE_UNROLL
 #define SCORE_UNROLL 2
 #endif
+// 152 registers x 128 threads x 3 CTAs leave 7168 registers per SM: exactly one k_traceback_walk CTA, so the walks of the
+// previous batch run beside the score pass instead of waiting for its tail (153+ registers: whole step 0.5 % slower)
 #ifndef SCORE_MAXNREG
-#define SCORE_MAXNREG 168
+#define SCORE_MAXNREG 152
 #endif
 
 template <int K> constexpr int score_maxnreg() { return K <= 32 ? SCORE_MAXNREG : fill_maxnreg<K>(); }
@@ -181,8 +181,11 @@ __global__ void __maxnreg__(score_maxnreg<K>()) k_gotoh_score(const FillArgs a)
         const int64_t tcol = top_base_col(pco_rel, p - a.p0);
         const uint4 *tin = (a.top_in && valid) ? reinterpret_cast<const uint4 *>(a.top_in) + tcol : nullptr;
         uint4 *tout = (a.top_out && valid && t == a.top_out_lane) ? reinterpret_cast<uint4 *>(a.top_out) + tcol : nullptr;
-        uint4 tn = make_uint4(Z, NOPEN_ST, Z, 0u);
-        if (tin && t == 0 && Lb > 0) tn = tin[0];
+        // read TWO columns ahead (tnA = column x, tnB = column x + 1): one systolic step is shorter than the latency of
+        // an HBM read, and a value that has to be copied or used one step after its load stalls the whole warp
+        uint4 tnA = make_uint4(Z, NOPEN_ST, Z, 0u), tnB = tnA;
+        if (tin && t == 0 && Lb > 0) tnA = tin[0];
+        if (tin && t == 0 && Lb > 1) tnB = tin[1];
         // what this lane receives at its band columns, and its registers at the band's left edge
         uint4 *bandw = nullptr, *midw = nullptr;                         // indexed by column x
         uint32_t *leftp = nullptr;
@@ -196,15 +199,24 @@ __global__ void __maxnreg__(score_maxnreg<K>()) k_gotoh_score(const FillArgs a)
 
         // One systolic step.  STEADY = every lane of the warp is on an interior column of its read (no lane
         // idle, none on its last column): the votes, the activity branch and the edge body drop out.
-        auto step = [&](auto steady_tag, const int s) {
+        // WHICH: 0 / 1 = first / second step of an unrolled pair (the top-boundary registers alternate, no copies);
+        // 2 = a single step (uses tnA, then rotates)
+        auto step = [&](auto steady_tag, auto which_tag, const int s) {
             constexpr bool STEADY = decltype(steady_tag)::value;
+            constexpr int WHICH = decltype(which_tag)::value;
             const int x = s - t;
             dTop += e32;                                              // drift of (row t*K - 1, column x)
             uint32_t rH3 = __shfl_up_sync(0xffffffffu, botH3, 1, G);
             uint32_t rIY = __shfl_up_sync(0xffffffffu, botIY, 1, G);
             uint32_t rM = __shfl_up_sync(0xffffffffu, botM, 1, G);
-            if (t == 0) { rH3 = tn.x + dTop; rIY = tn.y + dTop; rM = tn.z + dTop; }   // free boundary above the padded top, or the saved row
-            if (tin && t == 0 && x + 1 >= 0 && x + 1 < Lb) tn = tin[x + 1];
+            {
+                const uint4 &tn = WHICH == 1 ? tnB : tnA;
+                if (t == 0) { rH3 = tn.x + dTop; rIY = tn.y + dTop; rM = tn.z + dTop; }   // free boundary above the padded top, or the saved row
+            }
+            if (WHICH == 2) tnA = tnB;
+            if (tin && t == 0 && x + 2 >= 0 && x + 2 < Lb) {
+                if (WHICH == 0) tnA = tin[x + 2]; else tnB = tin[x + 2];
+            }
             const bool active = STEADY || ((x >= 0) && (x < Lb));
             const bool lastCol = !STEADY && active && x == Lb - 1;
             const bool edge = !STEADY && __any_sync(0xffffffffu, lastCol);               // warp-uniform
@@ -274,11 +286,12 @@ __global__ void __maxnreg__(score_maxnreg<K>()) k_gotoh_score(const FillArgs a)
             const int d = xlo1 - (s - t);                                     // steps until this lane's (first) save
             const bool saves = (d >= 0 && d < SCORE_UNROLL) || (NSUB == 2 && d + Kb >= 0 && d + Kb < SCORE_UNROLL);
             if (s >= G && s + SCORE_UNROLL <= steady_end && !__any_sync(0xffffffffu, saves)) {
-#pragma unroll
-                for (int u = 0; u < SCORE_UNROLL; ++u) step(std::true_type{}, s + u);
+                static_assert(SCORE_UNROLL == 2, "the top-boundary registers alternate between the two steps of a pair");
+                step(std::true_type{}, std::integral_constant<int, 0>{}, s);
+                step(std::true_type{}, std::integral_constant<int, 1>{}, s + 1);
                 s += SCORE_UNROLL;
             } else {
-                step(std::false_type{}, s);
+                step(std::false_type{}, std::integral_constant<int, 2>{}, s);
                 ++s;
             }
         }
