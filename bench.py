@@ -421,7 +421,7 @@ def main():
         "classes": {"n_total": int(n_total), "unmodified": int(red.class_counts[0]), "nhej": int(red.class_counts[1]),
                     "hdr": int(red.class_counts[2]), "mixed": int(red.class_counts[3])},
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # the CPU leg is timed at N = 1 only (bounded sample, rank 0)
         line["cpu_baseline"] = cpu_baseline(args, amp, hdr, inc, buf, off)
     print(json.dumps(line))
     if world > 1:

@@ -407,7 +407,7 @@ int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_read
         fa.p0 = batch_start[b]; fa.p1 = batch_start[b + 1];
         fa.open = open_s; fa.ext = ext_s; fa.La = La; fa.one = 1;
         fa.top_out = nullptr; fa.top_out_lane = -1; fa.top_in = nullptr;
-        fa.band_B = 0; fa.band_W = 0; fa.band_K = 0; fa.band_row0 = 0; fa.band_tops = nullptr; fa.band_left = nullptr; fa.band_tb = nullptr;
+        fa.band_B = 0; fa.band_W = 0; fa.band_K = 0; fa.d_e = fa.d_eK = fa.d_eKb = fa.d_copen = 0; fa.band_row0 = 0; fa.band_tops = nullptr; fa.band_left = nullptr; fa.band_tb = nullptr;
         if (used[cur]) CK(cudaStreamWaitEvent(sf[cur], ctx->walk_done[cur], 0));     // scratch `cur` is free again
         span_begin(ctx, T_FILL, sf[cur]);
         CK(launch_fill(G, K, fa, ctx->num_sms, sf[cur]));
@@ -574,7 +574,7 @@ int run_plan_dual(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         fa.p0 = batch_start[b]; fa.p1 = batch_start[b + 1];
         fa.open = open_s; fa.ext = ext_s; fa.La = La; fa.one = 1;
         fa.top_out = top[cur]->as<uint32_t>(); fa.top_out_lane = t0 - 1; fa.top_in = nullptr;
-        fa.band_B = 0; fa.band_W = 0; fa.band_K = 0; fa.band_row0 = 0; fa.band_tops = nullptr; fa.band_left = nullptr; fa.band_tb = nullptr;
+        fa.band_B = 0; fa.band_W = 0; fa.band_K = 0; fa.d_e = fa.d_eK = fa.d_eKb = fa.d_copen = 0; fa.band_row0 = 0; fa.band_tops = nullptr; fa.band_left = nullptr; fa.band_tb = nullptr;
         FillArgs fh = fa;                                               // HDR pass: bottom Gh lanes
         fh.prof = ctx->prof_h.as<int32_t>();
         fh.tb = tbH[cur]->as<uint32_t>(); fh.lastrow = lrH[cur]->as<uint32_t>(); fh.lastcol = lcH[cur]->as<uint32_t>();
@@ -785,6 +785,8 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         fa.open = open_s; fa.ext = ext_s; fa.La = La; fa.one = 1;
         fa.top_out = dual ? top[cur]->as<uint32_t>() : nullptr; fa.top_out_lane = dual ? t0 - 1 : -1; fa.top_in = nullptr;
         fa.band_B = B; fa.band_W = W; fa.band_K = Kb; fa.band_row0 = -P;
+        fa.d_e = (uint32_t)ext_s * 0x10001u; fa.d_eK = fa.d_e * (uint32_t)K; fa.d_eKb = fa.d_e * (uint32_t)Kb;
+        fa.d_copen = ((uint32_t)(ext_s - open_s) & 0xffffu) * 0x10001u;
         fa.band_tops = ctx->btops[cur].as<uint32_t>(); fa.band_left = ctx->bleft[cur].as<uint32_t>();
         fa.band_tb = tbA[cur]->as<uint32_t>();
         FillArgs fh = fa;                                               // HDR pass: bottom Gh lanes

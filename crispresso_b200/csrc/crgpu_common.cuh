@@ -58,6 +58,9 @@ struct FillArgs {
     // the band_W read columns x in [xlo, xlo + band_W), xlo = band_row0 + u*band_K - band_B.
     int band_B, band_W;       // band_W = band_K + 2*band_B + 1; band_B = 0: not banded
     int band_K;               // rows per sub-strip of the band pass
+    // drift constants of the score pass, packed per half (host-computed so that the kernel takes them straight from the
+    // constant bank instead of re-deriving them from `ext` under register pressure): ext, ext*K, ext*band_K, ext - open
+    uint32_t d_e, d_eK, d_eKb, d_copen;
     int band_row0;            // amplicon row of lane 0's first slot (-P for a full tile, split - P for the HDR sub-tile)
     uint32_t *band_tops;      // [(p-p0)*G2 + u][band_topw()][4]: (max3, iy, m, 0) of the row above sub-strip u at columns xlo-1 .. xlo+W-1
     uint32_t *band_left;      // [(p-p0)*G2 + u][band_leftw(band_K)]: H3[band_K], IX[band_K], mlast of column xlo-1

@@ -141,14 +141,14 @@ __global__ void __maxnreg__(score_maxnreg<K>()) k_gotoh_score(const FillArgs a)
 
     const uint32_t Z = BIAS2;                                             // stored 0
     const uint32_t NOPEN_ST = BIAS2 - (uint32_t)a.open * 0x10001u;        // stored -open
-    const uint32_t e32 = (uint32_t)a.ext * 0x10001u;
-    const uint32_t eK = e32 * (uint32_t)K;
-    const uint32_t cOpen = ((uint32_t)(a.ext - a.open) & 0xffffu) * 0x10001u;   // per-half two's complement of ext - open
+    const uint32_t e32 = a.d_e;                                           // ext in both halves
+    const uint32_t eK = a.d_eK;                                           // ext * K
+    const uint32_t cOpen = a.d_copen;                                     // per-half two's complement of ext - open
     const uint32_t cA_last = lastLane ? e32 : cOpen;                      // amplicon row La-1: zero end-gap penalties
     const uint32_t cB_last = lastLane ? e32 : 0u;
     // band columns of this lane's upper sub-strip: xlo1+1 .. xlo1+W; of its lower one (NSUB == 2): shifted by Kb
     const int xlo1 = a.band_row0 + t * K - a.band_B - 1;
-    const uint32_t eKb = e32 * (uint32_t)Kb;
+    const uint32_t eKb = a.d_eKb;                                         // ext * Kb
 
     for (int base = a.p0 + warp_global * GPW; base < a.p1; base += nwarps * GPW) {
         const int p = base + gl;
