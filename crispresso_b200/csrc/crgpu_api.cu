@@ -46,7 +46,7 @@ void crgpu_destroy(crgpu_ctx *c)
     DBuf *all[] = {&c->reads, &c->offsets, &c->amp, &c->prof, &c->pc, &c->pc_off, &c->plen, &c->pair_lo, &c->pair_hi,
                    &c->order, &c->plan_hist, &c->plan_tab, &c->tb2, &c->lastrow2, &c->lastcol2, &c->tb, &c->lastrow, &c->lastcol, &c->errflag, &c->recs, &c->sref, &c->smark, &c->sqry, &c->ops, &c->ops_rc, &c->alleles, &c->prof_h, &c->amp_h, &c->tbh, &c->tbh2,
                    &c->top, &c->top2, &c->lastrow_h, &c->lastrow_h2, &c->lastcol_h, &c->lastcol_h2,
-                   &c->prof_s, &c->prof_hs, &c->btops[0], &c->btops[1], &c->bleft[0], &c->bleft[1], &c->btops_h[0], &c->btops_h[1], &c->bleft_h[0], &c->bleft_h[1], &c->escaped};
+                   &c->prof_s, &c->prof_hs, &c->join, &c->btops[0], &c->btops[1], &c->bleft[0], &c->bleft[1], &c->btops_h[0], &c->btops_h[1], &c->bleft_h[0], &c->bleft_h[1], &c->escaped};
     for (DBuf *b : all) b->release();
     for (auto &b : c->q_in) b.release();
     for (auto &b : c->q_out) b.release();
@@ -417,6 +417,7 @@ int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_read
         WalkArgs wa;
         wa.tb = fa.tb; wa.lastrow = fa.lastrow; wa.lastcol = fa.lastcol;
         wa.tb_upper = nullptr; wa.lastcol_upper = nullptr; wa.G_upper = 0; wa.split_row = 0;
+        wa.join_row = 0; wa.join_out = nullptr; wa.join_in = nullptr;
         wa.band_B = 0; wa.band_W = 0; wa.band_K = 0; wa.kdiv_magic = 0; wa.escaped = nullptr; wa.escape_bit = 0;
         wa.pc_off = fa.pc_off; wa.plen = fa.plen;
         wa.pair_lo = ctx->pair_lo.as<int32_t>(); wa.pair_hi = ctx->pair_hi.as<int32_t>();
@@ -590,6 +591,7 @@ int run_plan_dual(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         WalkArgs wa;
         wa.tb = fa.tb; wa.lastrow = fa.lastrow; wa.lastcol = fa.lastcol;
         wa.tb_upper = nullptr; wa.lastcol_upper = nullptr; wa.G_upper = 0; wa.split_row = 0;
+        wa.join_row = 0; wa.join_out = nullptr; wa.join_in = nullptr;
         wa.band_B = 0; wa.band_W = 0; wa.band_K = 0; wa.kdiv_magic = 0; wa.escaped = nullptr; wa.escape_bit = 0;
         wa.pc_off = fa.pc_off; wa.plen = fa.plen;
         wa.pair_lo = ctx->pair_lo.as<int32_t>(); wa.pair_hi = ctx->pair_hi.as<int32_t>();
@@ -744,6 +746,7 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     DBuf *tbA[2] = {&ctx->tb, &ctx->tb2}, *tbH[2] = {&ctx->tbh, &ctx->tbh2}, *top[2] = {&ctx->top, &ctx->top2};
     DBuf *lrA[2] = {&ctx->lastrow, &ctx->lastrow2}, *lcA[2] = {&ctx->lastcol, &ctx->lastcol2};
     DBuf *lrH[2] = {&ctx->lastrow_h, &ctx->lastrow_h2}, *lcH[2] = {&ctx->lastcol_h, &ctx->lastcol_h2};
+    if (dual) CK(ctx->join.reserve((size_t)max_bp * 2 * JOIN_STRIDE * 4));      // walks are serialised on one stream: one set
     for (int i = 0; i < (two ? 2 : 1); ++i) {
         CK(tbA[i]->reserve((size_t)max_bp * G * W * K * 2));
         CK(ctx->btops[i].reserve((size_t)max_bp * G * nsub * TOPW * 16));
@@ -816,6 +819,8 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         wa.tb = fa.band_tb; wa.lastrow = fa.lastrow; wa.lastcol = fa.lastcol;
         wa.tb_upper = nullptr; wa.lastcol_upper = nullptr; wa.G_upper = 0; wa.split_row = 0;
         wa.band_B = B; wa.band_W = W; wa.band_K = Kb; wa.kdiv_magic = magic; wa.escaped = d_escaped; wa.escape_bit = escape_bit;
+        wa.join_row = 0; wa.join_out = nullptr; wa.join_in = nullptr;
+        if (dual && !getenv("CRGPU_NO_JOIN")) { wa.join_row = split; wa.join_out = ctx->join.as<int32_t>(); }
         wa.pc_off = fa.pc_off; wa.plen = fa.plen;
         wa.pair_lo = ctx->pair_lo.as<int32_t>(); wa.pair_hi = ctx->pair_hi.as<int32_t>();
         wa.reads = d_reads; wa.offsets = d_offsets; wa.amplicon = ctx->amp.as<uint8_t>();
@@ -824,6 +829,7 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         wa.recs = d_recs; wa.ref_out = d_ref; wa.mark_out = d_mark; wa.qry_out = d_qry; wa.slot = slot;
         wa.out_index = nullptr; wa.rc_out = 0; wa.ops_out = d_ops; wa.ops_stride = ops_stride;
         CK(cudaStreamWaitEvent(s2, ctx->fill_done[cur], 0));
+        if (wa.join_out) CK(cudaMemsetAsync(wa.join_out, 0, (size_t)(fa.p1 - fa.p0) * 2 * JOIN_STRIDE * 4, s2));
         span_begin(ctx, T_WALK, s2);
         CK(launch_walk(wa, s2));
         if (dual) {
@@ -833,6 +839,7 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
             wh.amplicon = ctx->amp_h.as<uint8_t>();
             wh.GK = GKh; wh.G = Gh;
             wh.escape_bit = 2;
+            wh.join_out = nullptr; wh.join_in = wa.join_out;      // (join_row: the same split row)
             wh.recs = d_recs_hdr; wh.ref_out = wh.mark_out = wh.qry_out = nullptr; wh.ops_out = nullptr;
             CK(launch_walk(wh, s2));
         }

@@ -70,6 +70,8 @@ struct FillArgs {
 __host__ __device__ constexpr int band_topw(int W) { return (W + 2) & ~1; }          // columns, even
 __host__ __device__ constexpr int band_leftw(int K) { return 2 * K + 4; }           // words, 16-byte multiple
 
+constexpr int JOIN_NCK = 8, JOIN_CK = 8, JOIN_STRIDE = 4 + 4 * JOIN_NCK;    // checkpoints of the walk join (below)
+
 struct WalkArgs {
     const uint32_t *tb;
     // optional upper part: padded rows below `split_row` were computed by another pass with tile
@@ -102,6 +104,14 @@ struct WalkArgs {
     uint32_t *ops_out;        // optional: 2-bit op per column in walk order, row stride ops_stride words
     int64_t ops_stride;
     const int32_t *out_index; // optional: output row of read r (null: row r)
+    // Shared DP prefix: above padded row `join_row` the HDR walk reads the amplicon pass's own flags, so once both walks
+    // of a read are at the same cell in the same state there, the rest of the two walks is identical.  The amplicon walk
+    // records (x, state, n, ident) at JOIN_NCK checkpoint rows and its totals (join_out, JOIN_STRIDE ints per thread of the
+    // batch, zeroed by the host before the batch); the HDR walk (identity only) compares at the checkpoints and, on a match,
+    // adds the amplicon walk's remainder instead of walking it.
+    int join_row;             // 0: off
+    int32_t *join_out;        // amplicon walk: [2*(p-p0)+h][JOIN_STRIDE] = n_total, ident_total, -, -, then NCK x (x, state, n, ident)
+    const int32_t *join_in;   // HDR walk: the same buffer
     int rc_out;               // 1: the amplicon is a reverse complement; emit rows flipped back to the
                               // forward strand (CORE:1982-1990), left-aligned in the slot
 };

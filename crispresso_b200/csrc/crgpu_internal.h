@@ -66,6 +66,7 @@ struct crgpu_ctx {
     DBuf recs, sref, smark, sqry, ops, ops_rc, alleles;
     DBuf prof_h, amp_h, tbh, tbh2, top, top2, lastrow_h, lastrow_h2, lastcol_h, lastcol_h2;   // HDR pass of run_plan_dual
     bool share_prefix = true;
+    DBuf join;                                                      // amplicon walk -> HDR walk join records (WalkArgs.join_out)
     DBuf prof_s, prof_hs;                                           // drifted profiles of the score pass
     DBuf btops[2], bleft[2], btops_h[2], bleft_h[2], escaped;      // banded two-pass fill (run_plan_band)
     int n_escaped[2] = {0, 0};                                     // reads re-aligned after the last banded call (amplicon, HDR)

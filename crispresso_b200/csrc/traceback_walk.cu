@@ -79,7 +79,10 @@ __device__ int row0_ix(const uint8_t *b, int ca0, int j, int open, int ext, int 
     return v;
 }
 
-__global__ void __launch_bounds__(128) k_traceback_walk(const WalkArgs a)
+// JOIN: 0 = plain walk; 1 = amplicon walk that records where it crosses WalkArgs.join_row; 2 = HDR walk (identity only:
+// no text rows, no ops) that joins the amplicon walk's remainder there.  Separate instantiations keep each at 56 registers.
+template <int JOIN>
+__global__ void __launch_bounds__(128, 9) k_traceback_walk(const WalkArgs a)     // 9 CTAs/SM = at most 56 registers
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int npairs = a.p1 - a.p0;
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(128) k_traceback_walk(const WalkArgs a)
         if (v > best) { best = v; s1 = a.split_row + t * a.K + (int)lc[3 * t + 1 + h] - a.P; s2 = Lb - 1; }
     }
 
-    const bool want = a.ref_out != nullptr;
+    const bool want = JOIN != 2 && a.ref_out != nullptr;
     const int64_t slot = a.slot;
     const int64_t orow = a.out_index ? a.out_index[r] : r;
     // Columns are produced from the alignment's right end to its left end.  Forward strand: store
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(128) k_traceback_walk(const WalkArgs a)
     const bool rc = a.rc_out != 0;
     int n = 0, ident = 0;
     // 2-bit op per column for k_quantify, in walk order (entry 0 = last column of the forward strand)
-    uint32_t *opo = a.ops_out ? a.ops_out + orow * a.ops_stride : nullptr;
+    uint32_t *opo = (JOIN != 2 && a.ops_out) ? a.ops_out + orow * a.ops_stride : nullptr;
     uint32_t opw = 0;
 #define EMIT_OP(op) do { opw |= (uint32_t)(op) << ((n & 15) * 2); if ((n & 15) == 15) { if (opo) opo[n >> 4] = opw; opw = 0; } } while (0)
 #define OUTC(c) (rc ? comp_upper(c) : (c))
@@ -177,7 +180,34 @@ __global__ void __launch_bounds__(128) k_traceback_walk(const WalkArgs a)
 #define PF_LOAD(k) pf[k] = (y - (k) >= 0 && x - (k) >= 0) ? tb_at(y - (k), x - (k)) : (uint8_t)0
 #pragma unroll
     for (int k = 0; k < PF; ++k) PF_LOAD(k);
+    // Join with the amplicon walk of the same read above the shared-prefix row (WalkArgs.join_row).  The amplicon walk
+    // (JOIN 1) leaves (x, state, n, ident) at JOIN_NCK checkpoint rows, JOIN_CK rows apart, and its totals at the end; the
+    // HDR walk (JOIN 2) compares at each checkpoint until it is at the same cell in the same state, then adds the
+    // amplicon walk's remainder.  (Several checkpoints: a read edited at the cut site joins a few rows above the edit, and a
+    // warp is only as fast as its last thread.)  Records are indexed by the thread's slot in the batch and zeroed per batch.
+    bool shortcut = false;
+    int ck_y = a.join_row - 1 - P, ck_k = 0;
+    int32_t *jrec = JOIN != 0 ? a.join_out + (int64_t)idx * JOIN_STRIDE : nullptr;
     while (x >= 0 && y >= 0) {
+        if (JOIN != 0 && ck_k < JOIN_NCK && y <= ck_y) {
+            if (y == ck_y) {
+                const int st = 0x100 | prev | ((prev == 1 && contL) ? 4 : 0) | ((prev == 2 && contD) ? 8 : 0);
+                int4 *e = reinterpret_cast<int4 *>(jrec + 4 + 4 * ck_k);
+                if (JOIN == 1) *e = make_int4(x, st, n, ident);
+                else {
+                    const int4 v = *e;
+                    if (v.x == x && v.y == st) {
+                        const int2 tot = *reinterpret_cast<const int2 *>(jrec);
+                        if (tot.x > 0) {                               // (0: the amplicon walk left the band)
+                            n += tot.x - v.z; ident += tot.y - v.w;
+                            shortcut = true;
+                            break;
+                        }
+                    }
+                }
+            }
+            ck_y -= JOIN_CK; ++ck_k;
+        }
         const int f = pf[0];
         if (f == 0xff) {                               // the path left the band: this read is re-aligned with the full fill
             a.escaped[r] |= (uint8_t)a.escape_bit;
@@ -225,8 +255,11 @@ __global__ void __launch_bounds__(128) k_traceback_walk(const WalkArgs a)
         prev = dir;
     }
 #undef PF_LOAD
-    for (; x >= 0; --x) EMIT_GAP_A(b[x]);
-    for (; y >= 0; --y) EMIT_GAP_B(amp[y]);
+    if (!shortcut) {
+        for (; x >= 0; --x) EMIT_GAP_A(b[x]);
+        for (; y >= 0; --y) EMIT_GAP_B(amp[y]);
+    }
+    if (JOIN == 1) *reinterpret_cast<int2 *>(jrec) = make_int2(n, ident);
 #undef EMIT_GAP_A
 #undef EMIT_GAP_B
 #undef OUTC
@@ -373,7 +406,14 @@ cudaError_t launch_walk(const WalkArgs &a, cudaStream_t s)
 {
     const int nthreads = 2 * (a.p1 - a.p0);
     if (nthreads <= 0) return cudaSuccess;
-    k_traceback_walk<<<(nthreads + 127) / 128, 128, 0, s>>>(a);
+    const int grid = (nthreads + 127) / 128;
+    if (a.join_row > 0 && a.join_out) k_traceback_walk<1><<<grid, 128, 0, s>>>(a);
+    else if (a.join_row > 0 && a.join_in && !a.ref_out && !a.ops_out) {
+        WalkArgs b = a;
+        b.join_out = const_cast<int32_t *>(a.join_in);          // one pointer in the kernel: JOIN 1 writes it, JOIN 2 reads it
+        k_traceback_walk<2><<<grid, 128, 0, s>>>(b);
+    }
+    else k_traceback_walk<0><<<grid, 128, 0, s>>>(a);
     return cudaGetLastError();
 }
 
