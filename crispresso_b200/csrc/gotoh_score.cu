@@ -24,10 +24,6 @@
 #include <algorithm>
 #include <type_traits>
 
-#ifndef SCORE_HOIST_M
-#define SCORE_HOIST_M 1
-#endif
-
 namespace crgpu {
 
 // One read column for the K rows of this lane, drift coordinates.
@@ -44,7 +40,6 @@ __device__ __forceinline__ void score_column(Strip<K> &st, const int32_t *__rest
                                              uint32_t &botH3, uint32_t &botIY, uint32_t &botM,
                                              uint32_t &midH3, uint32_t &midIY, uint32_t &midM)
 {
-#if SCORE_HOIST_M
     // every m of the column first: m'[k] needs max3'[k-1, x-1], the value row k-1 is about to overwrite; with the
     // adds hoisted, each row's new max3 can be written over the old one in place
     uint32_t M[K];
@@ -56,24 +51,12 @@ __device__ __forceinline__ void score_column(Strip<K> &st, const int32_t *__rest
         M[4 * j + 2] = st.H3[4 * j + 1] + (uint32_t)S.z;
         M[4 * j + 3] = st.H3[4 * j + 2] + (uint32_t)S.w;
     }
-#else
-    int32_t S4[4];
-    int4 Snext = *reinterpret_cast<const int4 *>(prow);     // read 4 rows ahead of use
-#endif
     const uint32_t cV = (EDGE && isLastCol) ? e32 : cOpen;  // iy: what is added to the opening source
     const uint32_t bV = (EDGE && isLastCol) ? e32 : 0u;     // iy: what is added to the extended gap
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const uint32_t h0 = st.H3[k], ix0 = st.IX[k];
-#if SCORE_HOIST_M
         const uint32_t m = M[k];
-#else
-        if ((k & 3) == 0) {
-            S4[0] = Snext.x; S4[1] = Snext.y; S4[2] = Snext.z; S4[3] = Snext.w;
-            if (k + 4 < K) Snext = *reinterpret_cast<const int4 *>(prow + k + 4);
-        }
-        const uint32_t m = hd + (uint32_t)S4[k & 3];
-#endif
         uint32_t ix;
         if (k == K - 1) {                                    // the only slot that can be amplicon row La-1
             const uint32_t src = lastLane ? st.mlast : h0;
@@ -104,15 +87,13 @@ __device__ __forceinline__ void score_column(Strip<K> &st, const int32_t *__rest
         st.H3[k] = h3;
         st.IX[k] = ix;
         if (k == K - 1) st.mlast = m;
-        upH3 = h3; upIY = iy; upM = m; hd = h0;
+        upH3 = h3; upIY = iy; upM = m;
         if (NSUB == 2 && k == K / 2 - 1) { midH3 = h3; midIY = iy; midM = m; }   // top boundary of the lower sub-strip
     }
     botH3 = upH3; botIY = upIY; botM = upM;
 }
 
-#ifndef SCORE_UNROLL
-#define SCORE_UNROLL 2
-#endif
+constexpr int SCORE_UNROLL = 2;          // steady steps per loop iteration (x4 measured the same, x1 8 % slower)
 // 152 registers x 128 threads x 3 CTAs leave 7168 registers per SM: exactly one k_traceback_walk CTA, so the walks of the
 // previous batch run beside the score pass instead of waiting for its tail (153+ registers: whole step 0.5 % slower)
 #ifndef SCORE_MAXNREG
