@@ -100,6 +100,8 @@ def load():
     lib.crgpu_get_band.argtypes = [vp]
     lib.crgpu_get_band.restype = i32
     lib.crgpu_last_escaped.argtypes = [vp, ctypes.POINTER(ctypes.c_int * 2)]
+    lib.crgpu_set_diag_shortcut.argtypes = [vp, i32]
+    lib.crgpu_last_diag.argtypes = [vp, ctypes.POINTER(ctypes.c_int64 * 2)]
     lib.crgpu_sync.argtypes = [vp]
     lib.crgpu_stream.argtypes = [vp]
     lib.crgpu_stream.restype = vp
@@ -113,7 +115,7 @@ def load():
     lib.crgpu_fastq_index.argtypes = [vp, i32, vp, i64, i32, ctypes.POINTER(FastqOut)]
     lib.crgpu_flash_merge.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i64, ctypes.POINTER(MergeParams),
                                       ctypes.POINTER(MergeOut)]
-    for name in ("crgpu_create", "crgpu_set_overlap", "crgpu_set_share_prefix", "crgpu_set_band", "crgpu_last_escaped", "crgpu_set_traceback_budget", "crgpu_last_timing", "crgpu_last_fill_breakdown", "crgpu_sync", "crgpu_qualfilter",
+    for name in ("crgpu_create", "crgpu_set_diag_shortcut", "crgpu_last_diag", "crgpu_set_overlap", "crgpu_set_share_prefix", "crgpu_set_band", "crgpu_last_escaped", "crgpu_set_traceback_budget", "crgpu_last_timing", "crgpu_last_fill_breakdown", "crgpu_sync", "crgpu_qualfilter",
                  "crgpu_align", "crgpu_quantify", "crgpu_align_quantify", "crgpu_int_peak", "crgpu_flash_merge", "crgpu_fastq_index"):
         getattr(lib, name).restype = i32
     _lib = lib
@@ -182,6 +184,16 @@ class Context:
         """(amplicon pass, HDR pass) reads of the last fused call that left the band and were re-aligned."""
         out = (ctypes.c_int * 2)()
         self.check(self.lib.crgpu_last_escaped(self.handle, ctypes.byref(out)))
+        return int(out[0]), int(out[1])
+
+    def set_diag_shortcut(self, on):
+        """Diagonal shortcut of the banded fill (default on); results never depend on it."""
+        self.check(self.lib.crgpu_set_diag_shortcut(self.handle, 1 if on else 0))
+
+    def last_diag(self):
+        """(read pairs of the last fused call's banded passes, pairs that still needed band pass + walk)."""
+        out = (ctypes.c_int64 * 2)()
+        self.check(self.lib.crgpu_last_diag(self.handle, ctypes.byref(out)))
         return int(out[0]), int(out[1])
 
     def last_fill_breakdown(self):

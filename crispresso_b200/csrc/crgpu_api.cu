@@ -46,7 +46,8 @@ void crgpu_destroy(crgpu_ctx *c)
     DBuf *all[] = {&c->reads, &c->offsets, &c->amp, &c->prof, &c->pc, &c->pc_off, &c->plen, &c->pair_lo, &c->pair_hi,
                    &c->order, &c->plan_hist, &c->plan_tab, &c->tb2, &c->lastrow2, &c->lastcol2, &c->tb, &c->lastrow, &c->lastcol, &c->errflag, &c->recs, &c->sref, &c->smark, &c->sqry, &c->ops, &c->ops_rc, &c->alleles, &c->prof_h, &c->amp_h, &c->tbh, &c->tbh2,
                    &c->top, &c->top2, &c->lastrow_h, &c->lastrow_h2, &c->lastcol_h, &c->lastcol_h2,
-                   &c->prof_s, &c->prof_hs, &c->join, &c->btops[0], &c->btops[1], &c->bleft[0], &c->bleft[1], &c->btops_h[0], &c->btops_h[1], &c->bleft_h[0], &c->bleft_h[1], &c->escaped};
+                   &c->prof_s, &c->prof_hs, &c->join, &c->btops[0], &c->btops[1], &c->bleft[0], &c->bleft[1], &c->btops_h[0], &c->btops_h[1], &c->bleft_h[0], &c->bleft_h[1], &c->escaped,
+                   &c->joinb, &c->fastflags, &c->need[0], &c->need[1], &c->plist[0], &c->plist[1], &c->selscratch[0], &c->selscratch[1], &c->need_cnt};
     for (DBuf *b : all) b->release();
     for (auto &b : c->q_in) b.release();
     for (auto &b : c->q_out) b.release();
@@ -92,6 +93,20 @@ int crgpu_set_band(crgpu_ctx *c, int half_width)
 }
 
 int crgpu_get_band(const crgpu_ctx *c) { return c ? c->band_B : -1; }
+
+int crgpu_set_diag_shortcut(crgpu_ctx *c, int on)
+{
+    if (!c) return CRGPU_E_ARG;
+    c->diag = on != 0;
+    return CRGPU_OK;
+}
+
+int crgpu_last_diag(const crgpu_ctx *c, int64_t out[2])
+{
+    if (!c || !out) return CRGPU_E_ARG;
+    out[0] = c->n_diag_pairs[0]; out[1] = c->n_diag_pairs[1];
+    return CRGPU_OK;
+}
 
 int crgpu_last_escaped(const crgpu_ctx *c, int out[2])
 {
@@ -632,7 +647,7 @@ int run_plan_dual(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
 int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon, int La, const uint8_t *d_reads,
                   const int64_t *d_offsets, double gapopen, double gapextend, crgpu_aln_rec *d_recs, crgpu_aln_rec *d_recs_hdr,
                   uint8_t *d_ref, uint8_t *d_mark, uint8_t *d_qry, int64_t slot, int64_t *n_cells, int64_t *n_cells_computed,
-                  uint32_t *d_ops, int64_t ops_stride, uint8_t *d_escaped, int escape_bit, bool *done)
+                  uint32_t *d_ops, int64_t ops_stride, uint8_t *d_escaped, int escape_bit, uint8_t *d_fast, bool *done)
 {
     *done = false;
     const PairPlan &pl = ctx->plan;
@@ -705,14 +720,15 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     for (size_t b = 0; b + 1 < batch_start.size(); ++b)
         max_cols = std::max(max_cols, plan_pc_off(pl, batch_start[b + 1]) - plan_pc_off(pl, batch_start[b]));
     if (n_cells) *n_cells += (dual ? 2 : 1) * (int64_t)La * pl.sum_len;
+    int64_t band_cells_all = 0;
     {
         // score pass: every cell (HDR: the rows below the split); band pass: at most W columns per lane
         const int64_t band_cols = std::min<int64_t>((int64_t)W * pl.nsub, pl.sum_len);
         const int64_t score_cells = ((int64_t)La + (dual ? (int64_t)(La - (split - P)) : 0)) * pl.sum_len;
         const int64_t band_cells = ((int64_t)GK + (dual ? (int64_t)GKh : 0)) * band_cols;
-        if (n_cells_computed) *n_cells_computed += score_cells + band_cells;
+        band_cells_all = band_cells;
+        if (n_cells_computed) *n_cells_computed += score_cells;
         ctx->cells_kind[1] += score_cells;
-        ctx->cells_kind[2] += band_cells;
     }
 
     // ---- profiles ----
@@ -746,12 +762,27 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     DBuf *tbA[2] = {&ctx->tb, &ctx->tb2}, *tbH[2] = {&ctx->tbh, &ctx->tbh2}, *top[2] = {&ctx->top, &ctx->top2};
     DBuf *lrA[2] = {&ctx->lastrow, &ctx->lastrow2}, *lcA[2] = {&ctx->lastcol, &ctx->lastcol2};
     DBuf *lrH[2] = {&ctx->lastrow_h, &ctx->lastrow_h2}, *lcH[2] = {&ctx->lastcol_h, &ctx->lastcol_h2};
-    if (dual) CK(ctx->join.reserve((size_t)max_bp * 2 * JOIN_STRIDE * 4));      // walks are serialised on one stream: one set
+    if (dual) {                                                                 // one set of join records per scratch set
+        CK(ctx->join.reserve((size_t)max_bp * 2 * JOIN_STRIDE * 4));
+        CK(ctx->joinb.reserve((size_t)max_bp * 2 * JOIN_STRIDE * 4));
+    }
+    const bool diag = ctx->diag && !getenv("CRGPU_NO_DIAG");
+    const size_t nbatches = batch_start.size() - 1;
+    const size_t selbytes = select_scratch_bytes(max_bp);
+    if (diag) {
+        if (!d_fast) return fail(ctx, CRGPU_E_ARG, "run_plan_band: the diagonal shortcut needs the per-read flag array");
+        CK(ctx->need_cnt.reserve(nbatches * 4));
+        CK(cudaMemsetAsync(ctx->need_cnt.p, 0, nbatches * 4, ctx->stream));
+    }
     for (int i = 0; i < (two ? 2 : 1); ++i) {
         CK(tbA[i]->reserve((size_t)max_bp * G * W * K * 2));
         CK(ctx->btops[i].reserve((size_t)max_bp * G * nsub * TOPW * 16));
         CK(ctx->bleft[i].reserve((size_t)max_bp * G * nsub * LEFTW * 4));
         CK(lrA[i]->reserve((size_t)max_bp * 12)); CK(lcA[i]->reserve((size_t)max_bp * G * 12));
+        if (diag) {
+            CK(ctx->need[i].reserve((size_t)max_bp)); CK(ctx->plist[i].reserve((size_t)max_bp * 4));
+            CK(ctx->selscratch[i].reserve(selbytes));
+        }
         if (dual) {
             CK(tbH[i]->reserve((size_t)max_bp * Gh * W * K * 2));
             CK(ctx->btops_h[i].reserve((size_t)max_bp * Gh * nsub * TOPW * 16));
@@ -809,18 +840,13 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         CK(launch_fill(G, K, fas, ctx->num_sms, sf[cur], 1));
         if (dual) CK(launch_fill(Gh, K, fhs, ctx->num_sms, sf[cur], 1));
         span_end(ctx, dual ? 2 : 1);
-        span_begin(ctx, T_BAND, sf[cur]);
-        CK(launch_fill(G, K, fa, ctx->num_sms, sf[cur], 2));
-        if (dual) CK(launch_fill(Gh, K, fh, ctx->num_sms, sf[cur], 2));
-        span_end(ctx, dual ? 2 : 1);
-        CK(cudaEventRecord(ctx->fill_done[cur], sf[cur]));
 
         WalkArgs wa;
         wa.tb = fa.band_tb; wa.lastrow = fa.lastrow; wa.lastcol = fa.lastcol;
         wa.tb_upper = nullptr; wa.lastcol_upper = nullptr; wa.G_upper = 0; wa.split_row = 0;
         wa.band_B = B; wa.band_W = W; wa.band_K = Kb; wa.kdiv_magic = magic; wa.escaped = d_escaped; wa.escape_bit = escape_bit;
         wa.join_row = 0; wa.join_out = nullptr; wa.join_in = nullptr;
-        if (dual && !getenv("CRGPU_NO_JOIN")) { wa.join_row = split; wa.join_out = ctx->join.as<int32_t>(); }
+        if (dual && !getenv("CRGPU_NO_JOIN")) { wa.join_row = split; wa.join_out = (cur ? ctx->joinb : ctx->join).as<int32_t>(); }
         wa.pc_off = fa.pc_off; wa.plen = fa.plen;
         wa.pair_lo = ctx->pair_lo.as<int32_t>(); wa.pair_hi = ctx->pair_hi.as<int32_t>();
         wa.reads = d_reads; wa.offsets = d_offsets; wa.amplicon = ctx->amp.as<uint8_t>();
@@ -828,12 +854,8 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         wa.open = open_s; wa.ext = ext_s; wa.scale = scale;
         wa.recs = d_recs; wa.ref_out = d_ref; wa.mark_out = d_mark; wa.qry_out = d_qry; wa.slot = slot;
         wa.out_index = nullptr; wa.rc_out = 0; wa.ops_out = d_ops; wa.ops_stride = ops_stride;
-        CK(cudaStreamWaitEvent(s2, ctx->fill_done[cur], 0));
-        if (wa.join_out) CK(cudaMemsetAsync(wa.join_out, 0, (size_t)(fa.p1 - fa.p0) * 2 * JOIN_STRIDE * 4, s2));
-        span_begin(ctx, T_WALK, s2);
-        CK(launch_walk(wa, s2));
+        WalkArgs wh = wa;                                               // HDR alignment: identity only
         if (dual) {
-            WalkArgs wh = wa;                                           // HDR alignment: identity only
             wh.tb = fh.band_tb; wh.lastrow = fh.lastrow; wh.lastcol = fh.lastcol;
             wh.tb_upper = fa.band_tb; wh.lastcol_upper = fa.lastcol; wh.G_upper = G; wh.split_row = split;
             wh.amplicon = ctx->amp_h.as<uint8_t>();
@@ -841,13 +863,57 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
             wh.escape_bit = 2;
             wh.join_out = nullptr; wh.join_in = wa.join_out;      // (join_row: the same split row)
             wh.recs = d_recs_hdr; wh.ref_out = wh.mark_out = wh.qry_out = nullptr; wh.ops_out = nullptr;
-            CK(launch_walk(wh, s2));
         }
+        if (wa.join_out) CK(cudaMemsetAsync(wa.join_out, 0, (size_t)(fa.p1 - fa.p0) * 2 * JOIN_STRIDE * 4, sf[cur]));
+        if (diag) {
+            // diagonal shortcut: alignments whose traceback is provably the diagonal through the start cell are emitted
+            // here, right after the score pass; the band pass and the walks below only visit the remaining pairs
+            int *d_cnt = ctx->need_cnt.as<int>() + b;
+            WalkArgs wd = wa;
+            wd.diag = 1; wd.fast = d_fast; wd.fast_bit = escape_bit; wd.need = ctx->need[cur].as<uint8_t>(); wd.need_or = 0;
+            span_begin(ctx, T_WALK, sf[cur]);
+            CK(launch_walk(wd, sf[cur]));
+            if (dual) {
+                WalkArgs whd = wh;
+                whd.diag = 1; whd.fast = d_fast; whd.fast_bit = 2; whd.need = wd.need; whd.need_or = 1;
+                whd.join_in = nullptr;
+                CK(launch_walk(whd, sf[cur]));
+            }
+            span_end(ctx, dual ? 2 : 1);
+            CK(select_flagged(wd.need, fa.p1 - fa.p0, 1, ctx->plist[cur].as<int32_t>(), d_cnt, ctx->selscratch[cur].p, selbytes, sf[cur]));
+            fa.pair_list = fh.pair_list = wa.pair_list = wh.pair_list = ctx->plist[cur].as<int32_t>();
+            fa.pair_list_n = fh.pair_list_n = wa.pair_list_n = wh.pair_list_n = d_cnt;
+            wa.fast = wh.fast = d_fast; wa.fast_bit = escape_bit; wh.fast_bit = 2;
+        }
+        span_begin(ctx, T_BAND, sf[cur]);
+        CK(launch_fill(G, K, fa, ctx->num_sms, sf[cur], 2));
+        if (dual) CK(launch_fill(Gh, K, fh, ctx->num_sms, sf[cur], 2));
+        span_end(ctx, dual ? 2 : 1);
+        CK(cudaEventRecord(ctx->fill_done[cur], sf[cur]));
+
+        CK(cudaStreamWaitEvent(s2, ctx->fill_done[cur], 0));
+        span_begin(ctx, T_WALK, s2);
+        CK(launch_walk(wa, s2));
+        if (dual) CK(launch_walk(wh, s2));
         span_end(ctx, dual ? 2 : 1);
         CK(cudaEventRecord(ctx->walk_done[cur], s2));
         used[cur] = true;
     }
     for (int i = 0; i < 2; ++i) if (used[i]) CK(cudaStreamWaitEvent(s, ctx->walk_done[i], 0));
+    // cells the band pass evaluated: every pair, or the pairs the diagonal shortcut left over
+    int64_t band_cells = band_cells_all;
+    ctx->n_diag_pairs[0] += pl.np;
+    if (diag) {
+        std::vector<int> hc(nbatches, 0);
+        CK(cudaMemcpyAsync(hc.data(), ctx->need_cnt.p, nbatches * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        int64_t left = 0;
+        for (int c : hc) left += c;
+        ctx->n_diag_pairs[1] += left;
+        band_cells = (int64_t)((double)band_cells_all * (double)left / (double)std::max(pl.np, 1));
+    } else ctx->n_diag_pairs[1] += pl.np;
+    if (n_cells_computed) *n_cells_computed += band_cells;
+    ctx->cells_kind[2] += band_cells;
     *done = true;
     return CRGPU_OK;
 }

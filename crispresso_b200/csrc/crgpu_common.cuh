@@ -65,6 +65,10 @@ struct FillArgs {
     uint32_t *band_tops;      // [(p-p0)*G2 + u][band_topw()][4]: (max3, iy, m, 0) of the row above sub-strip u at columns xlo-1 .. xlo+W-1
     uint32_t *band_left;      // [(p-p0)*G2 + u][band_leftw(band_K)]: H3[band_K], IX[band_K], mlast of column xlo-1
     uint32_t *band_tb;        // [(p-p0)*G2 + u][band_W][band_K/2]: flag words of the band columns      (G2 = G*K/band_K)
+    // Diagonal shortcut (DESIGN.md "Diagonal shortcut"): the band pass only visits the pairs of the batch that still need a
+    // traceback -- pair_list[0 .. *pair_list_n) holds their indices relative to p0 (null: every pair of the batch)
+    const int32_t *pair_list = nullptr;
+    const int *pair_list_n = nullptr;
 };
 
 __host__ __device__ constexpr int band_topw(int W) { return (W + 2) & ~1; }          // columns, even
@@ -114,6 +118,20 @@ struct WalkArgs {
     const int32_t *join_in;   // HDR walk: the same buffer
     int rc_out;               // 1: the amplicon is a reverse complement; emit rows flipped back to the
                               // forward strand (CORE:1982-1990), left-aligned in the slot
+    // Diagonal shortcut (DESIGN.md "Diagonal shortcut").  If the score of the start cell equals the sum of the
+    // substitution scores along the diagonal through it, needle's traceback IS that diagonal (every cell on it has
+    // m == max(m,ix,iy)), so the alignment is emitted without any flag.  diag = 1 selects the probing kernel
+    // (k_traceback_walk<JOIN, true>): it emits the diagonal alignments, sets fast[read] |= fast_bit for them and
+    // need[pair - p0] (stored when need_or == 0, OR-ed otherwise) for pairs with a read it could not finish.
+    // diag = 0 (the walk over flags): skips reads with fast[read] & fast_bit, and -- with pair_list -- only visits the
+    // listed pairs (indices relative to p0).
+    int diag = 0;
+    uint8_t *fast = nullptr;  // [n reads] or null
+    int fast_bit = 0;
+    uint8_t *need = nullptr;  // [p1 - p0] (diag = 1 only)
+    int need_or = 0;
+    const int32_t *pair_list = nullptr;   // diag = 0: pairs to walk, or null (all)
+    const int *pair_list_n = nullptr;
 };
 
 }  // namespace crgpu

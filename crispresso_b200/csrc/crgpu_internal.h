@@ -66,12 +66,17 @@ struct crgpu_ctx {
     DBuf recs, sref, smark, sqry, ops, ops_rc, alleles;
     DBuf prof_h, amp_h, tbh, tbh2, top, top2, lastrow_h, lastrow_h2, lastcol_h, lastcol_h2;   // HDR pass of run_plan_dual
     bool share_prefix = true;
-    DBuf join;                                                      // amplicon walk -> HDR walk join records (WalkArgs.join_out)
+    DBuf join, joinb;                                                      // amplicon walk -> HDR walk join records (WalkArgs.join_out)
     DBuf prof_s, prof_hs;                                           // drifted profiles of the score pass
     DBuf btops[2], bleft[2], btops_h[2], bleft_h[2], escaped;      // banded two-pass fill (run_plan_band)
     int n_escaped[2] = {0, 0};                                     // reads re-aligned after the last banded call (amplicon, HDR)
     int band_holdoff = 0;                                          // calls left that skip the band (set when > 25 % of a call's reads escaped)
     int band_B = 16;                                               // band half-width in read columns; 0 = single-pass fill
+    // diagonal shortcut of the banded fill (run_plan_band): alignments whose traceback is provably the diagonal through
+    // the start cell are emitted right after the score pass; only the other pairs go through the band pass and the walk
+    bool diag = true;
+    DBuf fastflags, need[2], plist[2], selscratch[2], need_cnt;
+    int64_t n_diag_pairs[2] = {0, 0};                              // last call: pairs of the batches / pairs that needed the band pass
     DBuf q_in[8], q_out[4];
     DBuf aux[8];
     // timing
@@ -187,5 +192,5 @@ int run_plan_dual(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
 int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon, int La, const uint8_t *d_reads,
                   const int64_t *d_offsets, double gapopen, double gapextend, crgpu_aln_rec *d_recs, crgpu_aln_rec *d_recs_hdr,
                   uint8_t *d_ref, uint8_t *d_mark, uint8_t *d_qry, int64_t slot, int64_t *n_cells, int64_t *n_cells_computed,
-                  uint32_t *d_ops, int64_t ops_stride, uint8_t *d_escaped, int escape_bit, bool *done);
+                  uint32_t *d_ops, int64_t ops_stride, uint8_t *d_escaped, int escape_bit, uint8_t *d_fast, bool *done);
 }  // namespace crgpu

@@ -277,13 +277,16 @@ __global__ void __maxnreg__(fill_maxnreg<K / NSUB>()) k_gotoh_band(const FillArg
     const uint32_t one = (uint32_t)a.one;
     const int W = a.band_W;
     const uint4 FREE = make_uint4(Z, NOPEN_ST, Z, 0u);
-    const int64_t total = (int64_t)(a.p1 - a.p0) * G2;
+    // (diagonal shortcut: only the pairs that still need a traceback, FillArgs.pair_list)
+    const int64_t total = (int64_t)(a.pair_list ? *a.pair_list_n : a.p1 - a.p0) * G2;
 
     for (int64_t base = (int64_t)warp_global * 32; base < total; base += (int64_t)nwarps * 32) {
-        const int64_t sub_id = base + lane;                               // (pair - p0) * G2 + u
-        const bool valid = sub_id < total;
-        const int pr = valid ? (int)(sub_id / G2) : 0;
-        const int u = valid ? (int)(sub_id - (int64_t)pr * G2) : 0;
+        const int64_t slot_id = base + lane;                              // (position in the list) * G2 + u
+        const bool valid = slot_id < total;
+        const int pj = valid ? (int)(slot_id / G2) : 0;
+        const int u = valid ? (int)(slot_id - (int64_t)pj * G2) : 0;
+        const int pr = (valid && a.pair_list) ? a.pair_list[pj] : pj;     // pair - p0
+        const int64_t sub_id = (int64_t)pr * G2 + u;
         const int t = u / NSUB, hh = u - t * NSUB;
         const bool lastLane = (u == G2 - 1);                              // owns amplicon row La-1 in its last slot
         const uint32_t nopen16_last = lastLane ? 0u : nopen16;

@@ -198,6 +198,7 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
     if (has_hdr != ((quant->flags & CRGPU_Q_HAS_HDR) != 0)) return fail(ctx, CRGPU_E_ARG, "CRGPU_Q_HAS_HDR must match path->hdr_amplicon");
     timing_reset(ctx);
     ctx->n_escaped[0] = ctx->n_escaped[1] = 0;
+    ctx->n_diag_pairs[0] = ctx->n_diag_pairs[1] = 0;
     out->rc_n = 0;
     if (n == 0) return CRGPU_OK;
     if (!out->kept || !out->aln || !out->recs) return fail(ctx, CRGPU_E_ARG, "kept/aln/recs are required");
@@ -264,23 +265,27 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
         CK(ctx->escaped.reserve((size_t)n));
         d_esc = ctx->escaped.as<uint8_t>();
         CK(cudaMemsetAsync(d_esc, 0, (size_t)n, s));
+        // diagonal shortcut: per-read bits 1 / 2 = the alignment vs the amplicon / the HDR amplicon needed no traceback
+        CK(ctx->fastflags.reserve((size_t)n));
+        uint8_t *d_fast = ctx->fastflags.as<uint8_t>();
+        CK(cudaMemsetAsync(d_fast, 0, (size_t)n, s));
         bool done = false;
         if (has_hdr && path->hdr_amplicon_len == amplicon_len) {
             rc = run_plan_band(ctx, amplicon, path->hdr_amplicon, amplicon_len, d_reads, d_off, path->gapopen, path->gapextend,
-                               d_aln, d_aln_hdr, d_ref, d_mark, d_qry, slot, &cells, &cells_computed, d_ops, ops_stride, d_esc, 1, &done);
+                               d_aln, d_aln_hdr, d_ref, d_mark, d_qry, slot, &cells, &cells_computed, d_ops, ops_stride, d_esc, 1, d_fast, &done);
             if (rc) { cudaStreamSynchronize(s); return rc; }
             if (done) amp_done = hdr_done = banded = true;
         }
         if (!amp_done) {
             rc = run_plan_band(ctx, amplicon, nullptr, amplicon_len, d_reads, d_off, path->gapopen, path->gapextend,
-                               d_aln, nullptr, d_ref, d_mark, d_qry, slot, &cells, &cells_computed, d_ops, ops_stride, d_esc, 1, &done);
+                               d_aln, nullptr, d_ref, d_mark, d_qry, slot, &cells, &cells_computed, d_ops, ops_stride, d_esc, 1, d_fast, &done);
             if (rc) { cudaStreamSynchronize(s); return rc; }
             if (done) {
                 amp_done = banded = true;
                 if (has_hdr) {
                     rc = run_plan_band(ctx, path->hdr_amplicon, nullptr, path->hdr_amplicon_len, d_reads, d_off, path->gapopen,
                                        path->gapextend, d_aln_hdr, nullptr, nullptr, nullptr, nullptr, slot, &cells, &cells_computed,
-                                       nullptr, 0, d_esc, 2, &done);
+                                       nullptr, 0, d_esc, 2, d_fast, &done);
                     if (rc) { cudaStreamSynchronize(s); return rc; }
                     hdr_done = done;
                 }

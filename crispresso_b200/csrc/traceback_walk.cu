@@ -81,17 +81,33 @@ __device__ int row0_ix(const uint8_t *b, int ca0, int j, int open, int ext, int 
 
 // JOIN: 0 = plain walk; 1 = amplicon walk that records where it crosses WalkArgs.join_row; 2 = HDR walk (identity only:
 // no text rows, no ops) that joins the amplicon walk's remainder there.  Separate instantiations keep each at 56 registers.
-template <int JOIN>
+//
+// DIAG (the diagonal shortcut): the probing kernel.  Claim: if the score of needle's start cell c_n equals
+// D_n, the sum of the substitution scores along the diagonal c_0 (on row 0 or column 0) .. c_n, the traceback is that
+// diagonal.  Proof: m[c_0] = S_0 (end gaps are free, App. A.2) and m[c_i] = S_i + max3[c_{i-1}] >= S_i + m[c_{i-1}]
+// (A.3), so m[c_i] >= D_i; max3[c_n] = D_n then forces max3[c_i] = m[c_i] = D_i all the way down (a larger max3
+// anywhere would propagate into m[c_n] > D_n).  The walk starts with prev = 0 and takes the diagonal whenever
+// m >= ix and m >= iy (A.4), which keeps prev = 0.  Such an alignment is emitted here by the walk loop itself running
+// on all-zero flags -- no flag byte is read, and the band pass never has to produce one for it.
+template <int JOIN, bool DIAG>
 __global__ void __launch_bounds__(128, 9) k_traceback_walk(const WalkArgs a)     // 9 CTAs/SM = at most 56 registers
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int npairs = a.p1 - a.p0;
-    if (idx >= 2 * npairs) return;
-    const int p = a.p0 + (idx >> 1);
+    int pj = idx >> 1;                                   // pair of the batch (relative to p0)
+    bool live = pj < npairs;
+    if (!DIAG && a.pair_list) {
+        live = pj < *a.pair_list_n;
+        pj = live ? a.pair_list[pj] : 0;
+    }
+    if (!DIAG && !live) return;
+    const int p = a.p0 + (live ? pj : 0);
     const int h = idx & 1;
     const int rlo = a.pair_lo[p], rhi = a.pair_hi[p];
-    if (h && rhi == rlo) return;
+    if (h && rhi == rlo) live = false;
+    if (!DIAG && !live) return;
     const int r = h ? rhi : rlo;
+    if (!DIAG && a.fast && (a.fast[r] & a.fast_bit)) return;       // emitted by the probing kernel
     const int La = a.La, Lb = a.plen[p];
     const uint8_t *b = a.reads + a.offsets[r];
     const uint8_t *amp = a.amplicon;
@@ -114,6 +130,24 @@ __global__ void __launch_bounds__(128, 9) k_traceback_walk(const WalkArgs a)    
     for (int t = 0; t < a.G; ++t) {
         const int v = half16(lc[3 * t], h);
         if (v > best) { best = v; s1 = a.split_row + t * a.K + (int)lc[3 * t + 1 + h] - a.P; s2 = Lb - 1; }
+    }
+
+    if (DIAG) {
+        // every thread of the warp votes (no early return above): the two reads of a pair are neighbouring lanes
+        bool isdiag = false;
+        if (live) {
+            const int len = (s1 < s2 ? s1 : s2) + 1;
+            int sum = 0;
+            for (int j = 0; j < len; ++j) sum += ednafull(base_code(amp[s1 - j]), base_code(b[s2 - j]));
+            isdiag = sum * a.scale + BIAS == best;
+        }
+        const unsigned votes = __ballot_sync(0xffffffffu, live && !isdiag);
+        if (!(threadIdx.x & 1) && pj < npairs) {
+            const uint8_t v = (uint8_t)((votes >> (threadIdx.x & 30)) & 3u ? 1 : 0);
+            if (a.need_or) a.need[pj] |= v; else a.need[pj] = v;
+        }
+        if (!isdiag) return;
+        a.fast[r] |= (uint8_t)a.fast_bit;
     }
 
     const bool want = JOIN != 2 && a.ref_out != nullptr;
@@ -177,7 +211,8 @@ __global__ void __launch_bounds__(128, 9) k_traceback_walk(const WalkArgs a)    
     // a LEFT / DOWN step invalidates the window and refills it with PF independent loads.
     constexpr int PF = 8;
     uint8_t pf[PF];
-#define PF_LOAD(k) pf[k] = (y - (k) >= 0 && x - (k) >= 0) ? tb_at(y - (k), x - (k)) : (uint8_t)0
+    // (DIAG: the alignment is known to be the diagonal through the start cell -- every flag on it reads as 0)
+#define PF_LOAD(k) pf[k] = (!DIAG && y - (k) >= 0 && x - (k) >= 0) ? tb_at(y - (k), x - (k)) : (uint8_t)0
 #pragma unroll
     for (int k = 0; k < PF; ++k) PF_LOAD(k);
     // Join with the amplicon walk of the same read above the shared-prefix row (WalkArgs.join_row).  The amplicon walk
@@ -187,7 +222,7 @@ __global__ void __launch_bounds__(128, 9) k_traceback_walk(const WalkArgs a)    
     // warp is only as fast as its last thread.)  Records are indexed by the thread's slot in the batch and zeroed per batch.
     bool shortcut = false;
     int ck_y = a.join_row - 1 - P, ck_k = 0;
-    int32_t *jrec = JOIN != 0 ? a.join_out + (int64_t)idx * JOIN_STRIDE : nullptr;
+    int32_t *jrec = JOIN != 0 ? a.join_out + ((int64_t)(p - a.p0) * 2 + h) * JOIN_STRIDE : nullptr;
     while (x >= 0 && y >= 0) {
         if (JOIN != 0 && ck_k < JOIN_NCK && y <= ck_y) {
             if (y == ck_y) {
@@ -230,9 +265,11 @@ __global__ void __launch_bounds__(128, 9) k_traceback_walk(const WalkArgs a)    
             if (want) { ro[dirn * n] = OUTC(ca); mo[dirn * n] = same ? '|' : '.'; qo[dirn * n] = OUTC(cb); }
             EMIT_OP(same ? 0 : 1);
             ++n; --x; --y;
+            if (!DIAG) {
 #pragma unroll
-            for (int k = 0; k < PF - 1; ++k) pf[k] = pf[k + 1];
-            PF_LOAD(PF - 1);
+                for (int k = 0; k < PF - 1; ++k) pf[k] = pf[k + 1];
+                PF_LOAD(PF - 1);
+            }
         } else if (dir == 1) {
             // the next cell (y, x-1) continues LEFT iff ix[y,x-1] - gex(y) == ix[y,x].  The fill
             // kernel evaluates that with gex = gapextend except on amplicon row La-1; needle uses
@@ -407,13 +444,19 @@ cudaError_t launch_walk(const WalkArgs &a, cudaStream_t s)
     const int nthreads = 2 * (a.p1 - a.p0);
     if (nthreads <= 0) return cudaSuccess;
     const int grid = (nthreads + 127) / 128;
-    if (a.join_row > 0 && a.join_out) k_traceback_walk<1><<<grid, 128, 0, s>>>(a);
+    if (a.diag) {
+        // probing kernel of the diagonal shortcut; an amplicon alignment it emits still leaves its join records
+        if (!a.fast || !a.need) return cudaErrorInvalidValue;
+        if (a.join_row > 0 && a.join_out) k_traceback_walk<1, true><<<grid, 128, 0, s>>>(a);
+        else k_traceback_walk<0, true><<<grid, 128, 0, s>>>(a);
+    }
+    else if (a.join_row > 0 && a.join_out) k_traceback_walk<1, false><<<grid, 128, 0, s>>>(a);
     else if (a.join_row > 0 && a.join_in && !a.ref_out && !a.ops_out) {
         WalkArgs b = a;
         b.join_out = const_cast<int32_t *>(a.join_in);          // one pointer in the kernel: JOIN 1 writes it, JOIN 2 reads it
-        k_traceback_walk<2><<<grid, 128, 0, s>>>(b);
+        k_traceback_walk<2, false><<<grid, 128, 0, s>>>(b);
     }
-    else k_traceback_walk<0><<<grid, 128, 0, s>>>(a);
+    else k_traceback_walk<0, false><<<grid, 128, 0, s>>>(a);
     return cudaGetLastError();
 }
 

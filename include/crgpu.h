@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CRGPU_ABI_VERSION 3
+#define CRGPU_ABI_VERSION 4
 
 enum {
     CRGPU_OK = 0,
@@ -78,6 +78,14 @@ int crgpu_get_band(const crgpu_ctx *ctx);
 /* Reads the last crgpu_align_quantify call re-aligned with the single-pass fill because their traceback
  * left the band: out[0] amplicon pass, out[1] HDR-amplicon pass. */
 int crgpu_last_escaped(const crgpu_ctx *ctx, int out[2]);
+/* Diagonal shortcut of the banded fill (default on).  Right after the score pass an alignment whose start-cell score
+ * equals the sum of the substitution scores along the diagonal through the start cell is emitted directly: needle's
+ * traceback is then provably that diagonal (DESIGN.md "Diagonal shortcut"), so only the remaining read pairs go through
+ * the band pass and the walk.  Results never depend on this. */
+int crgpu_set_diag_shortcut(crgpu_ctx *ctx, int on);
+/* Last crgpu_align_quantify call: out[0] = read pairs of the banded passes, out[1] = pairs that still needed the band
+ * pass + walk (equal when the shortcut is off). */
+int crgpu_last_diag(const crgpu_ctx *ctx, int64_t out[2]);
 /* Device time (ms, CUDA events on the context's stream) spent in each kernel family during
  * the LAST call on this context, and launch counts.  out_ms[0..5] = encode, fill, walk,
  * quantify, qualfilter, other;  out_launches likewise. */

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(build.build())
     for name in declared_functions():
         assert hasattr(lib, name), name
-    assert lib.crgpu_abi_version() == 3
+    assert lib.crgpu_abi_version() == 4
 
 
 def test_no_cpu_fallback_without_a_gpu():

@@ -239,3 +239,48 @@ def test_band_holds_off_after_a_call_whose_reads_mostly_escape(ctx):
         assert ctx.last_escaped()[0] * 4 > 800
     finally:
         ctx.set_band(16)
+
+
+@pytest.mark.parametrize("La,read_len,sigma,hdr_on", [(250, 250, 0.0, True), (300, 300, 8.0, False), (200, 151, 0.0, False),
+                                                      (150, 220, 6.0, True), (600, 600, 0.0, True)])
+def test_diagonal_shortcut_changes_nothing(La, read_len, sigma, hdr_on):
+    """Alignments whose start-cell score equals the substitution-score sum of the diagonal through the start cell are
+    emitted right after the score pass, without flags (the traceback is provably that diagonal); only the other read
+    pairs go through the band pass and the walk.  Every output must equal the run with the shortcut off -- text rows,
+    records, HDR identities, reductions -- and most pairs of an amplicon read set must take the shortcut."""
+    from crispresso_b200 import Context
+    seed = 900 + La
+    amp, guide, cut, hdr = synth.make_case(seed, La, hdr=hdr_on)
+    packed = synth.make_reads(amp, hdr, cut, 1500, seed=seed, read_len=read_len, len_sigma=sigma, rc_frac=0.03, n_rate=0.001)
+    flags = hotpath.quant_flags(hdr or "")
+    c = Context(0)
+    try:
+        c.set_traceback_budget(24 << 20)
+        c.set_diag_shortcut(False)
+        ref = hotpath.run_hot_path(c, amp, packed, hdr_amplicon=hdr, flags=flags, want_rows=True, min_identity_score=40.0)
+        total, left = c.last_diag()
+        assert total == left and total > 0
+        for share in (True, False):
+            c.set_diag_shortcut(True)
+            c.set_share_prefix(share)
+            got = hotpath.run_hot_path(c, amp, packed, hdr_amplicon=hdr, flags=flags, want_rows=True, min_identity_score=40.0)
+            total, left = c.last_diag()
+            if read_len == La and sigma == 0.0:
+                assert left < 0.6 * total, (total, left)     # ~20 % of the reads carry an indel: ~36 % of the pairs
+            got.red.n_cells_computed = ref.red.n_cells_computed
+            assert np.array_equal(got.red.flat(), ref.red.flat()), share
+            assert np.array_equal(got.aln, ref.aln) and np.array_equal(got.recs, ref.recs) and np.array_equal(got.kept, ref.kept)
+            assert np.array_equal(got.tenths_rep, ref.tenths_rep)
+            assert np.array_equal(got.rc_read, ref.rc_read) and np.array_equal(got.rc_aln, ref.rc_aln)
+            for k in range(3):
+                assert np.array_equal(got.rows[k], ref.rows[k])
+            # without text rows (the benchmark path): records and reductions again
+            lean = hotpath.run_hot_path(c, amp, packed, hdr_amplicon=hdr, flags=flags, min_identity_score=40.0)
+            lean.red.n_cells_computed = ref.red.n_cells_computed
+            assert np.array_equal(lean.red.flat(), ref.red.flat())
+            fields = [f for f in _lib.ALN_REC.names if f != "aln_off"]
+            for f in fields:
+                assert np.array_equal(lean.aln[f], ref.aln[f]), f
+            assert np.array_equal(lean.recs, ref.recs) and np.array_equal(lean.tenths_rep, ref.tenths_rep)
+    finally:
+        c.close()
