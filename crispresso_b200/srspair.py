@@ -42,17 +42,34 @@ def format_record(aname, bname, ref_row, markup, read_row, ident, score, gapopen
     return head + rows + "\n\n"
 
 
+FILE_TRAILER = "#---------------------------------------\n#---------------------------------------\n"
+
+
+def _num(x):
+    return ("%g" % x) if isinstance(x, float) else str(x)
+
+
+def file_header(asequence="amplicon.fa", bsequence="/dev/stdin", outfile="/dev/stdout", gapopen=10.0, gapextend=0.5,
+                awidth3=5000, rundate=None):
+    """The block needle writes once per run (ignored by parse_needle_output).  `rundate` is the only part of the
+    output that is not a function of the inputs; CRGPU_NEEDLE_RUNDATE pins it (reproducible captures)."""
+    import os
+    rundate = rundate or os.environ.get("CRGPU_NEEDLE_RUNDATE") or time.strftime("%a %e %b %Y %H:%M:%S")
+    aw = "" if awidth3 is None else "#    -awidth3=%s\n" % awidth3
+    return ("########################################\n# Program: needle\n# Rundate: %s\n"
+            "# Commandline: needle\n#    -asequence=%s\n#    -bsequence=%s\n#    -outfile=%s\n"
+            "#    -gapopen=%s\n#    -gapextend=%s\n%s# Align_format: srspair\n"
+            "# Report_file: %s\n########################################\n\n"
+            % (rundate, asequence, bsequence, outfile, _num(gapopen), _num(gapextend), aw, outfile))
+
+
 def write_needle_output(path, aname, bnames, recs, ref_rows, markup_rows, read_rows, gapopen=10.0, gapextend=0.5,
                         asequence="amplicon.fa"):
     """Write one srspair record per alignment (gzip if path ends with .gz)."""
     op = gzip.open if path.endswith(".gz") else open
     with op(path, "wt") as f:
-        f.write("########################################\n# Program: needle\n# Rundate: %s\n"
-                "# Commandline: needle\n#    -asequence=%s\n#    -bsequence=/dev/stdin\n#    -outfile=/dev/stdout\n"
-                "#    -gapopen=%s\n#    -gapextend=%s\n#    -awidth3=5000\n# Align_format: srspair\n"
-                "# Report_file: /dev/stdout\n########################################\n\n"
-                % (time.strftime("%a %e %b %Y %H:%M:%S"), asequence, gapopen, gapextend))
+        f.write(file_header(asequence, gapopen=gapopen, gapextend=gapextend))
         for i, b in enumerate(bnames):
             f.write(format_record(aname, b, ref_rows[i], markup_rows[i], read_rows[i], int(recs["ident"][i]),
                                   float(recs["score"][i]), gapopen, gapextend))
-        f.write("#---------------------------------------\n#---------------------------------------\n")
+        f.write(FILE_TRAILER)
