@@ -4,7 +4,7 @@ CRISPResso shells out to
     flash R1 R2 --allow-outies --max-overlap M --min-overlap m -f <amplicon len> -r <read len> -s <sd> -z -d DIR
 (CRISPResso/CRISPRessoCORE.py:1655-1664) and goes on with DIR/out.extendedFrags.fastq.gz (CORE:1677).  With
 `crispresso_b200/bin` first on PATH the UNMODIFIED reference merges its read pairs with crgpu_flash_merge
-(FLASH 1.2.11 semantics: SURVEY.md App. D, oracle/flash_merge.py) and finds the files FLASH would have
+(FLASH 1.2.11 semantics: SURVEY.md App. D) and finds the files FLASH would have
 written: out.extendedFrags / out.notCombined_{1,2} (.fastq or .fastq.gz), out.hist, out.histogram.
 -f / -r / -s only steer FLASH's default for --max-overlap, which CRISPResso always passes explicitly.
 No CPU fallback: without libcrgpu.so / a B200 the program exits with status 1.

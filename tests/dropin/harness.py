@@ -26,6 +26,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
+REQUEST_FASTA_DIR = "/tmp/crgpu_dropin_requests"
 RUNDATE = "Mon 19 Oct 2026 00:00:00"        # pins the only non-deterministic line of the srspair header
 
 
@@ -120,7 +121,9 @@ def load_needle_request(path, workdir):
     with gzip.open(path, "rb") as f:
         d = json.loads(f.read().decode())
     key = os.path.basename(path)[:-len(".req.json.gz")]
-    fa = os.path.join(workdir, key + "_a.fa")
+    # a fixed place: the path is echoed in the srspair header ("#    -asequence=..."), and the answers must not depend on it
+    os.makedirs(REQUEST_FASTA_DIR, exist_ok=True)
+    fa = os.path.join(REQUEST_FASTA_DIR, key + "_a.fa")
     with open(fa, "wt") as f:
         f.write(d["afasta"])
     argv = [("-asequence=" + fa) if t == "-asequence=@AFASTA@" else t for t in d["argv"]]
