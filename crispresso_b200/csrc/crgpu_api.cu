@@ -268,7 +268,7 @@ int build_plan(crgpu_ctx *ctx, const uint8_t *d_reads, const int64_t *d_offsets,
     CK(cudaMemcpyAsync(d_read_start, read_start.data(), (size_t)NB * 8, cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(d_segs, pl.segs.data(), (size_t)nseg * sizeof(HostSeg), cudaMemcpyHostToDevice, s));
     CK(ctx->order.reserve((size_t)nsub * 4));
-    CK(ctx->pc.reserve((size_t)std::max<int64_t>(pcs, 1)));
+    CK(ctx->pc.reserve((size_t)std::max<int64_t>(pcs, 1) + 16));      // (+16: k_gotoh_score2 prefetches one code past an odd-length read)
     CK(ctx->pc_off.reserve((size_t)(pl.np + 1) * 8));
     CK(ctx->plen.reserve((size_t)pl.np * 4));
     CK(ctx->pair_lo.reserve((size_t)pl.np * 4));
@@ -651,7 +651,7 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
 {
     *done = false;
     const PairPlan &pl = ctx->plan;
-    const int B = ctx->band_B;
+    int B = ctx->band_B;
     if (B <= 0 || getenv("CRGPU_NO_BAND") || pl.np == 0 || pl.nsub == 0) return CRGPU_OK;
     if (La < CRGPU_MIN_LEN || La > CRGPU_MAX_AMPLICON) return CRGPU_OK;      // let run_plan report it
     int scale, open_s, ext_s;
@@ -675,6 +675,9 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     int G, K;
     if (!choose_tile(La, &G, &K)) return CRGPU_OK;
     const int GK = G * K, P = GK - La;
+    // k_gotoh_score2 takes two read columns per step and saves a sub-strip's left edge after the SECOND one: every
+    // sub-strip's first band column xlo = u*Kb - P - B has to be even (Kb is), so an odd P + B widens the band by one
+    if ((P + B) & 1) ++B;
     // the band pass works on sub-strips of Kb rows: half a lane's strip when that keeps 16-byte flag stores
     const int nsub = (K % 16 == 0 && !getenv("CRGPU_NO_SUBSTRIP")) ? 2 : 1;
     const int Kb = K / nsub;
@@ -704,7 +707,7 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     // persistent score kernels: a warp of k_gotoh_score owns pairs w, w + wave, ..., so a batch of 9.2 waves costs 10
     int64_t bp = (int64_t)(ctx->tb_budget / pair_bytes);
     {
-        const int64_t wave = getenv("CRGPU_NO_WAVE_ALIGN") ? 1 : std::max<int64_t>(1, score_wave_pairs(dual ? Gh : G, K, nsub, ctx->num_sms));
+        const int64_t wave = getenv("CRGPU_NO_WAVE_ALIGN") ? 1 : std::max<int64_t>(1, (getenv("CRGPU_SCORE_V1") ? score_wave_pairs : score2_wave_pairs)(dual ? Gh : G, K, nsub, ctx->num_sms));
         int64_t want = std::max<int64_t>(((int64_t)pl.np + 7) / 8, 16384);
         if (want >= 4 * wave) {                   // (small calls, e.g. the chunks of a pipelined run, measured better unaligned)
             want = (want + wave - 1) / wave * wave;

@@ -155,6 +155,7 @@ bool tile_available(int G, int K);
 cudaError_t launch_fill(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream, int kind = 0);
 // pairs one resident wave of k_gotoh_score<G,K,nsub> covers (0: no such kernel)
 int64_t score_wave_pairs(int G, int K, int nsub, int num_sms);
+int64_t score2_wave_pairs(int G, int K, int nsub, int num_sms);
 cudaError_t launch_encode(const uint8_t *reads, const int64_t *offsets, const int32_t *pair_lo, const int32_t *pair_hi,
                           const int64_t *pc_off, int npairs, uint8_t *pc, int *err, int num_sms, cudaStream_t s);
 cudaError_t launch_walk(const WalkArgs &a, cudaStream_t s);

@@ -433,7 +433,10 @@ bool tile_available(int G, int K)
 cudaError_t launch_fill(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream, int kind)
 {
     if (kind < 0 || kind > 2) return cudaErrorInvalidValue;
-    if (kind == 1) return launch_score(G, K, a, num_sms, stream);
+    if (kind == 1) {
+        static const bool v1 = getenv("CRGPU_SCORE_V1") != nullptr;      // one column per step (A/B runs)
+        return v1 ? launch_score(G, K, a, num_sms, stream) : launch_score2(G, K, a, num_sms, stream);
+    }
 #define CASE(g, k) if (G == g && K == k) return launch_tile<g, k>(a, num_sms, stream, kind);
     CASE(4, 16) CASE(4, 24) CASE(4, 32) CASE(4, 40) CASE(8, 16) CASE(8, 24) CASE(8, 32) CASE(8, 40)
     CASE(16, 16) CASE(16, 24) CASE(16, 32) CASE(16, 40) CASE(32, 24) CASE(32, 32) CASE(4, 48) CASE(8, 48) CASE(16, 48)

@@ -1,0 +1,368 @@
+// gotoh_score2.cu -- k_gotoh_score2<G,K,NSUB>: score pass of the banded two-pass fill, TWO read columns per
+// systolic step (DESIGN.md "Score pass").
+//
+// Same DP, same drift coordinates, same outputs as the one-column kernel it replaces (needle's
+// embAlignPathCalcWithEndGapPenalties as CRISPResso runs it, CRISPResso/CRISPRessoCORE.py:1791-1806; SURVEY.md
+// App. A.1-A.3, exact integer form A.6):
+//
+//     v'[r,x] = v[r,x] + ext * (r + x)
+//     m'  = (S + 2 ext) + max3'[r-1,x-1]
+//     ix' = max(max3'[r,x-1] + (ext - open), ix'[r,x-1])       VIADDMNMX.S16x2
+//     iy' = max(max3'[r-1,x] + (ext - open), iy'[r-1,x])       VIADDMNMX.S16x2
+//     max3' = VIMNMX3.S16x2(m', ix', iy')
+//
+// The one-column kernel was bound by the dependent chain iy' -> max3' -> iy' down the K rows of a strip: two
+// instructions of 4 cycles each per row, with three warps per scheduler to hide them (0.42 of the integer-ALU
+// ceiling, ncu: 31 % of the stall samples fixed-latency waits).  Here lane t works on read columns 2j and 2j + 1 in
+// the same step, the second column one row behind the first:
+//
+//     iteration k:   A = cell (row k, column 2j)        B = cell (row k - 1, column 2j + 1)
+//
+// A and B are independent (B needs A's results of iterations k - 1 and k - 2), so every thread carries two chains
+// and the eight instructions of an iteration fill the eight cycles of its critical path.  Column 2j's values live
+// in a three-row window of registers; the state arrays H3 / IX go from column 2j - 1 straight to column 2j + 1, in
+// place.  The per-step overhead (shuffles, addresses, boundary loads, scans) is paid once per two columns.
+//
+// What leaves the kernel is unchanged: start-cell summaries (last amplicon row / last read column), the rows
+// handed to the band pass (band_tops), the registers at the band's left edge (band_left), the shared-prefix row
+// (top_out) -- all converted back to plain values.  The band's left edge is always an odd column (the host makes
+// P + B even, run_plan_band), i.e. the second column of a step, so the registers to save are the state arrays.
+#include "gotoh_tile.cuh"
+#include <algorithm>
+#include <type_traits>
+
+namespace crgpu {
+
+// Two read columns (x0 = 2j, x1 = 2j + 1) for the K rows of this lane, drift coordinates.
+//  TAIL = false: both columns are interior columns of the read for every lane of the warp.
+//  TAIL = true : per-lane flags -- last0 / last1: that column is the read's LAST column (iy opens from m only, zero
+//  penalties: SURVEY App. A.2/A.3); do1 = false: column x1 is past the read's end (odd length), the state then keeps
+//  column x0's values.  The whole warp runs this body with per-lane parameters, no divergence.
+template <int K, bool TAIL, int NSUB>
+__device__ __forceinline__ void score_columns2(Strip<K> &st, const int32_t *__restrict__ prow0, const int32_t *__restrict__ prow1,
+                                               uint32_t aH, uint32_t aY, uint32_t aM,      // row above, column x0
+                                               uint32_t bH, uint32_t bY, uint32_t bM,      // row above, column x1
+                                               const uint32_t hd,                          // max3'[row above, x0 - 1]
+                                               const uint32_t cOpen, const uint32_t cA_last, const uint32_t cB_last,
+                                               const uint32_t e32, const bool lastLane,
+                                               const bool last0, const bool last1, const bool do1,
+                                               uint32_t (&bot0)[3], uint32_t (&bot1)[3], uint32_t (&mid0)[3], uint32_t (&mid1)[3])
+{
+    const uint32_t cV0 = (TAIL && last0) ? e32 : cOpen, bV0 = (TAIL && last0) ? e32 : 0u;
+    const uint32_t cV1 = (TAIL && last1) ? e32 : cOpen, bV1 = (TAIL && last1) ? e32 : 0u;
+    uint32_t dg1 = aH;                       // max3'[row j - 1, x0]: diagonal source of column x1's row j
+    uint32_t h0p = 0, ix0p = 0, m0p = 0;     // column x0, row k - 1
+    int4 S0 = make_int4(0, 0, 0, 0), S1 = make_int4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k <= K; ++k) {
+        uint32_t h0 = 0, ix0 = 0, m0 = 0, iy0 = 0;
+        if (k < K) {                                                     // A: row k of column x0
+            if ((k & 3) == 0) S0 = *reinterpret_cast<const int4 *>(prow0 + k);
+            const int32_t s = (k & 3) == 0 ? S0.x : (k & 3) == 1 ? S0.y : (k & 3) == 2 ? S0.z : S0.w;
+            m0 = (k == 0 ? hd : st.H3[k - 1]) + (uint32_t)s;
+            if (k == K - 1) {                                            // the only slot that can be amplicon row La-1
+                const uint32_t src = lastLane ? st.mlast : st.H3[k];
+                ix0 = vaddmax2(src, cA_last, st.IX[k] + cB_last);
+            } else {
+                ix0 = vaddmax2(st.H3[k], cOpen, st.IX[k]);
+            }
+            if (TAIL) iy0 = vaddmax2(last0 ? aM : aH, cV0, aY + bV0);
+            else iy0 = vaddmax2(aH, cOpen, aY);
+            h0 = __vimax3_s16x2(m0, ix0, iy0);
+        }
+        if (k >= 1) {                                                    // B: row j = k - 1 of column x1
+            constexpr int dummy = 0; (void)dummy;
+            const int j = k - 1;
+            if ((j & 3) == 0) S1 = *reinterpret_cast<const int4 *>(prow1 + j);
+            const int32_t s = (j & 3) == 0 ? S1.x : (j & 3) == 1 ? S1.y : (j & 3) == 2 ? S1.z : S1.w;
+            const uint32_t m1 = dg1 + (uint32_t)s;
+            uint32_t ix1;
+            if (j == K - 1) {
+                const uint32_t src = lastLane ? m0p : h0p;
+                ix1 = vaddmax2(src, cA_last, ix0p + cB_last);
+            } else {
+                ix1 = vaddmax2(h0p, cOpen, ix0p);
+            }
+            uint32_t iy1;
+            if (TAIL) iy1 = vaddmax2(last1 ? bM : bH, cV1, bY + bV1);
+            else iy1 = vaddmax2(bH, cOpen, bY);
+            const uint32_t h1 = __vimax3_s16x2(m1, ix1, iy1);
+            if (TAIL) {
+                st.H3[j] = do1 ? h1 : h0p;
+                st.IX[j] = do1 ? ix1 : ix0p;
+                if (j == K - 1) st.mlast = do1 ? m1 : m0p;
+            } else {
+                st.H3[j] = h1;
+                st.IX[j] = ix1;
+                if (j == K - 1) st.mlast = m1;
+            }
+            bH = h1; bY = iy1; bM = m1;
+            if (NSUB == 2 && j == K / 2 - 1) { mid1[0] = h1; mid1[1] = iy1; mid1[2] = m1; }
+            dg1 = h0p;
+        }
+        if (k < K) {
+            aH = h0; aY = iy0; aM = m0;
+            if (NSUB == 2 && k == K / 2 - 1) { mid0[0] = h0; mid0[1] = iy0; mid0[2] = m0; }
+            h0p = h0; ix0p = ix0; m0p = m0;
+        }
+    }
+    bot0[0] = aH; bot0[1] = aY; bot0[2] = aM;
+    bot1[0] = bH; bot1[1] = bY; bot1[2] = bM;
+}
+
+#ifndef SCORE2_MAXNREG
+#define SCORE2_MAXNREG 152
+#endif
+template <int K> constexpr int score2_maxnreg() { return K <= 32 ? SCORE2_MAXNREG : fill_maxnreg<K>(); }
+
+template <int G, int K, int NSUB>
+__global__ void __maxnreg__(score2_maxnreg<K>()) k_gotoh_score2(const FillArgs a)
+{
+    static_assert(K % 4 == 0 && (32 % G) == 0 && (NSUB == 1 || (NSUB == 2 && K % 16 == 0)), "bad tile");
+    constexpr int Kb = K / NSUB;                                          // rows per sub-strip of the band pass
+    constexpr int PS = prof_stride(G, K);
+    extern __shared__ __align__(128) int32_t sprof[];
+    __shared__ __align__(8) uint64_t mbar;
+    stage_profile(sprof, &mbar, a.prof, NPAIR * PS * 4);       // a.prof: the drifted table (S + 2 ext)
+
+    const int lane = threadIdx.x & 31;
+    const int t = lane % G;
+    const int gl = lane / G;
+    constexpr int GPW = 32 / G;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const bool lastLane = (t == G - 1);
+
+    const uint32_t Z = BIAS2;                                             // stored 0
+    const uint32_t NOPEN_ST = BIAS2 - (uint32_t)a.open * 0x10001u;        // stored -open
+    const uint32_t e32 = a.d_e;                                           // ext in both halves
+    const uint32_t eK = a.d_eK;                                           // ext * K
+    const uint32_t eKb = a.d_eKb;                                         // ext * Kb
+    const uint32_t cOpen = a.d_copen;                                     // per-half two's complement of ext - open
+    const uint32_t cA_last = lastLane ? e32 : cOpen;                      // amplicon row La-1: zero end-gap penalties
+    const uint32_t cB_last = lastLane ? e32 : 0u;
+    // band columns of this lane's upper sub-strip: xlo1+1 .. xlo1+W; of its lower one (NSUB == 2): shifted by Kb.
+    // xlo1 is odd (host: P + B even), i.e. always the second column of a step
+    const int xlo1 = a.band_row0 + t * K - a.band_B - 1;
+    const int32_t *const prof_t = sprof + t * strip_stride(K);
+
+    for (int base = a.p0 + warp_global * GPW; base < a.p1; base += nwarps * GPW) {
+        const int p = base + gl;
+        const bool valid = p < a.p1;
+        const int Lb = valid ? a.plen[p] : 0;
+        const int nst = (Lb + 1) >> 1;                                    // column pairs of this lane's read
+        const int steps = __reduce_max_sync(0xffffffffu, nst) + G - 1;
+        const int64_t pco = valid ? a.pc_off[p] : 0;
+        const int64_t pco_rel = valid ? pco - a.pc_off[a.p0] : 0;
+        const uint8_t *pcp = a.pc + pco;
+        uint32_t *lrp = a.lastrow + (int64_t)(p - a.p0) * 3;             // (best, x_lo, x_hi) of amplicon row La-1
+        uint32_t *lcp = a.lastcol + ((int64_t)(p - a.p0) * G + t) * 3;   // (best, slot_lo, slot_hi) of this lane's rows, column Lb-1
+        const int firstRealSlot = (G * K - a.La) - t * K;                // slots below it are padding rows
+
+        Strip<K> st;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {                                    // boundary column x = -1: max3 = 0, ix = -open
+            const uint32_t d = e32 * (uint32_t)(t * K + k - 1);
+            st.H3[k] = Z + d; st.IX[k] = NOPEN_ST + d;
+        }
+        st.mlast = Z + e32 * (uint32_t)(t * K + K - 2);
+        uint32_t bot0[3] = {Z, NOPEN_ST, Z}, bot1[3] = {Z, NOPEN_ST, Z};
+        uint32_t hd0 = Z + e32 * (uint32_t)(t * K - 2);                  // max3[row above, -1] = 0
+        uint32_t rowBest = 0;                                            // stored scores are > 0: 0 is -infinity
+        int rowPosLo = 0, rowPosHi = 0;
+        int cpn0 = 0, cpn1 = 0;
+        if (t == 0 && Lb > 0) { cpn0 = pcp[0]; cpn1 = pcp[Lb > 1 ? 1 : 0]; }
+        // top boundary (plain values) from the pass that owns the rows above (shared DP prefix), one step ahead
+        const int64_t tcol = top_base_col(pco_rel, p - a.p0);
+        const uint4 *tin = (a.top_in && valid) ? reinterpret_cast<const uint4 *>(a.top_in) + tcol : nullptr;
+        uint4 *tout = (a.top_out && valid && t == a.top_out_lane) ? reinterpret_cast<uint4 *>(a.top_out) + tcol : nullptr;
+        uint4 tnA = make_uint4(Z, NOPEN_ST, Z, 0u), tnB = tnA;
+        if (tin && t == 0 && Lb > 0) tnA = tin[0];
+        if (tin && t == 0 && Lb > 1) tnB = tin[1];
+        // what this lane receives at its band columns, and its registers at the band's left edge
+        uint4 *bandw = nullptr, *midw = nullptr;                         // indexed by column x
+        uint32_t *leftp = nullptr;
+        if (valid && a.band_tops) {
+            const int64_t sub_id = ((int64_t)(p - a.p0) * G + t) * NSUB;   // this lane's upper sub-strip
+            if (t > 0) bandw = reinterpret_cast<uint4 *>(a.band_tops) + sub_id * band_topw(a.band_W) - xlo1;
+            if (NSUB == 2) midw = reinterpret_cast<uint4 *>(a.band_tops) + (sub_id + 1) * band_topw(a.band_W) - (xlo1 + Kb);
+            leftp = a.band_left + sub_id * band_leftw(Kb);
+        }
+
+        // One systolic step: lane t works on columns x0 = 2 (s - t) and x0 + 1.
+        auto step = [&](auto tail_tag, const int s) {
+            constexpr bool TAIL = decltype(tail_tag)::value;
+            const int x0 = 2 * (s - t), x1 = x0 + 1;
+            uint32_t r0H = __shfl_up_sync(0xffffffffu, bot0[0], 1, G);
+            uint32_t r0Y = __shfl_up_sync(0xffffffffu, bot0[1], 1, G);
+            uint32_t r0M = __shfl_up_sync(0xffffffffu, bot0[2], 1, G);
+            uint32_t r1H = __shfl_up_sync(0xffffffffu, bot1[0], 1, G);
+            uint32_t r1Y = __shfl_up_sync(0xffffffffu, bot1[1], 1, G);
+            uint32_t r1M = __shfl_up_sync(0xffffffffu, bot1[2], 1, G);
+            const uint32_t dTop0 = e32 * (uint32_t)(t * K - 1 + x0);      // drift of (row t*K - 1, column x0)
+            const uint32_t dTop1 = dTop0 + e32;
+            if (t == 0) {                                                 // free boundary above the padded top, or the saved row
+                r0H = tnA.x + dTop0; r0Y = tnA.y + dTop0; r0M = tnA.z + dTop0;
+                r1H = tnB.x + dTop1; r1Y = tnB.y + dTop1; r1M = tnB.z + dTop1;
+            }
+            const bool active = !TAIL || (x0 >= 0 && x0 < Lb);
+            const bool do1 = !TAIL || x1 < Lb;
+            const bool last0 = TAIL && active && x0 == Lb - 1;
+            const bool last1 = TAIL && active && x1 == Lb - 1;
+            // (a steady step prefetches one code past an odd-length read: never index the profile with it)
+            const int cp0 = cpn0, cp1 = do1 ? cpn1 : cpn0;
+            if (TAIL) {
+                if (x0 + 2 >= 0 && x0 + 2 < Lb) {
+                    cpn0 = pcp[x0 + 2];
+                    cpn1 = pcp[x0 + 3 < Lb ? x0 + 3 : x0 + 2];
+                    if (tin && t == 0) { tnA = tin[x0 + 2]; if (x0 + 3 < Lb) tnB = tin[x0 + 3]; }
+                }
+            } else {
+                // (x0 + 3 may be Lb for an odd length: one byte / one column past the read, inside the allocations; never used)
+                cpn0 = pcp[x0 + 2];
+                cpn1 = pcp[x0 + 3];
+                if (tin && t == 0) { tnA = tin[x0 + 2]; tnB = tin[x0 + 3]; }
+            }
+            if (active) {
+                if (bandw) {
+                    if ((unsigned)(x0 - xlo1) <= (unsigned)a.band_W) bandw[x0] = make_uint4(r0H - dTop0, r0Y - dTop0, r0M - dTop0, 0u);
+                    if (do1 && (unsigned)(x1 - xlo1) <= (unsigned)a.band_W) bandw[x1] = make_uint4(r1H - dTop1, r1Y - dTop1, r1M - dTop1, 0u);
+                }
+                uint32_t mid0[3] = {Z, Z, Z}, mid1[3] = {Z, Z, Z};
+                score_columns2<K, TAIL, NSUB>(st, prof_t + cp0 * PS, prof_t + cp1 * PS, r0H, r0Y, r0M, r1H, r1Y, r1M, hd0,
+                                              cOpen, cA_last, cB_last, e32, lastLane, last0, last1, do1, bot0, bot1, mid0, mid1);
+                hd0 = r1H;                                                // max3'[row above, x1] for the next step's x0
+                if (NSUB == 2 && midw) {
+                    const uint32_t dMid0 = dTop0 + eKb, dMid1 = dMid0 + e32;      // drift of (row t*K + Kb - 1, column x)
+                    if ((unsigned)(x0 - xlo1 - Kb) <= (unsigned)a.band_W) midw[x0] = make_uint4(mid0[0] - dMid0, mid0[1] - dMid0, mid0[2] - dMid0, 0u);
+                    if (do1 && (unsigned)(x1 - xlo1 - Kb) <= (unsigned)a.band_W) midw[x1] = make_uint4(mid1[0] - dMid1, mid1[1] - dMid1, mid1[2] - dMid1, 0u);
+                }
+                // start-cell scan along the last amplicon row (meaningful in the last lane only), on plain values:
+                // first column whose max(m,ix,iy) is strictly greater than all columns before it
+                const uint32_t dBot0 = dTop0 + eK, dBot1 = dBot0 + e32;   // drift of this lane's bottom row at x0 / x1
+                {
+                    const uint32_t nb = vmax2(rowBest, bot0[0] - dBot0);
+                    const uint32_t d = nb ^ rowBest;
+                    if (d & 0xffffu) rowPosLo = x0;
+                    if (d >> 16) rowPosHi = x0;
+                    rowBest = nb;
+                }
+                if (do1) {
+                    const uint32_t nb = vmax2(rowBest, bot1[0] - dBot1);
+                    const uint32_t d = nb ^ rowBest;
+                    if (d & 0xffffu) rowPosLo = x1;
+                    if (d >> 16) rowPosHi = x1;
+                    rowBest = nb;
+                }
+                if (tout) {
+                    tout[x0] = make_uint4(bot0[0] - dBot0, bot0[1] - dBot0, bot0[2] - dBot0, 0u);
+                    if (do1) tout[x1] = make_uint4(bot1[0] - dBot1, bot1[1] - dBot1, bot1[2] - dBot1, 0u);
+                }
+                if (leftp) {
+                    // registers after column xlo-1 of a sub-strip (always a second column): the band pass starts from them
+                    // (scalar stores on purpose: vector stores would make ptxas shuffle 2K registers into aligned quads)
+                    if (x1 == xlo1) {
+                        uint32_t d = dTop1;
+#pragma unroll
+                        for (int k = 0; k < Kb; ++k) { d += e32; leftp[k] = st.H3[k] - d; leftp[Kb + k] = st.IX[k] - d; }
+                        if (NSUB == 1) leftp[2 * Kb] = st.mlast - d;
+                    }
+                    if (NSUB == 2 && x1 == xlo1 + Kb) {
+                        uint32_t *lp = leftp + band_leftw(Kb);
+                        uint32_t d = dTop1 + eKb;
+#pragma unroll
+                        for (int k = 0; k < Kb; ++k) { d += e32; lp[k] = st.H3[Kb + k] - d; lp[Kb + k] = st.IX[Kb + k] - d; }
+                        lp[2 * Kb] = st.mlast - d;
+                    }
+                }
+                if (TAIL && (last0 || last1)) {
+                    // start-cell scan down the last read column (App. A.4) on plain values: first row whose max(m,ix,iy)
+                    // is strictly greater than everything above it; padded rows are not part of the matrix.  The state
+                    // arrays hold the last column (x1, or x0 when the length is odd: do1 = false).
+                    uint32_t colBest = 0, d = last0 ? dTop0 : dTop1;
+                    int colPosLo = 0, colPosHi = 0;
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        d += e32;
+                        if (k >= firstRealSlot) {
+                            const uint32_t nb = vmax2(colBest, st.H3[k] - d);
+                            const uint32_t df = nb ^ colBest;
+                            if (df & 0xffffu) colPosLo = k;
+                            if (df >> 16) colPosHi = k;
+                            colBest = nb;
+                        }
+                    }
+                    lcp[0] = colBest; lcp[1] = (uint32_t)colPosLo; lcp[2] = (uint32_t)colPosHi;
+                    if (lastLane) { lrp[0] = rowBest; lrp[1] = (uint32_t)rowPosLo; lrp[2] = (uint32_t)rowPosHi; }
+                }
+            }
+        };
+        // Steps G-1 .. nst_min-2 are steady for the whole warp: every lane on interior columns of its read.
+        const int nst_min = __reduce_min_sync(0xffffffffu, nst);
+        const int steady_end = min(nst_min - 1, steps);                       // first non-steady step after the steady run
+        int s = 0;
+        for (; s < min(G - 1, steps); ++s) step(std::true_type{}, s);
+        for (; s < steady_end; ++s) step(std::false_type{}, s);
+        for (; s < steps; ++s) step(std::true_type{}, s);
+    }
+}
+
+template <int G, int K, int NSUB>
+static cudaError_t launch_score2_tile(const FillArgs &a, int num_sms, cudaStream_t stream)
+{
+    const size_t smem = (size_t)NPAIR * prof_stride(G, K) * 4;
+    // (per call: the attribute is per device, and a process may hold contexts on several devices)
+    cudaError_t e = cudaFuncSetAttribute(k_gotoh_score2<G, K, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int blocks_per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_gotoh_score2<G, K, NSUB>, 128, smem);
+    if (e != cudaSuccess) return e;
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    const int npairs = a.p1 - a.p0;
+    const int groups_per_block = 4 * (32 / G);
+    int grid = (npairs + groups_per_block - 1) / groups_per_block;
+    const int cap = num_sms * blocks_per_sm;            // persistent: a multiple of the SM count
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    k_gotoh_score2<G, K, NSUB><<<grid, 128, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+// the band pass works on sub-strips of a.band_K rows: K (one per lane) or K/2 (two per lane, K % 16 == 0)
+template <int G, int K>
+static cudaError_t launch_score2_sub(const FillArgs &a, int num_sms, cudaStream_t stream)
+{
+    if (a.band_K == K) return launch_score2_tile<G, K, 1>(a, num_sms, stream);
+    if constexpr (K % 16 == 0) { if (2 * a.band_K == K) return launch_score2_tile<G, K, 2>(a, num_sms, stream); }
+    return cudaErrorInvalidValue;
+}
+
+template <int G, int K, int NSUB>
+static int64_t wave_pairs2_tile(int num_sms)
+{
+    const size_t smem = (size_t)NPAIR * prof_stride(G, K) * 4;
+    int bps = 0;
+    if (cudaFuncSetAttribute(k_gotoh_score2<G, K, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_gotoh_score2<G, K, NSUB>, 128, smem) != cudaSuccess) return 0;
+    return (int64_t)num_sms * std::max(bps, 1) * 4 * (32 / G);
+}
+
+int64_t score2_wave_pairs(int G, int K, int nsub, int num_sms)
+{
+#define CASE(g, k) if (G == g && K == k) { if (nsub == 1) return wave_pairs2_tile<g, k, 1>(num_sms); if constexpr (k % 16 == 0) { if (nsub == 2) return wave_pairs2_tile<g, k, 2>(num_sms); } return 0; }
+    CASE(4, 16) CASE(4, 24) CASE(4, 32) CASE(4, 40) CASE(8, 16) CASE(8, 24) CASE(8, 32) CASE(8, 40)
+    CASE(16, 16) CASE(16, 24) CASE(16, 32) CASE(16, 40) CASE(32, 24) CASE(32, 32) CASE(4, 48) CASE(8, 48) CASE(16, 48)
+#undef CASE
+    return 0;
+}
+
+cudaError_t launch_score2(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream)
+{
+#define CASE(g, k) if (G == g && K == k) return launch_score2_sub<g, k>(a, num_sms, stream);
+    CASE(4, 16) CASE(4, 24) CASE(4, 32) CASE(4, 40) CASE(8, 16) CASE(8, 24) CASE(8, 32) CASE(8, 40)
+    CASE(16, 16) CASE(16, 24) CASE(16, 32) CASE(16, 40) CASE(32, 24) CASE(32, 32) CASE(4, 48) CASE(8, 48) CASE(16, 48)
+#undef CASE
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace crgpu

@@ -74,5 +74,7 @@ __device__ __forceinline__ int64_t top_base_col(int64_t pco_rel, int pair_rel) {
 
 // launch of the score pass (gotoh_score.cu)
 cudaError_t launch_score(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream);
+// the same pass, two read columns per systolic step (gotoh_score2.cu; needs an odd band left edge: P + B even)
+cudaError_t launch_score2(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream);
 
 }  // namespace crgpu
