@@ -338,7 +338,7 @@ def main():
     # per cell, peak = the measured single-pipe rate.  Per-kernel durations come from one extra step right after the
     # timed region (same data) with the stream overlap off, so every launch runs alone between its CUDA events.
     kinds = {}
-    for kname, label in (("score", "k_gotoh_score<G,K> (score pass, drift coordinates, no flags)"),
+    for kname, label in (("score", "k_gotoh_score2<G,K> (score pass: drift coordinates, two read columns per step, no flags)"),
                          ("band", "k_gotoh_band<G,K> (band pass, flags)"),
                          ("full", "k_gotoh_fill<G,K> (single pass with flags: band escapes + RC rescue)")):
         ms_k, ln_k, cells_k = iso_kinds[kname]

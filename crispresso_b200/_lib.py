@@ -80,10 +80,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("CRGPU_LIB", LIB_PATH)         # (a differently built libcrgpu for A/B measurements)
+    if not os.path.exists(path):
         raise ImportError("crispresso_b200: %s is missing -- run `python -m crispresso_b200.build` "
-                          "(there is no CPU fallback)" % LIB_PATH)
-    lib = ctypes.CDLL(LIB_PATH)
+                          "(there is no CPU fallback)" % path)
+    lib = ctypes.CDLL(path)
     vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double
     lib.crgpu_abi_version.restype = i32
     lib.crgpu_create.argtypes = [ctypes.POINTER(vp), i32]

@@ -11,7 +11,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["gotoh_fill.cu", "gotoh_score.cu", "gotoh_score2.cu", "traceback_walk.cu", "quantify.cu", "int_peak.cu", "crgpu_api.cu", "hotpath.cu", "alleles.cu",
+SOURCES = ["gotoh_fill.cu", "gotoh_score2.cu", "traceback_walk.cu", "quantify.cu", "int_peak.cu", "crgpu_api.cu", "hotpath.cu", "alleles.cu",
            "flash_merge.cu", "fastq_index.cu"]
 LIB = os.path.join(HERE, "libcrgpu.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]

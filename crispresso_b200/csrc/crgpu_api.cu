@@ -495,7 +495,7 @@ int run_plan_dual(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     if (Gh == 0) return CRGPU_OK;
     const int t0 = G - Gh, split = t0 * K, GKh = Gh * K;
     const int maxlen = pl.maxlen;
-    // the score pass adds a drift of up to ext * (rows + columns) to every value (gotoh_score.cu)
+    // the score pass adds a drift of up to ext * (rows + columns) to every value (gotoh_score2.cu)
     if ((int64_t)scale * 5 * std::min(La, maxlen) + (int64_t)ext_s * (GK + maxlen + 2) + 64 >= MAX_ABS_SCORE ||
         (int64_t)2 * open_s + (int64_t)ext_s * (La + maxlen + 2) + 8 * scale + 64 >= MAX_ABS_SCORE)
         return CRGPU_OK;
@@ -693,7 +693,7 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     }
     const int t0 = G - Gh, split = dual ? t0 * K : 0, GKh = Gh * K;
     const int maxlen = pl.maxlen;
-    // the score pass adds a drift of up to ext * (rows + columns) to every value (gotoh_score.cu)
+    // the score pass adds a drift of up to ext * (rows + columns) to every value (gotoh_score2.cu)
     if ((int64_t)scale * 5 * std::min(La, maxlen) + (int64_t)ext_s * (GK + maxlen + 2) + 64 >= MAX_ABS_SCORE ||
         (int64_t)2 * open_s + (int64_t)ext_s * (La + maxlen + 2) + 8 * scale + 64 >= MAX_ABS_SCORE)
         return CRGPU_OK;
@@ -704,10 +704,10 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     const size_t sub_bytes = (size_t)TOPW * 16 + (size_t)LEFTW * 4 + (size_t)W * Kb * 2;      // per sub-strip
     const size_t pair_bytes = sub_bytes * (size_t)(G + Gh) * nsub + (dual ? (size_t)(maxlen + 2) * 16 : 0);
     // ~8 batches per call (the walks of one batch overlap the fills of the next), each a whole number of WAVES of the
-    // persistent score kernels: a warp of k_gotoh_score owns pairs w, w + wave, ..., so a batch of 9.2 waves costs 10
+    // persistent score kernels: a warp of k_gotoh_score2 owns pairs w, w + wave, ..., so a batch of 9.2 waves costs 10
     int64_t bp = (int64_t)(ctx->tb_budget / pair_bytes);
     {
-        const int64_t wave = getenv("CRGPU_NO_WAVE_ALIGN") ? 1 : std::max<int64_t>(1, (getenv("CRGPU_SCORE_V1") ? score_wave_pairs : score2_wave_pairs)(dual ? Gh : G, K, nsub, ctx->num_sms));
+        const int64_t wave = getenv("CRGPU_NO_WAVE_ALIGN") ? 1 : std::max<int64_t>(1, score2_wave_pairs(dual ? Gh : G, K, nsub, ctx->num_sms));
         int64_t want = std::max<int64_t>(((int64_t)pl.np + 7) / 8, 16384);
         if (want >= 4 * wave) {                   // (small calls, e.g. the chunks of a pipelined run, measured better unaligned)
             want = (want + wave - 1) / wave * wave;
@@ -735,7 +735,7 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     }
 
     // ---- profiles ----
-    // `add` = 2 ext for the score pass, which works in drift coordinates (gotoh_score.cu); padding rows score 0 (+ add)
+    // `add` = 2 ext for the score pass, which works in drift coordinates (gotoh_score2.cu); padding rows score 0 (+ add)
     auto build_prof = [&](const std::vector<int> &code, int g, int row0, int add, std::vector<int32_t> &prof) {
         const int PS = prof_stride(g, K), SS = strip_stride(K);
         prof.assign((size_t)NPAIR * PS, 0);
@@ -782,6 +782,8 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         CK(ctx->btops[i].reserve((size_t)max_bp * G * nsub * TOPW * 16));
         CK(ctx->bleft[i].reserve((size_t)max_bp * G * nsub * LEFTW * 4));
         CK(lrA[i]->reserve((size_t)max_bp * 12)); CK(lcA[i]->reserve((size_t)max_bp * G * 12));
+        CK(ctx->rowvals[i].reserve((size_t)(max_cols + max_bp + 2) * 4));
+        if (dual) CK(ctx->rowvals_h[i].reserve((size_t)(max_cols + max_bp + 2) * 4));
         if (diag) {
             CK(ctx->need[i].reserve((size_t)max_bp)); CK(ctx->plist[i].reserve((size_t)max_bp * 4));
             CK(ctx->selscratch[i].reserve(selbytes));
@@ -826,12 +828,15 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         fa.d_copen = ((uint32_t)(ext_s - open_s) & 0xffffu) * 0x10001u;
         fa.band_tops = ctx->btops[cur].as<uint32_t>(); fa.band_left = ctx->bleft[cur].as<uint32_t>();
         fa.band_tb = tbA[cur]->as<uint32_t>();
+        fa.lastrow_vals = ctx->rowvals[cur].as<uint32_t>();
         FillArgs fh = fa;                                               // HDR pass: bottom Gh lanes
         if (dual) {
             fh.prof = ctx->prof_h.as<int32_t>();
             fh.lastrow = lrH[cur]->as<uint32_t>(); fh.lastcol = lcH[cur]->as<uint32_t>();
             fh.La = GKh;                                                // no padding rows inside the sub-tile
             fh.top_out = nullptr; fh.top_out_lane = -1; fh.top_in = top[cur]->as<uint32_t>();
+            fh.top_in_row = split - 1;                                  // the amplicon pass saved its tile row split - 1
+            fh.lastrow_vals = ctx->rowvals_h[cur].as<uint32_t>();
             fh.band_row0 = split - P;
             fh.band_tops = ctx->btops_h[cur].as<uint32_t>(); fh.band_left = ctx->bleft_h[cur].as<uint32_t>();
             fh.band_tb = tbH[cur]->as<uint32_t>();

@@ -52,7 +52,12 @@ struct FillArgs {
     uint32_t *top_out;        // [(pc_off[p]-pc_off[p0]) + x][4] or null
     int top_out_lane;
     const uint32_t *top_in;   // same layout, or null (free end-gap boundary)
-    // Banded two-pass fill (DESIGN.md "Band"): k_gotoh_score evaluates every cell without flags and saves the state
+    // banded fill: top_out / top_in hold the score pass's drift coordinates, + ext * (top_in_row + x), top_in_row = the
+    // row of the saved values in the frame of the pass that wrote them
+    int top_in_row = 0;
+    uint32_t *lastrow_vals = nullptr;   // score pass: max3 of the last tile row per column (drifted), indexed like top_out by
+                                        // top_base_col(); k_lastrow_scan turns it into `lastrow`
+    // Banded two-pass fill (DESIGN.md "Band"): k_gotoh_score2 evaluates every cell without flags and saves the state
     // k_gotoh_band needs to re-evaluate -- with flags -- only a diagonal band.  The band pass works on SUB-STRIPS of
     // band_K rows (band_K = K, or K/2 when that is a multiple of 8): sub-strip u = t*(K/band_K) + hh of a pair covers
     // the band_W read columns x in [xlo, xlo + band_W), xlo = band_row0 + u*band_K - band_B.
@@ -62,7 +67,8 @@ struct FillArgs {
     // constant bank instead of re-deriving them from `ext` under register pressure): ext, ext*K, ext*band_K, ext - open
     uint32_t d_e, d_eK, d_eKb, d_copen;
     int band_row0;            // amplicon row of lane 0's first slot (-P for a full tile, split - P for the HDR sub-tile)
-    uint32_t *band_tops;      // [(p-p0)*G2 + u][band_topw()][4]: (max3, iy, m, 0) of the row above sub-strip u at columns xlo-1 .. xlo+W-1
+    uint32_t *band_tops;      // [(p-p0)*G2 + u][band_topw()][4]: (max3, iy, m, -) of the row above sub-strip u at columns xlo-2 .. xlo+W,
+                              // in the score pass's drift coordinates: + ext * (u*band_K - 1 + x)
     uint32_t *band_left;      // [(p-p0)*G2 + u][band_leftw(band_K)]: H3[band_K], IX[band_K], mlast of column xlo-1
     uint32_t *band_tb;        // [(p-p0)*G2 + u][band_W][band_K/2]: flag words of the band columns      (G2 = G*K/band_K)
     // Diagonal shortcut (DESIGN.md "Diagonal shortcut"): the band pass only visits the pairs of the batch that still need a
@@ -71,7 +77,9 @@ struct FillArgs {
     const int *pair_list_n = nullptr;
 };
 
-__host__ __device__ constexpr int band_topw(int W) { return (W + 2) & ~1; }          // columns, even
+// columns xlo-2 .. xlo+W of a sub-strip (W odd): the band pass reads xlo-1 .. xlo+W-1; k_gotoh_score2 stores both
+// columns of every step that touches them
+__host__ __device__ constexpr int band_topw(int W) { return (W + 4) & ~1; }
 __host__ __device__ constexpr int band_leftw(int K) { return 2 * K + 4; }           // words, 16-byte multiple
 
 constexpr int JOIN_NCK = 8, JOIN_CK = 8, JOIN_STRIDE = 4 + 4 * JOIN_NCK;    // checkpoints of the walk join (below)

@@ -69,6 +69,7 @@ struct crgpu_ctx {
     DBuf join, joinb;                                                      // amplicon walk -> HDR walk join records (WalkArgs.join_out)
     DBuf prof_s, prof_hs;                                           // drifted profiles of the score pass
     DBuf btops[2], bleft[2], btops_h[2], bleft_h[2], escaped;      // banded two-pass fill (run_plan_band)
+    DBuf rowvals[2], rowvals_h[2];                                 // score pass: last-row values per column (k_lastrow_scan)
     int n_escaped[2] = {0, 0};                                     // reads re-aligned after the last banded call (amplicon, HDR)
     int band_holdoff = 0;                                          // calls left that skip the band (set when > 25 % of a call's reads escaped)
     int band_B = 16;                                               // band half-width in read columns; 0 = single-pass fill
@@ -153,8 +154,7 @@ namespace crgpu {
 bool choose_tile(int La, int *G, int *K);
 bool tile_available(int G, int K);
 cudaError_t launch_fill(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream, int kind = 0);
-// pairs one resident wave of k_gotoh_score<G,K,nsub> covers (0: no such kernel)
-int64_t score_wave_pairs(int G, int K, int nsub, int num_sms);
+// pairs one resident wave of k_gotoh_score2<G,K,nsub> covers (0: no such kernel)
 int64_t score2_wave_pairs(int G, int K, int nsub, int num_sms);
 cudaError_t launch_encode(const uint8_t *reads, const int64_t *offsets, const int32_t *pair_lo, const int32_t *pair_hi,
                           const int64_t *pc_off, int npairs, uint8_t *pc, int *err, int num_sms, cudaStream_t s);

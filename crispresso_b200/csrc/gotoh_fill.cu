@@ -24,7 +24,7 @@
 //
 // Banded two-pass variant (FillArgs.band_B > 0; DESIGN.md "Band"): 16 of the ~22 instructions per cell
 // pair produce the traceback flags, but a traceback only ever reads the cells on its path, and the path
-// of an amplicon read hugs the main diagonal.  k_gotoh_score<G,K> (gotoh_score.cu) therefore evaluates every cell
+// of an amplicon read hugs the main diagonal.  k_gotoh_score2<G,K> (gotoh_score2.cu) therefore evaluates every cell
 // WITHOUT flags (scores, start-cell scan) and saves, per lane, what it received from the lane above at
 // the columns of a diagonal band and its register state at the band's left edge; k_gotoh_band<G,K>
 // re-evaluates only the band columns of every lane with flags -- lanes are independent there, the top
@@ -300,9 +300,13 @@ __global__ void __maxnreg__(fill_maxnreg<K / NSUB>()) k_gotoh_band(const FillArg
         const int x0 = max(xlo, 0), x1 = min(xlo + W - 1, Lb - 1);       // this sub-strip's columns; empty when x0 > x1
         // source of the top boundary: the row above (saved by the score pass), the pass that owns the rows above the
         // sub-tile, or the free boundary.  Indexed so that src[x] is column x.
+        // Both come from the score pass in its drift coordinates: value + ext * (srow + x), srow = the row's index in the
+        // frame of the pass that wrote it (u*Kb - 1 here; a.top_in_row for the shared-prefix row).
         const uint4 *src = nullptr;
-        if (u > 0) src = reinterpret_cast<const uint4 *>(a.band_tops) + (valid ? sub_id : 0) * band_topw(W) - (xlo - 1);
-        else if (a.top_in) src = reinterpret_cast<const uint4 *>(a.top_in) + top_base_col(pco_rel, pr);
+        int srow = 0;
+        if (u > 0) { src = reinterpret_cast<const uint4 *>(a.band_tops) + (valid ? sub_id : 0) * band_topw(W) - (xlo - 2); srow = u * Kb - 1; }
+        else if (a.top_in) { src = reinterpret_cast<const uint4 *>(a.top_in) + top_base_col(pco_rel, pr); srow = a.top_in_row; }
+        auto plain = [&](uint4 v, int x) { const uint32_t d = ext32 * (uint32_t)(srow + x); return make_uint4(v.x - d, v.y - d, v.z - d, 0u); };
         uint32_t *tbl = a.band_tb + (valid ? sub_id : 0) * W * (Kb / 2);
         const int32_t *pbase = sprof + t * strip_stride(K) + hh * Kb;
 
@@ -317,7 +321,7 @@ __global__ void __maxnreg__(fill_maxnreg<K / NSUB>()) k_gotoh_band(const FillArg
                 st.IX[4 * j] = w.x; st.IX[4 * j + 1] = w.y; st.IX[4 * j + 2] = w.z; st.IX[4 * j + 3] = w.w;
             }
             st.mlast = lp[Kb / 2].x;
-            if (src) hd0 = src[x0 - 1].x;
+            if (src) hd0 = src[x0 - 1].x - ext32 * (uint32_t)(srow + x0 - 1);
         } else {
 #pragma unroll
             for (int k = 0; k < Kb; ++k) { st.H3[k] = Z; st.IX[k] = NOPEN_ST; }
@@ -332,7 +336,7 @@ __global__ void __maxnreg__(fill_maxnreg<K / NSUB>()) k_gotoh_band(const FillArg
         for (int i = 0; i < W; ++i) {
             const int x = xlo + i;
             const bool active = x >= x0 && x <= x1;
-            const uint4 r = rn;
+            const uint4 r = src ? plain(rn, x) : rn;             // (un-drifted at use, one column after the load)
             const int cp = cp_next;
             if (x + 1 >= x0 && x + 1 <= x1) { if (src) rn = src[x + 1]; cp_next = pcp[x + 1]; }
             const bool firstCol = active && x == 0, lastCol = active && x == Lb - 1;
@@ -433,10 +437,7 @@ bool tile_available(int G, int K)
 cudaError_t launch_fill(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream, int kind)
 {
     if (kind < 0 || kind > 2) return cudaErrorInvalidValue;
-    if (kind == 1) {
-        static const bool v1 = getenv("CRGPU_SCORE_V1") != nullptr;      // one column per step (A/B runs)
-        return v1 ? launch_score(G, K, a, num_sms, stream) : launch_score2(G, K, a, num_sms, stream);
-    }
+    if (kind == 1) return launch_score2(G, K, a, num_sms, stream);
 #define CASE(g, k) if (G == g && K == k) return launch_tile<g, k>(a, num_sms, stream, kind);
     CASE(4, 16) CASE(4, 24) CASE(4, 32) CASE(4, 40) CASE(8, 16) CASE(8, 24) CASE(8, 32) CASE(8, 40)
     CASE(16, 16) CASE(16, 24) CASE(16, 32) CASE(16, 40) CASE(32, 24) CASE(32, 32) CASE(4, 48) CASE(8, 48) CASE(16, 48)

@@ -33,13 +33,21 @@
 
 namespace crgpu {
 
+// 16 bytes of the profile table by 32-bit shared address (the table is read-only after staging: not volatile)
+__device__ __forceinline__ int4 lds128(uint32_t addr)
+{
+    int4 v;
+    asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
 // Two read columns (x0 = 2j, x1 = 2j + 1) for the K rows of this lane, drift coordinates.
 //  TAIL = false: both columns are interior columns of the read for every lane of the warp.
 //  TAIL = true : per-lane flags -- last0 / last1: that column is the read's LAST column (iy opens from m only, zero
 //  penalties: SURVEY App. A.2/A.3); do1 = false: column x1 is past the read's end (odd length), the state then keeps
 //  column x0's values.  The whole warp runs this body with per-lane parameters, no divergence.
 template <int K, bool TAIL, int NSUB>
-__device__ __forceinline__ void score_columns2(Strip<K> &st, const int32_t *__restrict__ prow0, const int32_t *__restrict__ prow1,
+__device__ __forceinline__ void score_columns2(Strip<K> &st, const uint32_t prow0, const uint32_t prow1,   // shared-memory addresses
                                                uint32_t aH, uint32_t aY, uint32_t aM,      // row above, column x0
                                                uint32_t bH, uint32_t bY, uint32_t bM,      // row above, column x1
                                                const uint32_t hd,                          // max3'[row above, x0 - 1]
@@ -57,7 +65,7 @@ __device__ __forceinline__ void score_columns2(Strip<K> &st, const int32_t *__re
     for (int k = 0; k <= K; ++k) {
         uint32_t h0 = 0, ix0 = 0, m0 = 0, iy0 = 0;
         if (k < K) {                                                     // A: row k of column x0
-            if ((k & 3) == 0) S0 = *reinterpret_cast<const int4 *>(prow0 + k);
+            if ((k & 3) == 0) S0 = lds128(prow0 + k * 4);
             const int32_t s = (k & 3) == 0 ? S0.x : (k & 3) == 1 ? S0.y : (k & 3) == 2 ? S0.z : S0.w;
             m0 = (k == 0 ? hd : st.H3[k - 1]) + (uint32_t)s;
             if (k == K - 1) {                                            // the only slot that can be amplicon row La-1
@@ -71,9 +79,8 @@ __device__ __forceinline__ void score_columns2(Strip<K> &st, const int32_t *__re
             h0 = __vimax3_s16x2(m0, ix0, iy0);
         }
         if (k >= 1) {                                                    // B: row j = k - 1 of column x1
-            constexpr int dummy = 0; (void)dummy;
             const int j = k - 1;
-            if ((j & 3) == 0) S1 = *reinterpret_cast<const int4 *>(prow1 + j);
+            if ((j & 3) == 0) S1 = lds128(prow1 + j * 4);
             const int32_t s = (j & 3) == 0 ? S1.x : (j & 3) == 1 ? S1.y : (j & 3) == 2 ? S1.z : S1.w;
             const uint32_t m1 = dg1 + (uint32_t)s;
             uint32_t ix1;
@@ -115,6 +122,11 @@ __device__ __forceinline__ void score_columns2(Strip<K> &st, const int32_t *__re
 #endif
 template <int K> constexpr int score2_maxnreg() { return K <= 32 ? SCORE2_MAXNREG : fill_maxnreg<K>(); }
 
+// k_gotoh_score2 leaves everything it saves per column in DRIFT coordinates (no subtraction in the step):
+//   band_tops  (row above sub-strip u, column x)  : + ext * (u*Kb - 1 + x)      un-drifted by k_gotoh_band
+//   top_out    (bottom row of lane top_out_lane)  : + ext * (row + x)           consumers get FillArgs.top_in_row
+//   lastrow_vals (last tile row, one word / column): + ext * (G*K - 1 + x)      un-drifted by k_lastrow_scan
+// band_left (once per pair and sub-strip) and lastcol (once per pair and lane) hold plain values.
 template <int G, int K, int NSUB>
 __global__ void __maxnreg__(score2_maxnreg<K>()) k_gotoh_score2(const FillArgs a)
 {
@@ -136,15 +148,23 @@ __global__ void __maxnreg__(score2_maxnreg<K>()) k_gotoh_score2(const FillArgs a
     const uint32_t Z = BIAS2;                                             // stored 0
     const uint32_t NOPEN_ST = BIAS2 - (uint32_t)a.open * 0x10001u;        // stored -open
     const uint32_t e32 = a.d_e;                                           // ext in both halves
-    const uint32_t eK = a.d_eK;                                           // ext * K
-    const uint32_t eKb = a.d_eKb;                                         // ext * Kb
     const uint32_t cOpen = a.d_copen;                                     // per-half two's complement of ext - open
     const uint32_t cA_last = lastLane ? e32 : cOpen;                      // amplicon row La-1: zero end-gap penalties
     const uint32_t cB_last = lastLane ? e32 : 0u;
-    // band columns of this lane's upper sub-strip: xlo1+1 .. xlo1+W; of its lower one (NSUB == 2): shifted by Kb.
-    // xlo1 is odd (host: P + B even), i.e. always the second column of a step
+    // Band columns of this lane's upper sub-strip: xlo1 .. xlo1+W (xlo1 = first band column - 1); of its lower one
+    // (NSUB == 2): shifted by Kb.  xlo1 is odd (host: P + B even) and W is odd, so the steps that touch the window
+    // are those with x0 in [xlo1 - 1, xlo1 + W]: step s - sBand in [0, (W+1)/2]; both columns of such a step are
+    // stored (band_topw has room for the two extra columns).  The registers at the left edge are saved in the first
+    // of those steps (its second column is xlo1).
     const int xlo1 = a.band_row0 + t * K - a.band_B - 1;
-    const int32_t *const prof_t = sprof + t * strip_stride(K);
+    const int sBand = a.band_tops ? t + ((xlo1 - 1) >> 1) : (1 << 29);    // (no band: never)
+    const unsigned nBand = (unsigned)((a.band_W + 1) >> 1);
+    const uint32_t sprof_t = smem_u32(sprof) + (uint32_t)(t * strip_stride(K) * 4);
+    const bool isTout = a.top_out && t == a.top_out_lane;
+    const bool isRow = a.lastrow_vals && lastLane;
+    // top boundary of lane 0: the free boundary (plain constants + this lane's drift) or the saved row of the pass that
+    // owns the rows above (drifted in that pass's frame: row a.top_in_row; here it is row -1)
+    const uint32_t tinAdj = e32 * (uint32_t)(-1 - a.top_in_row);
 
     for (int base = a.p0 + warp_global * GPW; base < a.p1; base += nwarps * GPW) {
         const int p = base + gl;
@@ -155,8 +175,6 @@ __global__ void __maxnreg__(score2_maxnreg<K>()) k_gotoh_score2(const FillArgs a
         const int64_t pco = valid ? a.pc_off[p] : 0;
         const int64_t pco_rel = valid ? pco - a.pc_off[a.p0] : 0;
         const uint8_t *pcp = a.pc + pco;
-        uint32_t *lrp = a.lastrow + (int64_t)(p - a.p0) * 3;             // (best, x_lo, x_hi) of amplicon row La-1
-        uint32_t *lcp = a.lastcol + ((int64_t)(p - a.p0) * G + t) * 3;   // (best, slot_lo, slot_hi) of this lane's rows, column Lb-1
         const int firstRealSlot = (G * K - a.La) - t * K;                // slots below it are padding rows
 
         Strip<K> st;
@@ -168,26 +186,24 @@ __global__ void __maxnreg__(score2_maxnreg<K>()) k_gotoh_score2(const FillArgs a
         st.mlast = Z + e32 * (uint32_t)(t * K + K - 2);
         uint32_t bot0[3] = {Z, NOPEN_ST, Z}, bot1[3] = {Z, NOPEN_ST, Z};
         uint32_t hd0 = Z + e32 * (uint32_t)(t * K - 2);                  // max3[row above, -1] = 0
-        uint32_t rowBest = 0;                                            // stored scores are > 0: 0 is -infinity
-        int rowPosLo = 0, rowPosHi = 0;
         int cpn0 = 0, cpn1 = 0;
         if (t == 0 && Lb > 0) { cpn0 = pcp[0]; cpn1 = pcp[Lb > 1 ? 1 : 0]; }
-        // top boundary (plain values) from the pass that owns the rows above (shared DP prefix), one step ahead
         const int64_t tcol = top_base_col(pco_rel, p - a.p0);
         const uint4 *tin = (a.top_in && valid) ? reinterpret_cast<const uint4 *>(a.top_in) + tcol : nullptr;
-        uint4 *tout = (a.top_out && valid && t == a.top_out_lane) ? reinterpret_cast<uint4 *>(a.top_out) + tcol : nullptr;
+        uint4 *tout = reinterpret_cast<uint4 *>(a.top_out) + tcol;                         // used by lane top_out_lane only
+        uint32_t *rowv = a.lastrow_vals + tcol;                                            // used by the last lane only
+        const bool useTin = tin && t == 0;
         uint4 tnA = make_uint4(Z, NOPEN_ST, Z, 0u), tnB = tnA;
-        if (tin && t == 0 && Lb > 0) tnA = tin[0];
-        if (tin && t == 0 && Lb > 1) tnB = tin[1];
-        // what this lane receives at its band columns, and its registers at the band's left edge
-        uint4 *bandw = nullptr, *midw = nullptr;                         // indexed by column x
-        uint32_t *leftp = nullptr;
-        if (valid && a.band_tops) {
-            const int64_t sub_id = ((int64_t)(p - a.p0) * G + t) * NSUB;   // this lane's upper sub-strip
-            if (t > 0) bandw = reinterpret_cast<uint4 *>(a.band_tops) + sub_id * band_topw(a.band_W) - xlo1;
-            if (NSUB == 2) midw = reinterpret_cast<uint4 *>(a.band_tops) + (sub_id + 1) * band_topw(a.band_W) - (xlo1 + Kb);
-            leftp = a.band_left + sub_id * band_leftw(Kb);
-        }
+        if (useTin && Lb > 0) tnA = tin[0];
+        if (useTin && Lb > 1) tnB = tin[1];
+        // what this lane receives at its band columns (bandw[x]: column x of the upper sub-strip; the lower one's slot
+        // for the same column is MIDOFF further), and its registers at the band's left edge
+        const int64_t sub_id = ((int64_t)(p - a.p0) * G + t) * NSUB;     // this lane's upper sub-strip
+        const int TOPW = band_topw(a.band_W);
+        uint4 *bandw = reinterpret_cast<uint4 *>(a.band_tops) + sub_id * TOPW - (xlo1 - 1);
+        const int MIDOFF = TOPW - Kb;
+        uint32_t *leftp = a.band_left + sub_id * band_leftw(Kb);
+        const int sB = valid ? sBand : (1 << 29);
 
         // One systolic step: lane t works on columns x0 = 2 (s - t) and x0 + 1.
         auto step = [&](auto tail_tag, const int s) {
@@ -199,11 +215,11 @@ __global__ void __maxnreg__(score2_maxnreg<K>()) k_gotoh_score2(const FillArgs a
             uint32_t r1H = __shfl_up_sync(0xffffffffu, bot1[0], 1, G);
             uint32_t r1Y = __shfl_up_sync(0xffffffffu, bot1[1], 1, G);
             uint32_t r1M = __shfl_up_sync(0xffffffffu, bot1[2], 1, G);
-            const uint32_t dTop0 = e32 * (uint32_t)(t * K - 1 + x0);      // drift of (row t*K - 1, column x0)
-            const uint32_t dTop1 = dTop0 + e32;
-            if (t == 0) {                                                 // free boundary above the padded top, or the saved row
-                r0H = tnA.x + dTop0; r0Y = tnA.y + dTop0; r0M = tnA.z + dTop0;
-                r1H = tnB.x + dTop1; r1Y = tnB.y + dTop1; r1M = tnB.z + dTop1;
+            if (t == 0) {
+                const uint32_t d0 = e32 * (uint32_t)(x0 - 1);             // drift of (row -1, column x0)
+                const uint32_t adj0 = useTin ? tinAdj : d0, adj1 = useTin ? tinAdj : d0 + e32;
+                r0H = tnA.x + adj0; r0Y = tnA.y + adj0; r0M = tnA.z + adj0;
+                r1H = tnB.x + adj1; r1Y = tnB.y + adj1; r1M = tnB.z + adj1;
             }
             const bool active = !TAIL || (x0 >= 0 && x0 < Lb);
             const bool do1 = !TAIL || x1 < Lb;
@@ -215,85 +231,52 @@ __global__ void __maxnreg__(score2_maxnreg<K>()) k_gotoh_score2(const FillArgs a
                 if (x0 + 2 >= 0 && x0 + 2 < Lb) {
                     cpn0 = pcp[x0 + 2];
                     cpn1 = pcp[x0 + 3 < Lb ? x0 + 3 : x0 + 2];
-                    if (tin && t == 0) { tnA = tin[x0 + 2]; if (x0 + 3 < Lb) tnB = tin[x0 + 3]; }
+                    if (useTin) { tnA = tin[x0 + 2]; if (x0 + 3 < Lb) tnB = tin[x0 + 3]; }
                 }
             } else {
                 // (x0 + 3 may be Lb for an odd length: one byte / one column past the read, inside the allocations; never used)
                 cpn0 = pcp[x0 + 2];
                 cpn1 = pcp[x0 + 3];
-                if (tin && t == 0) { tnA = tin[x0 + 2]; tnB = tin[x0 + 3]; }
+                if (useTin) { tnA = tin[x0 + 2]; tnB = tin[x0 + 3]; }
             }
             if (active) {
-                if (bandw) {
-                    if ((unsigned)(x0 - xlo1) <= (unsigned)a.band_W) bandw[x0] = make_uint4(r0H - dTop0, r0Y - dTop0, r0M - dTop0, 0u);
-                    if (do1 && (unsigned)(x1 - xlo1) <= (unsigned)a.band_W) bandw[x1] = make_uint4(r1H - dTop1, r1Y - dTop1, r1M - dTop1, 0u);
+                const bool inBand = (unsigned)(s - sB) <= nBand;
+                if (inBand && t > 0) {
+                    bandw[x0] = make_uint4(r0H, r0Y, r0M, r0H);
+                    bandw[x1] = make_uint4(r1H, r1Y, r1M, r1H);
                 }
                 uint32_t mid0[3] = {Z, Z, Z}, mid1[3] = {Z, Z, Z};
-                score_columns2<K, TAIL, NSUB>(st, prof_t + cp0 * PS, prof_t + cp1 * PS, r0H, r0Y, r0M, r1H, r1Y, r1M, hd0,
-                                              cOpen, cA_last, cB_last, e32, lastLane, last0, last1, do1, bot0, bot1, mid0, mid1);
+                score_columns2<K, TAIL, NSUB>(st, sprof_t + (uint32_t)cp0 * (PS * 4), sprof_t + (uint32_t)cp1 * (PS * 4), r0H, r0Y, r0M,
+                                              r1H, r1Y, r1M, hd0, cOpen, cA_last, cB_last, e32, lastLane, last0, last1, do1,
+                                              bot0, bot1, mid0, mid1);
                 hd0 = r1H;                                                // max3'[row above, x1] for the next step's x0
-                if (NSUB == 2 && midw) {
-                    const uint32_t dMid0 = dTop0 + eKb, dMid1 = dMid0 + e32;      // drift of (row t*K + Kb - 1, column x)
-                    if ((unsigned)(x0 - xlo1 - Kb) <= (unsigned)a.band_W) midw[x0] = make_uint4(mid0[0] - dMid0, mid0[1] - dMid0, mid0[2] - dMid0, 0u);
-                    if (do1 && (unsigned)(x1 - xlo1 - Kb) <= (unsigned)a.band_W) midw[x1] = make_uint4(mid1[0] - dMid1, mid1[1] - dMid1, mid1[2] - dMid1, 0u);
+                if (NSUB == 2 && (unsigned)(s - sB - Kb / 2) <= nBand) {
+                    bandw[x0 + MIDOFF] = make_uint4(mid0[0], mid0[1], mid0[2], mid0[0]);
+                    bandw[x1 + MIDOFF] = make_uint4(mid1[0], mid1[1], mid1[2], mid1[0]);
                 }
-                // start-cell scan along the last amplicon row (meaningful in the last lane only), on plain values:
-                // first column whose max(m,ix,iy) is strictly greater than all columns before it
-                const uint32_t dBot0 = dTop0 + eK, dBot1 = dBot0 + e32;   // drift of this lane's bottom row at x0 / x1
-                {
-                    const uint32_t nb = vmax2(rowBest, bot0[0] - dBot0);
-                    const uint32_t d = nb ^ rowBest;
-                    if (d & 0xffffu) rowPosLo = x0;
-                    if (d >> 16) rowPosHi = x0;
-                    rowBest = nb;
+                if (isTout) {
+                    tout[x0] = make_uint4(bot0[0], bot0[1], bot0[2], bot0[0]);
+                    if (do1) tout[x1] = make_uint4(bot1[0], bot1[1], bot1[2], bot1[0]);
                 }
-                if (do1) {
-                    const uint32_t nb = vmax2(rowBest, bot1[0] - dBot1);
-                    const uint32_t d = nb ^ rowBest;
-                    if (d & 0xffffu) rowPosLo = x1;
-                    if (d >> 16) rowPosHi = x1;
-                    rowBest = nb;
+                if (isRow) {
+                    // (the start-cell scan along the last amplicon row is k_lastrow_scan's)
+                    if (do1) *reinterpret_cast<uint2 *>(rowv + x0) = make_uint2(bot0[0], bot1[0]);
+                    else rowv[x0] = bot0[0];
                 }
-                if (tout) {
-                    tout[x0] = make_uint4(bot0[0] - dBot0, bot0[1] - dBot0, bot0[2] - dBot0, 0u);
-                    if (do1) tout[x1] = make_uint4(bot1[0] - dBot1, bot1[1] - dBot1, bot1[2] - dBot1, 0u);
-                }
-                if (leftp) {
-                    // registers after column xlo-1 of a sub-strip (always a second column): the band pass starts from them
-                    // (scalar stores on purpose: vector stores would make ptxas shuffle 2K registers into aligned quads)
-                    if (x1 == xlo1) {
-                        uint32_t d = dTop1;
+                // registers after column xlo-1 of a sub-strip (always a second column): the band pass starts from them
+                // (scalar stores on purpose: vector stores would make ptxas shuffle 2K registers into aligned quads)
+                if (s == sB) {
+                    uint32_t d = e32 * (uint32_t)(t * K - 1 + x1);
 #pragma unroll
-                        for (int k = 0; k < Kb; ++k) { d += e32; leftp[k] = st.H3[k] - d; leftp[Kb + k] = st.IX[k] - d; }
-                        if (NSUB == 1) leftp[2 * Kb] = st.mlast - d;
-                    }
-                    if (NSUB == 2 && x1 == xlo1 + Kb) {
-                        uint32_t *lp = leftp + band_leftw(Kb);
-                        uint32_t d = dTop1 + eKb;
-#pragma unroll
-                        for (int k = 0; k < Kb; ++k) { d += e32; lp[k] = st.H3[Kb + k] - d; lp[Kb + k] = st.IX[Kb + k] - d; }
-                        lp[2 * Kb] = st.mlast - d;
-                    }
+                    for (int k = 0; k < Kb; ++k) { d += e32; leftp[k] = st.H3[k] - d; leftp[Kb + k] = st.IX[k] - d; }
+                    if (NSUB == 1) leftp[2 * Kb] = st.mlast - d;
                 }
-                if (TAIL && (last0 || last1)) {
-                    // start-cell scan down the last read column (App. A.4) on plain values: first row whose max(m,ix,iy)
-                    // is strictly greater than everything above it; padded rows are not part of the matrix.  The state
-                    // arrays hold the last column (x1, or x0 when the length is odd: do1 = false).
-                    uint32_t colBest = 0, d = last0 ? dTop0 : dTop1;
-                    int colPosLo = 0, colPosHi = 0;
+                if (NSUB == 2 && s == sB + Kb / 2) {
+                    uint32_t *lp = leftp + band_leftw(Kb);
+                    uint32_t d = e32 * (uint32_t)(t * K + Kb - 1 + x1);
 #pragma unroll
-                    for (int k = 0; k < K; ++k) {
-                        d += e32;
-                        if (k >= firstRealSlot) {
-                            const uint32_t nb = vmax2(colBest, st.H3[k] - d);
-                            const uint32_t df = nb ^ colBest;
-                            if (df & 0xffffu) colPosLo = k;
-                            if (df >> 16) colPosHi = k;
-                            colBest = nb;
-                        }
-                    }
-                    lcp[0] = colBest; lcp[1] = (uint32_t)colPosLo; lcp[2] = (uint32_t)colPosHi;
-                    if (lastLane) { lrp[0] = rowBest; lrp[1] = (uint32_t)rowPosLo; lrp[2] = (uint32_t)rowPosHi; }
+                    for (int k = 0; k < Kb; ++k) { d += e32; lp[k] = st.H3[Kb + k] - d; lp[Kb + k] = st.IX[Kb + k] - d; }
+                    lp[2 * Kb] = st.mlast - d;
                 }
             }
         };
@@ -304,6 +287,55 @@ __global__ void __maxnreg__(score2_maxnreg<K>()) k_gotoh_score2(const FillArgs a
         for (; s < min(G - 1, steps); ++s) step(std::true_type{}, s);
         for (; s < steady_end; ++s) step(std::false_type{}, s);
         for (; s < steps; ++s) step(std::true_type{}, s);
+
+        // start-cell scan down the last read column (App. A.4) on plain values: first row whose max(m,ix,iy) is
+        // strictly greater than everything above it; padded rows are not part of the matrix.  A lane is idle after
+        // its last column, so its state arrays still hold it: all lanes of the warp scan together.
+        if (valid) {
+            uint32_t colBest = 0, d = e32 * (uint32_t)(t * K - 1 + Lb - 1);
+            int colPosLo = 0, colPosHi = 0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                d += e32;
+                if (k >= firstRealSlot) {
+                    const uint32_t nb = vmax2(colBest, st.H3[k] - d);
+                    const uint32_t df = nb ^ colBest;
+                    if (df & 0xffffu) colPosLo = k;
+                    if (df >> 16) colPosHi = k;
+                    colBest = nb;
+                }
+            }
+            uint32_t *lcp = a.lastcol + ((int64_t)(p - a.p0) * G + t) * 3;   // (best, slot_lo, slot_hi) of this lane's rows, column Lb-1
+            lcp[0] = colBest; lcp[1] = (uint32_t)colPosLo; lcp[2] = (uint32_t)colPosHi;
+        }
+    }
+}
+
+// Start-cell scan along the last amplicon row (App. A.4): first column whose max(m,ix,iy) is strictly greater than all
+// columns before it, per read of a pair.  One warp per pair over the words k_gotoh_score2's last lane stored per
+// column (drifted: + ext * (last_row + x)).  -> lastrow[pair] = (best, x_lo, x_hi), as the fill kernels write it.
+__global__ void __launch_bounds__(256) k_lastrow_scan(const FillArgs a, const int last_row)
+{
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= a.p1 - a.p0) return;
+    const int p = a.p0 + w;
+    const int Lb = a.plen[p];
+    const uint32_t *v = a.lastrow_vals + top_base_col(a.pc_off[p] - a.pc_off[a.p0], w);
+    // per half: key = value << 16 | (0xffff - x): the maximum is the largest value at its smallest column
+    uint32_t klo = 0, khi = 0;
+    for (int x = lane; x < Lb; x += 32) {
+        const uint32_t pv = v[x] - a.d_e * (uint32_t)(last_row + x);
+        const uint32_t inv = 0xffffu - (uint32_t)x;
+        klo = max(klo, ((pv & 0xffffu) << 16) | inv);
+        khi = max(khi, (pv & 0xffff0000u) | inv);
+    }
+    klo = __reduce_max_sync(0xffffffffu, klo);
+    khi = __reduce_max_sync(0xffffffffu, khi);
+    if (lane == 0) {
+        uint32_t *lrp = a.lastrow + (int64_t)w * 3;
+        lrp[0] = (klo >> 16) | (khi & 0xffff0000u);
+        lrp[1] = 0xffffu - (klo & 0xffffu);
+        lrp[2] = 0xffffu - (khi & 0xffffu);
     }
 }
 
@@ -325,6 +357,9 @@ static cudaError_t launch_score2_tile(const FillArgs &a, int num_sms, cudaStream
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
     k_gotoh_score2<G, K, NSUB><<<grid, 128, smem, stream>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_lastrow_scan<<<(npairs + 7) / 8, 256, 0, stream>>>(a, G * K - 1);
     return cudaGetLastError();
 }
 

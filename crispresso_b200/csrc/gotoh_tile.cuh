@@ -1,5 +1,5 @@
 // gotoh_tile.cuh -- pieces shared by the fill kernels (gotoh_fill.cu: single pass with flags + band pass;
-// gotoh_score.cu: score pass of the banded fill).
+// gotoh_score2.cu: score pass of the banded fill).
 #pragma once
 #include "crgpu_common.cuh"
 
@@ -72,9 +72,7 @@ __device__ __forceinline__ void stage_profile(int32_t *sprof, uint64_t *mbar, co
 __device__ __forceinline__ int64_t top_base_col(int64_t pco_rel, int pair_rel) { return (pco_rel + pair_rel + 1) & ~(int64_t)1; }
 
 
-// launch of the score pass (gotoh_score.cu)
-cudaError_t launch_score(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream);
-// the same pass, two read columns per systolic step (gotoh_score2.cu; needs an odd band left edge: P + B even)
+// launch of the score pass + the last-row scan (gotoh_score2.cu; needs an odd band left edge: P + B even)
 cudaError_t launch_score2(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream);
 
 }  // namespace crgpu

@@ -1,6 +1,6 @@
-"""Host model of the score pass's arithmetic (crispresso_b200/csrc/gotoh_score.cu).
+"""Host model of the score pass's arithmetic (crispresso_b200/csrc/gotoh_score2.cu).
 
-k_gotoh_score evaluates the Gotoh recurrences in drift coordinates v' = v + ext * (row + column), where a gap extension
+k_gotoh_score2 evaluates the Gotoh recurrences in drift coordinates v' = v + ext * (row + column), where a gap extension
 leaves a value unchanged.  This file restates, in plain Python integers, (a) the recurrences in the form the kernels use
 (H3 = max(m, ix, iy) as the opening source, needle's zero end-gap penalties on the last amplicon row / last read column) and
 (b) the same in drift coordinates with the kernel's constants, and checks cell by cell that (b) minus the drift is (a), and
@@ -49,7 +49,7 @@ def plain_dp(amp, read, open_s, ext_s, scale):
 
 
 def drift_dp(amp, read, open_s, ext_s, scale):
-    """The same matrices in drift coordinates, with the constants of gotoh_score.cu: S' = S + 2 ext, c = ext - open, and
+    """The same matrices in drift coordinates, with the constants of gotoh_score2.cu: S' = S + 2 ext, c = ext - open, and
     `+ ext` terms on the zero-penalty row / column; boundary values carry the drift of their (virtual) cell."""
     La, Lb = len(amp), len(read)
     e, c = ext_s, ext_s - open_s
