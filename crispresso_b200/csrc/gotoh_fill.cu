@@ -331,14 +331,14 @@ __global__ void __maxnreg__(fill_maxnreg<K / NSUB>()) k_gotoh_band(const FillArg
         int colPosLo = 0, colPosHi = 0;
         uint4 rn = FREE;
         int cp_next = 0;
-        if (x0 <= x1) { if (src) rn = src[x0]; cp_next = pcp[x0]; }
+        if (x0 <= x1) { if (src) rn = load_top3(src + x0); cp_next = pcp[x0]; }
 
         for (int i = 0; i < W; ++i) {
             const int x = xlo + i;
             const bool active = x >= x0 && x <= x1;
             const uint4 r = src ? plain(rn, x) : rn;             // (un-drifted at use, one column after the load)
             const int cp = cp_next;
-            if (x + 1 >= x0 && x + 1 <= x1) { if (src) rn = src[x + 1]; cp_next = pcp[x + 1]; }
+            if (x + 1 >= x0 && x + 1 <= x1) { if (src) rn = load_top3(src + x + 1); cp_next = pcp[x + 1]; }
             const bool firstCol = active && x == 0, lastCol = active && x == Lb - 1;
             const bool edge = __any_sync(0xffffffffu, firstCol || lastCol);   // warp-uniform
             if (active) {

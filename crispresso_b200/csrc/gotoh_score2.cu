@@ -194,8 +194,8 @@ __global__ void __maxnreg__(score2_maxnreg<K>()) k_gotoh_score2(const FillArgs a
         uint32_t *rowv = a.lastrow_vals + tcol;                                            // used by the last lane only
         const bool useTin = tin && t == 0;
         uint4 tnA = make_uint4(Z, NOPEN_ST, Z, 0u), tnB = tnA;
-        if (useTin && Lb > 0) tnA = tin[0];
-        if (useTin && Lb > 1) tnB = tin[1];
+        if (useTin && Lb > 0) tnA = load_top3(tin);
+        if (useTin && Lb > 1) tnB = load_top3(tin + 1);
         // what this lane receives at its band columns (bandw[x]: column x of the upper sub-strip; the lower one's slot
         // for the same column is MIDOFF further), and its registers at the band's left edge
         const int64_t sub_id = ((int64_t)(p - a.p0) * G + t) * NSUB;     // this lane's upper sub-strip
@@ -231,13 +231,13 @@ __global__ void __maxnreg__(score2_maxnreg<K>()) k_gotoh_score2(const FillArgs a
                 if (x0 + 2 >= 0 && x0 + 2 < Lb) {
                     cpn0 = pcp[x0 + 2];
                     cpn1 = pcp[x0 + 3 < Lb ? x0 + 3 : x0 + 2];
-                    if (useTin) { tnA = tin[x0 + 2]; if (x0 + 3 < Lb) tnB = tin[x0 + 3]; }
+                    if (useTin) { tnA = load_top3(tin + x0 + 2); if (x0 + 3 < Lb) tnB = load_top3(tin + x0 + 3); }
                 }
             } else {
                 // (x0 + 3 may be Lb for an odd length: one byte / one column past the read, inside the allocations; never used)
                 cpn0 = pcp[x0 + 2];
                 cpn1 = pcp[x0 + 3];
-                if (useTin) { tnA = tin[x0 + 2]; tnB = tin[x0 + 3]; }
+                if (useTin) { tnA = load_top3(tin + x0 + 2); tnB = load_top3(tin + x0 + 3); }
             }
             if (active) {
                 const bool inBand = (unsigned)(s - sB) <= nBand;

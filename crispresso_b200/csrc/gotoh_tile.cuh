@@ -72,6 +72,16 @@ __device__ __forceinline__ void stage_profile(int32_t *sprof, uint64_t *mbar, co
 __device__ __forceinline__ int64_t top_base_col(int64_t pco_rel, int pair_rel) { return (pco_rel + pair_rel + 1) & ~(int64_t)1; }
 
 
+// (max3, iy, m) of a saved boundary row: 8 + 4 bytes, NOT one 16-byte load -- ptxas recycles the register of the unused
+// fourth word as a temporary in the middle of the step, and every such write then waits for the load in flight (a third
+// of the HDR pass's stall samples, ncu source page)
+__device__ __forceinline__ uint4 load_top3(const uint4 *q)
+{
+    const uint2 a = *reinterpret_cast<const uint2 *>(q);
+    const uint32_t c = reinterpret_cast<const uint32_t *>(q)[2];
+    return make_uint4(a.x, a.y, c, 0u);
+}
+
 // launch of the score pass + the last-row scan (gotoh_score2.cu; needs an odd band left edge: P + B even)
 cudaError_t launch_score2(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream);
 
