@@ -53,7 +53,7 @@ def needle_align(ctx, amplicon, reads, gapopen=10.0, gapextend=0.5, want_rows=Tr
     """
     buf, offsets = reads if isinstance(reads, tuple) else pack_reads(reads)
     n = len(offsets) - 1
-    amp = amplicon.encode() if isinstance(amplicon, str) else bytes(amplicon)
+    amp = (amplicon.encode() if isinstance(amplicon, str) else bytes(amplicon)).upper()      # (CORE:1288)
     recs = np.zeros(n, dtype=_lib.ALN_REC)
     if n == 0:
         return recs, [], [], []

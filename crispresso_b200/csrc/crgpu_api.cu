@@ -12,26 +12,42 @@ int crgpu_create(crgpu_ctx **out, int device)
 {
     if (!out) return CRGPU_E_ARG;
     *out = nullptr;
-    int ndev = 0;
+    int ndev = 0, prev = -1;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return CRGPU_E_CUDA;
+    cudaGetDevice(&prev);
     if (cudaSetDevice(device) != cudaSuccess) return CRGPU_E_CUDA;
     crgpu_ctx *c = new crgpu_ctx();
     c->device = device;
+    auto bail = [&]() {
+        if (c->stream) cudaStreamDestroy(c->stream);
+        if (c->stream2) cudaStreamDestroy(c->stream2);
+        if (c->stream3) cudaStreamDestroy(c->stream3);
+        if (c->ready) cudaEventDestroy(c->ready);
+        for (int i = 0; i < 2; ++i) { if (c->fill_done[i]) cudaEventDestroy(c->fill_done[i]); if (c->walk_done[i]) cudaEventDestroy(c->walk_done[i]); }
+        delete c;
+        if (prev >= 0) cudaSetDevice(prev);
+        return CRGPU_E_CUDA;
+    };
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return CRGPU_E_CUDA; }
-    if (prop.major != 10) { delete c; return CRGPU_E_CUDA; }   // sm_100a SASS only: no other target, no fallback
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail();
+    if (prop.major != 10) return bail();                       // sm_100a SASS only: no other target, no fallback
     c->num_sms = prop.multiProcessorCount;
-    // The traceback walk reads one byte per visited cell from scattered sectors: ask L2 not to
-    // over-fetch neighbouring sectors from HBM (a hint; DESIGN.md "k_traceback_walk").
-    if (!getenv("CRGPU_NO_L2_HINT")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return CRGPU_E_CUDA; }
-    if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete c; return CRGPU_E_CUDA; }
-    if (cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking) != cudaSuccess) { delete c; return CRGPU_E_CUDA; }
-    cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming);
-    for (int i = 0; i < 2; ++i) {
-        cudaEventCreateWithFlags(&c->fill_done[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&c->walk_done[i], cudaEventDisableTiming);
+    // The traceback walk reads one byte per visited cell from scattered sectors: CRGPU_L2_HINT=1 asks L2 not to over-fetch
+    // neighbouring sectors from HBM.  A device-wide limit (it measured neutral, profiles/r01_notes.md), so it is opt-in
+    // and crgpu_destroy puts the previous value back.
+    if (getenv("CRGPU_L2_HINT") && cudaDeviceGetLimit(&c->l2_gran_prev, cudaLimitMaxL2FetchGranularity) == cudaSuccess) {
+        if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32) == cudaSuccess) c->l2_gran_set = true;
+        else cudaGetLastError();
     }
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail();
+    if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) return bail();
+    if (cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking) != cudaSuccess) return bail();
+    if (cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming) != cudaSuccess) return bail();
+    for (int i = 0; i < 2; ++i) {
+        if (cudaEventCreateWithFlags(&c->fill_done[i], cudaEventDisableTiming) != cudaSuccess) return bail();
+        if (cudaEventCreateWithFlags(&c->walk_done[i], cudaEventDisableTiming) != cudaSuccess) return bail();
+    }
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);      // the caller's current device is not ours to change
     *out = c;
     return CRGPU_OK;
 }
@@ -39,7 +55,10 @@ int crgpu_create(crgpu_ctx **out, int device)
 void crgpu_destroy(crgpu_ctx *c)
 {
     if (!c) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
     cudaSetDevice(c->device);
+    if (c->l2_gran_set) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, c->l2_gran_prev);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->stream2);
     cudaStreamSynchronize(c->stream3);
@@ -47,7 +66,9 @@ void crgpu_destroy(crgpu_ctx *c)
                    &c->order, &c->plan_hist, &c->plan_tab, &c->tb2, &c->lastrow2, &c->lastcol2, &c->tb, &c->lastrow, &c->lastcol, &c->errflag, &c->recs, &c->sref, &c->smark, &c->sqry, &c->ops, &c->ops_rc, &c->alleles, &c->prof_h, &c->amp_h, &c->tbh, &c->tbh2,
                    &c->top, &c->top2, &c->lastrow_h, &c->lastrow_h2, &c->lastcol_h, &c->lastcol_h2,
                    &c->prof_s, &c->prof_hs, &c->join, &c->btops[0], &c->btops[1], &c->bleft[0], &c->bleft[1], &c->btops_h[0], &c->btops_h[1], &c->bleft_h[0], &c->bleft_h[1], &c->escaped,
-                   &c->joinb, &c->fastflags, &c->need[0], &c->need[1], &c->plist[0], &c->plist[1], &c->selscratch[0], &c->selscratch[1], &c->need_cnt};
+                   &c->joinb, &c->fastflags, &c->need[0], &c->need[1], &c->plist[0], &c->plist[1], &c->plist2[0], &c->plist2[1], &c->selscratch[0], &c->selscratch[1], &c->need_cnt,
+                   &c->rowvals[0], &c->rowvals[1], &c->rowvals_h[0], &c->rowvals_h[1], &c->badbase,
+                   &c->need_read[0], &c->need_read[1], &c->rlist[0], &c->rlist[1]};
     for (DBuf *b : all) b->release();
     for (auto &b : c->q_in) b.release();
     for (auto &b : c->q_out) b.release();
@@ -58,7 +79,9 @@ void crgpu_destroy(crgpu_ctx *c)
     cudaStreamDestroy(c->stream3);
     cudaStreamDestroy(c->stream2);
     cudaStreamDestroy(c->stream);
+    const int dev = c->device;
     delete c;
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
 }
 
 const char *crgpu_last_error(const crgpu_ctx *c) { return c ? c->err.c_str() : "null context"; }
@@ -139,7 +162,7 @@ int crgpu_last_fill_breakdown(const crgpu_ctx *c, double out_ms[3], int64_t out_
     return CRGPU_OK;
 }
 
-int crgpu_sync(crgpu_ctx *ctx)
+static int sync_impl(crgpu_ctx *ctx)
 {
     if (!ctx) return CRGPU_E_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -149,7 +172,7 @@ int crgpu_sync(crgpu_ctx *ctx)
 
 void *crgpu_stream(crgpu_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
-int crgpu_qualfilter(crgpu_ctx *ctx, int mem, const uint8_t *qual, const int64_t *offsets, int64_t n,
+static int qualfilter_impl(crgpu_ctx *ctx, int mem, const uint8_t *qual, const int64_t *offsets, int64_t n,
                      int min_mean_q, int min_single_q, uint8_t *keep)
 {
     if (!ctx) return CRGPU_E_ARG;
@@ -182,6 +205,9 @@ int crgpu_qualfilter(crgpu_ctx *ctx, int mem, const uint8_t *qual, const int64_t
 // Alignment core shared by crgpu_align and crgpu_align_quantify.  All pointers are DEVICE
 // pointers except h_offsets (host copy of the offsets, needed to pair reads by length).
 // ---------------------------------------------------------------------------------------------
+// the reference upper-cases the amplicon before anything else (CORE:1288); the walkers copy these bytes into the text rows
+static char host_upper(char c) { return (c >= 'a' && c <= 'z') ? (char)(c - 32) : c; }
+
 static int host_code(char c)
 {
     switch (c) {
@@ -278,7 +304,7 @@ int build_plan(crgpu_ctx *ctx, const uint8_t *d_reads, const int64_t *d_offsets,
     CK(launch_build_pairs(d_segs, nseg, pl.np, ctx->order.as<int32_t>(), ctx->pair_lo.as<int32_t>(), ctx->pair_hi.as<int32_t>(),
                           ctx->plen.as<int32_t>(), ctx->pc_off.as<int64_t>(), pcs, s));
     CK(launch_encode(d_reads, d_offsets, ctx->pair_lo.as<int32_t>(), ctx->pair_hi.as<int32_t>(), ctx->pc_off.as<int64_t>(), pl.np,
-                     ctx->pc.as<uint8_t>(), d_err, ctx->num_sms, s));
+                     ctx->pc.as<uint8_t>(), d_err, ctx->d_bad, ctx->num_sms, s));
     span_end(ctx, 3);
     CK(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));    // read_start / segs are locals of this frame
@@ -322,7 +348,7 @@ int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_read
     for (int i = 0; i < La; ++i) {
         acode[i] = host_code(amplicon[i]);
         if (acode[i] < 0) return fail(ctx, CRGPU_E_ALIGN, "amplicon has a base outside ACGTN at %d", i);
-        amp_up[i] = amplicon[i];
+        amp_up[i] = host_upper(amplicon[i]);
     }
     if (pl.np == 0) return CRGPU_OK;
     int G, K;
@@ -482,7 +508,7 @@ int run_plan_dual(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     for (int i = 0; i < La; ++i) {
         acode[i] = host_code(amplicon[i]); hcode[i] = host_code(hdr_amplicon[i]);
         if (acode[i] < 0 || hcode[i] < 0) return CRGPU_OK;
-        amp_up[i] = amplicon[i]; hdr_up[i] = hdr_amplicon[i];
+        amp_up[i] = host_upper(amplicon[i]); hdr_up[i] = host_upper(hdr_amplicon[i]);
         if (d == La && acode[i] != hcode[i]) d = i;
     }
     int G, K;
@@ -664,11 +690,11 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     for (int i = 0; i < La; ++i) {
         acode[i] = host_code(amplicon[i]);
         if (acode[i] < 0) return CRGPU_OK;
-        amp_up[i] = amplicon[i];
+        amp_up[i] = host_upper(amplicon[i]);
         if (dual) {
             hcode[i] = host_code(hdr_amplicon[i]);
             if (hcode[i] < 0) return CRGPU_OK;
-            hdr_up[i] = hdr_amplicon[i];
+            hdr_up[i] = host_upper(hdr_amplicon[i]);
             if (d == La && acode[i] != hcode[i]) d = i;
         }
     }
@@ -723,13 +749,14 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     for (size_t b = 0; b + 1 < batch_start.size(); ++b)
         max_cols = std::max(max_cols, plan_pc_off(pl, batch_start[b + 1]) - plan_pc_off(pl, batch_start[b]));
     if (n_cells) *n_cells += (dual ? 2 : 1) * (int64_t)La * pl.sum_len;
-    int64_t band_cells_all = 0;
+    int64_t band_cells_all = 0, band_cells_hdr = 0;
     {
         // score pass: every cell (HDR: the rows below the split); band pass: at most W columns per lane
         const int64_t band_cols = std::min<int64_t>((int64_t)W * pl.nsub, pl.sum_len);
         const int64_t score_cells = ((int64_t)La + (dual ? (int64_t)(La - (split - P)) : 0)) * pl.sum_len;
         const int64_t band_cells = ((int64_t)GK + (dual ? (int64_t)GKh : 0)) * band_cols;
         band_cells_all = band_cells;
+        band_cells_hdr = dual ? (int64_t)GKh * band_cols : 0;        // (the shortcut only thins out the amplicon pass)
         if (n_cells_computed) *n_cells_computed += score_cells;
         ctx->cells_kind[1] += score_cells;
     }
@@ -769,13 +796,14 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         CK(ctx->join.reserve((size_t)max_bp * 2 * JOIN_STRIDE * 4));
         CK(ctx->joinb.reserve((size_t)max_bp * 2 * JOIN_STRIDE * 4));
     }
-    const bool diag = ctx->diag && !getenv("CRGPU_NO_DIAG");
+    // (with an HDR amplicon the shortcut relies on the walk join: the HDR walk of a shortcut read must end at a checkpoint)
+    const bool diag = ctx->diag && !getenv("CRGPU_NO_DIAG") && !(dual && getenv("CRGPU_NO_JOIN"));
     const size_t nbatches = batch_start.size() - 1;
-    const size_t selbytes = select_scratch_bytes(max_bp);
+    const size_t selbytes = select_scratch_bytes((int64_t)max_bp * 2);
     if (diag) {
         if (!d_fast) return fail(ctx, CRGPU_E_ARG, "run_plan_band: the diagonal shortcut needs the per-read flag array");
-        CK(ctx->need_cnt.reserve(nbatches * 4));
-        CK(cudaMemsetAsync(ctx->need_cnt.p, 0, nbatches * 4, ctx->stream));
+        CK(ctx->need_cnt.reserve(nbatches * 12));
+        CK(cudaMemsetAsync(ctx->need_cnt.p, 0, nbatches * 12, ctx->stream));
     }
     for (int i = 0; i < (two ? 2 : 1); ++i) {
         CK(tbA[i]->reserve((size_t)max_bp * G * W * K * 2));
@@ -786,6 +814,8 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         if (dual) CK(ctx->rowvals_h[i].reserve((size_t)(max_cols + max_bp + 2) * 4));
         if (diag) {
             CK(ctx->need[i].reserve((size_t)max_bp)); CK(ctx->plist[i].reserve((size_t)max_bp * 4));
+            CK(ctx->need_read[i].reserve((size_t)max_bp * 2)); CK(ctx->rlist[i].reserve((size_t)max_bp * 8));
+            if (dual) CK(ctx->plist2[i].reserve((size_t)max_bp * 4));
             CK(ctx->selscratch[i].reserve(selbytes));
         }
         if (dual) {
@@ -872,31 +902,47 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
             wh.join_out = nullptr; wh.join_in = wa.join_out;      // (join_row: the same split row)
             wh.recs = d_recs_hdr; wh.ref_out = wh.mark_out = wh.qry_out = nullptr; wh.ops_out = nullptr;
         }
+        FillArgs fa_up;                                                 // (amplicon band of the shortcut pairs: rows above the split)
         if (wa.join_out) CK(cudaMemsetAsync(wa.join_out, 0, (size_t)(fa.p1 - fa.p0) * 2 * JOIN_STRIDE * 4, sf[cur]));
         if (diag) {
-            // diagonal shortcut: alignments whose traceback is provably the diagonal through the start cell are emitted
-            // here, right after the score pass; the band pass and the walks below only visit the remaining pairs
+            // diagonal shortcut: amplicon alignments whose traceback is provably the diagonal through the start cell are
+            // emitted here, right after the score pass; the amplicon band pass and walk below only visit the remaining
+            // pairs.  (The HDR alignments of a run with an HDR amplicon keep the full path: an unedited read is not
+            // diagonal against the HDR amplicon, and its walk ends at the first join checkpoint above the split anyway.)
             int *d_cnt = ctx->need_cnt.as<int>() + b;
             WalkArgs wd = wa;
-            wd.diag = 1; wd.fast = d_fast; wd.fast_bit = escape_bit; wd.need = ctx->need[cur].as<uint8_t>(); wd.need_or = 0;
+            wd.fast = d_fast; wd.fast_bit = escape_bit; wd.need = ctx->need[cur].as<uint8_t>();
+            CK(cudaMemsetAsync(wd.need, 2, (size_t)(fa.p1 - fa.p0), sf[cur]));      // 2: both alignments took the shortcut (so far)
+            wd.need_read = ctx->need_read[cur].as<uint8_t>();
+            CK(cudaMemsetAsync(wd.need_read, 0, (size_t)2 * (fa.p1 - fa.p0), sf[cur]));
             span_begin(ctx, T_WALK, sf[cur]);
-            CK(launch_walk(wd, sf[cur]));
-            if (dual) {
-                WalkArgs whd = wh;
-                whd.diag = 1; whd.fast = d_fast; whd.fast_bit = 2; whd.need = wd.need; whd.need_or = 1;
-                whd.join_in = nullptr;
-                CK(launch_walk(whd, sf[cur]));
-            }
-            span_end(ctx, dual ? 2 : 1);
+            CK(launch_diag_emit(wd, sf[cur]));
+            span_end(ctx, 1);
             CK(select_flagged(wd.need, fa.p1 - fa.p0, 1, ctx->plist[cur].as<int32_t>(), d_cnt, ctx->selscratch[cur].p, selbytes, sf[cur]));
-            fa.pair_list = fh.pair_list = wa.pair_list = wh.pair_list = ctx->plist[cur].as<int32_t>();
-            fa.pair_list_n = fh.pair_list_n = wa.pair_list_n = wh.pair_list_n = d_cnt;
-            wa.fast = wh.fast = d_fast; wa.fast_bit = escape_bit; wh.fast_bit = 2;
+            fa.pair_list = ctx->plist[cur].as<int32_t>();
+            fa.pair_list_n = d_cnt;
+            // ... and the walk only the alignments that did not take it
+            int *d_cnt3 = ctx->need_cnt.as<int>() + 2 * nbatches + b;
+            CK(select_flagged(wd.need_read, 2 * (fa.p1 - fa.p0), 1, ctx->rlist[cur].as<int32_t>(), d_cnt3, ctx->selscratch[cur].p, selbytes, sf[cur]));
+            wa.read_list = ctx->rlist[cur].as<int32_t>(); wa.read_list_n = d_cnt3;
+            wa.fast = d_fast; wa.fast_bit = escape_bit;
+            if (dual) {
+                // the HDR walk of such a pair still needs the amplicon pass's flags for the rows right above the split, until it
+                // meets the amplicon alignment's diagonal at a join checkpoint: ~32 rows of sub-strips for those pairs
+                int *d_cnt2 = ctx->need_cnt.as<int>() + nbatches + b;
+                CK(select_flagged(wd.need, fa.p1 - fa.p0, 2, ctx->plist2[cur].as<int32_t>(), d_cnt2, ctx->selscratch[cur].p, selbytes, sf[cur]));
+                const int nup = std::min(split / Kb, (32 + Kb - 1) / Kb);
+                fa_up = fa;
+                fa_up.pair_list = ctx->plist2[cur].as<int32_t>(); fa_up.pair_list_n = d_cnt2;
+                fa_up.sub_lo = split / Kb - nup; fa_up.sub_n = nup;
+                wh.upper_need = wd.need; wh.upper_lo = fa_up.sub_lo * Kb;
+            }
         }
         span_begin(ctx, T_BAND, sf[cur]);
         CK(launch_fill(G, K, fa, ctx->num_sms, sf[cur], 2));
         if (dual) CK(launch_fill(Gh, K, fh, ctx->num_sms, sf[cur], 2));
-        span_end(ctx, dual ? 2 : 1);
+        if (fa_up.sub_n > 0) CK(launch_fill(G, K, fa_up, ctx->num_sms, sf[cur], 2));
+        span_end(ctx, (dual ? 2 : 1) + (fa_up.sub_n > 0 ? 1 : 0));
         CK(cudaEventRecord(ctx->fill_done[cur], sf[cur]));
 
         CK(cudaStreamWaitEvent(s2, ctx->fill_done[cur], 0));
@@ -918,7 +964,7 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         int64_t left = 0;
         for (int c : hc) left += c;
         ctx->n_diag_pairs[1] += left;
-        band_cells = (int64_t)((double)band_cells_all * (double)left / (double)std::max(pl.np, 1));
+        band_cells = band_cells_hdr + (int64_t)((double)(band_cells_all - band_cells_hdr) * (double)left / (double)std::max(pl.np, 1));
     } else ctx->n_diag_pairs[1] += pl.np;
     if (n_cells_computed) *n_cells_computed += band_cells;
     ctx->cells_kind[2] += band_cells;
@@ -930,7 +976,7 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
 
 extern "C" {
 
-int crgpu_align(crgpu_ctx *ctx, int mem, const char *amplicon, int amplicon_len,
+static int align_impl(crgpu_ctx *ctx, int mem, const char *amplicon, int amplicon_len,
                 const uint8_t *reads, const int64_t *offsets, int64_t n, double gapopen, double gapextend,
                 crgpu_aln_rec *recs, uint8_t *ref_out, uint8_t *mark_out, uint8_t *qry_out, int64_t slot)
 {
@@ -963,11 +1009,16 @@ int crgpu_align(crgpu_ctx *ctx, int mem, const char *amplicon, int amplicon_len,
             d_ref = ctx->sref.as<uint8_t>(); d_mark = ctx->smark.as<uint8_t>(); d_qry = ctx->sqry.as<uint8_t>();
         }
     }
+    CK(ctx->badbase.reserve((size_t)n));
+    CK(cudaMemsetAsync(ctx->badbase.p, 0, (size_t)n, s));
+    ctx->d_bad = ctx->badbase.as<uint8_t>();
     int rc = build_plan(ctx, d_reads, d_off, nullptr, n);
     if (rc == CRGPU_OK)
         rc = run_plan(ctx, amplicon, amplicon_len, d_reads, d_off, nullptr, 0, gapopen, gapextend, d_recs, d_ref, d_mark, d_qry,
                       slot, nullptr);
+    ctx->d_bad = nullptr;
     if (rc != CRGPU_OK) { cudaStreamSynchronize(s); return rc; }
+    CK(launch_clear_bad_recs(d_recs, ctx->badbase.as<uint8_t>(), n, slot, s));
     if (mem == CRGPU_MEM_HOST) {
         CK(cudaMemcpyAsync(recs, d_recs, (size_t)n * sizeof(crgpu_aln_rec), cudaMemcpyDeviceToHost, s));
         if (want) {
@@ -981,7 +1032,7 @@ int crgpu_align(crgpu_ctx *ctx, int mem, const char *amplicon, int amplicon_len,
     return CRGPU_OK;
 }
 
-int crgpu_int_peak(crgpu_ctx *ctx, int which, double *lane_ops_per_s)
+static int int_peak_impl(crgpu_ctx *ctx, int which, double *lane_ops_per_s)
 {
     if (!ctx || !lane_ops_per_s) return CRGPU_E_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -1006,6 +1057,38 @@ int crgpu_int_peak(crgpu_ctx *ctx, int which, double *lane_ops_per_s)
     cudaEventDestroy(a); cudaEventDestroy(b);
     *lane_ops_per_s = best;
     return CRGPU_OK;
+}
+
+// ---- the exported entry points: device guard + "no work of a failed call is left running" (ApiGuard, crgpu_internal.h)
+int crgpu_sync(crgpu_ctx *ctx)
+{
+    if (!ctx) return CRGPU_E_ARG;
+    ApiGuard guard(ctx);
+    return guard.done(sync_impl(ctx));
+}
+
+int crgpu_qualfilter(crgpu_ctx *ctx, int mem, const uint8_t *qual, const int64_t *offsets, int64_t n,
+                     int min_mean_q, int min_single_q, uint8_t *keep)
+{
+    if (!ctx) return CRGPU_E_ARG;
+    ApiGuard guard(ctx);
+    return guard.done(qualfilter_impl(ctx, mem, qual, offsets, n, min_mean_q, min_single_q, keep));
+}
+
+int crgpu_align(crgpu_ctx *ctx, int mem, const char *amplicon, int amplicon_len,
+                const uint8_t *reads, const int64_t *offsets, int64_t n, double gapopen, double gapextend,
+                crgpu_aln_rec *recs, uint8_t *ref_out, uint8_t *mark_out, uint8_t *qry_out, int64_t slot)
+{
+    if (!ctx) return CRGPU_E_ARG;
+    ApiGuard guard(ctx);
+    return guard.done(align_impl(ctx, mem, amplicon, amplicon_len, reads, offsets, n, gapopen, gapextend, recs, ref_out, mark_out, qry_out, slot));
+}
+
+int crgpu_int_peak(crgpu_ctx *ctx, int which, double *lane_ops_per_s)
+{
+    if (!ctx) return CRGPU_E_ARG;
+    ApiGuard guard(ctx);
+    return guard.done(int_peak_impl(ctx, which, lane_ops_per_s));
 }
 
 }  // extern "C"

@@ -75,6 +75,10 @@ struct FillArgs {
     // traceback -- pair_list[0 .. *pair_list_n) holds their indices relative to p0 (null: every pair of the batch)
     const int32_t *pair_list = nullptr;
     const int *pair_list_n = nullptr;
+    // ... and, with sub_n > 0, only sub-strips sub_lo .. sub_lo + sub_n - 1 of those pairs (the rows right above the split
+    // of a shared-prefix run, for pairs whose amplicon alignments both took the shortcut: the HDR walk needs a few flags
+    // there before it meets the amplicon walk's path)
+    int sub_lo = 0, sub_n = 0;
 };
 
 // columns xlo-2 .. xlo+W of a sub-strip (W odd): the band pass reads xlo-1 .. xlo+W-1; k_gotoh_score2 stores both
@@ -128,18 +132,20 @@ struct WalkArgs {
                               // forward strand (CORE:1982-1990), left-aligned in the slot
     // Diagonal shortcut (DESIGN.md "Diagonal shortcut").  If the score of the start cell equals the sum of the
     // substitution scores along the diagonal through it, needle's traceback IS that diagonal (every cell on it has
-    // m == max(m,ix,iy)), so the alignment is emitted without any flag.  diag = 1 selects the probing kernel
-    // (k_traceback_walk<JOIN, true>): it emits the diagonal alignments, sets fast[read] |= fast_bit for them and
-    // need[pair - p0] (stored when need_or == 0, OR-ed otherwise) for pairs with a read it could not finish.
-    // diag = 0 (the walk over flags): skips reads with fast[read] & fast_bit, and -- with pair_list -- only visits the
-    // listed pairs (indices relative to p0).
-    int diag = 0;
+    // m == max(m,ix,iy)), so the alignment is emitted without any flag by k_diag_emit (one warp per read): it sets
+    // fast[read] |= fast_bit for those and need[pair - p0] = 1 (set to 2 by the caller beforehand) for pairs with a
+    // read it could not finish.  k_traceback_walk skips reads with fast[read] & fast_bit and -- with read_list -- only visits the listed
+    // alignments.
     uint8_t *fast = nullptr;  // [n reads] or null
     int fast_bit = 0;
-    uint8_t *need = nullptr;  // [p1 - p0] (diag = 1 only)
-    int need_or = 0;
-    const int32_t *pair_list = nullptr;   // diag = 0: pairs to walk, or null (all)
-    const int *pair_list_n = nullptr;
+    uint8_t *need = nullptr;  // [p1 - p0] (k_diag_emit only)
+    uint8_t *need_read = nullptr;         // [2 (p1 - p0)] (k_diag_emit only, zeroed by the caller): 1 = this alignment needs the walk
+    const int32_t *read_list = nullptr;   // k_traceback_walk: the alignments to walk, 2 (pair - p0) + half each, or null (all)
+    const int *read_list_n = nullptr;
+    // HDR walk over a shared prefix: !(upper_need[pair - p0] & 1) means both amplicon alignments of the pair took the
+    // shortcut and the amplicon pass wrote flags only for padded rows >= upper_lo; null: flags exist for every pair and row
+    const uint8_t *upper_need = nullptr;
+    int upper_lo = 0;
 };
 
 }  // namespace crgpu

@@ -55,6 +55,8 @@ struct crgpu_ctx {
     cudaStream_t stream2 = nullptr;      // traceback walks run here, overlapped with the next batch's fill
     cudaStream_t stream3 = nullptr;      // odd fill batches: their CTAs back-fill the SMs the previous fill's tail vacates
     cudaEvent_t ready = nullptr;
+    size_t l2_gran_prev = 0;             // CRGPU_L2_HINT: the device's L2 fetch granularity before crgpu_create changed it
+    bool l2_gran_set = false;
     cudaStream_t span_stream = nullptr;
     cudaEvent_t fill_done[2] = {nullptr, nullptr}, walk_done[2] = {nullptr, nullptr};
     size_t tb_budget = (size_t)8 << 30;
@@ -69,14 +71,18 @@ struct crgpu_ctx {
     DBuf join, joinb;                                                      // amplicon walk -> HDR walk join records (WalkArgs.join_out)
     DBuf prof_s, prof_hs;                                           // drifted profiles of the score pass
     DBuf btops[2], bleft[2], btops_h[2], bleft_h[2], escaped;      // banded two-pass fill (run_plan_band)
-    DBuf rowvals[2], rowvals_h[2];                                 // score pass: last-row values per column (k_lastrow_scan)
+    DBuf rowvals[2], rowvals_h[2];
+    // reads with a base outside ACGTN(U) are not aligned but reported per read: one byte per read of the CALL in flight
+    // (crgpu_align, crgpu_align_quantify), null otherwise (build_plan then fails the call)
+    DBuf badbase;
+    uint8_t *d_bad = nullptr;                                 // score pass: last-row values per column (k_lastrow_scan)
     int n_escaped[2] = {0, 0};                                     // reads re-aligned after the last banded call (amplicon, HDR)
     int band_holdoff = 0;                                          // calls left that skip the band (set when > 25 % of a call's reads escaped)
     int band_B = 16;                                               // band half-width in read columns; 0 = single-pass fill
     // diagonal shortcut of the banded fill (run_plan_band): alignments whose traceback is provably the diagonal through
     // the start cell are emitted right after the score pass; only the other pairs go through the band pass and the walk
     bool diag = true;
-    DBuf fastflags, need[2], plist[2], selscratch[2], need_cnt;
+    DBuf fastflags, need[2], plist[2], plist2[2], need_read[2], rlist[2], selscratch[2], need_cnt;
     int64_t n_diag_pairs[2] = {0, 0};                              // last call: pairs of the batches / pairs that needed the band pass
     DBuf q_in[8], q_out[4];
     DBuf aux[8];
@@ -150,6 +156,28 @@ inline void timing_collect(crgpu_ctx *c)
 
 #define fail crgpu_fail
 
+// Every exported entry point runs inside one of these: the context's device is made current for the call and the caller's
+// is restored afterwards; after a FAILED call everything it queued on the context's three streams is waited for, so that
+// nothing is still writing caller buffers (CRGPU_MEM_DEVICE) once the error has been returned.
+struct ApiGuard {
+    crgpu_ctx *c;
+    int prev = -1;
+    explicit ApiGuard(crgpu_ctx *ctx) : c(ctx)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != c->device) cudaSetDevice(c->device);
+    }
+    int done(int rc)
+    {
+        if (rc != CRGPU_OK) {
+            cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3);
+            cudaGetLastError();                       // (a sticky launch error has been reported through rc already)
+        }
+        return rc;
+    }
+    ~ApiGuard() { if (prev >= 0 && prev != c->device) cudaSetDevice(prev); }
+};
+
 namespace crgpu {
 bool choose_tile(int La, int *G, int *K);
 bool tile_available(int G, int K);
@@ -157,8 +185,10 @@ cudaError_t launch_fill(int G, int K, const FillArgs &a, int num_sms, cudaStream
 // pairs one resident wave of k_gotoh_score2<G,K,nsub> covers (0: no such kernel)
 int64_t score2_wave_pairs(int G, int K, int nsub, int num_sms);
 cudaError_t launch_encode(const uint8_t *reads, const int64_t *offsets, const int32_t *pair_lo, const int32_t *pair_hi,
-                          const int64_t *pc_off, int npairs, uint8_t *pc, int *err, int num_sms, cudaStream_t s);
+                          const int64_t *pc_off, int npairs, uint8_t *pc, int *err, uint8_t *bad, int num_sms, cudaStream_t s);
+cudaError_t launch_clear_bad_recs(crgpu_aln_rec *recs, const uint8_t *bad, int64_t n, int64_t slot, cudaStream_t s);
 cudaError_t launch_walk(const WalkArgs &a, cudaStream_t s);
+cudaError_t launch_diag_emit(const WalkArgs &a, cudaStream_t s);
 cudaError_t launch_qualfilter(const uint8_t *qual, const int64_t *offsets, int64_t n, int q, int sq, uint8_t *keep,
                               int num_sms, cudaStream_t s);
 cudaError_t launch_int_peak(int which, int num_sms, int iters, unsigned *sink, cudaStream_t s, double *lane_ops);

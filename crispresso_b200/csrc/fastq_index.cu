@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(128) k_fastq_gather(const uint8_t *__restrict_
 
 using namespace crgpu;
 
-extern "C" int crgpu_fastq_index(crgpu_ctx *ctx, int mem, const uint8_t *text, int64_t nbytes, int final_chunk,
+static int fastq_index_impl(crgpu_ctx *ctx, int mem, const uint8_t *text, int64_t nbytes, int final_chunk,
                                  crgpu_fastq_out *out)
 {
     if (!ctx) return CRGPU_E_ARG;
@@ -299,4 +299,13 @@ extern "C" int crgpu_fastq_index(crgpu_ctx *ctx, int mem, const uint8_t *text, i
     CK(cudaStreamSynchronize(s));
     timing_collect(ctx);
     return CRGPU_OK;
+}
+
+// the exported entry point: device guard + "no work of a failed call is left running" (ApiGuard, crgpu_internal.h)
+extern "C" int crgpu_fastq_index(crgpu_ctx *ctx, int mem, const uint8_t *text, int64_t nbytes, int final_chunk,
+                                 crgpu_fastq_out *out)
+{
+    if (!ctx) return CRGPU_E_ARG;
+    ApiGuard guard(ctx);
+    return guard.done(fastq_index_impl(ctx, mem, text, nbytes, final_chunk, out));
 }

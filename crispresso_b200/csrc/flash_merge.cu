@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(128) k_merge_emit(const EmitArgs a)
 
 using namespace crgpu;
 
-extern "C" int crgpu_flash_merge(crgpu_ctx *ctx, int mem, const uint8_t *seq1, const uint8_t *qual1, const int64_t *off1,
+static int flash_merge_impl(crgpu_ctx *ctx, int mem, const uint8_t *seq1, const uint8_t *qual1, const int64_t *off1,
                                  const uint8_t *seq2, const uint8_t *qual2, const int64_t *off2, int64_t n,
                                  const crgpu_merge_params *prm, crgpu_merge_out *out)
 {
@@ -389,4 +389,14 @@ extern "C" int crgpu_flash_merge(crgpu_ctx *ctx, int mem, const uint8_t *seq1, c
     out->bytes = total;
     timing_collect(ctx);
     return CRGPU_OK;
+}
+
+// the exported entry point: device guard + "no work of a failed call is left running" (ApiGuard, crgpu_internal.h)
+extern "C" int crgpu_flash_merge(crgpu_ctx *ctx, int mem, const uint8_t *seq1, const uint8_t *qual1, const int64_t *off1,
+                                 const uint8_t *seq2, const uint8_t *qual2, const int64_t *off2, int64_t n,
+                                 const crgpu_merge_params *prm, crgpu_merge_out *out)
+{
+    if (!ctx) return CRGPU_E_ARG;
+    ApiGuard guard(ctx);
+    return guard.done(flash_merge_impl(ctx, mem, seq1, qual1, off1, seq2, qual2, off2, n, prm, out));
 }

@@ -278,13 +278,15 @@ __global__ void __maxnreg__(fill_maxnreg<K / NSUB>()) k_gotoh_band(const FillArg
     const int W = a.band_W;
     const uint4 FREE = make_uint4(Z, NOPEN_ST, Z, 0u);
     // (diagonal shortcut: only the pairs that still need a traceback, FillArgs.pair_list)
-    const int64_t total = (int64_t)(a.pair_list ? *a.pair_list_n : a.p1 - a.p0) * G2;
+    // (... and, with sub_n > 0, only sub-strips sub_lo .. sub_lo + sub_n - 1 of those pairs)
+    const int G2run = a.sub_n > 0 ? a.sub_n : G2;
+    const int64_t total = (int64_t)(a.pair_list ? *a.pair_list_n : a.p1 - a.p0) * G2run;
 
     for (int64_t base = (int64_t)warp_global * 32; base < total; base += (int64_t)nwarps * 32) {
         const int64_t slot_id = base + lane;                              // (position in the list) * G2 + u
         const bool valid = slot_id < total;
-        const int pj = valid ? (int)(slot_id / G2) : 0;
-        const int u = valid ? (int)(slot_id - (int64_t)pj * G2) : 0;
+        const int pj = valid ? (int)(slot_id / G2run) : 0;
+        const int u = valid ? a.sub_lo + (int)(slot_id - (int64_t)pj * G2run) : 0;
         const int pr = (valid && a.pair_list) ? a.pair_list[pj] : pj;     // pair - p0
         const int64_t sub_id = (int64_t)pr * G2 + u;
         const int t = u / NSUB, hh = u - t * NSUB;
@@ -361,18 +363,17 @@ __global__ void __maxnreg__(fill_maxnreg<K / NSUB>()) k_gotoh_band(const FillArg
 // ---- host-side dispatch ----------------------------------------------------------------
 struct Tile { int G, K; };
 
+// (attribute + occupancy per call: both are per DEVICE, a process may hold contexts on several devices and drive them
+// from several threads, and the two runtime calls cost microseconds)
 template <typename Kern>
-static cudaError_t launch_persistent(Kern kern, bool &configured, int &blocks_per_sm, size_t smem, int64_t blocks_wanted,
-                                     const FillArgs &a, int num_sms, cudaStream_t stream)
+static cudaError_t launch_persistent(Kern kern, size_t smem, int64_t blocks_wanted, const FillArgs &a, int num_sms, cudaStream_t stream)
 {
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, 128, smem);
-        if (e != cudaSuccess) return e;
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-        configured = true;
-    }
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int blocks_per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, 128, smem);
+    if (e != cudaSuccess) return e;
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
     int64_t grid = blocks_wanted;
     const int cap = num_sms * blocks_per_sm;            // persistent: a multiple of the SM count
     if (grid > cap) grid = cap;
@@ -388,19 +389,12 @@ static cudaError_t launch_tile(const FillArgs &a, int num_sms, cudaStream_t stre
     const size_t smem = (size_t)NPAIR * prof_stride(G, K) * 4;
     const int npairs = a.p1 - a.p0;
     if (kind == 0) {
-        static bool configured = false; static int bps = 1;
         const int groups_per_block = 4 * (32 / G);
-        return launch_persistent(k_gotoh_fill<G, K>, configured, bps, smem, (npairs + groups_per_block - 1) / groups_per_block, a, num_sms, stream);
+        return launch_persistent(k_gotoh_fill<G, K>, smem, (npairs + groups_per_block - 1) / groups_per_block, a, num_sms, stream);
     }
-    if (a.band_K == K) {
-        static bool configured = false; static int bps = 1;
-        return launch_persistent(k_gotoh_band<G, K, 1>, configured, bps, smem, ((int64_t)npairs * G + 127) / 128, a, num_sms, stream);
-    }
+    if (a.band_K == K) return launch_persistent(k_gotoh_band<G, K, 1>, smem, ((int64_t)npairs * G + 127) / 128, a, num_sms, stream);
     if constexpr (K % 16 == 0) {
-        if (2 * a.band_K == K) {
-            static bool configured = false; static int bps = 1;
-            return launch_persistent(k_gotoh_band<G, K, 2>, configured, bps, smem, ((int64_t)npairs * G * 2 + 127) / 128, a, num_sms, stream);
-        }
+        if (2 * a.band_K == K) return launch_persistent(k_gotoh_band<G, K, 2>, smem, ((int64_t)npairs * G * 2 + 127) / 128, a, num_sms, stream);
     }
     return cudaErrorInvalidValue;
 }

@@ -11,7 +11,7 @@ cudaError_t launch_rows_to_ops(const uint8_t *ref, const uint8_t *mark, const ui
                                const int32_t *alnlen, int64_t n, uint32_t *ops, int64_t ops_stride, cudaStream_t s);
 cudaError_t launch_prepare_rows(const crgpu_aln_rec *ref, const crgpu_aln_rec *rep, int64_t n, double min_identity,
                                 int32_t *tenths_ref, int32_t *tenths_rep, int32_t *aln_off, int32_t *alnlen, uint8_t *unmod,
-                                uint8_t *flags_out, cudaStream_t s);
+                                uint8_t *flags_out, const uint8_t *bad, cudaStream_t s);
 cudaError_t launch_prepare_rc_rows(const crgpu_aln_rec *rc, const int32_t *rc_read, int64_t n, double min_identity,
                                    int32_t *tenths_ref, int32_t *aln_off, int32_t *alnlen, uint8_t *unmod, uint8_t *active,
                                    uint8_t *kept, cudaStream_t s);
@@ -93,7 +93,7 @@ using namespace crgpu;
 
 extern "C" {
 
-int crgpu_quantify(crgpu_ctx *ctx, int mem, const crgpu_quant_params *params,
+static int quantify_impl(crgpu_ctx *ctx, int mem, const crgpu_quant_params *params,
                    const uint8_t *ref_rows, const uint8_t *mark_rows, const uint8_t *qry_rows, int64_t slot,
                    const int32_t *aln_off, const int32_t *alnlen,
                    const int32_t *tenths_ref, const int32_t *tenths_rep, const uint8_t *unmodified_in,
@@ -180,7 +180,7 @@ static std::string revcomp_upper(const char *s, int n)
     return out;
 }
 
-int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int amplicon_len,
+static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, int amplicon_len,
                          const crgpu_path_params *path, const crgpu_quant_params *quant,
                          const uint8_t *reads, const int64_t *offsets, int64_t n, crgpu_path_out *out)
 {
@@ -192,6 +192,8 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
     if (n >= (int64_t)1 << 31) return fail(ctx, CRGPU_E_ARG, "too many reads in one call");
     const bool want_rows = out->ref_rows || out->mark_rows || out->qry_rows;
     if (want_rows && !(out->ref_rows && out->mark_rows && out->qry_rows)) return fail(ctx, CRGPU_E_ARG, "pass all three row buffers or none");
+    // (the caller sized its row buffers as n x slot: the library must not pick the slot for it, in either memory mode)
+    if (want_rows && out->slot <= 0) return fail(ctx, CRGPU_E_ARG, "out->slot must be set when rows are requested");
     const bool want_rc_rows = out->rc_ref_rows || out->rc_mark_rows || out->rc_qry_rows;
     if (want_rc_rows && !(out->rc_ref_rows && out->rc_mark_rows && out->rc_qry_rows)) return fail(ctx, CRGPU_E_ARG, "pass all three rc row buffers or none");
     const bool has_hdr = path->hdr_amplicon != nullptr && path->hdr_amplicon_len > 0;
@@ -216,6 +218,11 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
         CK(cudaMemcpyAsync(ctx->offsets.p, offsets, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, s));
         d_reads = ctx->reads.as<uint8_t>(); d_off = ctx->offsets.as<int64_t>();
     }
+    // reads with a base outside ACGTN(U) are flagged here by every build_plan of this call and reported through kept bit 3
+    CK(ctx->badbase.reserve((size_t)n));
+    CK(cudaMemsetAsync(ctx->badbase.p, 0, (size_t)n, s));
+    struct BadScope { crgpu_ctx *c; ~BadScope() { c->d_bad = nullptr; } } bad_scope{ctx};
+    ctx->d_bad = ctx->badbase.as<uint8_t>();
     // pairing plan of the whole read set: shared by the amplicon and the HDR-amplicon pass
     int rc = build_plan(ctx, d_reads, d_off, nullptr, n);
     if (rc) { cudaStreamSynchronize(s); return rc; }
@@ -350,7 +357,8 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
     int32_t *d_aln_off = ctx->q_in[1].as<int32_t>(), *d_alnlen = ctx->q_in[2].as<int32_t>(), *d_tref = ctx->q_in[3].as<int32_t>();
     uint8_t *d_unmod = ctx->q_in[5].as<uint8_t>();
     span_begin(ctx, T_OTHER);
-    CK(launch_prepare_rows(d_aln, d_aln_hdr, n, path->min_identity_score, d_tref, d_trep, d_aln_off, d_alnlen, d_unmod, d_kept, s));
+    CK(launch_prepare_rows(d_aln, d_aln_hdr, n, path->min_identity_score, d_tref, d_trep, d_aln_off, d_alnlen, d_unmod, d_kept,
+                           ctx->d_bad, s));
     span_end(ctx);
 
     // reads with score_ref < min_identity, in read order: compacted on the device (cub::DeviceSelect),
@@ -526,6 +534,29 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
     out->n_cells_computed += cells_computed;
     timing_collect(ctx);
     return CRGPU_OK;
+}
+
+// ---- the exported entry points: device guard + "no work of a failed call is left running" (ApiGuard, crgpu_internal.h)
+int crgpu_quantify(crgpu_ctx *ctx, int mem, const crgpu_quant_params *params,
+                   const uint8_t *ref_rows, const uint8_t *mark_rows, const uint8_t *qry_rows, int64_t slot,
+                   const int32_t *aln_off, const int32_t *alnlen,
+                   const int32_t *tenths_ref, const int32_t *tenths_rep, const uint8_t *unmodified_in,
+                   int64_t n, crgpu_read_rec *out_recs,
+                   int64_t *vectors, int64_t *hist_inframe, int64_t *hist_frameshift, int32_t hist_len,
+                   int32_t hist_zero, int64_t *counters)
+{
+    if (!ctx) return CRGPU_E_ARG;
+    ApiGuard guard(ctx);
+    return guard.done(quantify_impl(ctx, mem, params, ref_rows, mark_rows, qry_rows, slot, aln_off, alnlen, tenths_ref, tenths_rep, unmodified_in, n, out_recs, vectors, hist_inframe, hist_frameshift, hist_len, hist_zero, counters));
+}
+
+int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int amplicon_len,
+                         const crgpu_path_params *path, const crgpu_quant_params *quant,
+                         const uint8_t *reads, const int64_t *offsets, int64_t n, crgpu_path_out *out)
+{
+    if (!ctx) return CRGPU_E_ARG;
+    ApiGuard guard(ctx);
+    return guard.done(align_quantify_impl(ctx, mem, amplicon, amplicon_len, path, quant, reads, offsets, n, out));
 }
 
 }  // extern "C"

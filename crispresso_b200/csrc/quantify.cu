@@ -295,13 +295,20 @@ cudaError_t launch_quantify(const QuantArgs &a, cudaStream_t s)
 
 // From the alignment records of the forward pass(es): SoA views the quantifier wants plus the
 // keep / rescue decision of CORE:1843-1871.  flags_out[i]: bit0 = forward row kept, bit2 = goes to
-// the reverse-complement rescue (score_ref < min_identity).
+// the reverse-complement rescue (score_ref < min_identity), bit3 = not aligned (a base outside ACGTN(U)).
 __global__ void k_prepare_rows(const crgpu_aln_rec *__restrict__ ref, const crgpu_aln_rec *__restrict__ rep, int64_t n,
                                double min_identity, int32_t *tenths_ref, int32_t *tenths_rep, int32_t *aln_off,
-                               int32_t *alnlen, uint8_t *unmod, uint8_t *flags_out)
+                               int32_t *alnlen, uint8_t *unmod, uint8_t *flags_out, const uint8_t *__restrict__ bad)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (bad && bad[i]) {
+        // a base outside ACGTN(U): the read was not aligned (k_encode_pairs); bit3 reports it, nothing else looks at it
+        tenths_ref[i] = 0; if (tenths_rep) tenths_rep[i] = -1;
+        aln_off[i] = 0; alnlen[i] = 0; unmod[i] = 0;
+        if (flags_out) flags_out[i] = 8;
+        return;
+    }
     const int tr = ref[i].tenths;
     const int tp = rep ? rep[i].tenths : -1;
     tenths_ref[i] = tr;
@@ -336,11 +343,11 @@ __global__ void k_prepare_rc_rows(const crgpu_aln_rec *__restrict__ rc, const in
 
 cudaError_t launch_prepare_rows(const crgpu_aln_rec *ref, const crgpu_aln_rec *rep, int64_t n, double min_identity,
                                 int32_t *tenths_ref, int32_t *tenths_rep, int32_t *aln_off, int32_t *alnlen, uint8_t *unmod,
-                                uint8_t *flags_out, cudaStream_t s)
+                                uint8_t *flags_out, const uint8_t *bad, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
     k_prepare_rows<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(ref, rep, n, min_identity, tenths_ref, tenths_rep, aln_off,
-                                                              alnlen, unmod, flags_out);
+                                                              alnlen, unmod, flags_out, bad);
     return cudaGetLastError();
 }
 

@@ -30,26 +30,44 @@ __device__ __forceinline__ int ednafull(int ca, int cb)
     return ca == cb ? 5 : -4;
 }
 
-// One warp per pair: pc[pc_off[p]+x] = code(lo[x]) + 5*code(hi[x]); a base outside ACGTN(U)
-// raises *err (the call then fails with CRGPU_E_ALIGN -- no silent substitution).
+// One warp per pair: pc[pc_off[p]+x] = code(lo[x]) + 5*code(hi[x]).  A base outside ACGTN(U) -- an IUPAC ambiguity code,
+// which needle would score with EDNAFULL's ambiguity rows -- is not aligned: bad[read] = 1 and the read is reported
+// (kept bit 3 / an empty record, include/crgpu.h); it is encoded as A so that the pass over its pair stays defined.
+// Without `bad` the call fails with CRGPU_E_ALIGN (*err) -- no silent substitution either way.
 __global__ void k_encode_pairs(const uint8_t *__restrict__ reads, const int64_t *__restrict__ offsets,
                                const int32_t *__restrict__ pair_lo, const int32_t *__restrict__ pair_hi,
-                               const int64_t *__restrict__ pc_off, int npairs, uint8_t *__restrict__ pc, int *err)
+                               const int64_t *__restrict__ pc_off, int npairs, uint8_t *__restrict__ pc, int *err,
+                               uint8_t *__restrict__ bad)
 {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int p = warp; p < npairs; p += nwarps) {
-        const uint8_t *lo = reads + offsets[pair_lo[p]];
-        const uint8_t *hi = reads + offsets[pair_hi[p]];
+        const int rl = pair_lo[p], rh = pair_hi[p];
+        const uint8_t *lo = reads + offsets[rl];
+        const uint8_t *hi = reads + offsets[rh];
         const int64_t o = pc_off[p];
         const int len = (int)(pc_off[p + 1] - o);
         for (int x = lane; x < len; x += 32) {
-            const int cl = base_code(lo[x]), ch = base_code(hi[x]);
-            if (cl < 0 || ch < 0) { atomicOr(err, 1); pc[o + x] = 0; }
-            else pc[o + x] = (uint8_t)(cl + NCODE * ch);
+            int cl = base_code(lo[x]), ch = base_code(hi[x]);
+            if (cl < 0 || ch < 0) {
+                if (bad) { if (cl < 0) bad[rl] = 1; if (ch < 0) bad[rh] = 1; }
+                else atomicOr(err, 1);
+                cl = cl < 0 ? 0 : cl; ch = ch < 0 ? 0 : ch;
+            }
+            pc[o + x] = (uint8_t)(cl + NCODE * ch);
         }
     }
+}
+
+// crgpu_align: a read that was not aligned (bad[read]) comes back as an empty record (alnlen 0, identity 0, aln_off = slot)
+__global__ void k_clear_bad_recs(crgpu_aln_rec *recs, const uint8_t *__restrict__ bad, int64_t n, int64_t slot)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !bad[i]) return;
+    crgpu_aln_rec r = recs[i];
+    r.score = 0.f; r.alnlen = 0; r.ident = 0; r.tenths = 0; r.aln_off = (int32_t)slot; r.start1 = -1; r.start2 = -1;
+    recs[i] = r;
 }
 
 // reverse_complement() of the reference upper-cases and complements (CORE:141-144)
@@ -82,32 +100,24 @@ __device__ int row0_ix(const uint8_t *b, int ca0, int j, int open, int ext, int 
 // JOIN: 0 = plain walk; 1 = amplicon walk that records where it crosses WalkArgs.join_row; 2 = HDR walk (identity only:
 // no text rows, no ops) that joins the amplicon walk's remainder there.  Separate instantiations keep each at 56 registers.
 //
-// DIAG (the diagonal shortcut): the probing kernel.  Claim: if the score of needle's start cell c_n equals
-// D_n, the sum of the substitution scores along the diagonal c_0 (on row 0 or column 0) .. c_n, the traceback is that
-// diagonal.  Proof: m[c_0] = S_0 (end gaps are free, App. A.2) and m[c_i] = S_i + max3[c_{i-1}] >= S_i + m[c_{i-1}]
-// (A.3), so m[c_i] >= D_i; max3[c_n] = D_n then forces max3[c_i] = m[c_i] = D_i all the way down (a larger max3
-// anywhere would propagate into m[c_n] > D_n).  The walk starts with prev = 0 and takes the diagonal whenever
-// m >= ix and m >= iy (A.4), which keeps prev = 0.  Such an alignment is emitted here by the walk loop itself running
-// on all-zero flags -- no flag byte is read, and the band pass never has to produce one for it.
-template <int JOIN, bool DIAG>
+// Reads the diagonal shortcut already emitted (WalkArgs.fast) are skipped; with WalkArgs.read_list only the listed
+// alignments of the batch are visited.
+template <int JOIN>
 __global__ void __launch_bounds__(128, 9) k_traceback_walk(const WalkArgs a)     // 9 CTAs/SM = at most 56 registers
 {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int npairs = a.p1 - a.p0;
-    int pj = idx >> 1;                                   // pair of the batch (relative to p0)
-    bool live = pj < npairs;
-    if (!DIAG && a.pair_list) {
-        live = pj < *a.pair_list_n;
-        pj = live ? a.pair_list[pj] : 0;
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.read_list) {
+        if (idx >= *a.read_list_n) return;
+        idx = a.read_list[idx];
     }
-    if (!DIAG && !live) return;
-    const int p = a.p0 + (live ? pj : 0);
+    const int pj = idx >> 1;                             // pair of the batch (relative to p0)
+    if (pj >= a.p1 - a.p0) return;
+    const int p = a.p0 + pj;
     const int h = idx & 1;
     const int rlo = a.pair_lo[p], rhi = a.pair_hi[p];
-    if (h && rhi == rlo) live = false;
-    if (!DIAG && !live) return;
+    if (h && rhi == rlo) return;
     const int r = h ? rhi : rlo;
-    if (!DIAG && a.fast && (a.fast[r] & a.fast_bit)) return;       // emitted by the probing kernel
+    if (a.fast && (a.fast[r] & a.fast_bit)) return;                // emitted by k_diag_emit
     const int La = a.La, Lb = a.plen[p];
     const uint8_t *b = a.reads + a.offsets[r];
     const uint8_t *amp = a.amplicon;
@@ -130,24 +140,6 @@ __global__ void __launch_bounds__(128, 9) k_traceback_walk(const WalkArgs a)    
     for (int t = 0; t < a.G; ++t) {
         const int v = half16(lc[3 * t], h);
         if (v > best) { best = v; s1 = a.split_row + t * a.K + (int)lc[3 * t + 1 + h] - a.P; s2 = Lb - 1; }
-    }
-
-    if (DIAG) {
-        // every thread of the warp votes (no early return above): the two reads of a pair are neighbouring lanes
-        bool isdiag = false;
-        if (live) {
-            const int len = (s1 < s2 ? s1 : s2) + 1;
-            int sum = 0;
-            for (int j = 0; j < len; ++j) sum += ednafull(base_code(amp[s1 - j]), base_code(b[s2 - j]));
-            isdiag = sum * a.scale + BIAS == best;
-        }
-        const unsigned votes = __ballot_sync(0xffffffffu, live && !isdiag);
-        if (!(threadIdx.x & 1) && pj < npairs) {
-            const uint8_t v = (uint8_t)((votes >> (threadIdx.x & 30)) & 3u ? 1 : 0);
-            if (a.need_or) a.need[pj] |= v; else a.need[pj] = v;
-        }
-        if (!isdiag) return;
-        a.fast[r] |= (uint8_t)a.fast_bit;
     }
 
     const bool want = JOIN != 2 && a.ref_out != nullptr;
@@ -189,8 +181,13 @@ __global__ void __launch_bounds__(128, 9) k_traceback_walk(const WalkArgs a)    
     const int P = a.P;
     // flag byte of cell (yy, xx).  Banded fill: sub-strip u = padded row / band_K holds columns [u*band_K - P - B, +W) only;
     // anything else reads as 0xff (never a flag byte), which ends the walk with an escape when it is consumed.
+    // (HDR walk of a pair whose amplicon alignments were both emitted by the diagonal shortcut: the amplicon pass made flags
+    //  only for the rows right above the split.  Such a walk meets the amplicon alignment's diagonal -- and ends at a join
+    //  checkpoint -- within a few rows; otherwise the escape marker sends the read to the full fill.)
+    const int upper_lo = (a.upper_need && !(a.upper_need[pair_rel] & 1)) ? a.upper_lo : 0;
     auto tb_at = [&](int yy, int xx) -> uint8_t {
         const int v = yy + P;
+        if (v < upper_lo) return (uint8_t)0xff;
         if (band) {
             const int tf = (int)__umulhi((unsigned)v, a.kdiv_magic);           // sub-strip
             const int rr = v - tf * a.band_K;
@@ -211,8 +208,7 @@ __global__ void __launch_bounds__(128, 9) k_traceback_walk(const WalkArgs a)    
     // a LEFT / DOWN step invalidates the window and refills it with PF independent loads.
     constexpr int PF = 8;
     uint8_t pf[PF];
-    // (DIAG: the alignment is known to be the diagonal through the start cell -- every flag on it reads as 0)
-#define PF_LOAD(k) pf[k] = (!DIAG && y - (k) >= 0 && x - (k) >= 0) ? tb_at(y - (k), x - (k)) : (uint8_t)0
+#define PF_LOAD(k) pf[k] = (y - (k) >= 0 && x - (k) >= 0) ? tb_at(y - (k), x - (k)) : (uint8_t)0
 #pragma unroll
     for (int k = 0; k < PF; ++k) PF_LOAD(k);
     // Join with the amplicon walk of the same read above the shared-prefix row (WalkArgs.join_row).  The amplicon walk
@@ -265,11 +261,9 @@ __global__ void __launch_bounds__(128, 9) k_traceback_walk(const WalkArgs a)    
             if (want) { ro[dirn * n] = OUTC(ca); mo[dirn * n] = same ? '|' : '.'; qo[dirn * n] = OUTC(cb); }
             EMIT_OP(same ? 0 : 1);
             ++n; --x; --y;
-            if (!DIAG) {
 #pragma unroll
-                for (int k = 0; k < PF - 1; ++k) pf[k] = pf[k + 1];
-                PF_LOAD(PF - 1);
-            }
+            for (int k = 0; k < PF - 1; ++k) pf[k] = pf[k + 1];
+            PF_LOAD(PF - 1);
         } else if (dir == 1) {
             // the next cell (y, x-1) continues LEFT iff ix[y,x-1] - gex(y) == ix[y,x].  The fill
             // kernel evaluates that with gex = gapextend except on amplicon row La-1; needle uses
@@ -430,13 +424,149 @@ cudaError_t launch_build_pairs(const void *segs, int nseg, int np, const int32_t
 
 // ---- launch wrappers (called from crgpu_api.cu) -------------------------------------------
 cudaError_t launch_encode(const uint8_t *reads, const int64_t *offsets, const int32_t *pair_lo, const int32_t *pair_hi,
-                          const int64_t *pc_off, int npairs, uint8_t *pc, int *err, int num_sms, cudaStream_t s)
+                          const int64_t *pc_off, int npairs, uint8_t *pc, int *err, uint8_t *bad, int num_sms, cudaStream_t s)
 {
     int grid = (npairs + 3) / 4;
     if (grid > num_sms * 16) grid = num_sms * 16;
     if (grid < 1) grid = 1;
-    k_encode_pairs<<<grid, 128, 0, s>>>(reads, offsets, pair_lo, pair_hi, pc_off, npairs, pc, err);
+    k_encode_pairs<<<grid, 128, 0, s>>>(reads, offsets, pair_lo, pair_hi, pc_off, npairs, pc, err, bad);
     return cudaGetLastError();
+}
+
+cudaError_t launch_clear_bad_recs(crgpu_aln_rec *recs, const uint8_t *bad, int64_t n, int64_t slot, cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    k_clear_bad_recs<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(recs, bad, n, slot);
+    return cudaGetLastError();
+}
+
+// Diagonal shortcut (DESIGN.md "Diagonal shortcut"), one WARP per read.  Claim: if the score of needle's start cell
+// c_n equals D_n, the sum of the substitution scores along the diagonal c_0 (on row 0 or column 0) .. c_n, the
+// traceback is that diagonal.  Proof: m[c_0] = S_0 (end gaps are free, App. A.2) and m[c_i] = S_i + max3[c_{i-1}] >=
+// S_i + m[c_{i-1}] (A.3), so m[c_i] >= D_i; max3[c_n] = D_n then forces max3[c_i] = m[c_i] = D_i all the way down (a
+// larger max3 anywhere would propagate into m[c_n] > D_n).  The walk starts with prev = 0 and takes the diagonal
+// whenever m >= ix and m >= iy (A.4), which keeps prev = 0.
+// One pass over the candidate alignment, 32 columns at a time, in the order k_traceback_walk emits them (App. A.5:
+// trailing end gaps, the diagonal, leading end gaps): it sums the diagonal's scores and writes ops / text rows as it goes;
+// when the sum confirms the claim the record, fast[read] |= fast_bit and (JOIN = 1) the walk's join records follow --
+// state 0x100 = previous move diagonal at every checkpoint row on the path.  Otherwise need[pair - p0] = 1 and
+// need_read[2 (pair - p0) + half] = 1: k_traceback_walk rewrites everything this kernel wrote for the read.
+template <int JOIN>
+__global__ void __launch_bounds__(256) k_diag_emit(const WalkArgs a)
+{
+    __shared__ int8_t lut[256];                                    // byte -> base code (one entry per thread)
+    lut[threadIdx.x] = (int8_t)base_code((uint8_t)threadIdx.x);
+    __syncthreads();
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int pj = w >> 1, h = w & 1;
+    if (pj >= a.p1 - a.p0) return;
+    const int p = a.p0 + pj;
+    const int rlo = a.pair_lo[p], rhi = a.pair_hi[p];
+    if (h && rhi == rlo) return;
+    const int r = h ? rhi : rlo;
+    const int La = a.La, Lb = a.plen[p];
+    const uint8_t *b = a.reads + a.offsets[r];
+    const uint8_t *amp = a.amplicon;
+    // start cell, as k_traceback_walk combines it: lane t looks at lane t's column summary, the warp keeps the first maximum
+    int best = half16(a.lastrow[(int64_t)pj * 3], h), s1 = La - 1, s2 = (int)a.lastrow[(int64_t)pj * 3 + 1 + h];
+    {
+        const int nu = a.tb_upper ? a.split_row / a.K : 0;         // lanes of the pass that owns the rows above the split
+        int v = -1, row = 0;
+        if (lane < nu) {
+            const uint32_t *q = a.lastcol_upper + ((int64_t)pj * a.G_upper + lane) * 3;
+            v = half16(q[0], h); row = lane * a.K + (int)q[1 + h] - a.P;
+        } else if (lane < nu + a.G) {
+            const uint32_t *q = a.lastcol + ((int64_t)pj * a.G + (lane - nu)) * 3;
+            v = half16(q[0], h); row = a.split_row + (lane - nu) * a.K + (int)q[1 + h] - a.P;
+        }
+        // strictly greater than the last row's best and than every earlier lane's: max value, then the lowest lane
+        const unsigned key = v > best ? ((unsigned)v << 8) | (unsigned)(255 - lane) : 0u;
+        const unsigned top = __reduce_max_sync(0xffffffffu, key);
+        if (top) {
+            const int src = 255 - (int)(top & 0xffu);
+            best = (int)(top >> 8); s1 = __shfl_sync(0xffffffffu, row, src); s2 = Lb - 1;
+        }
+    }
+    const int len = (s1 < s2 ? s1 : s2) + 1;                        // cells of the diagonal through the start cell
+
+    const bool want = a.ref_out != nullptr;
+    const int64_t slot = a.slot;
+    const int64_t orow = a.out_index ? a.out_index[r] : r;
+    const bool rc = a.rc_out != 0;
+    const int dirn = rc ? 1 : -1;
+    const int64_t first = rc ? 0 : slot - 1;
+    uint8_t *ro = want ? a.ref_out + orow * slot + first : nullptr;
+    uint8_t *mo = want ? a.mark_out + orow * slot + first : nullptr;
+    uint8_t *qo = want ? a.qry_out + orow * slot + first : nullptr;
+    uint32_t *opo = a.ops_out ? a.ops_out + orow * a.ops_stride : nullptr;
+    // columns in walk order (0 = the alignment's right end): T1 read bases opposite gaps, T2 amplicon bases opposite
+    // gaps (one of the two is empty: the start cell is on the last row or the last column), the diagonal, then the
+    // leftover read bases, then the leftover amplicon bases (again one of them is empty)
+    const int T1 = Lb - 1 - s2, T2 = La - 1 - s1, L1 = s2 + 1 - len;
+    const int d0 = T1 + T2, d1 = d0 + len, e1 = d1 + L1, n = e1 + (s1 + 1 - len);
+    // join checkpoints: rows ck_y0, ck_y0 - CK, ...; checkpoint k sits on diagonal cell j = jk0 + k CK (column d0 + j)
+    const int jk0 = s1 - (a.join_row - 1 - a.P);
+    int ck_ident = 0;                                               // lane k: identities before checkpoint k's cell
+    int ident = 0, sum = 0;
+    for (int c0 = 0; c0 < n; c0 += 32) {
+        const int c = c0 + lane;
+        int op = 0;
+        uint8_t ca = '-', cb = '-';
+        bool same = false;
+        if (c < n) {
+            if (c < T1) { op = 2; cb = b[Lb - 1 - c]; }
+            else if (c < d0) { op = 3; ca = amp[La - 1 - (c - T1)]; }
+            else if (c < d1) {
+                ca = amp[s1 - (c - d0)]; cb = b[s2 - (c - d0)];
+                const int xa = lut[ca], xb = lut[cb];
+                same = xa == xb;
+                op = same ? 0 : 1;
+                sum += (xa == 4 || xb == 4) ? (same ? -1 : -2) : (same ? 5 : -4);
+            }
+            else if (c < e1) { op = 2; cb = b[s2 - len - (c - d1)]; }
+            else { op = 3; ca = amp[s1 - len - (c - e1)]; }
+            if (want) {
+                ro[dirn * c] = (ca == '-' || !rc) ? ca : comp_upper(ca);
+                mo[dirn * c] = op >= 2 ? ' ' : (same ? '|' : '.');
+                qo[dirn * c] = (cb == '-' || !rc) ? cb : comp_upper(cb);
+            }
+        }
+        const unsigned eq = __ballot_sync(0xffffffffu, same);
+        if (JOIN == 1 && lane < JOIN_NCK) {
+            const int cc = d0 + jk0 + lane * JOIN_CK;               // column of checkpoint `lane`
+            if (cc >= c0 && cc < c0 + 32) ck_ident = ident + __popc(eq & ((1u << (cc - c0)) - 1u));
+        }
+        ident += __popc(eq);
+        const unsigned word = __reduce_or_sync(lane < 16 ? 0x0000ffffu : 0xffff0000u, (unsigned)op << ((lane & 15) * 2));
+        if (opo && (lane & 15) == 0 && c < n) opo[c >> 4] = word;
+    }
+    sum = __reduce_add_sync(0xffffffffu, sum);
+    if (sum * a.scale + BIAS != best) {
+        if (lane == 0) { a.need[pj] = 1; if (a.need_read) a.need_read[2 * pj + h] = 1; }      // (need: set to 2 by the caller beforehand)
+        return;
+    }
+    if (JOIN == 1) {
+        int32_t *jrec = a.join_out + ((int64_t)pj * 2 + h) * JOIN_STRIDE;
+        if (lane < JOIN_NCK) {
+            // the walk is about to consume the diagonal cell of the checkpoint row: (x, state, columns so far, identities so far)
+            const int j = jk0 + lane * JOIN_CK, y = s1 - j, x = s2 - j;
+            if (j >= 0 && y >= 0 && x >= 0) *reinterpret_cast<int4 *>(jrec + 4 + 4 * lane) = make_int4(x, 0x100, d0 + j, ck_ident);
+        }
+        if (lane == 0) *reinterpret_cast<int2 *>(jrec) = make_int2(n, ident);
+    }
+    if (lane != 0) return;
+    a.fast[r] |= (uint8_t)a.fast_bit;
+    crgpu_aln_rec rec;
+    rec.score = (float)(best - BIAS) / (float)a.scale;
+    rec.alnlen = n;
+    rec.ident = ident;
+    const float fpct = __fdiv_rn(100.0f * (float)ident, (float)n);     // App. B.3, as in k_traceback_walk
+    rec.tenths = __double2int_rn((double)fpct * 10.0);
+    rec.aln_off = rc ? 0 : (int32_t)(slot - n);
+    rec.start1 = s1;
+    rec.start2 = s2;
+    rec.read_len = Lb;
+    reinterpret_cast<crgpu_aln_rec *>(a.recs)[orow] = rec;
 }
 
 cudaError_t launch_walk(const WalkArgs &a, cudaStream_t s)
@@ -444,19 +574,26 @@ cudaError_t launch_walk(const WalkArgs &a, cudaStream_t s)
     const int nthreads = 2 * (a.p1 - a.p0);
     if (nthreads <= 0) return cudaSuccess;
     const int grid = (nthreads + 127) / 128;
-    if (a.diag) {
-        // probing kernel of the diagonal shortcut; an amplicon alignment it emits still leaves its join records
-        if (!a.fast || !a.need) return cudaErrorInvalidValue;
-        if (a.join_row > 0 && a.join_out) k_traceback_walk<1, true><<<grid, 128, 0, s>>>(a);
-        else k_traceback_walk<0, true><<<grid, 128, 0, s>>>(a);
-    }
-    else if (a.join_row > 0 && a.join_out) k_traceback_walk<1, false><<<grid, 128, 0, s>>>(a);
+    if (a.join_row > 0 && a.join_out) k_traceback_walk<1><<<grid, 128, 0, s>>>(a);
     else if (a.join_row > 0 && a.join_in && !a.ref_out && !a.ops_out) {
         WalkArgs b = a;
         b.join_out = const_cast<int32_t *>(a.join_in);          // one pointer in the kernel: JOIN 1 writes it, JOIN 2 reads it
-        k_traceback_walk<2, false><<<grid, 128, 0, s>>>(b);
+        k_traceback_walk<2><<<grid, 128, 0, s>>>(b);
     }
-    else k_traceback_walk<0, false><<<grid, 128, 0, s>>>(a);
+    else k_traceback_walk<0><<<grid, 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+// probing kernel of the diagonal shortcut (a.need zeroed by the caller); an amplicon alignment it emits still leaves
+// its join records
+cudaError_t launch_diag_emit(const WalkArgs &a, cudaStream_t s)
+{
+    const int64_t nwarps = 2 * (int64_t)(a.p1 - a.p0);
+    if (nwarps <= 0) return cudaSuccess;
+    if (!a.fast || !a.need) return cudaErrorInvalidValue;
+    const int grid = (int)((nwarps + 7) / 8);
+    if (a.join_row > 0 && a.join_out) k_diag_emit<1><<<grid, 256, 0, s>>>(a);
+    else k_diag_emit<0><<<grid, 256, 0, s>>>(a);
     return cudaGetLastError();
 }
 

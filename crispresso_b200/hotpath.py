@@ -137,6 +137,11 @@ class Reductions:
         return np.concatenate([self.vectors.ravel(), self.hist_inframe, self.hist_frameshift, self.counters,
                                self.class_counts, np.array([self.n_total, self.n_cells, self.n_cells_computed], np.int64)])
 
+    def results(self):
+        """flat() without n_cells_computed: the cells the kernels evaluated are a work counter that depends on how the
+        reads were batched (band decision, diagonal shortcut), not a result."""
+        return self.flat()[:-1]
+
     def load_flat(self, v):
         v = np.asarray(v, dtype=np.int64)
         o = 0
@@ -257,9 +262,16 @@ def process_df_chunk(chunk_input, ctx, INCLUDE_IDXS, LEN_AMPLICON, EXON_POSITION
             red.counter("non_modified_non_frameshift"), red.counter("splicing_sites_modified"))
 
 
-HotPathResult = namedtuple("HotPathResult", [
-    "kept", "aln", "tenths_rep", "recs", "rows", "slot", "rc_read", "rc_aln", "rc_recs", "rc_rows", "red",
-    "allele_row", "allele_count", "allele_n"], defaults=(None, None, 0))
+class HotPathResult(namedtuple("HotPathResult", [
+        "kept", "aln", "tenths_rep", "recs", "rows", "slot", "rc_read", "rc_aln", "rc_recs", "rc_rows", "red",
+        "allele_row", "allele_count", "allele_n"], defaults=(None, None, 0))):
+    __slots__ = ()
+
+    @property
+    def bad_base(self):
+        """1 where a read had a base outside ACGTN(U): such a read is not aligned and takes part in no count (needle would
+        score an IUPAC ambiguity code with EDNAFULL's ambiguity rows; kept bit 3, include/crgpu.h)."""
+        return (self.kept >> 3) & 1
 
 
 def run_hot_path(ctx, amplicon, reads, gapopen=10.0, gapextend=0.5, min_identity_score=60.0, hdr_amplicon=None,

@@ -17,12 +17,12 @@ out = {"kept": torch.zeros(n, dtype=torch.uint8, device="cuda"), "aln": torch.ze
        "recs": torch.zeros(n * 16, dtype=torch.uint8, device="cuda"), "tenths_rep": torch.zeros(n, dtype=torch.int32, device="cuda")}
 ptrs = {k: v.data_ptr() for k, v in out.items()}
 torch.cuda.synchronize()
-for hdr_on in (True, False):
-    for diag in ((False, True) if "--diag" in sys.argv else (False,)):
+for hdr_on in ((True,) if "--hdr-only" in sys.argv else (True, False)):
+    for diag in ((True,) if "--diag-only" in sys.argv else (False, True) if "--diag" in sys.argv else (False,)):
         ctx.set_diag_shortcut(diag)
         best = None
         wall = 1e9
-        for it in range(4):
+        for it in range(1 if "--once" in sys.argv else 4):
             t0 = time.perf_counter()
             hotpath.run_hot_path(ctx, amp, None, hdr_amplicon=hdr if hdr_on else None, flags=flags if hdr_on else hotpath.quant_flags(""), inc=inc,
                                  device_inputs=(d_buf.data_ptr(), d_off.data_ptr(), n, La, ptrs))

@@ -106,8 +106,11 @@ def test_batching_is_invisible(ctx):
 
 
 def test_errors_are_loud(ctx):
+    # a read with an IUPAC code outside ACGTN(U) is not aligned, and says so: an empty record, the other reads unaffected
+    recs, r, m, q = aligner.needle_align(ctx, "ACGTACGTAC", ["ACGTRYACGT", "ACGTACGTAC"])
+    assert (int(recs["alnlen"][0]), r[0], q[0]) == (0, "", "") and (int(recs["tenths"][1]), q[1]) == (1000, "ACGTACGTAC")
     with pytest.raises(CrgpuError):
-        aligner.needle_align(ctx, "ACGTACGTAC", ["ACGTRYACGT"])          # IUPAC code outside ACGTN
+        aligner.needle_align(ctx, "ACGTRCGTAC", ["ACGTACGTAC"])          # ... in the AMPLICON it is an argument error
     with pytest.raises(CrgpuError):
         aligner.needle_align(ctx, "ACGTACGTAC", ["A"])                   # shorter than CRGPU_MIN_LEN
     with pytest.raises(CrgpuError):

@@ -102,7 +102,7 @@ def test_cfg2_full_size_properties(ctx):
     red = hotpath.Reductions(250)
     hotpath.run_hot_path(ctx, amp, (buf[:off[h]], off[:h + 1]), hdr_amplicon=hdr, flags=flags, inc=inc, red=red)
     hotpath.run_hot_path(ctx, amp, (buf[off[h]:], off[h:] - off[h]), hdr_amplicon=hdr, flags=flags, inc=inc, red=red)
-    assert np.array_equal(red.flat(), res.red.flat())
+    assert np.array_equal(red.results(), res.red.results())
 
 
 def test_chunked_run_equals_single_call_and_large_600bp_batch(ctx):
@@ -113,5 +113,5 @@ def test_chunked_run_equals_single_call_and_large_600bp_batch(ctx):
     inc = hotpath.include_mask(600, hotpath.cut_points_from_guides(amp, guide), 1, 15, 15)
     whole = hotpath.run_hot_path(ctx, amp, packed, flags=hotpath.quant_flags(), inc=inc).red
     chunked = distributed.run_chunked(ctx, amp, packed, chunk_reads=17000, flags=hotpath.quant_flags(), inc=inc)
-    assert np.array_equal(whole.flat(), chunked.flat())
+    assert np.array_equal(whole.results(), chunked.results())
     assert whole.n_cells == 600 * 600 * 60000 and whole.n_total == 60000

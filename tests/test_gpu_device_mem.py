@@ -51,7 +51,7 @@ def test_fused_path_device_memory_matches_host_memory(ctx):
     torch.cuda.synchronize()
     hotpath.run_hot_path(ctx, amp, None, hdr_amplicon=hdr, flags=flags, inc=inc, red=red,
                          device_inputs=(d_buf.data_ptr(), d_off.data_ptr(), n, 0, {k: v.data_ptr() for k, v in out.items()}))
-    assert np.array_equal(red.flat(), host.red.flat())
+    assert np.array_equal(red.results(), host.red.results())
     assert np.array_equal(out["kept"].cpu().numpy(), host.kept)
     assert np.array_equal(out["aln"].cpu().numpy().view(_lib.ALN_REC), host.aln)
     assert np.array_equal(out["recs"].cpu().numpy().view(_lib.READ_REC), host.recs)
@@ -87,5 +87,5 @@ def test_two_contexts_and_overlap_toggle_agree(ctx):
         other.close()
     c = hotpath.run_hot_path(ctx, amp, packed, hdr_amplicon=hdr, flags=hotpath.quant_flags(hdr))
     for r in (a, b):
-        assert np.array_equal(r.red.flat(), c.red.flat())
+        assert np.array_equal(r.red.results(), c.red.results())
         assert np.array_equal(r.aln, c.aln) and np.array_equal(r.recs, c.recs) and np.array_equal(r.kept, c.kept)

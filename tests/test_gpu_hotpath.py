@@ -105,7 +105,7 @@ def test_reductions_do_not_depend_on_sharding(ctx):
     h = 1000
     hotpath.run_hot_path(ctx, amp, (buf[:off[h]].copy(), off[:h + 1].copy()), hdr_amplicon=hdr, flags=flags, inc=inc, red=red)
     hotpath.run_hot_path(ctx, amp, (buf[off[h]:].copy(), (off[h:] - off[h]).copy()), hdr_amplicon=hdr, flags=flags, inc=inc, red=red)
-    assert np.array_equal(whole.flat(), red.flat())
+    assert np.array_equal(whole.results(), red.results())
 
 
 def test_shared_dp_prefix_of_the_hdr_pass_changes_nothing(ctx):
@@ -265,8 +265,10 @@ def test_diagonal_shortcut_changes_nothing(La, read_len, sigma, hdr_on):
             c.set_share_prefix(share)
             got = hotpath.run_hot_path(c, amp, packed, hdr_amplicon=hdr, flags=flags, want_rows=True, min_identity_score=40.0)
             total, left = c.last_diag()
-            if read_len == La and sigma == 0.0:
-                assert left < 0.6 * total, (total, left)     # ~20 % of the reads carry an indel: ~36 % of the pairs
+            if read_len == La and sigma == 0.0 and (share or not hdr_on):
+                # the amplicon pass: ~30 % of the reads are edited or HDR reads, i.e. ~half of the pairs hold one (without
+                # the shared prefix the HDR amplicon is a pass of its own, where only the HDR reads are diagonal)
+                assert left < 0.6 * total, (total, left)
             got.red.n_cells_computed = ref.red.n_cells_computed
             assert np.array_equal(got.red.flat(), ref.red.flat()), share
             assert np.array_equal(got.aln, ref.aln) and np.array_equal(got.recs, ref.recs) and np.array_equal(got.kept, ref.kept)

@@ -116,5 +116,5 @@ def test_device_memory_chain_merge_then_align_and_quantify(ctx):
     torch.cuda.synchronize()
     hotpath.run_hot_path(ctx, amp, None, inc=inc, min_identity_score=60.0, red=red,
                          device_inputs=(d_seq.data_ptr(), d_off.data_ptr(), m, 0, {k: v.data_ptr() for k, v in outd.items()}))
-    assert np.array_equal(red.flat(), ref.red.flat())
+    assert np.array_equal(red.results(), ref.red.results())      # (all but n_cells_computed, a work counter)
     assert ref.red.n_total > 0.5 * m
