@@ -43,9 +43,8 @@ def parse():
     ap.add_argument("--reads", type=int, default=1 << 20, help="reads per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=200000, help="reads in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-chunk", type=int, default=0, help="reads per crgpu_align_quantify call of the end-to-end arm "
-                                                               "(default: reads / contexts, measured best: t9 sweep in profiles/r01c_notes.md)")
-    ap.add_argument("--e2e-contexts", type=int, default=2, help="contexts (host threads) the end-to-end arm alternates between")
+    ap.add_argument("--e2e-chunk", type=int, default=0, help="reads per staged chunk of the end-to-end arm (default: reads / 2)")
+    ap.add_argument("--e2e-alleles", type=int, default=1 << 16, help="capacity of the per-chunk allele table of the end-to-end arm")
     return ap.parse_args()
 
 
@@ -184,7 +183,6 @@ def main():
     amp, guide, cut, hdr, buf, off, inc = workload(n, rank)
     L = len(amp)
     flags = hotpath.quant_flags(hdr)
-    h2d_bytes = int(buf.nbytes + off.nbytes)          # + 8 bytes per chunk of the end-to-end arm (chunk-relative offsets)
 
     # integer issue peaks, measured live: (i) both integer pipes -- dependency-free IADD chains that
     # ptxas splits 1:1 over the alu (IADD3) and fma (IMAD.IADD) pipes, and a VIMNMX.S16x2 + IMAD 1:1 mix; (ii) the
@@ -270,14 +268,17 @@ def main():
     n_total = red.n_total
 
     # ---- end-to-end arm: pinned HOST buffers through the public host API -------------------------
-    # hotpath.run_hot_path_pipelined = crgpu_align_quantify (C ABI, CRGPU_MEM_HOST) on read chunks that alternate
-    # between two contexts, each driven by its own host thread: H2D of the reads and D2H of the per-read records of
-    # one chunk overlap the kernels of the other; everything is inside the timed region.
-    p_buf = torch.from_numpy(buf).pin_memory()
-    p_off = torch.from_numpy(off).pin_memory()
+    # hotpath.StagedPipeline on ONE context: every step's reads travel as BAM 4-bit codes (crgpu_stage_reads, asynchronous
+    # H2D on the library's copy stream + unpack on the device) in chunks; the copy of the next chunk -- of this step or of the
+    # next one, as in a stream of batches -- runs while crgpu_align_quantify_staged works on the current chunk.  Every step
+    # brings back what CORE:2892-3992 consumes: per-read records, the RC-rescue rows, all reductions and the allele table.
     if args.e2e_chunk <= 0:
-        args.e2e_chunk = (n + args.e2e_contexts - 1) // args.e2e_contexts
-    n_chunks = (n + args.e2e_chunk - 1) // args.e2e_chunk
+        args.e2e_chunk = n            # (measured: one chunk per step 37.9 ms, two 44.7, four 58.1 -- per-call costs)
+    bounds = [(lo, min(n, lo + args.e2e_chunk)) for lo in range(0, n, args.e2e_chunk)]
+    assert all(int(off[lo]) % 2 == 0 for lo, _hi in bounds), "packed chunks start on even base offsets"
+    n_chunks = len(bounds)
+    p_packed = torch.from_numpy(hotpath.pack_bam4(buf)).pin_memory()
+    p_offs = [torch.from_numpy((off[lo:hi + 1] - off[lo]).astype(np.int64)).pin_memory() for lo, hi in bounds]
     pinned = {
         "kept": torch.zeros(n, dtype=torch.uint8).pin_memory(),
         "aln": torch.zeros(n * _lib.ALN_REC.itemsize, dtype=torch.uint8).pin_memory(),
@@ -286,28 +287,40 @@ def main():
         "rc_read": torch.zeros(n, dtype=torch.int32).pin_memory(),
         "rc_aln": torch.zeros(n * _lib.ALN_REC.itemsize, dtype=torch.uint8).pin_memory(),
         "rc_recs": torch.zeros(n * _lib.READ_REC.itemsize, dtype=torch.uint8).pin_memory(),
-        "offsets": torch.zeros(n + n_chunks, dtype=torch.int64).pin_memory(),
     }
     outs = {k: v.numpy() for k, v in pinned.items()}
     for k, dt in (("aln", _lib.ALN_REC), ("rc_aln", _lib.ALN_REC), ("recs", _lib.READ_REC), ("rc_recs", _lib.READ_REC)):
         outs[k] = outs[k].view(dt)
-    e2e_ctxs = [ctx] + [Context(local) for _ in range(args.e2e_contexts - 1)]
-    host_reads = (p_buf.numpy(), p_off.numpy())
+    packed_np = p_packed.numpy()
+    pipe = hotpath.StagedPipeline(ctx, amp, hdr_amplicon=hdr, flags=flags, inc=inc, alleles=args.e2e_alleles, deferred=True)
 
-    def step_host():
-        red = hotpath.Reductions(L)
-        hotpath.run_hot_path_pipelined(e2e_ctxs, amp, host_reads, chunk_reads=args.e2e_chunk, hdr_amplicon=hdr, flags=flags,
-                                       inc=inc, red=red, out=outs)
-        allreduce(red)
-        return red
+    def stage_chunk(c):
+        lo, hi = bounds[c]
+        pipe.stage(packed_np[int(off[lo]) // 2:(int(off[hi]) + 1) // 2], p_offs[c].numpy(), packed=True)
 
-    for _ in range(max(1, args.warmup - 1)):
-        red_h = step_host()
+    def run_host_steps(k_steps):
+        """k_steps passes over the read set as one stream of chunks; returns the last step's (reductions, allele table)."""
+        last = None
+        stage_chunk(0)
+        for st in range(k_steps):
+            for c, (lo, hi) in enumerate(bounds):
+                if c + 1 < n_chunks:
+                    stage_chunk(c + 1)
+                elif st + 1 < k_steps:
+                    stage_chunk(0)                                   # the next step's first chunk
+                pipe.run({k: v[lo:hi] for k, v in outs.items()})
+            # (the per-read arrays of this step's last chunk travel behind the next step's kernels)
+            red_s, table = pipe.take_results(sync=False)
+            allreduce(red_s)
+            last = (red_s, table)
+        ctx.sync()                                                   # ... and are all in host memory here
+        return last
+
+    run_host_steps(max(1, args.warmup - 1))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ext_stream)
-    for _ in range(args.steps):
-        red_h = step_host()
+    red_h, alleles_h = run_host_steps(args.steps)
     e1.record(ext_stream)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -315,7 +328,9 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
-    d2h_bytes = int(n * (1 + _lib.ALN_REC.itemsize + _lib.READ_REC.itemsize + 4) + red_h.flat().nbytes * n_chunks)
+    h2d_bytes = int(p_packed.numel() + sum(o.numel() * 8 for o in p_offs))
+    d2h_bytes = int(n * (1 + _lib.ALN_REC.itemsize + _lib.READ_REC.itemsize + 4) + red_h.flat().nbytes * n_chunks +
+                    24 * len(alleles_h[0]))
     same = bool(np.array_equal(red_h.flat()[:-1], red.flat()[:-1]))     # every reduction (n_cells_computed aside: bookkeeping)
 
     if rank != 0:
@@ -383,8 +398,11 @@ def main():
                    "traceback scratch 8 GB per batch)" % (buf.nbytes >> 20), "parallelism": "reads sharded x%d" % world},
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": e2e_ms / args.steps, "results_equal_device_arm": same,
-                "api": "hotpath.run_hot_path_pipelined: crgpu_align_quantify(CRGPU_MEM_HOST) on %d-read chunks alternating "
-                       "between %d contexts / host threads" % (args.e2e_chunk, args.e2e_contexts)},
+                "distinct_alleles": len(alleles_h[0]),
+                "api": "hotpath.StagedPipeline on one context: crgpu_stage_reads (BAM 4-bit reads from pinned memory, asynchronous "
+                       "H2D on the library's copy stream, unpacked on the device; the next %d-read chunk is staged while the current "
+                       "one runs) + crgpu_align_quantify_staged (per-read records, RC-rescue rows, reductions and the allele table "
+                       "back in host memory: what CORE:2892-3992 consumes)" % args.e2e_chunk},
         "gpu_launches": int(sum(fam_launch.values())),
         "kernel_ms_per_step": {k: fam_ms[k] / args.steps for k in fam_ms},
         "roofline": {"bound": "int_alu", "kernel": kinds[dom]["kernel"], "achieved": kinds[dom]["achieved"], "peak": alu_pk,

@@ -9,6 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CRGPU_LIB") or os.path.join(HERE, "libcrgpu.so")     # CRGPU_LIB: experiment builds (scripts/)
 
 MEM_HOST, MEM_DEVICE = 0, 1
+READS_BYTES, READS_BAM4 = 0, 1
 E_CUDA, E_ARG, E_ALIGN, E_NOMEM = 1, 2, 3, 4
 
 ALN_REC = np.dtype([("score", "<f4"), ("alnlen", "<i4"), ("ident", "<i4"), ("tenths", "<i4"),
@@ -44,7 +45,7 @@ class PathOut(ctypes.Structure):
                 ("hist_len", ctypes.c_int32), ("hist_zero", ctypes.c_int32), ("counters", ctypes.c_void_p),
                 ("class_counts", ctypes.c_int64 * 4), ("n_total", ctypes.c_int64), ("n_cells", ctypes.c_int64),
                 ("allele_cap", ctypes.c_int64), ("allele_n", ctypes.c_int64), ("allele_row", ctypes.c_void_p),
-                ("allele_count", ctypes.c_void_p), ("n_cells_computed", ctypes.c_int64)]
+                ("allele_count", ctypes.c_void_p), ("n_cells_computed", ctypes.c_int64), ("allele_key", ctypes.c_void_p)]
 
 
 class MergeParams(ctypes.Structure):
@@ -113,11 +114,16 @@ def load():
     lib.crgpu_align_quantify.argtypes = [vp, i32, ctypes.c_char_p, i32, ctypes.POINTER(PathParams),
                                          ctypes.POINTER(QuantParams), vp, vp, i64, ctypes.POINTER(PathOut)]
     lib.crgpu_int_peak.argtypes = [vp, i32, ctypes.POINTER(dbl)]
+    lib.crgpu_stage_reads.argtypes = [vp, i32, i32, vp, vp, i64]
+    lib.crgpu_set_deferred_outputs.argtypes = [vp, i32]
+    lib.crgpu_align_quantify_staged.argtypes = [vp, i32, ctypes.c_char_p, i32, ctypes.POINTER(PathParams), ctypes.POINTER(QuantParams),
+                                                ctypes.POINTER(PathOut)]
     lib.crgpu_fastq_index.argtypes = [vp, i32, vp, i64, i32, ctypes.POINTER(FastqOut)]
     lib.crgpu_flash_merge.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i64, ctypes.POINTER(MergeParams),
                                       ctypes.POINTER(MergeOut)]
     for name in ("crgpu_create", "crgpu_set_diag_shortcut", "crgpu_last_diag", "crgpu_set_overlap", "crgpu_set_share_prefix", "crgpu_set_band", "crgpu_last_escaped", "crgpu_set_traceback_budget", "crgpu_last_timing", "crgpu_last_fill_breakdown", "crgpu_sync", "crgpu_qualfilter",
-                 "crgpu_align", "crgpu_quantify", "crgpu_align_quantify", "crgpu_int_peak", "crgpu_flash_merge", "crgpu_fastq_index"):
+                 "crgpu_align", "crgpu_quantify", "crgpu_align_quantify", "crgpu_int_peak", "crgpu_flash_merge", "crgpu_fastq_index",
+                 "crgpu_stage_reads", "crgpu_align_quantify_staged", "crgpu_set_deferred_outputs"):
         getattr(lib, name).restype = i32
     _lib = lib
     return lib

@@ -114,6 +114,19 @@ __global__ void k_gather_i32(const int32_t *__restrict__ src, const int32_t *__r
     if (i < m) out[i] = src[idx[i]];
 }
 
+// the two hashes of the k-th most frequent allele: what a caller that quantifies a read set in several calls merges the
+// per-call allele tables by
+__global__ void k_allele_keys(const uint64_t *__restrict__ ukeys, const uint64_t *__restrict__ chk, const int32_t *__restrict__ rep,
+                              const int32_t *__restrict__ sgid, const int *__restrict__ nruns, uint64_t *__restrict__ out, int64_t m)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const int g = sgid[k];
+    const bool ok = g < *nruns && rep[g] >= 0;
+    out[2 * k] = ok ? ukeys[g] : 0;
+    out[2 * k + 1] = ok ? chk[rep[g]] : 0;
+}
+
 // Group the rows; returns the number of alleles (runs with a non-zero count) and, sorted by count
 // descending, up to `cap` (representative row, count) pairs in host arrays.
 // tmp: caller-provided scratch allocator callback is avoided: all scratch comes in through `scratch`
@@ -130,18 +143,18 @@ size_t allele_scratch_bytes(int64_t m)
     if (c > t) t = c;
     if (d > t) t = d;
     t = (t + 255) & ~(size_t)255;
-    // keys, chk, skeys, ukeys (8 B) + rows, srows, counts, starts, rep, gid, scounts, sgid (4 B) + nruns/err
-    return t + (size_t)m * (4 * 8 + 8 * 4) + 1024;
+    // keys, chk, skeys, ukeys (8 B) + rows, srows, counts, starts, rep, gid, scounts, sgid (4 B) + key pairs (16 B) + nruns/err
+    return t + (size_t)m * (4 * 8 + 8 * 4 + 16) + 1024;
 }
 
 cudaError_t allele_groups(const uint8_t *reads, const int64_t *offsets, int64_t n, const uint8_t *kept, const int32_t *rc_read,
                           int64_t nrc, const uint32_t *ops_fw, const uint32_t *ops_rc, int64_t ops_stride,
                           const crgpu_aln_rec *aln_fw, const crgpu_aln_rec *aln_rc, const crgpu_read_rec *rec_fw,
                           const crgpu_read_rec *rec_rc, void *scratch, size_t scratch_bytes, cudaStream_t s,
-                          int32_t **d_rep_sorted, int32_t **d_count_sorted, int **d_nruns, int **d_err)
+                          int32_t **d_rep_sorted, int32_t **d_count_sorted, int **d_nruns, int **d_err, uint64_t **d_key_pairs)
 {
     const int64_t m = n + nrc;
-    size_t tmp_bytes = scratch_bytes - ((size_t)m * (4 * 8 + 8 * 4) + 1024);
+    size_t tmp_bytes = scratch_bytes - ((size_t)m * (4 * 8 + 8 * 4 + 16) + 1024);
     uint8_t *p = reinterpret_cast<uint8_t *>(scratch);
     void *tmp = p; p += tmp_bytes;
     uint64_t *keys = reinterpret_cast<uint64_t *>(p); p += m * 8;
@@ -156,6 +169,7 @@ cudaError_t allele_groups(const uint8_t *reads, const int64_t *offsets, int64_t 
     int32_t *gid = reinterpret_cast<int32_t *>(p); p += m * 4;
     int32_t *scounts = reinterpret_cast<int32_t *>(p); p += m * 4;
     int32_t *sgid = reinterpret_cast<int32_t *>(p); p += m * 4;
+    uint64_t *kpairs = reinterpret_cast<uint64_t *>(p); p += m * 16;
     int *nruns = reinterpret_cast<int *>(p); int *err = nruns + 1;
     cudaError_t e;
     if ((e = cudaMemsetAsync(nruns, 0, 8, s)) != cudaSuccess) return e;
@@ -176,6 +190,8 @@ cudaError_t allele_groups(const uint8_t *reads, const int64_t *offsets, int64_t 
     if ((e = cub::DeviceRadixSort::SortPairsDescending(tmp, tb, counts, scounts, gid, sgid, (int)m, 0, 32, s)) != cudaSuccess) return e;
     // representatives in the sorted order (the exclusive-sum buffer is free again)
     k_gather_i32<<<grid, 128, 0, s>>>(rep, sgid, starts, m);
+    k_allele_keys<<<grid, 128, 0, s>>>(ukeys, chk, rep, sgid, nruns, kpairs, m);
+    *d_key_pairs = kpairs;
     *d_rep_sorted = starts; *d_count_sorted = scounts; *d_nruns = nruns; *d_err = err;
     return cudaGetLastError();
 }

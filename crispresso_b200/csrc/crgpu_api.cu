@@ -22,6 +22,8 @@ int crgpu_create(crgpu_ctx **out, int device)
         if (c->stream) cudaStreamDestroy(c->stream);
         if (c->stream2) cudaStreamDestroy(c->stream2);
         if (c->stream3) cudaStreamDestroy(c->stream3);
+        if (c->stream_copy) cudaStreamDestroy(c->stream_copy);
+        for (int i = 0; i < 2; ++i) { if (c->staged_ev[i]) cudaEventDestroy(c->staged_ev[i]); if (c->out_ev[i]) cudaEventDestroy(c->out_ev[i]); }
         if (c->ready) cudaEventDestroy(c->ready);
         for (int i = 0; i < 2; ++i) { if (c->fill_done[i]) cudaEventDestroy(c->fill_done[i]); if (c->walk_done[i]) cudaEventDestroy(c->walk_done[i]); }
         delete c;
@@ -42,10 +44,13 @@ int crgpu_create(crgpu_ctx **out, int device)
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail();
     if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) return bail();
     if (cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking) != cudaSuccess) return bail();
+    if (cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking) != cudaSuccess) return bail();
     if (cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming) != cudaSuccess) return bail();
     for (int i = 0; i < 2; ++i) {
         if (cudaEventCreateWithFlags(&c->fill_done[i], cudaEventDisableTiming) != cudaSuccess) return bail();
         if (cudaEventCreateWithFlags(&c->walk_done[i], cudaEventDisableTiming) != cudaSuccess) return bail();
+        if (cudaEventCreateWithFlags(&c->staged_ev[i], cudaEventDisableTiming) != cudaSuccess) return bail();
+        if (cudaEventCreateWithFlags(&c->out_ev[i], cudaEventDisableTiming) != cudaSuccess) return bail();
     }
     if (prev >= 0 && prev != device) cudaSetDevice(prev);      // the caller's current device is not ours to change
     *out = c;
@@ -62,13 +67,15 @@ void crgpu_destroy(crgpu_ctx *c)
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->stream2);
     cudaStreamSynchronize(c->stream3);
+    cudaStreamSynchronize(c->stream_copy);
     DBuf *all[] = {&c->reads, &c->offsets, &c->amp, &c->prof, &c->pc, &c->pc_off, &c->plen, &c->pair_lo, &c->pair_hi,
                    &c->order, &c->plan_hist, &c->plan_tab, &c->tb2, &c->lastrow2, &c->lastcol2, &c->tb, &c->lastrow, &c->lastcol, &c->errflag, &c->recs, &c->sref, &c->smark, &c->sqry, &c->ops, &c->ops_rc, &c->alleles, &c->prof_h, &c->amp_h, &c->tbh, &c->tbh2,
                    &c->top, &c->top2, &c->lastrow_h, &c->lastrow_h2, &c->lastcol_h, &c->lastcol_h2,
                    &c->prof_s, &c->prof_hs, &c->join, &c->btops[0], &c->btops[1], &c->bleft[0], &c->bleft[1], &c->btops_h[0], &c->btops_h[1], &c->bleft_h[0], &c->bleft_h[1], &c->escaped,
                    &c->joinb, &c->fastflags, &c->need[0], &c->need[1], &c->plist[0], &c->plist[1], &c->plist2[0], &c->plist2[1], &c->selscratch[0], &c->selscratch[1], &c->need_cnt,
                    &c->rowvals[0], &c->rowvals[1], &c->rowvals_h[0], &c->rowvals_h[1], &c->badbase,
-                   &c->need_read[0], &c->need_read[1], &c->rlist[0], &c->rlist[1]};
+                   &c->need_read[0], &c->need_read[1], &c->rlist[0], &c->rlist[1],
+                   &c->stage_reads[0], &c->stage_reads[1], &c->stage_off[0], &c->stage_off[1], &c->stage_pack[0], &c->stage_pack[1]};
     for (DBuf *b : all) b->release();
     for (auto &b : c->q_in) b.release();
     for (auto &b : c->q_out) b.release();
@@ -76,6 +83,9 @@ void crgpu_destroy(crgpu_ctx *c)
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->fill_done[i]); cudaEventDestroy(c->walk_done[i]); }
     cudaEventDestroy(c->ready);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->staged_ev[i]); cudaEventDestroy(c->out_ev[i]); }
+    for (auto &slot : c->stage_out) for (auto &b : slot) b.release();
+    cudaStreamDestroy(c->stream_copy);
     cudaStreamDestroy(c->stream3);
     cudaStreamDestroy(c->stream2);
     cudaStreamDestroy(c->stream);
@@ -90,6 +100,13 @@ int crgpu_set_traceback_budget(crgpu_ctx *c, size_t bytes)
 {
     if (!c || bytes < ((size_t)16 << 20)) return CRGPU_E_ARG;
     c->tb_budget = bytes;
+    return CRGPU_OK;
+}
+
+int crgpu_set_deferred_outputs(crgpu_ctx *c, int on)
+{
+    if (!c) return CRGPU_E_ARG;
+    c->deferred_out = on != 0;
     return CRGPU_OK;
 }
 
@@ -167,6 +184,7 @@ static int sync_impl(crgpu_ctx *ctx)
     if (!ctx) return CRGPU_E_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream_copy));          // staged inputs / deferred outputs
     return CRGPU_OK;
 }
 
@@ -1032,6 +1050,61 @@ static int align_impl(crgpu_ctx *ctx, int mem, const char *amplicon, int amplico
     return CRGPU_OK;
 }
 
+// BAM's 4-bit base codes, two per byte, high nibble first -> one base per byte.  16 bases per thread.
+__global__ void k_unpack_bam4(const uint8_t *__restrict__ packed, int64_t nbases, uint8_t *__restrict__ out)
+{
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (i >= nbases) return;
+    const char *lut = "=ACMGRSVTWYHKDBN";
+    const int64_t left = nbases - i;
+    if (left >= 16) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(packed + i / 2);
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t two = ((q < 2 ? v.x : v.y) >> (16 * (q & 1))) & 0xffffu;     // bytes 2q, 2q+1 of the eight
+            w[q] = (uint32_t)(uint8_t)lut[(two >> 4) & 15] | ((uint32_t)(uint8_t)lut[two & 15] << 8) |
+                   ((uint32_t)(uint8_t)lut[(two >> 12) & 15] << 16) | ((uint32_t)(uint8_t)lut[(two >> 8) & 15] << 24);
+        }
+        *reinterpret_cast<uint4 *>(out + i) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+        for (int64_t j = i; j < nbases; ++j) {
+            const uint8_t bb = packed[j >> 1];
+            out[j] = (uint8_t)lut[(j & 1) ? (bb & 15) : (bb >> 4)];
+        }
+    }
+}
+
+static int stage_reads_impl(crgpu_ctx *ctx, int slot, int format, const uint8_t *reads, const int64_t *offsets, int64_t n)
+{
+    if (slot < 0 || slot > 1) return fail(ctx, CRGPU_E_ARG, "crgpu_stage_reads: slot must be 0 or 1");
+    if (format != CRGPU_READS_BYTES && format != CRGPU_READS_BAM4) return fail(ctx, CRGPU_E_ARG, "crgpu_stage_reads: unknown format");
+    if (n < 0 || (n > 0 && (!reads || !offsets)) || n >= (int64_t)1 << 31) return fail(ctx, CRGPU_E_ARG, "crgpu_stage_reads: bad argument");
+    ctx->stage_n[slot] = -1;
+    if (n == 0) { ctx->stage_n[slot] = 0; return CRGPU_OK; }
+    cudaStream_t cs = ctx->stream_copy;
+    const int64_t total = offsets[n] - offsets[0];
+    if (offsets[0] != 0 || total < 0) return fail(ctx, CRGPU_E_ARG, "crgpu_stage_reads: offsets must start at 0");
+    // (16 bytes of slack: the unpack kernel stores whole 16-byte groups)
+    CK(ctx->stage_reads[slot].reserve((size_t)std::max<int64_t>(total, 1) + 32));
+    CK(ctx->stage_off[slot].reserve((size_t)(n + 1) * 8));
+    CK(cudaMemcpyAsync(ctx->stage_off[slot].p, offsets, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, cs));
+    if (format == CRGPU_READS_BYTES) {
+        CK(cudaMemcpyAsync(ctx->stage_reads[slot].p, reads, (size_t)total, cudaMemcpyHostToDevice, cs));
+    } else {
+        const size_t pb = (size_t)((total + 1) / 2);
+        CK(ctx->stage_pack[slot].reserve(pb + 16));
+        CK(cudaMemcpyAsync(ctx->stage_pack[slot].p, reads, pb, cudaMemcpyHostToDevice, cs));
+        const int64_t nthreads = (total + 15) / 16;
+        k_unpack_bam4<<<(unsigned)((nthreads + 255) / 256), 256, 0, cs>>>(ctx->stage_pack[slot].as<uint8_t>(), total,
+                                                                         ctx->stage_reads[slot].as<uint8_t>());
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(ctx->staged_ev[slot], cs));
+    ctx->stage_n[slot] = n;
+    return CRGPU_OK;
+}
+
 static int int_peak_impl(crgpu_ctx *ctx, int which, double *lane_ops_per_s)
 {
     if (!ctx || !lane_ops_per_s) return CRGPU_E_ARG;
@@ -1060,6 +1133,15 @@ static int int_peak_impl(crgpu_ctx *ctx, int which, double *lane_ops_per_s)
 }
 
 // ---- the exported entry points: device guard + "no work of a failed call is left running" (ApiGuard, crgpu_internal.h)
+int crgpu_stage_reads(crgpu_ctx *ctx, int slot, int format, const uint8_t *reads, const int64_t *offsets, int64_t n)
+{
+    if (!ctx) return CRGPU_E_ARG;
+    ApiGuard guard(ctx);
+    const int rc = stage_reads_impl(ctx, slot, format, reads, offsets, n);
+    if (rc != CRGPU_OK) cudaStreamSynchronize(ctx->stream_copy);
+    return guard.done(rc);
+}
+
 int crgpu_sync(crgpu_ctx *ctx)
 {
     if (!ctx) return CRGPU_E_ARG;

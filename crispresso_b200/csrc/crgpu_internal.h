@@ -75,7 +75,16 @@ struct crgpu_ctx {
     // reads with a base outside ACGTN(U) are not aligned but reported per read: one byte per read of the CALL in flight
     // (crgpu_align, crgpu_align_quantify), null otherwise (build_plan then fails the call)
     DBuf badbase;
-    uint8_t *d_bad = nullptr;                                 // score pass: last-row values per column (k_lastrow_scan)
+    uint8_t *d_bad = nullptr;
+    // staged inputs (crgpu_stage_reads): two slots filled on the copy stream while the main stream computes
+    cudaStream_t stream_copy = nullptr;
+    cudaEvent_t staged_ev[2] = {nullptr, nullptr};
+    DBuf stage_reads[2], stage_off[2], stage_pack[2];
+    int64_t stage_n[2] = {-1, -1};
+    // deferred outputs of the staged calls: per-slot device buffers (kept, aln, recs, tenths_rep) + "they have left" events
+    bool deferred_out = false;
+    DBuf stage_out[2][4];
+    cudaEvent_t out_ev[2] = {nullptr, nullptr};                                 // score pass: last-row values per column (k_lastrow_scan)
     int n_escaped[2] = {0, 0};                                     // reads re-aligned after the last banded call (amplicon, HDR)
     int band_holdoff = 0;                                          // calls left that skip the band (set when > 25 % of a call's reads escaped)
     int band_B = 16;                                               // band half-width in read columns; 0 = single-pass fill
@@ -206,7 +215,7 @@ cudaError_t allele_groups(const uint8_t *reads, const int64_t *offsets, int64_t 
                           int64_t nrc, const uint32_t *ops_fw, const uint32_t *ops_rc, int64_t ops_stride,
                           const crgpu_aln_rec *aln_fw, const crgpu_aln_rec *aln_rc, const crgpu_read_rec *rec_fw,
                           const crgpu_read_rec *rec_rc, void *scratch, size_t scratch_bytes, cudaStream_t s,
-                          int32_t **d_rep_sorted, int32_t **d_count_sorted, int **d_nruns, int **d_err);
+                          int32_t **d_rep_sorted, int32_t **d_count_sorted, int **d_nruns, int **d_err, uint64_t **d_key_pairs);
 // alignment core (crgpu_api.cu): device pointers only
 int build_plan(crgpu_ctx *ctx, const uint8_t *d_reads, const int64_t *d_offsets, const int32_t *d_subset, int64_t nsub);
 int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_reads, const int64_t *d_offsets,

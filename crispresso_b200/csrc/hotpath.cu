@@ -180,9 +180,11 @@ static std::string revcomp_upper(const char *s, int n)
     return out;
 }
 
+// staged_slot >= 0: the reads are the batch crgpu_stage_reads put into that slot (device memory, filled on the copy stream);
+// every output is host memory, as with CRGPU_MEM_HOST
 static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, int amplicon_len,
                          const crgpu_path_params *path, const crgpu_quant_params *quant,
-                         const uint8_t *reads, const int64_t *offsets, int64_t n, crgpu_path_out *out)
+                         const uint8_t *reads, const int64_t *offsets, int64_t n, crgpu_path_out *out, int staged_slot = -1)
 {
     if (!ctx) return CRGPU_E_ARG;
     if (!amplicon || !path || !quant || !out || n < 0 || (n > 0 && (!reads || !offsets)))
@@ -210,7 +212,8 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
 
     // ---- inputs on the device ----
     const uint8_t *d_reads = reads; const int64_t *d_off = offsets;
-    if (host) {
+    if (staged_slot >= 0) CK(cudaStreamWaitEvent(s, ctx->staged_ev[staged_slot], 0));     // (pointers: the staging slot's)
+    else if (host) {
         const int64_t total = offsets[n];
         CK(ctx->reads.reserve((size_t)std::max<int64_t>(total, 1)));
         CK(ctx->offsets.reserve((size_t)(n + 1) * 8));
@@ -235,7 +238,16 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
     // ---- device outputs ----
     uint8_t *d_kept; crgpu_aln_rec *d_aln; crgpu_read_rec *d_recs; int32_t *d_trep;
     uint8_t *d_ref, *d_mark, *d_qry;
-    if (host) {
+    // deferred outputs (crgpu_set_deferred_outputs, staged calls only): the per-read arrays leave on the copy stream after
+    // the call has returned, from a per-slot set of device buffers that the next call (other slot) does not touch
+    const bool deferred = staged_slot >= 0 && ctx->deferred_out;
+    if (deferred) {
+        DBuf *o = ctx->stage_out[staged_slot];
+        CK(cudaStreamWaitEvent(s, ctx->out_ev[staged_slot], 0));          // the slot's previous outputs have left
+        CK(o[0].reserve((size_t)n)); CK(o[1].reserve((size_t)n * sizeof(crgpu_aln_rec)));
+        CK(o[2].reserve((size_t)n * sizeof(crgpu_read_rec))); CK(o[3].reserve((size_t)n * 4));
+        d_kept = o[0].as<uint8_t>(); d_aln = o[1].as<crgpu_aln_rec>(); d_recs = o[2].as<crgpu_read_rec>(); d_trep = o[3].as<int32_t>();
+    } else if (host) {
         CK(ctx->aux[0].reserve((size_t)n)); CK(ctx->recs.reserve((size_t)n * sizeof(crgpu_aln_rec)));
         CK(ctx->q_out[1].reserve((size_t)n * sizeof(crgpu_read_rec))); CK(ctx->q_in[4].reserve((size_t)n * 4));
         d_kept = ctx->aux[0].as<uint8_t>(); d_aln = ctx->recs.as<crgpu_aln_rec>();
@@ -467,11 +479,11 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
         const int64_t m = n + nrc;
         const size_t sb = allele_scratch_bytes(m);
         CK(ctx->alleles.reserve(sb));
-        int32_t *d_rep, *d_cnt; int *d_nruns, *d_aerr;
+        int32_t *d_rep, *d_cnt; int *d_nruns, *d_aerr; uint64_t *d_kp;
         span_begin(ctx, T_OTHER);
         CK(allele_groups(d_reads, d_off, n, d_kept, nrc ? ctx->aux[3].as<int32_t>() : nullptr, nrc, d_ops,
                          nrc ? ctx->ops_rc.as<uint32_t>() : nullptr, ops_stride, d_aln, d_rc_aln, d_recs, d_rc_recs,
-                         ctx->alleles.p, sb, s, &d_rep, &d_cnt, &d_nruns, &d_aerr));
+                         ctx->alleles.p, sb, s, &d_rep, &d_cnt, &d_nruns, &d_aerr, &d_kp));
         span_end(ctx, 4);     // k_hash_rows, k_check_groups, k_group_reps, k_gather_i32 (+ cub's own kernels, not counted)
         int h2[2] = {0, 0};
         CK(cudaMemcpyAsync(h2, d_nruns, 8, cudaMemcpyDeviceToHost, s));
@@ -482,6 +494,7 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
         if (take > 0) {
             CK(cudaMemcpyAsync(hrep.data(), d_rep, (size_t)take * 4, cudaMemcpyDeviceToHost, s));
             CK(cudaMemcpyAsync(hcnt.data(), d_cnt, (size_t)take * 4, cudaMemcpyDeviceToHost, s));
+            if (out->allele_key) CK(cudaMemcpyAsync(out->allele_key, d_kp, (size_t)take * 16, cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
         }
         int64_t na = 0;
@@ -502,10 +515,17 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
 
     // ---- 5. results ----
     if (host) {
-        CK(cudaMemcpyAsync(out->kept, d_kept, (size_t)n, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(out->aln, d_aln, (size_t)n * sizeof(crgpu_aln_rec), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(out->recs, d_recs, (size_t)n * sizeof(crgpu_read_rec), cudaMemcpyDeviceToHost, s));
-        if (out->tenths_rep) CK(cudaMemcpyAsync(out->tenths_rep, d_trep, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+        cudaStream_t so = s;
+        if (deferred) {                                    // ... valid after crgpu_sync
+            so = ctx->stream_copy;
+            CK(cudaEventRecord(ctx->ready, s));
+            CK(cudaStreamWaitEvent(so, ctx->ready, 0));
+        }
+        CK(cudaMemcpyAsync(out->kept, d_kept, (size_t)n, cudaMemcpyDeviceToHost, so));
+        CK(cudaMemcpyAsync(out->aln, d_aln, (size_t)n * sizeof(crgpu_aln_rec), cudaMemcpyDeviceToHost, so));
+        CK(cudaMemcpyAsync(out->recs, d_recs, (size_t)n * sizeof(crgpu_read_rec), cudaMemcpyDeviceToHost, so));
+        if (out->tenths_rep) CK(cudaMemcpyAsync(out->tenths_rep, d_trep, (size_t)n * 4, cudaMemcpyDeviceToHost, so));
+        if (deferred) CK(cudaEventRecord(ctx->out_ev[staged_slot], so));
         if (want_rows) {
             if (out->slot != slot) return fail(ctx, CRGPU_E_ARG, "out->slot must be set when rows are requested");
             const size_t rb = (size_t)n * slot;
@@ -537,6 +557,18 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
 }
 
 // ---- the exported entry points: device guard + "no work of a failed call is left running" (ApiGuard, crgpu_internal.h)
+int crgpu_align_quantify_staged(crgpu_ctx *ctx, int slot, const char *amplicon, int amplicon_len,
+                                const crgpu_path_params *path, const crgpu_quant_params *quant, crgpu_path_out *out)
+{
+    if (!ctx) return CRGPU_E_ARG;
+    ApiGuard guard(ctx);
+    if (slot < 0 || slot > 1 || ctx->stage_n[slot] < 0) return fail(ctx, CRGPU_E_ARG, "crgpu_align_quantify_staged: nothing staged in slot %d", slot);
+    const int64_t n = ctx->stage_n[slot];
+    ctx->stage_n[slot] = -1;                                        // consumed
+    return guard.done(align_quantify_impl(ctx, CRGPU_MEM_HOST, amplicon, amplicon_len, path, quant, ctx->stage_reads[slot].as<uint8_t>(),
+                                          ctx->stage_off[slot].as<int64_t>(), n, out, slot));
+}
+
 int crgpu_quantify(crgpu_ctx *ctx, int mem, const crgpu_quant_params *params,
                    const uint8_t *ref_rows, const uint8_t *mark_rows, const uint8_t *qry_rows, int64_t slot,
                    const int32_t *aln_off, const int32_t *alnlen,

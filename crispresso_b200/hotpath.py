@@ -458,6 +458,215 @@ def run_hot_path_pipelined(ctxs, amplicon, reads, chunk_reads=1 << 18, gapopen=1
     return HotPathResult(kept, aln, trep, recs, None, 0, rc_read[:pos], rc_aln[:pos], rc_recs[:pos], None, red)
 
 
+_BAM4 = np.zeros(256, np.uint8)
+for _i, _c in enumerate(b"=ACMGRSVTWYHKDBN"):
+    _BAM4[_c] = _i
+    _BAM4[ord(chr(_c).lower())] = _i
+
+
+def pack_bam4(buf):
+    """One base per byte -> BAM's 4-bit codes, two bases per byte, high nibble first, dense over the whole buffer (base j
+    is nibble j): the CRGPU_READS_BAM4 input format of crgpu_stage_reads (include/crgpu.h).  Offsets keep counting bases."""
+    codes = _BAM4[np.asarray(buf, dtype=np.uint8)]
+    if len(codes) & 1:
+        codes = np.concatenate([codes, np.zeros(1, np.uint8)])
+    return ((codes[0::2] << 4) | codes[1::2]).astype(np.uint8)
+
+
+class StagedPipeline:
+    """Batches of HOST-resident reads through ONE context with the PCIe copy of the next batch hidden behind the kernels
+    of the current one: ``stage`` starts the copy of a batch into one of the context's two staging slots
+    (crgpu_stage_reads: asynchronous, on the library's copy stream; keep the buffers pinned), ``run`` waits for the oldest
+    staged batch and quantifies it (crgpu_align_quantify_staged).  Reductions accumulate in ``red``; with ``alleles`` the
+    per-batch allele tables are merged by their 128-bit keys (``alleles_merged``).  Every read is independent and the
+    reductions are sums, so the results equal one call over all reads."""
+
+    def __init__(self, ctx, amplicon, gapopen=10.0, gapextend=0.5, min_identity_score=60.0, hdr_amplicon=None, flags=None,
+                 hdr_thr=98.0, inc=None, exon=None, splice=None, rc_rescue=True, red=None, alleles=0, deferred=False):
+        self.ctx = ctx
+        # deferred: the per-read arrays of a batch arrive behind the next batch's kernels; valid after take_results() / ctx.sync()
+        self.deferred = bool(deferred)
+        ctx.check(ctx.lib.crgpu_set_deferred_outputs(ctx.handle, 1 if deferred else 0))
+        self.amp = amplicon.upper().encode()
+        L = len(self.amp)
+        self.L = L
+        self.red = red or Reductions(L)
+        if flags is None:
+            flags = quant_flags(expected_hdr_amplicon_seq=hdr_amplicon or "")
+        if inc is None:
+            inc = np.ones(L, np.uint8)
+        self._keep = []
+        self.qp = _quant_params(L, flags, hdr_thr, inc, exon, splice, self._keep)
+        self.pp = _lib.PathParams()
+        self.pp.gapopen, self.pp.gapextend, self.pp.min_identity_score = float(gapopen), float(gapextend), float(min_identity_score)
+        self._hdr_b = hdr_amplicon.upper().encode() if hdr_amplicon else None
+        self.pp.hdr_amplicon, self.pp.hdr_amplicon_len = self._hdr_b, len(self._hdr_b) if self._hdr_b else 0
+        self.pp.rc_rescue = 1 if rc_rescue else 0
+        self.alleles = int(alleles)
+        if self.alleles:
+            self._arow = np.zeros(self.alleles, np.int32)
+            self._acnt = np.zeros(self.alleles, np.int64)
+            self._akey = np.zeros(2 * self.alleles, np.uint64)
+        self._tables = []                    # per batch: (keys[na, 2], counts[na], rows[na], batch index[na])
+        self._queue = []                     # staged, not yet run: (slot, n, buffers kept alive)
+        self._next = 0
+        self.batches = 0
+
+    def stage(self, reads, offsets, packed=False):
+        """Start copying a batch: ``reads`` u8 (one base per byte, or pack_bam4 output with packed=True), ``offsets`` i64[n+1]
+        starting at 0, counting bases.  At most two batches can be staged and not yet run."""
+        if len(self._queue) >= 2:
+            raise RuntimeError("both staging slots are in use: run() a batch first")
+        n = len(offsets) - 1
+        slot = self._next
+        self.ctx.check(self.ctx.lib.crgpu_stage_reads(self.ctx.handle, slot, _lib.READS_BAM4 if packed else _lib.READS_BYTES,
+                                                      _lib.ptr(reads), _lib.ptr(offsets), n))
+        self._queue.append((slot, n, (reads, offsets)))
+        self._next ^= 1
+        return n
+
+    def run(self, out):
+        """Quantify the oldest staged batch of n reads.  ``out``: arrays (views) ``kept`` u8[n], ``aln`` ALN_REC[n], ``recs``
+        READ_REC[n], optional ``tenths_rep`` i32[n], ``rc_read`` i32[n], ``rc_aln`` ALN_REC[n], ``rc_recs`` READ_REC[n].
+        Returns (n, number of RC rows)."""
+        slot, n, _alive = self._queue.pop(0)
+        red = self.red
+        po = _lib.PathOut()
+        po.vectors, po.hist_inframe, po.hist_frameshift = red.vectors.ctypes.data, red.hist_inframe.ctypes.data, red.hist_frameshift.ctypes.data
+        po.hist_len, po.hist_zero, po.counters = HIST_LEN, HIST_ZERO, red.counters.ctypes.data
+        po.kept, po.aln, po.recs = _lib.ptr(out["kept"]), _lib.ptr(out["aln"]), _lib.ptr(out["recs"])
+        if out.get("tenths_rep") is not None:
+            po.tenths_rep = _lib.ptr(out["tenths_rep"])
+        po.slot = 0
+        if out.get("rc_read") is not None:
+            po.rc_cap = n
+            po.rc_read, po.rc_aln, po.rc_recs = _lib.ptr(out["rc_read"]), _lib.ptr(out["rc_aln"]), _lib.ptr(out["rc_recs"])
+        if self.alleles:
+            po.allele_cap, po.allele_row, po.allele_count = self.alleles, self._arow.ctypes.data, self._acnt.ctypes.data
+            po.allele_key = self._akey.ctypes.data
+        self.ctx.check(self.ctx.lib.crgpu_align_quantify_staged(self.ctx.handle, slot, self.amp, self.L, ctypes.byref(self.pp),
+                                                                ctypes.byref(self.qp), ctypes.byref(po)))
+        red.class_counts += np.array(list(po.class_counts), np.int64)
+        red.n_total += int(po.n_total)
+        red.n_cells += int(po.n_cells)
+        red.n_cells_computed += int(po.n_cells_computed)
+        if self.alleles:
+            na = int(po.allele_n)
+            if na > self.alleles:
+                raise ValueError("a batch holds %d distinct alleles, more than alleles=%d: its table would be truncated" % (na, self.alleles))
+            self._tables.append((self._akey[:2 * na].reshape(na, 2).copy(), self._acnt[:na].copy(), self._arow[:na].copy(),
+                                 np.full(na, self.batches, np.int32)))
+        self.batches += 1
+        return n, int(po.rc_n)
+
+    def take_results(self, sync=True):
+        """(reductions, merged allele table) of the batches run since the last call; both start afresh afterwards (batches
+        already staged stay staged: a stream of read sets can keep the copy of the next set's first batch in flight).
+        With deferred outputs the per-read arrays of the last batch are still travelling: sync=True waits for them;
+        sync=False leaves them to arrive behind the next batch's kernels (valid after the next-but-one run() or ctx.sync())."""
+        if self.deferred and sync:
+            self.ctx.sync()
+        red, table = self.red, self.alleles_merged()
+        self.red = Reductions(self.L)
+        self._tables = []
+        self.batches = 0
+        return red, table
+
+    def alleles_merged(self):
+        """(counts i64[A], batch i32[A], row i32[A]) most frequent first: the per-batch tables merged by their two 64-bit
+        keys; ``row`` is the representative's row within its batch (read index i for a forward row, n_batch + j for that
+        batch's RC row j)."""
+        if not self._tables:
+            return np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int32)
+        keys = np.concatenate([t[0] for t in self._tables])
+        cnt = np.concatenate([t[1] for t in self._tables])
+        row = np.concatenate([t[2] for t in self._tables])
+        bat = np.concatenate([t[3] for t in self._tables])
+        _u, first, inv = np.unique(keys[:, 0], return_index=True, return_inverse=True)
+        if not np.array_equal(keys[first, 1][inv], keys[:, 1]):
+            raise RuntimeError("allele merge: two alleles share their first 64-bit key")
+        total = np.zeros(len(first), np.int64)
+        np.add.at(total, inv, cnt)
+        order = np.argsort(-total, kind="stable")
+        return total[order], bat[first][order], row[first][order]
+
+
+def run_hot_path_staged(ctx, amplicon, reads, chunk_reads=1 << 19, packed=None, out=None, **kw):
+    """run_hot_path for HOST-resident reads through StagedPipeline: the read set is cut into chunks of ~``chunk_reads``, the
+    copy of chunk c + 1 overlaps the kernels of chunk c.  ``reads`` = (buffer, offsets); ``packed`` = pack_bam4(buffer) to
+    send 4 bits per base instead of 8 (chunks then start on even base offsets).  Per-read outputs in read order, RC rows
+    in read order, reductions and (with ``alleles=``) the merged allele table as ``(allele_row, allele_count)`` where a row
+    >= n is RC row (row - n) of the returned list.  Text rows need the single call (run_hot_path)."""
+    buf, offsets = reads
+    n = len(offsets) - 1
+    pipe = StagedPipeline(ctx, amplicon, **kw)
+    out = out or {}
+
+    def arr(name, dtype, size):
+        a = out.get(name)
+        return a if a is not None else np.zeros(size, dtype)
+
+    kept, aln, recs = arr("kept", np.uint8, n), arr("aln", _lib.ALN_REC, n), arr("recs", _lib.READ_REC, n)
+    trep = out.get("tenths_rep")
+    if trep is None:
+        trep = np.full(n, -1, np.int32)
+    rc_read, rc_aln, rc_recs = arr("rc_read", np.int32, n), arr("rc_aln", _lib.ALN_REC, n), arr("rc_recs", _lib.READ_REC, n)
+    # chunk boundaries (on even base offsets when the reads travel packed)
+    bounds, lo = [], 0
+    while lo < n:
+        hi = min(n, lo + int(chunk_reads))
+        while packed is not None and hi < n and (int(offsets[hi]) & 1):
+            hi += 1
+        bounds.append((lo, hi))
+        lo = hi
+    off_stage = arr("offsets", np.int64, n + len(bounds))
+
+    def stage(c):
+        lo, hi = bounds[c]
+        offs = off_stage[lo + c:lo + c + (hi - lo) + 1]
+        np.subtract(offsets[lo:hi + 1], offsets[lo], out=offs)
+        b0, b1 = int(offsets[lo]), int(offsets[hi])
+        if packed is not None:
+            pipe.stage(packed[b0 // 2:(b1 + 1) // 2], offs, packed=True)
+        else:
+            pipe.stage(buf[b0:b1], offs)
+
+    nrcs = []
+    if bounds:
+        stage(0)
+    for c, (lo, hi) in enumerate(bounds):
+        if c + 1 < len(bounds):
+            stage(c + 1)
+        view = {"kept": kept[lo:hi], "aln": aln[lo:hi], "recs": recs[lo:hi], "tenths_rep": trep[lo:hi],
+                "rc_read": rc_read[lo:hi], "rc_aln": rc_aln[lo:hi], "rc_recs": rc_recs[lo:hi]}
+        _m, nrc = pipe.run(view)
+        nrcs.append(nrc)
+    if pipe.deferred:
+        ctx.sync()                           # the per-read arrays of the last chunks are still on their way
+    # RC rows: each chunk left its own compact, read-ordered list at [lo, lo + nrc); close the gaps
+    pos, rc_base = 0, []
+    for c, (lo, hi) in enumerate(bounds):
+        k = nrcs[c]
+        rc_base.append(pos)
+        if k:
+            rc_read[pos:pos + k] = rc_read[lo:lo + k] + lo
+            if pos != lo:
+                rc_aln[pos:pos + k] = rc_aln[lo:lo + k]
+                rc_recs[pos:pos + k] = rc_recs[lo:lo + k]
+            pos += k
+    allele_row = allele_count = None
+    allele_n = 0
+    if pipe.alleles:
+        allele_count, bat, row = pipe.alleles_merged()
+        allele_n = len(allele_count)
+        los = np.array([lo for lo, _hi in bounds], np.int64)[bat]
+        sizes = np.array([hi - lo for lo, hi in bounds], np.int64)[bat]
+        rcb = np.array(rc_base, np.int64)[bat]
+        allele_row = np.where(row < sizes, los + row, n + rcb + (row - sizes))
+    return HotPathResult(kept, aln, trep, recs, None, 0, rc_read[:pos], rc_aln[:pos], rc_recs[:pos], None, pipe.red,
+                         allele_row, allele_count, allele_n)
+
+
 def build_dataframe(res, read_names, has_hdr=False, amplicon=None):
     """df_needle_alignment as run_crispresso holds it after CORE:2072 and the quantification
     (CORE:2864): index ID, columns score_ref [score_repaired score_diff] length ref_seq align_str

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CRGPU_ABI_VERSION 4
+#define CRGPU_ABI_VERSION 5
 
 enum {
     CRGPU_OK = 0,
@@ -217,7 +217,8 @@ typedef struct {
 typedef struct {
     /* forward rows, indexed by read; per-read arrays follow `mem` */
     uint8_t *kept;                         /* [n] bit0: forward row kept, bit1: RC row kept,
-                                              bit2: read was re-aligned to the reverse complement */
+                                              bit2: read was re-aligned to the reverse complement,
+                                              bit3: not aligned -- a base outside ACGTN(U) (alone: no other bit is set) */
     crgpu_aln_rec *aln;                    /* [n] alignment vs the amplicon */
     int32_t *tenths_rep;                   /* [n] identity tenths vs the HDR amplicon (-1 = NaN / no HDR); may be NULL */
     crgpu_read_rec *recs;                  /* [n] valid where kept&1 */
@@ -249,11 +250,31 @@ typedef struct {
     int64_t n_cells_computed;              /* OUT (added): DP cells actually evaluated.  Less than n_cells when the HDR
                                               pass reuses the DP rows it shares with the amplicon pass (same-length HDR
                                               amplicon: all rows above the first differing base are identical) */
+    uint64_t *allele_key;                  /* [2 * allele_cap] or NULL; HOST: two independent 64-bit hashes of allele k's
+                                              grouping key.  A caller that quantifies one read set in several calls (chunks)
+                                              merges the per-call tables by them (hotpath.run_hot_path_pipelined) */
 } crgpu_path_out;
 
 int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int amplicon_len,
                          const crgpu_path_params *path, const crgpu_quant_params *quant,
                          const uint8_t *reads, const int64_t *offsets, int64_t n, crgpu_path_out *out);
+
+/* ---- staged inputs: the NEXT batch of reads is copied while the current one is computed ------- *
+ * crgpu_stage_reads starts the host-to-device copy of a batch on the context's copy stream into staging slot 0 or 1
+ * and returns at once (`reads` / `offsets` must stay valid -- and should be pinned -- until the batch has been
+ * consumed); crgpu_align_quantify_staged waits for that copy and runs crgpu_align_quantify on the batch, with every
+ * output in HOST memory.  Typical loop: stage(0, b0); for k: stage((k+1)&1, b[k+1]); align_quantify_staged(k&1).
+ * format: CRGPU_READS_BYTES = one base per byte, as everywhere else; CRGPU_READS_BAM4 = two bases per byte in BAM's
+ * 4-bit codes "=ACMGRSVTWYHKDBN", high nibble first, dense (base j of the batch is nibble j; offsets count BASES):
+ * half the bytes over PCIe, unpacked on the device.  Codes other than A C G T N are reported per read (kept bit 3). */
+enum { CRGPU_READS_BYTES = 0, CRGPU_READS_BAM4 = 1 };
+/* on = 1: crgpu_align_quantify_staged returns as soon as the reductions, the RC-rescue rows and the allele table are in
+ * host memory; the per-read arrays (kept, aln, recs, tenths_rep) follow on the copy stream, behind the next batch's
+ * kernels, and are valid after crgpu_sync (or after the staged call two batches later has returned). */
+int crgpu_set_deferred_outputs(crgpu_ctx *ctx, int on);
+int crgpu_stage_reads(crgpu_ctx *ctx, int slot, int format, const uint8_t *reads, const int64_t *offsets, int64_t n);
+int crgpu_align_quantify_staged(crgpu_ctx *ctx, int slot, const char *amplicon, int amplicon_len,
+                                const crgpu_path_params *path, const crgpu_quant_params *quant, crgpu_path_out *out);
 
 /* ---- S0: paired-end merge -- the `flash` subprocess of CORE:1655-1664 -------------- *
  * `flash R1 R2 --allow-outies --max-overlap M --min-overlap m` (FLASH 1.2.11; default maximum mismatch

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(build.build())
     for name in declared_functions():
         assert hasattr(lib, name), name
-    assert lib.crgpu_abi_version() == 4
+    assert lib.crgpu_abi_version() == 5
 
 
 def test_no_cpu_fallback_without_a_gpu():
@@ -43,7 +43,7 @@ def test_struct_layouts_match_the_header():
     assert _lib.ALN_REC.itemsize == 32 and _lib.READ_REC.itemsize == 16
     assert ctypes.sizeof(_lib.QuantParams) == 40
     assert ctypes.sizeof(_lib.PathParams) == 40
-    assert ctypes.sizeof(_lib.PathOut) == 8 * 8 + 8 * 8 + 3 * 8 + 8 + 8 + 4 * 8 + 2 * 8 + 4 * 8 + 8
+    assert ctypes.sizeof(_lib.PathOut) == 8 * 8 + 8 * 8 + 3 * 8 + 8 + 8 + 4 * 8 + 2 * 8 + 4 * 8 + 8 + 8
 
 
 def test_product_never_imports_the_oracle():

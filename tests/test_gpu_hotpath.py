@@ -220,6 +220,57 @@ def test_pipelined_chunks_on_two_contexts_equal_one_call(ctx):
         other.close()
 
 
+def test_staged_pipeline_equals_one_call(ctx):
+    """hotpath.run_hot_path_staged -- crgpu_stage_reads (one base per byte, or BAM 4-bit codes unpacked on the device) on the
+    copy stream while crgpu_align_quantify_staged works on the previous chunk -- must return what one call over all reads
+    returns: per-read records, the RC-rescue list, every reduction, and the same allele table (merged by key)."""
+    amp, guide, cut, hdr = synth.make_case(33, 200)
+    packed_reads = synth.make_reads(amp, hdr, cut, 2400, seed=34, read_len=200, rc_frac=0.07, n_rate=0.002)
+    buf, off = packed_reads
+    buf = buf.copy()
+    buf[off[17] + 5] = ord("R")                                   # one IUPAC code: reported per read in either format
+    inc = hotpath.include_mask(len(amp), hotpath.cut_points_from_guides(amp, guide), 1, 15, 15)
+    flags = hotpath.quant_flags(hdr)
+    one = hotpath.run_hot_path(ctx, amp, (buf, off), hdr_amplicon=hdr, flags=flags, inc=inc, want_rows=True, alleles=4096)
+    assert one.bad_base[17] == 1 and int(one.bad_base.sum()) == 1
+    text = {}
+    for k in range(one.allele_n):                                 # allele (text rows + class + counts) -> #Reads
+        row = int(one.allele_row[k])
+        text[_allele_text(one, row)] = int(one.allele_count[k])
+    for chunk, fmt, deferred in ((700, None, False), (1000, "bam4", True), (300, None, True), (4096, "bam4", False)):
+        pk = hotpath.pack_bam4(buf) if fmt else None
+        got = hotpath.run_hot_path_staged(ctx, amp, (buf, off), chunk_reads=chunk, packed=pk, hdr_amplicon=hdr, flags=flags,
+                                          inc=inc, alleles=4096, deferred=deferred)
+        assert np.array_equal(got.kept, one.kept)
+        fields = [f for f in _lib.ALN_REC.names if f != "aln_off"]
+        for f in fields:
+            assert np.array_equal(got.aln[f], one.aln[f]), f
+        assert np.array_equal(got.tenths_rep, one.tenths_rep) and got.recs.tobytes() == one.recs.tobytes()
+        assert len(one.rc_read) > 0 and np.array_equal(got.rc_read, one.rc_read)
+        for f in fields:
+            assert np.array_equal(got.rc_aln[f], one.rc_aln[f]), f
+        assert got.rc_recs.tobytes() == one.rc_recs.tobytes()
+        assert np.array_equal(got.red.results(), one.red.results())
+        assert got.allele_n == one.allele_n and sorted(got.allele_count.tolist()) == sorted(one.allele_count.tolist())
+        # every merged allele's representative row spells an allele of the single call, with that call's count
+        for k in range(got.allele_n):
+            assert text[_allele_text(one, int(got.allele_row[k]))] == int(got.allele_count[k])
+
+
+def _allele_text(res, row):
+    """Grouping key of the reference's allele table (CORE:2923-2946) for forward row `row` (or RC row row - n) of a
+    want_rows result."""
+    n = len(res.kept)
+    if row < n:
+        r = res.recs[row]
+        o = int(res.aln["aln_off"][row])
+        return (res.rows[0][row, o:].tobytes().decode(), res.rows[2][row, o:].tobytes().decode(), int(r["cls"]), int(r["n_mutated"]),
+                int(r["n_inserted"]), int(r["n_deleted"]))
+    j = row - n
+    r = res.rc_recs[j]
+    return (res.rc_rows[0][j], res.rc_rows[2][j], int(r["cls"]), int(r["n_mutated"]), int(r["n_inserted"]), int(r["n_deleted"]))
+
+
 def test_band_holds_off_after_a_call_whose_reads_mostly_escape(ctx):
     """More than a quarter of the reads leaving the band means the band costs more than it saves: the next calls run
     the single-pass fill (same results, no escapes) until crgpu_set_band is called again."""

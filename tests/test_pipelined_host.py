@@ -14,6 +14,31 @@ class _FakeLib:
 
     def __init__(self):
         self.calls = []
+        self.staged = {}
+
+    def crgpu_set_deferred_outputs(self, handle, on):
+        return 0
+
+    def crgpu_stage_reads(self, handle, slot, fmt, reads_addr, offs_addr, n):
+        """Copies the batch (as the library would, onto the device) so that a caller that drops its buffers early is caught."""
+        offs = np.ctypeslib.as_array(ctypes.cast(offs_addr, ctypes.POINTER(ctypes.c_int64)), (n + 1,)).copy()
+        assert offs[0] == 0
+        total = int(offs[n])
+        nbytes = (total + 1) // 2 if fmt == _lib.READS_BAM4 else total
+        raw = np.ctypeslib.as_array(ctypes.cast(reads_addr, ctypes.POINTER(ctypes.c_uint8)), (nbytes,)).copy()
+        if fmt == _lib.READS_BAM4:
+            lut = np.frombuffer(b"=ACMGRSVTWYHKDBN", np.uint8)
+            both = np.empty(2 * nbytes, np.uint8)
+            both[0::2], both[1::2] = lut[raw >> 4], lut[raw & 15]
+            raw = both[:total].copy()
+        assert slot in (0, 1) and slot not in self.staged, "slot staged twice without a run in between"
+        self.staged[slot] = (raw, offs, n)
+        return 0
+
+    def crgpu_align_quantify_staged(self, handle, slot, amp, L, pp, qp, po):
+        raw, offs, n = self.staged.pop(slot)
+        self._keep = (raw, offs)
+        return self.crgpu_align_quantify(handle, _lib.MEM_HOST, amp, L, pp, qp, raw.ctypes.data, offs.ctypes.data, n, po)
 
     def crgpu_align_quantify(self, handle, mem, amp, L, pp, qp, reads_addr, offs_addr, n, po):
         assert mem == _lib.MEM_HOST
@@ -51,6 +76,18 @@ class _FakeLib:
                 rc_read[nrc] = i
                 rc_aln[nrc]["alnlen"], rc_recs[nrc]["n_deleted"] = len(seq), h % 17
                 nrc += 1
+        if po.allele_cap:
+            # alleles of the stand-in: kept rows grouped by crc32 % 13, keys = (group, group * 7 + 1)
+            groups = {}
+            for i in range(n):
+                if kept[i]:
+                    groups.setdefault(zlib.crc32(bytes(buf[offs[i]:offs[i + 1]])) % 13, []).append(i)
+            table = sorted(groups.items(), key=lambda kv: -len(kv[1]))
+            arow, acnt = view(po.allele_row, np.int32, po.allele_cap), view(po.allele_count, np.int64, po.allele_cap)
+            akey = view(po.allele_key, np.uint64, 2 * po.allele_cap)
+            for k, (g, members) in enumerate(table[:po.allele_cap]):
+                arow[k], acnt[k], akey[2 * k], akey[2 * k + 1] = members[0], len(members), g, g * 7 + 1
+            po.allele_n = len(table)
         po.rc_n, po.n_total, po.n_cells = nrc, po.n_total + n, po.n_cells + int(offs[n]) * L
         po.n_cells_computed += int(offs[n]) * L
         return 0
@@ -59,6 +96,9 @@ class _FakeLib:
 class _FakeCtx:
     def __init__(self, lib, handle):
         self.lib, self.handle = lib, handle
+
+    def sync(self):
+        pass
 
     def check(self, rc):
         assert rc == 0
@@ -104,3 +144,30 @@ def test_preallocated_outputs_are_used_in_place():
     got = hotpath.run_hot_path_pipelined([_FakeCtx(lib, 0), _FakeCtx(lib, 1)], amp, reads, chunk_reads=100, red=red, out=out)
     assert got.kept is out["kept"] and got.aln is out["aln"] and got.red is red
     assert red.n_total == n and int(red.class_counts.sum()) == n
+
+
+def test_staged_pipeline_equals_one_call_bytes_and_packed():
+    """hotpath.run_hot_path_staged (one context, the next chunk staged while the current one runs): chunk slicing, the
+    even-offset rule of the 4-bit format, RC-list compaction, reductions and the allele tables merged by key."""
+    amp = "ACGT" * 10
+    reads = _reads(1000, 5)
+    lib1 = _FakeLib()
+    one = hotpath.run_hot_path_staged(_FakeCtx(lib1, 1), amp, reads, chunk_reads=1 << 20, alleles=64)
+    assert lib1.calls == [(1, 1000)] and one.allele_n == 13 and int(one.allele_count.sum()) == int((one.kept & 1).sum())
+    packed = hotpath.pack_bam4(reads[0])
+    for chunk, pk in ((170, None), (64, None), (333, packed), (50, packed), (1000, packed)):
+        lib = _FakeLib()
+        got = hotpath.run_hot_path_staged(_FakeCtx(lib, 0), amp, reads, chunk_reads=chunk, packed=pk, alleles=64)
+        assert sum(c[1] for c in lib.calls) == 1000 and not lib.staged
+        for f in ("kept", "tenths_rep", "rc_read"):
+            assert np.array_equal(getattr(got, f), getattr(one, f)), f
+        for f in ("aln", "recs", "rc_aln", "rc_recs"):
+            assert getattr(got, f).tobytes() == getattr(one, f).tobytes(), f
+        assert np.array_equal(got.red.flat(), one.red.flat())
+        assert sorted(got.allele_count.tolist()) == sorted(one.allele_count.tolist()) and got.allele_n == one.allele_n
+        # a representative row belongs to its allele: same group key as the single call's representative with that count
+        def group(res, row):
+            b, o = reads
+            return zlib.crc32(bytes(b[o[row]:o[row + 1]])) % 13
+        assert {group(got, int(r)): int(c) for r, c in zip(got.allele_row, got.allele_count)} == \
+               {group(one, int(r)): int(c) for r, c in zip(one.allele_row, one.allele_count)}
