@@ -1,13 +1,19 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the CRISPResso hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--reads R]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--reads R] [--config cfg2|cfg3|cfg4|cfg5]
+                    [--scaling weak|strong]
 
 A "step" = one pass of the hot path (CORE:1791-2072 + 2773-2869: alignment to the amplicon AND the
 HDR amplicon with needle semantics, reverse-complement rescue, classification and all
 histograms) over one batch of synthetic reads.  Workload at any N: BASELINE.json configs[1]
 per GPU -- 2^20 single-end 250-bp reads vs a 250-bp amplicon + HDR amplicon (weak scaling: reads
 shard across ranks, one NCCL all-reduce of the int64 histogram block per step).
+
+--config selects another BASELINE.json workload: cfg3 = merged-PE-like reads N(300, 8) vs a 300-bp amplicon
+with a 120-bp coding sequence (frameshift analysis), no HDR; cfg4 = pooled amplicons (lengths uniform 150-400, one
+crgpu_align_quantify call per amplicon, as CRISPRessoPooled runs one CRISPResso per amplicon); cfg5 = 600-bp amplicon,
+600-bp reads, no HDR.  --scaling strong keeps the TOTAL reads per step fixed (--reads) and splits them over the ranks.
 
 Prints ONE JSON line (rank 0).  `value` = reads/s with inputs resident in HBM, `e2e` = the same
 through the C ABI with pinned HOST buffers (H2D of the reads and D2H of the per-read records
@@ -40,20 +46,66 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--reads", type=int, default=1 << 20, help="reads per GPU per step")
-    ap.add_argument("--cpu-sample", type=int, default=200000, help="reads in the CPU baseline sample")
+    ap.add_argument("--reads", type=int, default=1 << 20, help="reads per GPU per step (--scaling strong: per step over all GPUs)")
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"], help="BASELINE.json workload (headline: cfg2)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--pool-amplicons", type=int, default=16, help="cfg4: amplicons per GPU per step (reads are split evenly)")
+    ap.add_argument("--cpu-sample", type=int, default=100000, help="reads in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="reads per staged chunk of the end-to-end arm (default: reads / 2)")
     ap.add_argument("--e2e-alleles", type=int, default=1 << 16, help="capacity of the per-chunk allele table of the end-to-end arm")
     return ap.parse_args()
 
 
-def workload(n_reads, rank):
-    from crispresso_b200 import hotpath, synth
-    amp, guide, cut, hdr = synth.make_case(SEED, AMPLICON_LEN)
-    buf, off = synth.make_reads_fast(amp, hdr, cut, n_reads, seed=SEED + 17 * rank, read_len=READ_LEN)
-    inc = hotpath.include_mask(AMPLICON_LEN, hotpath.cut_points_from_guides(amp, guide), 1, 15, 15)
-    return amp, guide, cut, hdr, buf, off, inc
+class Job:
+    """One crgpu_align_quantify call of a step: an amplicon (+ HDR amplicon), its analysis options and its reads."""
+
+    def __init__(self, amp, guide, hdr, buf, off, window=1, coding=""):
+        from crispresso_b200 import hotpath
+        self.amp, self.hdr, self.buf, self.off = amp, hdr, buf, off
+        self.L = len(amp)
+        self.n = len(off) - 1
+        self.inc = hotpath.include_mask(self.L, hotpath.cut_points_from_guides(amp, guide), window, 15, 15)
+        self.exon = self.splice = None
+        if coding:
+            self.exon, self.splice = hotpath.exon_masks(amp, coding)
+        self.window, self.coding = window, coding
+        self.flags = hotpath.quant_flags(hdr or "", window_around_sgrna=window, coding_seq=coding)
+        self.kw = dict(hdr_amplicon=hdr, flags=self.flags, inc=self.inc, exon=self.exon, splice=self.splice)
+
+
+def workload(config, n_reads, rank, pool_amplicons=16):
+    """-> (jobs of one step on this rank, description)"""
+    from crispresso_b200 import synth
+    if config == "cfg2":
+        amp, guide, cut, hdr = synth.make_case(SEED, AMPLICON_LEN)
+        buf, off = synth.make_reads_fast(amp, hdr, cut, n_reads, seed=SEED + 17 * rank, read_len=READ_LEN)
+        return [Job(amp, guide, hdr, buf, off)], (
+            "cfg2: %d single-end %d-bp reads per GPU vs %d-bp amplicon + HDR amplicon (needle gapopen 10 / gapextend 0.5), "
+            "RC rescue, classification + histograms" % (n_reads, READ_LEN, AMPLICON_LEN))
+    if config == "cfg3":
+        amp, guide, cut, _ = synth.make_case(SEED + 3, 300, hdr=False)
+        buf, off = synth.make_reads_fast(amp, None, cut, n_reads, seed=SEED + 3 + 17 * rank, read_len=300, len_sigma=8.0, p_exact=0.8)
+        return [Job(amp, guide, None, buf, off, window=20, coding=amp[cut - 60:cut + 60])], (
+            "cfg3: %d merged-PE-like reads per GPU (lengths N(300, 8) clipped to [260, 340], 20 %% with an indel) vs a 300-bp amplicon, "
+            "120-bp coding sequence around the cut (frameshift analysis), window 20, no HDR amplicon" % n_reads)
+    if config == "cfg4":
+        rng = np.random.default_rng(SEED + 4)
+        lens = rng.integers(150, 401, size=200)                       # the 200 amplicons of the pooled run
+        mine = [int(x) for x in lens[(rank * pool_amplicons) % 200:][:pool_amplicons]]
+        while len(mine) < pool_amplicons:
+            mine += [int(x) for x in lens[:pool_amplicons - len(mine)]]
+        per = max(1, n_reads // pool_amplicons)
+        jobs = []
+        for j, L in enumerate(mine):
+            amp, guide, cut, _ = synth.make_case(SEED + 400 + 1000 * rank + j, L, hdr=False)
+            buf, off = synth.make_reads_fast(amp, None, cut, per, seed=SEED + 400 + 1000 * rank + j, read_len=L)
+            jobs.append(Job(amp, guide, None, buf, off))
+        return jobs, ("cfg4: %d pooled amplicons per GPU per step (lengths uniform 150-400: %s), %d reads each, one "
+                      "crgpu_align_quantify call per amplicon, no HDR amplicon" % (pool_amplicons, mine, per))
+    amp, guide, cut, _ = synth.make_case(SEED + 5, 600, hdr=False)
+    buf, off = synth.make_reads_fast(amp, None, cut, n_reads, seed=SEED + 5 + 17 * rank, read_len=600)
+    return [Job(amp, guide, None, buf, off)], "cfg5: %d single-end 600-bp reads per GPU vs a 600-bp amplicon, no HDR amplicon" % n_reads
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -103,54 +155,77 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_reference_step(amp, hdr, inc, buf, off, nthreads):
-    """One pass of the reference path restated on the CPU (oracle/): needle port on `nthreads`
-    host threads for the amplicon and the HDR amplicon + RC rescue + the Python per-read loop."""
-    from oracle import quantify
+def cpu_reference_step(job, sb, so, nthreads, use_reference=True):
+    """One pass of the reference path on the host.  Stage 1 -- needle for the amplicon and the HDR
+    amplicon + the RC rescue: the reference shells out to EMBOSS needle, a third-party binary that is not in this image, so
+    its C restatement (oracle/needle_oracle.c, float32 as needle) runs on `nthreads` pthreads.  Stage 2 -- quantification:
+    the reference's OWN unmodified process_df_chunk (CORE:428-753) through multiprocessing.Pool as run_crispresso drives it
+    with -p <cores> (CORE:2773-2838), imported from baseline/_ref (pip-installed copy) or /root/reference; when neither is
+    there, the oracle's Python restatement of it.  -> (seconds, result, stage seconds, kind of the quantifier)."""
+    from oracle import quantify, ref_quantify
+    process, qkind = None, "port (oracle/quantify.py)"
+    if use_reference and ref_quantify.available():
+        qkind = "reference (CRISPRessoCORE.process_df_chunk, mp.Pool of %d)" % nthreads
+
+        def process(*a):
+            return ref_quantify.process_rows_reference(*a, n_processes=nthreads)
+    stages = {}
+    opts = quantify.Opts(expected_hdr_amplicon_seq=job.hdr or "", coding_seq=job.coding, window_around_sgrna=job.window)
     t0 = time.time()
-    res = quantify.hot_path(amp, (buf, off), hdr_amplicon=hdr, opts=quantify.Opts(expected_hdr_amplicon_seq=hdr),
-                            include=np.nonzero(inc)[0], nthreads=nthreads, use_int=False)
-    return time.time() - t0, res
+    res = quantify.hot_path(job.amp, (sb, so), hdr_amplicon=job.hdr or "", opts=opts, include=np.nonzero(job.inc)[0],
+                            exon=np.nonzero(job.exon)[0] if job.exon is not None else (),
+                            splice=np.nonzero(job.splice)[0] if job.splice is not None else (),
+                            nthreads=nthreads, use_int=False, process=process, timings=stages)
+    return time.time() - t0, res, stages, qkind
 
 
-def cpu_baseline(args, amp, hdr, inc, buf, off):
-    n = min(args.cpu_sample, len(off) - 1)
-    sb, so = buf[:off[n]].copy(), off[:n + 1].copy()
+def cpu_baseline_dict(n, steps, dt, cells, stages, qkind, cores):
+    al, qu = stages.get("align_prepare_s", 0.0), stages.get("quantify_s", 0.0)
+    return {"value": n * steps / dt, "unit": "reads/s", "cores": cores,
+            "kind": "reference" if qkind.startswith("reference") else "port",
+            "gcups": cells / dt / 1e9,
+            "stages": {"needle": {"kind": "port (oracle/needle_oracle.c, float32 as EMBOSS needle 6.6.0; the binary is not in the image)",
+                                  "threads": cores, "reads_per_s": n * steps / al if al > 0 else None},
+                       "quantify": {"kind": qkind, "reads_per_s": n * steps / qu if qu > 0 else None}},
+            "sample": "%d reads/step x %d step(s) of the rank-0 workload: needle port on %d pthreads for every amplicon + RC rescue, "
+                      "then the quantification stage (%s), %.1f s" % (n, steps, cores, qkind, dt)}
+
+
+def cpu_baseline(args, job):
+    n = min(args.cpu_sample, job.n)
+    sb, so = job.buf[:job.off[n]].copy(), job.off[:n + 1].copy()
     cores = os.cpu_count() or 1
-    dt, res = cpu_reference_step(amp, hdr, inc, sb, so, cores)
-    return {"value": n / dt, "unit": "reads/s", "cores": cores, "kind": "port",
-            "gcups": res["n_cells"] / dt / 1e9,
-            "sample": "first %d reads of the rank-0 workload, both amplicons + RC rescue + quantification, "
-                      "C needle port on %d pthreads + single-process Python quantifier, %.1f s" % (n, cores, dt)}
+    dt, res, stages, qkind = cpu_reference_step(job, sb, so, cores)
+    return cpu_baseline_dict(n, 1, dt, res["n_cells"], stages, qkind, cores)
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    amp, guide, cut, hdr, buf, off, inc = workload(max(args.cpu_sample, 1), 0)
-    n = min(args.cpu_sample, len(off) - 1)
-    sb, so = buf[:off[n]].copy(), off[:n + 1].copy()
+    jobs, workload_text = workload(args.config, max(args.cpu_sample, 1), 0, 1 if args.config == "cfg4" else args.pool_amplicons)
+    job = jobs[0]
+    n = min(args.cpu_sample, job.n)
+    sb, so = job.buf[:job.off[n]].copy(), job.off[:n + 1].copy()
     cores = os.cpu_count() or 1
     for _ in range(args.warmup):
-        cpu_reference_step(amp, hdr, inc, sb[:so[200]].copy(), so[:201].copy(), cores)
+        cpu_reference_step(job, sb[:so[200]].copy(), so[:201].copy(), cores)
     t0 = time.time()
-    cells = 0
+    cells, stages, qkind = 0, {}, ""
     for _ in range(args.steps):
-        _dt, res = cpu_reference_step(amp, hdr, inc, sb, so, cores)
+        _dt, res, st, qkind = cpu_reference_step(job, sb, so, cores)
         cells += res["n_cells"]
+        for k, v in st.items():
+            stages[k] = stages.get(k, 0.0) + v
     dt = time.time() - t0
     value = n * args.steps / dt
     line = {
         "impl": "reference", "metric": "aligned_reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "gcups": cells / dt / 1e9,
-        "config": {"workload": "cfg2: single-end %d-bp reads vs %d-bp amplicon + HDR amplicon; CPU arm runs a bounded "
-                               "sample of %d reads per step" % (READ_LEN, AMPLICON_LEN, n), "reads_per_step": n},
-        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "port",
-                         "sample": "%d reads/step x %d steps; oracle C needle port (float32, as needle) on %d pthreads + "
-                                   "Python quantifier (the reference's own needle is a missing third-party binary)" % (
-                                       n, args.steps, cores)},
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "gcups": cells / dt / 1e9,
+        "config": {"workload": workload_text + "; the CPU arm runs a bounded sample of %d reads per step" % n, "name": args.config,
+                   "reads_per_step": n},
+        "cpu_baseline": cpu_baseline_dict(n, args.steps, dt, cells, stages, qkind, cores),
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -179,10 +254,11 @@ def main():
     ctx = Context(local)
     ext_stream = torch.cuda.ExternalStream(ctx.stream_ptr(), device=torch.device("cuda", local))
 
-    n = args.reads
-    amp, guide, cut, hdr, buf, off, inc = workload(n, rank)
-    L = len(amp)
-    flags = hotpath.quant_flags(hdr)
+    # reads of one step on this rank: --reads per GPU (weak scaling), or --reads over all ranks (strong scaling)
+    n = args.reads if args.scaling == "weak" else max(1, args.reads // world)
+    jobs, workload_text = workload(args.config, n, rank, args.pool_amplicons)
+    n = sum(j.n for j in jobs)
+    n_alignments = sum(j.n * (2 if j.hdr else 1) for j in jobs)
 
     # integer issue peaks, measured live: (i) both integer pipes -- dependency-free IADD chains that
     # ptxas splits 1:1 over the alu (IADD3) and fma (IMAD.IADD) pipes, and a VIMNMX.S16x2 + IMAD 1:1 mix; (ii) the
@@ -191,36 +267,42 @@ def main():
     alu_peak = max(ctx.int_peak(2), ctx.int_peak(3), ctx.int_peak(5))
 
     # ---- device-resident arm ------------------------------------------------------------------
-    d_buf = torch.from_numpy(buf).cuda()
-    d_off = torch.from_numpy(off).cuda()
-    dev_out = {
-        "kept": torch.zeros(n, dtype=torch.uint8, device="cuda"),
-        "aln": torch.zeros(n * _lib.ALN_REC.itemsize, dtype=torch.uint8, device="cuda"),
-        "recs": torch.zeros(n * _lib.READ_REC.itemsize, dtype=torch.uint8, device="cuda"),
-        "tenths_rep": torch.zeros(n, dtype=torch.int32, device="cuda"),
-    }
-    dev_ptrs = {k: v.data_ptr() for k, v in dev_out.items()}
+    for j in jobs:
+        j.d_buf = torch.from_numpy(j.buf).cuda()
+        j.d_off = torch.from_numpy(j.off).cuda()
+        j.dev_out = {
+            "kept": torch.zeros(j.n, dtype=torch.uint8, device="cuda"),
+            "aln": torch.zeros(j.n * _lib.ALN_REC.itemsize, dtype=torch.uint8, device="cuda"),
+            "recs": torch.zeros(j.n * _lib.READ_REC.itemsize, dtype=torch.uint8, device="cuda"),
+            "tenths_rep": torch.zeros(j.n, dtype=torch.int32, device="cuda"),
+        }
+        j.dev_ptrs = {k: v.data_ptr() for k, v in j.dev_out.items()}
     torch.cuda.synchronize()          # torch initialises these on its own stream; the library uses another
 
     from crispresso_b200.distributed import allreduce_reductions
 
-    def allreduce(red):
-        allreduce_reductions(red, device=torch.device("cuda", local))
+    def allreduce(reds):
+        for red in reds:
+            allreduce_reductions(red, device=torch.device("cuda", local))
 
     fam_ms = {k: 0.0 for k in Context.TIMING_NAMES}
     fam_launch = {k: 0 for k in Context.TIMING_NAMES}
 
     def step_device(record=False):
-        red = hotpath.Reductions(L)
-        hotpath.run_hot_path(ctx, amp, None, hdr_amplicon=hdr, flags=flags, inc=inc, red=red,
-                             device_inputs=(d_buf.data_ptr(), d_off.data_ptr(), n, READ_LEN, dev_ptrs))
-        if record:
-            ms, ln = ctx.last_timing()
-            for k in ms:
-                fam_ms[k] += ms[k]
-                fam_launch[k] += ln[k]
-        allreduce(red)
-        return red
+        reds = []
+        for j in jobs:
+            red = hotpath.Reductions(j.L)
+            hotpath.run_hot_path(ctx, j.amp, None, red=red, device_inputs=(j.d_buf.data_ptr(), j.d_off.data_ptr(), j.n, 0, j.dev_ptrs),
+                                 **j.kw)
+            if record:
+                ms, ln = ctx.last_timing()
+                for k in ms:
+                    fam_ms[k] += ms[k]
+                    fam_launch[k] += ln[k]
+            reds.append(red)
+        if args.config != "cfg4":          # (pooled amplicons: every amplicon is a result set of its own, nothing to reduce)
+            allreduce(reds)
+        return reds
 
     def barrier():
         torch.cuda.synchronize()
@@ -229,7 +311,7 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        red = step_device()
+        reds = step_device()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -240,23 +322,25 @@ def main():
     t_wall0 = time.time()
     ev0.record(ext_stream)
     for _ in range(args.steps):
-        red = step_device(record=True)
+        reds = step_device(record=True)
     ev1.record(ext_stream)
     barrier()
     t_wall1 = time.time()
     dev_ms = ev0.elapsed_time(ev1)
     # one extra, untimed step with the walk/fill overlap off: per-kernel times without a co-running kernel
     iso_ms = {k: 0.0 for k in Context.TIMING_NAMES}
-    iso_ln = {k: 0 for k in Context.TIMING_NAMES}
+    iso_kinds = {k: [0.0, 0, 0] for k in ("score", "band", "full")}
+    iso_computed = 0
     ctx.set_overlap(False)
-    iso_red = hotpath.Reductions(L)
-    hotpath.run_hot_path(ctx, amp, None, hdr_amplicon=hdr, flags=flags, inc=inc, red=iso_red,
-                         device_inputs=(d_buf.data_ptr(), d_off.data_ptr(), n, READ_LEN, dev_ptrs))
-    ms_, ln_ = ctx.last_timing()
-    iso_kinds = ctx.last_fill_breakdown()
-    for k in ms_:
-        iso_ms[k] += ms_[k]
-        iso_ln[k] += ln_[k]
+    for j in jobs:
+        iso_red = hotpath.Reductions(j.L)
+        hotpath.run_hot_path(ctx, j.amp, None, red=iso_red, device_inputs=(j.d_buf.data_ptr(), j.d_off.data_ptr(), j.n, 0, j.dev_ptrs), **j.kw)
+        ms_, _ln = ctx.last_timing()
+        for k in ms_:
+            iso_ms[k] += ms_[k]
+        for k, (ms_k, ln_k, cells_k) in ctx.last_fill_breakdown().items():
+            iso_kinds[k][0] += ms_k; iso_kinds[k][1] += ln_k; iso_kinds[k][2] += cells_k
+        iso_computed += iso_red.n_cells_computed
     ctx.set_overlap(True)
     torch.cuda.synchronize()
     t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
@@ -264,55 +348,62 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms = float(t.item())
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    cells_step = red.n_cells if world == 1 else None
-    n_total = red.n_total
+    red = reds[0]
+    n_total = sum(r.n_total for r in reds)
 
     # ---- end-to-end arm: pinned HOST buffers through the public host API -------------------------
     # hotpath.StagedPipeline on ONE context: every step's reads travel as BAM 4-bit codes (crgpu_stage_reads, asynchronous
-    # H2D on the library's copy stream + unpack on the device) in chunks; the copy of the next chunk -- of this step or of the
-    # next one, as in a stream of batches -- runs while crgpu_align_quantify_staged works on the current chunk.  Every step
-    # brings back what CORE:2892-3992 consumes: per-read records, the RC-rescue rows, all reductions and the allele table.
-    if args.e2e_chunk <= 0:
-        args.e2e_chunk = n            # (measured: one chunk per step 37.9 ms, two 44.7, four 58.1 -- per-call costs)
-    bounds = [(lo, min(n, lo + args.e2e_chunk)) for lo in range(0, n, args.e2e_chunk)]
-    assert all(int(off[lo]) % 2 == 0 for lo, _hi in bounds), "packed chunks start on even base offsets"
-    n_chunks = len(bounds)
-    p_packed = torch.from_numpy(hotpath.pack_bam4(buf)).pin_memory()
-    p_offs = [torch.from_numpy((off[lo:hi + 1] - off[lo]).astype(np.int64)).pin_memory() for lo, hi in bounds]
-    pinned = {
-        "kept": torch.zeros(n, dtype=torch.uint8).pin_memory(),
-        "aln": torch.zeros(n * _lib.ALN_REC.itemsize, dtype=torch.uint8).pin_memory(),
-        "recs": torch.zeros(n * _lib.READ_REC.itemsize, dtype=torch.uint8).pin_memory(),
-        "tenths_rep": torch.zeros(n, dtype=torch.int32).pin_memory(),
-        "rc_read": torch.zeros(n, dtype=torch.int32).pin_memory(),
-        "rc_aln": torch.zeros(n * _lib.ALN_REC.itemsize, dtype=torch.uint8).pin_memory(),
-        "rc_recs": torch.zeros(n * _lib.READ_REC.itemsize, dtype=torch.uint8).pin_memory(),
-    }
-    outs = {k: v.numpy() for k, v in pinned.items()}
-    for k, dt in (("aln", _lib.ALN_REC), ("rc_aln", _lib.ALN_REC), ("recs", _lib.READ_REC), ("rc_recs", _lib.READ_REC)):
-        outs[k] = outs[k].view(dt)
-    packed_np = p_packed.numpy()
-    pipe = hotpath.StagedPipeline(ctx, amp, hdr_amplicon=hdr, flags=flags, inc=inc, alleles=args.e2e_alleles, deferred=True)
-
-    def stage_chunk(c):
-        lo, hi = bounds[c]
-        pipe.stage(packed_np[int(off[lo]) // 2:(int(off[hi]) + 1) // 2], p_offs[c].numpy(), packed=True)
+    # H2D on the library's copy stream + unpack on the device) in chunks; the copy of the next chunk -- of this job, the next
+    # job or the next step, as in a stream of batches -- runs while crgpu_align_quantify_staged works on the current chunk.
+    # Every job brings back what CORE:2892-3992 consumes: per-read records, the RC-rescue rows, all reductions and the allele
+    # table (the per-read arrays travel behind the next chunk's kernels; all of them are in host memory before the clock stops).
+    items = []                               # the chunks of one step, in order: (job, lo, hi, packed bytes view, offsets, outputs)
+    for j in jobs:
+        chunk = args.e2e_chunk if args.e2e_chunk > 0 else j.n      # (measured: one chunk per call 37.9 ms, two 44.7, four 58.1)
+        j.p_packed = torch.from_numpy(hotpath.pack_bam4(j.buf)).pin_memory()
+        packed_np = j.p_packed.numpy()
+        j.pinned = {
+            "kept": torch.zeros(j.n, dtype=torch.uint8).pin_memory(),
+            "aln": torch.zeros(j.n * _lib.ALN_REC.itemsize, dtype=torch.uint8).pin_memory(),
+            "recs": torch.zeros(j.n * _lib.READ_REC.itemsize, dtype=torch.uint8).pin_memory(),
+            "tenths_rep": torch.zeros(j.n, dtype=torch.int32).pin_memory(),
+            "rc_read": torch.zeros(j.n, dtype=torch.int32).pin_memory(),
+            "rc_aln": torch.zeros(j.n * _lib.ALN_REC.itemsize, dtype=torch.uint8).pin_memory(),
+            "rc_recs": torch.zeros(j.n * _lib.READ_REC.itemsize, dtype=torch.uint8).pin_memory(),
+        }
+        outs = {k: v.numpy() for k, v in j.pinned.items()}
+        for k, dt in (("aln", _lib.ALN_REC), ("rc_aln", _lib.ALN_REC), ("recs", _lib.READ_REC), ("rc_recs", _lib.READ_REC)):
+            outs[k] = outs[k].view(dt)
+        j.pipe = hotpath.StagedPipeline(ctx, j.amp, alleles=args.e2e_alleles, deferred=True, **j.kw)
+        j.p_offs = []
+        lo = 0
+        while lo < j.n:
+            hi = min(j.n, lo + chunk)
+            while hi < j.n and (int(j.off[hi]) & 1):                  # packed chunks start on even base offsets
+                hi += 1
+            po = torch.from_numpy((j.off[lo:hi + 1] - j.off[lo]).astype(np.int64)).pin_memory()
+            j.p_offs.append(po)
+            items.append((j, packed_np[int(j.off[lo]) // 2:(int(j.off[hi]) + 1) // 2], po.numpy(), {k: v[lo:hi] for k, v in outs.items()},
+                          hi == j.n))
+            lo = hi
+    n_chunks = len(items)
 
     def run_host_steps(k_steps):
-        """k_steps passes over the read set as one stream of chunks; returns the last step's (reductions, allele table)."""
-        last = None
-        stage_chunk(0)
+        """k_steps passes over the step's chunks as one stream; returns the last step's [(reductions, allele table)] per job."""
+        last = []
+        items[0][0].pipe.stage(items[0][1], items[0][2], packed=True)
         for st in range(k_steps):
-            for c, (lo, hi) in enumerate(bounds):
-                if c + 1 < n_chunks:
-                    stage_chunk(c + 1)
-                elif st + 1 < k_steps:
-                    stage_chunk(0)                                   # the next step's first chunk
-                pipe.run({k: v[lo:hi] for k, v in outs.items()})
-            # (the per-read arrays of this step's last chunk travel behind the next step's kernels)
-            red_s, table = pipe.take_results(sync=False)
-            allreduce(red_s)
-            last = (red_s, table)
+            last = []
+            for c, (j, _pk, _po, out, job_done) in enumerate(items):
+                nxt = items[c + 1] if c + 1 < n_chunks else (items[0] if st + 1 < k_steps else None)
+                if nxt is not None:
+                    nxt[0].pipe.stage(nxt[1], nxt[2], packed=True)
+                j.pipe.run(out)
+                if job_done:
+                    # (the per-read arrays of this job's last chunk travel behind the next chunk's kernels)
+                    last.append(j.pipe.take_results(sync=False))
+            if args.config != "cfg4":
+                allreduce([r for r, _t in last])
         ctx.sync()                                                   # ... and are all in host memory here
         return last
 
@@ -320,7 +411,7 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ext_stream)
-    red_h, alleles_h = run_host_steps(args.steps)
+    host_res = run_host_steps(args.steps)
     e1.record(ext_stream)
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -328,10 +419,10 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
-    h2d_bytes = int(p_packed.numel() + sum(o.numel() * 8 for o in p_offs))
-    d2h_bytes = int(n * (1 + _lib.ALN_REC.itemsize + _lib.READ_REC.itemsize + 4) + red_h.flat().nbytes * n_chunks +
-                    24 * len(alleles_h[0]))
-    same = bool(np.array_equal(red_h.flat()[:-1], red.flat()[:-1]))     # every reduction (n_cells_computed aside: bookkeeping)
+    h2d_bytes = int(sum(j.p_packed.numel() + sum(o.numel() * 8 for o in j.p_offs) for j in jobs))
+    n_alleles = int(sum(len(tb[0]) for _r, tb in host_res))
+    d2h_bytes = int(n * (1 + _lib.ALN_REC.itemsize + _lib.READ_REC.itemsize + 4) + sum(r.flat().nbytes for r, _t in host_res) + 24 * n_alleles)
+    same = all(bool(np.array_equal(rh.flat()[:-1], rd.flat()[:-1])) for (rh, _t), rd in zip(host_res, reds))   # (n_cells_computed aside)
 
     if rank != 0:
         if world > 1:
@@ -341,11 +432,12 @@ def main():
     total_reads = n * world * args.steps
     value = total_reads / (dev_ms * 1e-3)
     e2e_value = total_reads / (e2e_ms * 1e-3)
-    cells_per_rank_step = 2.0 * L * float(off[-1])          # amplicon + HDR amplicon, full DP matrices (RC rescue cells are extra)
+    # full DP matrices of every alignment made: amplicon (+ HDR amplicon) x read (RC rescue cells are extra)
+    cells_per_rank_step = float(sum((2 if j.hdr else 1) * j.L * float(j.off[-1]) for j in jobs))
     # cells the fill launches of one step actually evaluate (score pass: every cell once, the HDR pass only the rows
     # below the shared prefix; band pass: the band columns again, with flags; escapes and the RC rescue: single-pass
     # fill) -- the numerators of the kernel rooflines
-    computed_per_step = float(iso_red.n_cells_computed)
+    computed_per_step = float(iso_computed)
     peak = int_peak / 1e12
     alu_pk = alu_peak / 1e12
     # Roofline model: per packed cell pair the recurrences need 1 add + 2 VIADDMNMX.S16x2 + 1
@@ -385,24 +477,25 @@ def main():
         pass
     line = {
         "metric": "aligned_reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "int16x2", "data": "synthetic",
         "gcups": (cells_per_rank_step * world * args.steps) / (dev_ms * 1e-3) / 1e9,
         "gcups_note": "La x Lb of every alignment made (2 per read) / time; `gcups_evaluated` counts only the DP cells the "
                       "kernels evaluate (the HDR pass reuses the rows it shares with the amplicon pass; the band pass evaluates the "
                       "band columns a second time, with flags; bit-identical results)",
         "gcups_evaluated": (computed_per_step * world * args.steps) / (dev_ms * 1e-3) / 1e9,
-        "config": {"workload": "cfg2: %d single-end %d-bp reads per GPU vs %d-bp amplicon + HDR amplicon (needle "
-                               "gapopen 10 / gapextend 0.5), RC rescue, classification + histograms" % (n, READ_LEN, L),
-                   "reads_per_gpu_per_step": n, "alignments_per_read": 2, "l2": "inputs and traceback exceed L2 (reads %d MB, "
-                   "traceback scratch 8 GB per batch)" % (buf.nbytes >> 20), "parallelism": "reads sharded x%d" % world},
+        "config": {"workload": workload_text, "name": args.config, "reads_per_gpu_per_step": n,
+                   "alignments_per_read": n_alignments / max(n, 1), "calls_per_step": len(jobs),
+                   "l2": "inputs and traceback exceed L2 (reads %d MB per GPU per step, traceback scratch up to 8 GB per batch)" % (
+                       sum(j.buf.nbytes for j in jobs) >> 20),
+                   "parallelism": "reads sharded x%d (%s scaling)" % (world, args.scaling)},
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": e2e_ms / args.steps, "results_equal_device_arm": same,
-                "distinct_alleles": len(alleles_h[0]),
+                "distinct_alleles": n_alleles,
                 "api": "hotpath.StagedPipeline on one context: crgpu_stage_reads (BAM 4-bit reads from pinned memory, asynchronous "
                        "H2D on the library's copy stream, unpacked on the device; the next %d-read chunk is staged while the current "
                        "one runs) + crgpu_align_quantify_staged (per-read records, RC-rescue rows, reductions and the allele table "
-                       "back in host memory: what CORE:2892-3992 consumes)" % args.e2e_chunk},
+                       "back in host memory: what CORE:2892-3992 consumes)" % (args.e2e_chunk if args.e2e_chunk > 0 else max(j.n for j in jobs))},
         "gpu_launches": int(sum(fam_launch.values())),
         "kernel_ms_per_step": {k: fam_ms[k] / args.steps for k in fam_ms},
         "roofline": {"bound": "int_alu", "kernel": kinds[dom]["kernel"], "achieved": kinds[dom]["achieved"], "peak": alu_pk,
@@ -436,11 +529,12 @@ def main():
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else "fallback"},
         "band": {"half_width": ctx.band(), "escaped_amplicon_hdr": list(ctx.last_escaped())},
         "clocks": clocks,
-        "classes": {"n_total": int(n_total), "unmodified": int(red.class_counts[0]), "nhej": int(red.class_counts[1]),
-                    "hdr": int(red.class_counts[2]), "mixed": int(red.class_counts[3])},
+        "classes": {"n_total": int(n_total), "unmodified": int(sum(r.class_counts[0] for r in reds)),
+                    "nhej": int(sum(r.class_counts[1] for r in reds)), "hdr": int(sum(r.class_counts[2] for r in reds)),
+                    "mixed": int(sum(r.class_counts[3] for r in reds))},
     }
     if not args.no_cpu_baseline and world == 1:          # the CPU leg is timed at N = 1 only (bounded sample, rank 0)
-        line["cpu_baseline"] = cpu_baseline(args, amp, hdr, inc, buf, off)
+        line["cpu_baseline"] = cpu_baseline(args, jobs[0])
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

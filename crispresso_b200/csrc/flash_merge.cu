@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(MERGE_WARPS * 32) k_merge_decide(const MergeAr
             } else {
                 const int i = i_out0 + (win - n_in);
                 a.pos[p] = i; a.kind[p] = 2; a.mlen[p] = (int64_t)(l2 - i); a.flag[p] = 1;
+                atomicAdd(a.err + 1, 1);                         // outies (a.err[1]); innies = merged - outies
             }
         }
     }
@@ -345,11 +346,12 @@ static int flash_merge_impl(crgpu_ctx *ctx, int mem, const uint8_t *seq1, const 
     span_end(ctx, 5);
     int64_t total = 0;
     int32_t nm = 0;
-    int herr = 0;
+    int herr2[2] = {0, 0};
     CK(cudaMemcpyAsync(&total, d_boff + n, 8, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(&nm, d_cidx + n, 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(herr2, d_err, 8, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    const int herr = herr2[0];
     if (herr) return fail(ctx, CRGPU_E_ALIGN, "crgpu_flash_merge: a mate is longer than %d bases or holds a base outside ACGTN", MERGE_MAXLEN);
     if (total > out->cap_bytes || nm > out->cap_reads)
         return fail(ctx, CRGPU_E_ARG, "crgpu_flash_merge: output capacity too small (need %lld bytes, %d reads)", (long long)total, nm);
@@ -373,7 +375,6 @@ static int flash_merge_impl(crgpu_ctx *ctx, int mem, const uint8_t *seq1, const 
     CK(cudaGetLastError());
     span_end(ctx, 1);
     CK(cudaMemcpyAsync(d_ooff + nm, d_boff + n, 8, cudaMemcpyDeviceToDevice, s));
-    // innie / outie counts: kind is 0/1/2, outies = (sum(kind) - n_merged)
     if (mem == CRGPU_MEM_HOST) {
         CK(cudaMemcpyAsync(out->pos, d_pos, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(out->kind, d_kind, (size_t)n, cudaMemcpyDeviceToHost, s));
@@ -386,6 +387,8 @@ static int flash_merge_impl(crgpu_ctx *ctx, int mem, const uint8_t *seq1, const 
     }
     CK(cudaStreamSynchronize(s));
     out->n_merged = nm;
+    out->n_outie = herr2[1];
+    out->n_innie = (int64_t)nm - herr2[1];
     out->bytes = total;
     timing_collect(ctx);
     return CRGPU_OK;

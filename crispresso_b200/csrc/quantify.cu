@@ -79,11 +79,13 @@ struct OpReader {
 };
 constexpr int OP_MATCH = 0, OP_MISMATCH = 1, OP_INS = 2, OP_DEL = 3;
 
-__global__ void __launch_bounds__(128) k_quantify(const QuantArgs a)
+// One kept row.  `sc`: the CTA's shared-memory copy of the nine scalar counters (4 frameshift counters, 4 class counts,
+// rows seen) -- every row bumps two or three of them, so they are reduced per warp (ptxas aggregates the uniform-address
+// shared atomics) and per CTA before one global atomic each; the per-position vectors and the histograms get few,
+// scattered hits per row and go straight to global memory.
+constexpr int NSCALAR = CRGPU_NUM_COUNTERS + 5;
+__device__ __forceinline__ void quantify_row(const QuantArgs &a, const int64_t i, unsigned *sc)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
-    if (a.active && !(a.active[i] & a.active_bit)) return;
     const int L = a.L, W = a.W, flags = a.flags;
     const int n = a.alnlen[i];
     const OpReader ops{a.ops + i * a.ops_stride, n, a.ops_reversed != 0};
@@ -113,11 +115,11 @@ __global__ void __launch_bounds__(128) k_quantify(const QuantArgs a)
         }
         if (uniform) unmod = true;
     }
-    atomicAdd(a.counters + CRGPU_NUM_COUNTERS + 4, 1ull);            // rows seen (n_total)
+    atomicAdd(sc + CRGPU_NUM_COUNTERS + 4, 1u);            // rows seen (n_total)
     if (unmod) {                                                     // CORE:480-481
         rec.cls = CRGPU_C_UNMODIFIED;
         a.recs[i] = rec;
-        atomicAdd(a.counters + CRGPU_NUM_COUNTERS + 0, 1ull);
+        atomicAdd(sc + CRGPU_NUM_COUNTERS + 0, 1u);
         return;
     }
 
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(128) k_quantify(const QuantArgs a)
         add_bits(V + (size_t)CRGPU_V_ANY * L, A, W);                  // also for rows re-classified UNMODIFIED (Q8)
     }
     const int cls_slot = cls == CRGPU_C_UNMODIFIED ? 0 : cls == CRGPU_C_NHEJ ? 1 : cls == CRGPU_C_HDR ? 2 : 3;
-    atomicAdd(a.counters + CRGPU_NUM_COUNTERS + cls_slot, 1ull);
+    atomicAdd(sc + CRGPU_NUM_COUNTERS + cls_slot, 1u);
     if (cls == CRGPU_C_UNMODIFIED) { a.recs[i] = rec; return; }
 
     // ---- window filter for NHEJ (CORE:611-641) ----
@@ -265,25 +267,36 @@ __global__ void __launch_bounds__(128) k_quantify(const QuantArgs a)
         }
         if (del_exon > 0) { exons_modified = true; exon_len -= del_exon; have_len = true; }
         if (sub_exon) exons_modified = true;
-        if (spliced) atomicAdd(a.counters + CRGPU_K_SPLICING_MODIFIED, 1ull);
+        if (spliced) atomicAdd(sc + CRGPU_K_SPLICING_MODIFIED, 1u);
         if (exons_modified) {
             const int key = have_len ? exon_len : 0;
             const int bin = key + a.hist_zero;
             const bool inframe = !have_len || (key % 3) == 0;
             if (inframe) {
-                atomicAdd(a.counters + CRGPU_K_MOD_NON_FRAMESHIFT, 1ull);
+                atomicAdd(sc + CRGPU_K_MOD_NON_FRAMESHIFT, 1u);
                 if (bin >= 0 && bin < a.hist_len) atomicAdd(a.hist_in + bin, 1ull);
             } else {
-                atomicAdd(a.counters + CRGPU_K_MOD_FRAMESHIFT, 1ull);
+                atomicAdd(sc + CRGPU_K_MOD_FRAMESHIFT, 1u);
                 if (bin >= 0 && bin < a.hist_len) atomicAdd(a.hist_fs + bin, 1ull);
             }
         } else {
-            atomicAdd(a.counters + CRGPU_K_NON_MOD_NON_FRAMESHIFT, 1ull);
+            atomicAdd(sc + CRGPU_K_NON_MOD_NON_FRAMESHIFT, 1u);
             add_bits(V + (size_t)CRGPU_V_INS_NONCODING * L, I, W);
             add_bits(V + (size_t)CRGPU_V_DEL_NONCODING * L, Dflat, W);
             add_bits(V + (size_t)CRGPU_V_MUT_NONCODING * L, S, W);
         }
     }
+}
+
+__global__ void __launch_bounds__(128) k_quantify(const QuantArgs a)
+{
+    __shared__ unsigned sc[NSCALAR];
+    if (threadIdx.x < NSCALAR) sc[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < a.n && (!a.active || (a.active[i] & a.active_bit))) quantify_row(a, i, sc);
+    __syncthreads();
+    if (threadIdx.x < NSCALAR && sc[threadIdx.x]) atomicAdd(a.counters + threadIdx.x, (unsigned long long)sc[threadIdx.x]);
 }
 
 cudaError_t launch_quantify(const QuantArgs &a, cudaStream_t s)

@@ -1,11 +1,12 @@
 """Host side of seam S1 and of the FASTQ ingest: drop-ins for the reference's
 quality-filter functions (CRISPResso/CRISPRessoCORE.py:162-310) and FASTQ counters (CORE:313-348).
-gzip inflate stays on the host (zlib, on a worker thread so the next chunk inflates while the GPU
-indexes the current one); record splitting runs in crgpu_fastq_index, the per-read decision (mean
+gzip inflate stays on the host (zlib: one worker thread ahead of the GPU, and the members of a multi-member
+file -- bgzip / pigz -i / concatenated .gz -- on several threads at once); record splitting runs in crgpu_fastq_index, the per-read decision (mean
 phred >= q and min phred >= s) in k_qualfilter through crgpu_qualfilter.
 """
 import ctypes
 import gzip
+import os
 import threading
 import queue
 import zlib
@@ -56,7 +57,10 @@ def index_text(ctx, text, final=True, counts_only=False):
     return FastqBatch(text, seq[:total], qual[:total], offsets, ns, nl), int(fo.consumed), n, total
 
 
-def _inflate_chunks(path, chunk_bytes):
+INFLATE_WORKERS = min(8, os.cpu_count() or 1)
+
+
+def _inflate_chunks(path, chunk_bytes, parallel=True):
     """Generator of inflated byte chunks of a .gz (multi-member aware) or plain file."""
     if not path.endswith(".gz"):
         with open(path, "rb") as f:
@@ -65,6 +69,10 @@ def _inflate_chunks(path, chunk_bytes):
                 if not b:
                     return
                 yield b
+        return
+    if parallel and INFLATE_WORKERS > 1:
+        yield from _inflate_chunks_parallel(path, chunk_bytes, INFLATE_WORKERS)
+        return
     with open(path, "rb") as f:
         d = zlib.decompressobj(zlib.MAX_WBITS | 16)
         pending = b""
@@ -88,10 +96,92 @@ def _inflate_chunks(path, chunk_bytes):
             yield tail
 
 
+def _inflate_run(mm, start, stop, piece=1 << 16):
+    """Inflate the gzip members that start in [start, stop) of the mapped file, one after the other.  -> (offset after the
+    last of them, bytes), or None when no valid member starts at `start` (the magic bytes also occur inside compressed data)."""
+    out, pos, n = [], start, len(mm)
+    try:
+        while pos < stop:
+            d = zlib.decompressobj(zlib.MAX_WBITS | 16)
+            while not d.eof:
+                if pos >= n:
+                    return None                            # truncated: not a member (a damaged file is reported by the caller)
+                raw = mm[pos:pos + piece]
+                out.append(d.decompress(raw))
+                pos += len(raw) - len(d.unused_data)
+    except zlib.error:
+        return None
+    return pos, b"".join(out)
+
+
+def _inflate_chunks_parallel(path, chunk_bytes, workers, group_bytes=4 << 20):
+    """_inflate_chunks with the gzip MEMBERS of the file inflated on `workers` threads (zlib releases the GIL): the files
+    bgzip / pigz -i / bcl-convert write -- and any concatenation of .gz files -- are sequences of independent members.
+    Occurrences of the gzip magic at least `group_bytes` apart are candidate starts of a RUN of members; every run is
+    inflated up to the next candidate on a worker, ahead of the stitching point, and a result is used only if the run
+    starts exactly where the previous one ended -- a false candidate (magic bytes inside compressed data) or a member that
+    spans a candidate costs some wasted work and nothing else.  A file that is one big member (plain `gzip`) gains nothing:
+    it is handed to the serial path."""
+    import mmap
+    from concurrent.futures import ThreadPoolExecutor
+    with open(path, "rb") as f:
+        try:
+            mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+        except ValueError:                                 # empty file
+            return
+        try:
+            n = len(mm)
+            cands, p = [], mm.find(b"\x1f\x8b\x08")
+            while p >= 0:
+                if p + 10 <= n and (mm[p + 3] & 0xE0) == 0:                  # FLG: the reserved bits are zero in a real header
+                    cands.append(p)
+                    p = mm.find(b"\x1f\x8b\x08", p + group_bytes)
+                else:
+                    p = mm.find(b"\x1f\x8b\x08", p + 1)
+            if len(cands) < 3 or cands[0] != 0:
+                mm.close()
+                yield from _inflate_chunks(path, chunk_bytes, parallel=False)
+                return
+            stops = cands[1:] + [n]
+            with ThreadPoolExecutor(max_workers=workers) as ex:
+                futs, submitted = {}, 0
+                expect, buf, size, k = 0, [], 0, 0
+                while expect < n:
+                    while k < len(cands) and cands[k] < expect:              # runs that started inside a consumed member
+                        f2 = futs.pop(k, None)
+                        if f2 is not None:
+                            f2.cancel()
+                        k += 1
+                    while submitted < len(cands) and len(futs) < 2 * workers:
+                        if submitted >= k:
+                            futs[submitted] = ex.submit(_inflate_run, mm, cands[submitted], stops[submitted])
+                        submitted += 1
+                    if k < len(cands) and cands[k] == expect:
+                        res = futs.pop(k).result() if k in futs else _inflate_run(mm, expect, stops[k])
+                        k += 1
+                    else:                                                    # a gap up to the next candidate: inflate it here
+                        res = _inflate_run(mm, expect, cands[k] if k < len(cands) else n)
+                    if res is None:
+                        raise ValueError("%s: damaged gzip member at byte %d" % (path, expect))
+                    expect, data = res
+                    buf.append(data)
+                    size += len(data)
+                    if size >= chunk_bytes:
+                        yield b"".join(buf)
+                        buf, size = [], 0
+                if buf:
+                    yield b"".join(buf)
+        finally:
+            try:
+                mm.close()
+            except (BufferError, ValueError):
+                pass
+
+
 def stream_fastq(ctx, path, chunk_bytes=64 << 20):
     """Yield FastqBatch objects for a FASTQ(.gz) file.  A worker thread inflates ahead (zlib releases the
-    GIL) while the GPU indexes the current chunk; the incomplete record at the end of a chunk is carried
-    over to the next one."""
+    GIL; multi-member files on several threads, _inflate_chunks_parallel) while the GPU indexes the current
+    chunk; the incomplete record at the end of a chunk is carried over to the next one."""
     q = queue.Queue(maxsize=2)
 
     def worker():

@@ -508,28 +508,34 @@ class StagedPipeline:
             self._acnt = np.zeros(self.alleles, np.int64)
             self._akey = np.zeros(2 * self.alleles, np.uint64)
         self._tables = []                    # per batch: (keys[na, 2], counts[na], rows[na], batch index[na])
-        self._queue = []                     # staged, not yet run: (slot, n, buffers kept alive)
-        self._next = 0
+        # the two staging slots belong to the CONTEXT: pipelines of several amplicons can share one context (pooled runs),
+        # each staging its next batch while another one's runs -- first staged, first run
+        if not hasattr(ctx, "_staged"):
+            ctx._staged, ctx._stage_next = [], 0       # staged, not yet run: (slot, n, owner, buffers kept alive)
         self.batches = 0
 
     def stage(self, reads, offsets, packed=False):
         """Start copying a batch: ``reads`` u8 (one base per byte, or pack_bam4 output with packed=True), ``offsets`` i64[n+1]
         starting at 0, counting bases.  At most two batches can be staged and not yet run."""
-        if len(self._queue) >= 2:
+        ctx = self.ctx
+        if len(ctx._staged) >= 2:
             raise RuntimeError("both staging slots are in use: run() a batch first")
         n = len(offsets) - 1
-        slot = self._next
-        self.ctx.check(self.ctx.lib.crgpu_stage_reads(self.ctx.handle, slot, _lib.READS_BAM4 if packed else _lib.READS_BYTES,
-                                                      _lib.ptr(reads), _lib.ptr(offsets), n))
-        self._queue.append((slot, n, (reads, offsets)))
-        self._next ^= 1
+        slot = ctx._stage_next
+        ctx.check(ctx.lib.crgpu_stage_reads(ctx.handle, slot, _lib.READS_BAM4 if packed else _lib.READS_BYTES,
+                                            _lib.ptr(reads), _lib.ptr(offsets), n))
+        ctx._staged.append((slot, n, self, (reads, offsets)))
+        ctx._stage_next ^= 1
         return n
 
     def run(self, out):
         """Quantify the oldest staged batch of n reads.  ``out``: arrays (views) ``kept`` u8[n], ``aln`` ALN_REC[n], ``recs``
         READ_REC[n], optional ``tenths_rep`` i32[n], ``rc_read`` i32[n], ``rc_aln`` ALN_REC[n], ``rc_recs`` READ_REC[n].
         Returns (n, number of RC rows)."""
-        slot, n, _alive = self._queue.pop(0)
+        if not self.ctx._staged or self.ctx._staged[0][2] is not self:
+            raise RuntimeError("the oldest staged batch of this context belongs to another pipeline (or nothing is staged)")
+        slot, n, _owner, _alive = self.ctx._staged.pop(0)
+        self.ctx.check(self.ctx.lib.crgpu_set_deferred_outputs(self.ctx.handle, 1 if self.deferred else 0))
         red = self.red
         po = _lib.PathOut()
         po.vectors, po.hist_inframe, po.hist_frameshift = red.vectors.ctypes.data, red.hist_inframe.ctypes.data, red.hist_frameshift.ctypes.data

@@ -303,7 +303,7 @@ typedef struct {
                                       (reads, offsets) pair crgpu_align / crgpu_align_quantify consume */
     int32_t *index;                /* [cap_reads] pair index of merged read j */
     int64_t n_merged;              /* OUT */
-    int64_t n_innie, n_outie;      /* OUT (reserved; the shim counts `kind`) */
+    int64_t n_innie, n_outie;      /* OUT: merged pairs by kind (FLASH's "innie" / "outie" counts) */
     int64_t bytes;                 /* OUT: offsets[n_merged] */
 } crgpu_merge_out;
 

@@ -195,10 +195,14 @@ def process_rows(rows, opts, include, L, exon=(), splice=()):
 
 
 def hot_path(amplicon, reads, names=None, gapopen=10.0, gapextend=0.5, min_identity_score=60.0, hdr_amplicon="",
-             opts=None, include=None, exon=(), splice=(), nthreads=8, use_int=True):
+             opts=None, include=None, exon=(), splice=(), nthreads=8, use_int=True, process=None, timings=None):
     """CORE:1791-2072 + 2773-2869 on the CPU: needle (oracle) -> parse -> merge/filter -> RC rescue ->
     prep -> process_df_chunk.  reads: list of str or (buffer, offsets).  Returns a dict with the
-    row list (forward rows in read order, then _RC rows), per-row results and the reductions."""
+    row list (forward rows in read order, then _RC rows), per-row results and the reductions.
+    process: the quantification stage, process_rows (this file's restatement) or ref_quantify.process_rows_reference (the
+    reference's own process_df_chunk); timings: optional dict that receives the seconds of the stages."""
+    import time as _time
+    _t0 = _time.time()
     amplicon = amplicon.upper()
     L = len(amplicon)
     opts = opts or Opts(expected_hdr_amplicon_seq=hdr_amplicon)
@@ -243,7 +247,11 @@ def hot_path(amplicon, reads, names=None, gapopen=10.0, gapextend=0.5, min_ident
             r["align_str"], uniform = mask_n(r["ref_seq"], r["align_str"])
             if uniform:
                 r["UNMODIFIED"] = True
-    per_row, V, hist_in, hist_fs, cnt = process_rows(rows, opts, include, L, exon, splice)
+    _t1 = _time.time()
+    per_row, V, hist_in, hist_fs, cnt = (process or process_rows)(rows, opts, include, L, exon, splice)
+    if timings is not None:
+        timings["align_prepare_s"] = timings.get("align_prepare_s", 0.0) + (_t1 - _t0)
+        timings["quantify_s"] = timings.get("quantify_s", 0.0) + (_time.time() - _t1)
     classes = dict(UNMODIFIED=sum(p["UNMODIFIED"] for p in per_row), NHEJ=sum(p["NHEJ"] for p in per_row),
                    HDR=sum(p["HDR"] for p in per_row), MIXED=sum(p["MIXED"] for p in per_row))
     return dict(rows=rows, per_row=per_row, vectors=V, hist_inframe=hist_in, hist_frameshift=hist_fs, counters=cnt,

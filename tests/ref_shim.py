@@ -3,8 +3,9 @@
 The reference checks for `java`, `flash`, `needle` on PATH and imports matplotlib / seaborn /
 Biopython at import time (CORE:31-36, 349-368); none of them is needed by process_df_chunk.
 This shim puts three dummy executables on PATH and stub modules in sys.modules, then imports the
-reference from /root/reference.  Used only by tests/golden/make_golden.py and
-by tests that are skipped when /root/reference is absent (the GPU box).
+reference from /root/reference -- or from its installed copy baseline/_ref -- (SURVEY.md App. E).  Used by
+tests/golden/make_golden.py, by tests that are skipped when neither exists, and by the CPU baseline of bench.py
+(oracle/ref_quantify.py).
 """
 import os
 import stat
@@ -13,7 +14,12 @@ import tempfile
 import types
 from unittest import mock
 
+# the reference tree of the build container, else the copy `pip install --target baseline/_ref /root/reference` left in the
+# repo (git-ignored; it travels to the GPU box, where bench.py's CPU baseline times the reference's own process_df_chunk)
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_ROOT = "/root/reference"
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "CRISPResso")):
+    REFERENCE_ROOT = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")
 
 
 class PlotStub(object):
