@@ -34,6 +34,9 @@ int crgpu_create(crgpu_ctx **out, int device)
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail();
     if (prop.major != 10) return bail();                       // sm_100a SASS only: no other target, no fallback
     c->num_sms = prop.multiProcessorCount;
+    // scratch of ONE traceback batch (there are two sets): 24 GiB holds half of a 2^20-read call (band flags + boundary rows
+    // of 2^18 read pairs vs a 250-bp amplicon + HDR amplicon: ~15 GB), bounded by an eighth of the device's memory
+    c->tb_budget = std::min<size_t>((size_t)24 << 30, prop.totalGlobalMem / 8);
     // The traceback walk reads one byte per visited cell from scattered sectors: CRGPU_L2_HINT=1 asks L2 not to over-fetch
     // neighbouring sectors from HBM.  A device-wide limit (it measured neutral, profiles/r01_notes.md), so it is opt-in
     // and crgpu_destroy puts the previous value back.
@@ -752,7 +755,11 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     int64_t bp = (int64_t)(ctx->tb_budget / pair_bytes);
     {
         const int64_t wave = getenv("CRGPU_NO_WAVE_ALIGN") ? 1 : std::max<int64_t>(1, score2_wave_pairs(dual ? Gh : G, K, nsub, ctx->num_sms));
-        int64_t want = std::max<int64_t>(((int64_t)pl.np + 7) / 8, 16384);
+        // two batches per call (CRGPU_BATCHES): enough for the walks of one to run beside the fills of the other, and every
+        // extra batch pays the walk's latency floor -- ~0.4 ms for 40 k alignments as for 140 k -- again (2^20 reads + HDR,
+        // ms per call: 8 batches 33.8, 4: 31.7, 2: 30.5, 1: 31.6; profiles/r02_notes.md)
+        static const int nbatch = getenv("CRGPU_BATCHES") ? std::max(1, atoi(getenv("CRGPU_BATCHES"))) : 2;
+        int64_t want = std::max<int64_t>(((int64_t)pl.np + nbatch - 1) / nbatch, 16384);
         if (want >= 4 * wave) {                   // (small calls, e.g. the chunks of a pipelined run, measured better unaligned)
             want = (want + wave - 1) / wave * wave;
             if (bp >= wave) bp = bp / wave * wave;

@@ -57,8 +57,9 @@ int crgpu_abi_version(void);
 int crgpu_create(crgpu_ctx **ctx, int device);
 void crgpu_destroy(crgpu_ctx *ctx);
 const char *crgpu_last_error(const crgpu_ctx *ctx);
-/* Cap on the traceback scratch held in HBM per batch (bytes; default 8 GiB).  Reads are
- * processed in batches sized to this cap; results do not depend on it. */
+/* Cap on the traceback scratch held in HBM per batch (bytes; default: 24 GiB or an eighth of the device's memory,
+ * whichever is less; there are two such sets).  A call runs as two batches -- the walks of one beside the fills of the
+ * other -- or as many as this cap needs; results do not depend on it. */
 int crgpu_set_traceback_budget(crgpu_ctx *ctx, size_t bytes);
 /* Traceback walks of batch b normally run on a second stream, overlapped with the fill of batch b+1
  * (default on).  Turning it off serialises the kernels, which is what per-kernel timing wants. */

@@ -12,6 +12,9 @@ buf, off = synth.make_reads_fast(amp, hdr, cut, n, seed=1234, read_len=La)
 inc = hotpath.include_mask(La, hotpath.cut_points_from_guides(amp, guide), 1, 15, 15)
 flags = hotpath.quant_flags(hdr)
 ctx = Context(0)
+for a_ in sys.argv:
+    if a_.startswith("--budget="):
+        ctx.set_traceback_budget(int(float(a_.split("=")[1]) * (1 << 30)))
 d_buf = torch.from_numpy(buf).cuda(); d_off = torch.from_numpy(off).cuda()
 out = {"kept": torch.zeros(n, dtype=torch.uint8, device="cuda"), "aln": torch.zeros(n * 32, dtype=torch.uint8, device="cuda"),
        "recs": torch.zeros(n * 16, dtype=torch.uint8, device="cuda"), "tenths_rep": torch.zeros(n, dtype=torch.int32, device="cuda")}

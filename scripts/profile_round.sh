@@ -10,7 +10,7 @@ python bench.py --steps 5 --warmup 3 > $out/${tag}_bench_1gpu.json 2> $out/${tag
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $out/${tag}_ncu_list.log 2>&1
 # full sections: two batches of the banded fill + their walks, then the quantifier and the single-pass fill (escapes)
-ncu --set full --clock-control none --import-source on -k regex:"k_gotoh_score|k_gotoh_band|k_traceback_walk" \
+ncu --set full --clock-control none --import-source on -k regex:"k_gotoh_score|k_gotoh_band|k_traceback_walk|k_diag_emit" \
     -s 6 -c 12 -o $out/${tag}_kernels -f python bench.py --steps 1 --warmup 1 --reads 1048576 --no-cpu-baseline > $out/${tag}_ncu_full.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"k_quantify|k_gotoh_fill" \
     -c 3 -o $out/${tag}_kernels2 -f python bench.py --steps 1 --warmup 1 --reads 1048576 --no-cpu-baseline >> $out/${tag}_ncu_full.log 2>&1
