@@ -206,8 +206,12 @@ __global__ void __maxnreg__(score2_maxnreg<K>()) k_gotoh_score2(const FillArgs a
         const int sB = valid ? sBand : (1 << 29);
 
         // One systolic step: lane t works on columns x0 = 2 (s - t) and x0 + 1.
-        auto step = [&](auto tail_tag, const int s) {
-            constexpr bool TAIL = decltype(tail_tag)::value;
+        // MODE 0 = steady (every lane on interior columns of its read), 1 = tail (some lane on or past its last column pair:
+        // per-lane flags), 2 = head (lanes t > s have not started yet, nobody is near the end: the steady arithmetic behind
+        // an activity test)
+        auto step = [&](auto mode_tag, const int s) {
+            constexpr int MODE = decltype(mode_tag)::value;
+            constexpr bool TAIL = MODE == 1;
             const int x0 = 2 * (s - t), x1 = x0 + 1;
             uint32_t r0H = __shfl_up_sync(0xffffffffu, bot0[0], 1, G);
             uint32_t r0Y = __shfl_up_sync(0xffffffffu, bot0[1], 1, G);
@@ -221,13 +225,13 @@ __global__ void __maxnreg__(score2_maxnreg<K>()) k_gotoh_score2(const FillArgs a
                 r0H = tnA.x + adj0; r0Y = tnA.y + adj0; r0M = tnA.z + adj0;
                 r1H = tnB.x + adj1; r1Y = tnB.y + adj1; r1M = tnB.z + adj1;
             }
-            const bool active = !TAIL || (x0 >= 0 && x0 < Lb);
+            const bool active = MODE == 0 || (x0 >= 0 && (MODE == 2 || x0 < Lb));
             const bool do1 = !TAIL || x1 < Lb;
             const bool last0 = TAIL && active && x0 == Lb - 1;
             const bool last1 = TAIL && active && x1 == Lb - 1;
             // (a steady step prefetches one code past an odd-length read: never index the profile with it)
             const int cp0 = cpn0, cp1 = do1 ? cpn1 : cpn0;
-            if (TAIL) {
+            if (MODE != 0) {
                 if (x0 + 2 >= 0 && x0 + 2 < Lb) {
                     cpn0 = pcp[x0 + 2];
                     cpn1 = pcp[x0 + 3 < Lb ? x0 + 3 : x0 + 2];
@@ -284,9 +288,11 @@ __global__ void __maxnreg__(score2_maxnreg<K>()) k_gotoh_score2(const FillArgs a
         const int nst_min = __reduce_min_sync(0xffffffffu, nst);
         const int steady_end = min(nst_min - 1, steps);                       // first non-steady step after the steady run
         int s = 0;
-        for (; s < min(G - 1, steps); ++s) step(std::true_type{}, s);
-        for (; s < steady_end; ++s) step(std::false_type{}, s);
-        for (; s < steps; ++s) step(std::true_type{}, s);
+        if (steady_end >= G - 1)                                              // (no lane ends during the head)
+            for (; s < G - 1; ++s) step(std::integral_constant<int, 2>{}, s);
+        for (; s < min(G - 1, steps); ++s) step(std::integral_constant<int, 1>{}, s);
+        for (; s < steady_end; ++s) step(std::integral_constant<int, 0>{}, s);
+        for (; s < steps; ++s) step(std::integral_constant<int, 1>{}, s);
 
         // start-cell scan down the last read column (App. A.4) on plain values: first row whose max(m,ix,iy) is
         // strictly greater than everything above it; padded rows are not part of the matrix.  A lane is idle after
