@@ -54,6 +54,17 @@ __global__ void k_hash_rows(const uint8_t *__restrict__ reads, const int64_t *__
     if (!valid) { keys[r] = ~0ull; chk[r] = 0; return; }
     const uint8_t *b = reads + offsets[read];
     const int len = (int)(offsets[read + 1] - offsets[read]);
+    {
+        // identity 100.0: the row's three strings are the amplicon itself (CORE:2014), whatever the strand -- one allele,
+        // by far the most frequent one, so its rows skip the two hash chains.  (align_seq keeps the read's CASE: a read with
+        // a lower-case base is another allele and takes the long way.)
+        const int t = rc ? aln_rc[r - n].tenths : aln_fw[read].tenths;
+        if (t == 1000) {
+            uint32_t any = 0;
+            if (!rc) for (int i = 0; i < len; ++i) any |= b[i];          // (RC rows are upper-cased by the reference, CORE:141-144)
+            if (!(any & 0x20u)) { keys[r] = 0x243f6a8885a308d3ull; chk[r] = 0x13198a2e03707344ull; return; }
+        }
+    }
     uint64_t h1 = 0x9e3779b97f4a7c15ull, h2 = 0xc2b2ae3d27d4eb4full;
     // bases as they appear in align_seq: raw for forward rows, upper-cased reverse complement for RC rows
     for (int i = 0; i < len; ++i) {
