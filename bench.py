@@ -480,7 +480,8 @@ def main():
         "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "int16x2", "data": "synthetic",
         "gcups": (cells_per_rank_step * world * args.steps) / (dev_ms * 1e-3) / 1e9,
-        "gcups_note": "La x Lb of every alignment made (2 per read) / time; `gcups_evaluated` counts only the DP cells the "
+        "gcups_note": "La x Lb of every alignment delivered (2 per read with an HDR amplicon; reads identical to the amplicon are delivered "
+                      "without DP) / time; `gcups_evaluated` counts only the DP cells the "
                       "kernels evaluate (the HDR pass reuses the rows it shares with the amplicon pass; the band pass evaluates the "
                       "band columns a second time, with flags; bit-identical results)",
         "gcups_evaluated": (computed_per_step * world * args.steps) / (dev_ms * 1e-3) / 1e9,
@@ -528,6 +529,10 @@ def main():
                          "frac": (kinds["band"]["tcups"] * 1e3 / hbm_peak if "band" in kinds else None), "bytes_per_cell": 1.0,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else "fallback"},
         "band": {"half_width": ctx.band(), "escaped_amplicon_hdr": list(ctx.last_escaped())},
+        # work the last call of the step did NOT have to do (bit-identical results either way): reads that
+        # are the amplicon itself skip the DP (one representative stays); amplicon alignments whose traceback is provably the
+        # diagonal skip the band pass and the walk
+        "shortcuts": {"exact_reads_of_last_call": ctx.last_exact(), "pairs_in_plan_and_pairs_needing_the_amplicon_band": list(ctx.last_diag())},
         "clocks": clocks,
         "classes": {"n_total": int(n_total), "unmodified": int(sum(r.class_counts[0] for r in reds)),
                     "nhej": int(sum(r.class_counts[1] for r in reds)), "hdr": int(sum(r.class_counts[2] for r in reds)),

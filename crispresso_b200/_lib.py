@@ -116,6 +116,9 @@ def load():
     lib.crgpu_int_peak.argtypes = [vp, i32, ctypes.POINTER(dbl)]
     lib.crgpu_stage_reads.argtypes = [vp, i32, i32, vp, vp, i64]
     lib.crgpu_set_deferred_outputs.argtypes = [vp, i32]
+    lib.crgpu_set_exact_shortcut.argtypes = [vp, i32]
+    lib.crgpu_last_exact.argtypes = [vp]
+    lib.crgpu_last_exact.restype = i64
     lib.crgpu_align_quantify_staged.argtypes = [vp, i32, ctypes.c_char_p, i32, ctypes.POINTER(PathParams), ctypes.POINTER(QuantParams),
                                                 ctypes.POINTER(PathOut)]
     lib.crgpu_fastq_index.argtypes = [vp, i32, vp, i64, i32, ctypes.POINTER(FastqOut)]
@@ -123,7 +126,7 @@ def load():
                                       ctypes.POINTER(MergeOut)]
     for name in ("crgpu_create", "crgpu_set_diag_shortcut", "crgpu_last_diag", "crgpu_set_overlap", "crgpu_set_share_prefix", "crgpu_set_band", "crgpu_last_escaped", "crgpu_set_traceback_budget", "crgpu_last_timing", "crgpu_last_fill_breakdown", "crgpu_sync", "crgpu_qualfilter",
                  "crgpu_align", "crgpu_quantify", "crgpu_align_quantify", "crgpu_int_peak", "crgpu_flash_merge", "crgpu_fastq_index",
-                 "crgpu_stage_reads", "crgpu_align_quantify_staged", "crgpu_set_deferred_outputs"):
+                 "crgpu_stage_reads", "crgpu_align_quantify_staged", "crgpu_set_deferred_outputs", "crgpu_set_exact_shortcut"):
         getattr(lib, name).restype = i32
     _lib = lib
     return lib
@@ -192,6 +195,13 @@ class Context:
         out = (ctypes.c_int * 2)()
         self.check(self.lib.crgpu_last_escaped(self.handle, ctypes.byref(out)))
         return int(out[0]), int(out[1])
+
+    def set_exact_shortcut(self, on):
+        """Reads identical to the amplicon skip the DP (default on); results do not depend on it."""
+        self.check(self.lib.crgpu_set_exact_shortcut(self.handle, 1 if on else 0))
+
+    def last_exact(self):
+        return int(self.lib.crgpu_last_exact(self.handle))
 
     def set_diag_shortcut(self, on):
         """Diagonal shortcut of the banded fill (default on); results never depend on it."""

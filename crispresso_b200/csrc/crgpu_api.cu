@@ -78,7 +78,7 @@ void crgpu_destroy(crgpu_ctx *c)
                    &c->joinb, &c->fastflags, &c->need[0], &c->need[1], &c->plist[0], &c->plist[1], &c->plist2[0], &c->plist2[1], &c->selscratch[0], &c->selscratch[1], &c->need_cnt,
                    &c->rowvals[0], &c->rowvals[1], &c->rowvals_h[0], &c->rowvals_h[1], &c->badbase,
                    &c->need_read[0], &c->need_read[1], &c->rlist[0], &c->rlist[1],
-                   &c->stage_reads[0], &c->stage_reads[1], &c->stage_off[0], &c->stage_off[1], &c->stage_pack[0], &c->stage_pack[1]};
+                   &c->exact_go, &c->exact_sel, &c->stage_reads[0], &c->stage_reads[1], &c->stage_off[0], &c->stage_off[1], &c->stage_pack[0], &c->stage_pack[1]};
     for (DBuf *b : all) b->release();
     for (auto &b : c->q_in) b.release();
     for (auto &b : c->q_out) b.release();
@@ -105,6 +105,15 @@ int crgpu_set_traceback_budget(crgpu_ctx *c, size_t bytes)
     c->tb_budget = bytes;
     return CRGPU_OK;
 }
+
+int crgpu_set_exact_shortcut(crgpu_ctx *c, int on)
+{
+    if (!c) return CRGPU_E_ARG;
+    c->exact_shortcut = on != 0;
+    return CRGPU_OK;
+}
+
+int64_t crgpu_last_exact(const crgpu_ctx *c) { return c ? c->n_exact : -1; }
 
 int crgpu_set_deferred_outputs(crgpu_ctx *c, int on)
 {

@@ -91,6 +91,10 @@ struct crgpu_ctx {
     // diagonal shortcut of the banded fill (run_plan_band): alignments whose traceback is provably the diagonal through
     // the start cell are emitted right after the score pass; only the other pairs go through the band pass and the walk
     bool diag = true;
+    // exact-read shortcut (hotpath.cu): reads identical to the amplicon skip the DP
+    bool exact_shortcut = true;
+    int64_t n_exact = 0;                                           // last call: reads that skipped it
+    DBuf exact_go, exact_sel;
     DBuf fastflags, need[2], plist[2], plist2[2], need_read[2], rlist[2], selscratch[2], need_cnt;
     int64_t n_diag_pairs[2] = {0, 0};                              // last call: pairs of the batches / pairs that needed the band pass
     DBuf q_in[8], q_out[4];

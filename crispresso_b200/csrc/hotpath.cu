@@ -180,6 +180,70 @@ static std::string revcomp_upper(const char *s, int n)
     return out;
 }
 
+// ---- exact-read shortcut ------------------------------------------------------------------------------------------------
+// A read that IS the amplicon (same length, same bases, case aside; amplicon of A C G T only) aligns to it along the diagonal with
+// the maximum possible score 5 L -- every column scores at most 5 and a gap costs -- so needle's start cell is (L-1, L-1) and its
+// traceback the diagonal (the argument of k_diag_emit with D_n = 5 L); identity 100.0, UNMODIFIED (CORE:2014).  Its alignment to
+// the HDR amplicon is the same for every such read.  So these reads -- the largest group of an amplicon-sequencing run -- skip
+// the DP altogether: k_mark_exact finds them (one warp per read), ONE representative (the first) stays in the plan, and
+// k_emit_exact writes the others' records, ops and text rows and copies the representative's HDR record.
+__global__ void __launch_bounds__(256) k_mark_exact(const uint8_t *__restrict__ reads, const int64_t *__restrict__ offsets, int64_t n,
+                                                    const uint8_t *__restrict__ amp, int La, uint8_t *__restrict__ go, int *rep)
+{
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const int64_t o = offsets[r];
+    bool same = (offsets[r + 1] - o) == La;
+    if (same) {
+        for (int x = lane; x < La; x += 32) {
+            uint8_t c = reads[o + x];
+            if (c >= 'a' && c <= 'z') c -= 32;
+            same &= c == amp[x];
+        }
+    }
+    same = __all_sync(0xffffffffu, same);
+    if (lane == 0) {
+        go[r] = same ? 0 : 1;                                        // 1: goes through the DP
+        if (same) atomicMin(rep, (int)r);
+    }
+}
+
+__global__ void k_keep_representative(uint8_t *go, const int *rep, int64_t n)
+{
+    if (*rep >= 0 && *rep < n) go[*rep] = 3;                         // through the DP, and the source of the others' HDR record
+}
+
+struct ExactArgs {
+    const uint8_t *reads; const int64_t *offsets; int64_t n; const uint8_t *amp; int La; int scale5;
+    const uint8_t *go; const int *rep;
+    crgpu_aln_rec *aln, *aln_hdr;
+    uint32_t *ops; int64_t ops_stride;
+    uint8_t *ref, *mark, *qry; int64_t slot;
+};
+
+__global__ void __launch_bounds__(256) k_emit_exact(const ExactArgs a)
+{
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= a.n || a.go[r]) return;
+    const int L = a.La;
+    for (int w = lane; w < (L + 15) / 16; w += 32) a.ops[r * a.ops_stride + w] = 0;        // every column a match
+    if (a.ref) {
+        const uint8_t *b = a.reads + a.offsets[r];
+        const int64_t base = r * a.slot + (a.slot - L);                                    // right-aligned, as the walk leaves it
+        for (int x = lane; x < L; x += 32) { a.ref[base + x] = a.amp[x]; a.mark[base + x] = '|'; a.qry[base + x] = b[x]; }
+    }
+    if (lane) return;
+    crgpu_aln_rec rec;
+    rec.score = 5.0f * (float)L;
+    rec.alnlen = L; rec.ident = L; rec.tenths = 1000;
+    rec.aln_off = (int32_t)(a.slot - L);
+    rec.start1 = L - 1; rec.start2 = L - 1; rec.read_len = L;
+    a.aln[r] = rec;
+    if (a.aln_hdr) a.aln_hdr[r] = a.aln_hdr[*a.rep];
+}
+
 // staged_slot >= 0: the reads are the batch crgpu_stage_reads put into that slot (device memory, filled on the copy stream);
 // every output is host memory, as with CRGPU_MEM_HOST
 static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, int amplicon_len,
@@ -226,8 +290,47 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
     CK(cudaMemsetAsync(ctx->badbase.p, 0, (size_t)n, s));
     struct BadScope { crgpu_ctx *c; ~BadScope() { c->d_bad = nullptr; } } bad_scope{ctx};
     ctx->d_bad = ctx->badbase.as<uint8_t>();
-    // pairing plan of the whole read set: shared by the amplicon and the HDR-amplicon pass
-    int rc = build_plan(ctx, d_reads, d_off, nullptr, n);
+    // forward amplicon, upper case: the exact-read test here, the N mask of the quantifier below
+    bool plain_acgt = true;
+    CK(ctx->aux[6].reserve((size_t)amplicon_len + 16));
+    {
+        std::string up(amplicon, amplicon + amplicon_len);
+        for (auto &ch : up) {
+            if (ch >= 'a' && ch <= 'z') ch = (char)(ch - 32);
+            plain_acgt &= ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T';
+        }
+        CK(cudaMemcpyAsync(ctx->aux[6].p, up.data(), (size_t)amplicon_len, cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    // ---- 0. reads that ARE the amplicon need no DP (k_mark_exact above): all but one representative leave the plan ----
+    const int32_t *d_subset = nullptr;
+    int64_t nsub = n;
+    uint8_t *d_go = nullptr;
+    int *d_rep = nullptr;
+    ctx->n_exact = 0;
+    if (ctx->exact_shortcut && plain_acgt && !getenv("CRGPU_NO_EXACT")) {
+        const size_t sb = select_scratch_bytes(n);
+        CK(ctx->exact_go.reserve((size_t)n + 16)); CK(ctx->exact_sel.reserve((size_t)n * 4 + 16)); CK(ctx->alleles.reserve(sb));
+        d_go = ctx->exact_go.as<uint8_t>();
+        int32_t *d_sel = ctx->exact_sel.as<int32_t>();
+        int *d_cnt = reinterpret_cast<int *>(d_sel + n);
+        d_rep = d_cnt + 1;
+        const int big = 0x7fffffff;
+        CK(cudaMemcpyAsync(d_rep, &big, 4, cudaMemcpyHostToDevice, s));
+        span_begin(ctx, T_ENCODE);
+        k_mark_exact<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(d_reads, d_off, n, ctx->aux[6].as<uint8_t>(), amplicon_len, d_go, d_rep);
+        k_keep_representative<<<1, 1, 0, s>>>(d_go, d_rep, n);
+        CK(cudaGetLastError());
+        span_end(ctx, 2);
+        CK(select_flagged(d_go, n, 1, d_sel, d_cnt, ctx->alleles.p, sb, s));
+        int h_cnt = 0;
+        CK(cudaMemcpyAsync(&h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (h_cnt < n) { d_subset = d_sel; nsub = h_cnt; ctx->n_exact = n - h_cnt; }
+        else d_go = nullptr;                                          // no such read: the plan covers everything
+    }
+    // pairing plan of the read set (minus the exact reads): shared by the amplicon and the HDR-amplicon pass
+    int rc = build_plan(ctx, d_reads, d_off, d_subset, nsub);
     if (rc) { cudaStreamSynchronize(s); return rc; }
     const int maxlen = ctx->plan.maxlen;
     const int max_amp = std::max(amplicon_len, has_hdr ? path->hdr_amplicon_len : 0);
@@ -363,6 +466,19 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
         }
     }
 
+    if (d_go) {
+        // the exact reads: alignment = the diagonal (no DP), HDR record = the representative's
+        ExactArgs ea;
+        ea.reads = d_reads; ea.offsets = d_off; ea.n = n; ea.amp = ctx->aux[6].as<uint8_t>(); ea.La = amplicon_len; ea.scale5 = 0;
+        ea.go = d_go; ea.rep = d_rep; ea.aln = d_aln; ea.aln_hdr = d_aln_hdr; ea.ops = d_ops; ea.ops_stride = ops_stride;
+        ea.ref = d_ref; ea.mark = d_mark; ea.qry = d_qry; ea.slot = slot;
+        span_begin(ctx, T_WALK);
+        k_emit_exact<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(ea);
+        CK(cudaGetLastError());
+        span_end(ctx, 1);
+        cells += (int64_t)(has_hdr ? 2 : 1) * amplicon_len * amplicon_len * ctx->n_exact;
+    }
+
     // ---- 2. keep / rescue decision ----
     CK(ctx->q_in[1].reserve((size_t)n * 4)); CK(ctx->q_in[2].reserve((size_t)n * 4)); CK(ctx->q_in[3].reserve((size_t)n * 4));
     CK(ctx->q_in[5].reserve((size_t)n));
@@ -403,14 +519,7 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
     if (rc) return rc;
     QuantArgs qa{};
     fill_quant_args(&qa, quant, acc, d_bits, W, out->hist_zero);
-    // forward amplicon, upper case, for the N mask (run_plan leaves the amplicon of its LAST pass in ctx->amp)
-    CK(ctx->aux[6].reserve((size_t)amplicon_len));
-    {
-        std::string up(amplicon, amplicon + amplicon_len);
-        for (auto &ch : up) if (ch >= 'a' && ch <= 'z') ch = (char)(ch - 32);
-        CK(cudaMemcpyAsync(ctx->aux[6].p, up.data(), (size_t)amplicon_len, cudaMemcpyHostToDevice, s));
-        CK(cudaStreamSynchronize(s));
-    }
+    // (forward amplicon, upper case, for the N mask: uploaded to ctx->aux[6] at the top of the call)
     qa.ops = d_ops; qa.ops_stride = ops_stride; qa.ops_reversed = 1; qa.amp = ctx->aux[6].as<uint8_t>(); qa.alnlen = d_alnlen;
     qa.tenths_ref = d_tref; qa.tenths_rep = has_hdr ? d_trep : nullptr; qa.unmod_in = d_unmod;
     qa.active = d_kept; qa.active_bit = 1; qa.n = n; qa.recs = d_recs;

@@ -84,6 +84,12 @@ int crgpu_last_escaped(const crgpu_ctx *ctx, int out[2]);
  * traceback is then provably that diagonal (DESIGN.md "Diagonal shortcut"), so only the remaining read pairs go through
  * the band pass and the walk.  Results never depend on this. */
 int crgpu_set_diag_shortcut(crgpu_ctx *ctx, int on);
+/* Exact-read shortcut of crgpu_align_quantify (default on): a read that IS the amplicon (same length and bases, case aside;
+ * amplicon of A C G T only) aligns to it along the diagonal with the maximum possible score, identity 100.0, and to the HDR
+ * amplicon like every other such read -- so all but one representative skip the DP; their records, ops and text rows are
+ * written directly.  Results do not depend on it.  crgpu_last_exact: reads that skipped the DP in the last call. */
+int crgpu_set_exact_shortcut(crgpu_ctx *ctx, int on);
+int64_t crgpu_last_exact(const crgpu_ctx *ctx);
 /* Last crgpu_align_quantify call: out[0] = read pairs of the banded passes, out[1] = pairs that still needed the band
  * pass + walk (equal when the shortcut is off). */
 int crgpu_last_diag(const crgpu_ctx *ctx, int64_t out[2]);

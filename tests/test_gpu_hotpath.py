@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from crispresso_b200 import _lib, hotpath, synth
+from crispresso_b200 import _lib, aligner, hotpath, synth
 from oracle import quantify
 
 pytestmark = pytest.mark.gpu
@@ -120,6 +120,7 @@ def test_shared_dp_prefix_of_the_hdr_pass_changes_nothing(ctx):
         try:
             other.set_traceback_budget(32 << 20)
             other.set_band(0)                             # single-pass fill: evaluated cells are exactly the DP cells
+            other.set_exact_shortcut(False)               # (... of EVERY read)
             a = hotpath.run_hot_path(other, amp, packed, hdr_amplicon=hdr, flags=flags, want_rows=True)
             other.set_share_prefix(False)
             b = hotpath.run_hot_path(other, amp, packed, hdr_amplicon=hdr, flags=flags, want_rows=True)
@@ -139,10 +140,12 @@ def test_shared_dp_prefix_of_the_hdr_pass_changes_nothing(ctx):
     hdr2 = "T" + amp[1:] if amp[0] != "T" else "G" + amp[1:]
     packed = synth.make_reads(amp, hdr2, cut, 500, seed=75)
     ctx.set_band(0)
+    ctx.set_exact_shortcut(False)
     try:
         r = hotpath.run_hot_path(ctx, amp, packed, hdr_amplicon=hdr2, flags=hotpath.quant_flags(hdr2))
     finally:
         ctx.set_band(16)
+        ctx.set_exact_shortcut(True)
     assert r.red.n_cells_computed == r.red.n_cells
 
 
@@ -220,6 +223,55 @@ def test_pipelined_chunks_on_two_contexts_equal_one_call(ctx):
         other.close()
 
 
+@pytest.mark.parametrize("La,read_len,hdr_on,amp_n", [(250, 250, True, False), (180, 180, False, False), (300, 300, True, False),
+                                                        (200, 151, False, False), (160, 160, True, True)])
+def test_exact_read_shortcut_changes_nothing(La, read_len, hdr_on, amp_n):
+    """Reads identical to the amplicon (case aside) skip the DP: their records, ops, text rows and HDR identities are written
+    directly (one representative goes through the DP).  Every output must equal the run with the shortcut off, and most
+    unedited reads must take it (none when the amplicon holds an N: the argument needs the maximum score 5 L)."""
+    from crispresso_b200 import Context
+    seed = 700 + La
+    amp, guide, cut, hdr = synth.make_case(seed, La, hdr=hdr_on)
+    if amp_n:
+        amp = amp[:40] + "N" + amp[41:]
+        hdr = hdr[:40] + "N" + hdr[41:] if hdr else hdr
+    buf, off = synth.make_reads(amp.replace("N", "A"), hdr.replace("N", "A") if hdr else None, cut, 1600, seed=seed, read_len=read_len,
+                                rc_frac=0.03, sub_rate=0.001)
+    reads = [bytes(buf[off[i]:off[i + 1]]).decode() for i in range(1600)]
+    reads = reads + [r.lower() for r in reads[:40]] + [amp.replace("N", "A")] * 7            # lower-case copies, exact copies
+    packed = aligner.pack_reads(reads)
+    flags = hotpath.quant_flags(hdr or "")
+    inc = hotpath.include_mask(La, hotpath.cut_points_from_guides(amp, guide), 1, 15, 15)
+    c = Context(0)
+    try:
+        c.set_traceback_budget(24 << 20)
+        c.set_exact_shortcut(False)
+        ref = hotpath.run_hot_path(c, amp, packed, hdr_amplicon=hdr, flags=flags, inc=inc, want_rows=True, alleles=8192, min_identity_score=40.0)
+        assert c.last_exact() == 0
+        c.set_exact_shortcut(True)
+        got = hotpath.run_hot_path(c, amp, packed, hdr_amplicon=hdr, flags=flags, inc=inc, want_rows=True, alleles=8192, min_identity_score=40.0)
+        n_same = sum(1 for r in reads if r.upper() == amp)
+        assert c.last_exact() == (max(n_same - 1, 0) if not amp_n else 0)
+        if read_len == La and not amp_n:
+            assert c.last_exact() > 300
+        assert np.array_equal(got.red.results(), ref.red.results())
+        assert np.array_equal(got.aln, ref.aln) and np.array_equal(got.recs, ref.recs) and np.array_equal(got.kept, ref.kept)
+        assert np.array_equal(got.tenths_rep, ref.tenths_rep)
+        assert np.array_equal(got.rc_read, ref.rc_read) and np.array_equal(got.rc_aln, ref.rc_aln)
+        for k in range(3):
+            o = ref.aln["aln_off"]
+            for i in range(len(reads)):
+                assert np.array_equal(got.rows[k][i, o[i]:], ref.rows[k][i, o[i]:]), (k, i)
+        assert sorted(got.allele_count.tolist()) == sorted(ref.allele_count.tolist())
+        lean = hotpath.run_hot_path(c, amp, packed, hdr_amplicon=hdr, flags=flags, inc=inc, min_identity_score=40.0)
+        assert np.array_equal(lean.red.results(), ref.red.results()) and np.array_equal(lean.recs, ref.recs)
+        fields = [f for f in _lib.ALN_REC.names if f != "aln_off"]
+        for f in fields:
+            assert np.array_equal(lean.aln[f], ref.aln[f]), f
+    finally:
+        c.close()
+
+
 def test_staged_pipeline_equals_one_call(ctx):
     """hotpath.run_hot_path_staged -- crgpu_stage_reads (one base per byte, or BAM 4-bit codes unpacked on the device) on the
     copy stream while crgpu_align_quantify_staged works on the previous chunk -- must return what one call over all reads
@@ -278,6 +330,7 @@ def test_band_holds_off_after_a_call_whose_reads_mostly_escape(ctx):
     packed = synth.make_reads(amp, None, cut, 800, seed=42, read_len=250, p_exact=0.2, p_hdr=0.0)
     flags = hotpath.quant_flags("")
     ctx.set_band(1)
+    ctx.set_exact_shortcut(False)                         # (evaluated cells are compared with the DP cells of every read)
     try:
         first = hotpath.run_hot_path(ctx, amp, packed, flags=flags)
         assert ctx.last_escaped()[0] * 4 > 800
@@ -289,6 +342,7 @@ def test_band_holds_off_after_a_call_whose_reads_mostly_escape(ctx):
         hotpath.run_hot_path(ctx, amp, packed, flags=flags)
         assert ctx.last_escaped()[0] * 4 > 800
     finally:
+        ctx.set_exact_shortcut(True)
         ctx.set_band(16)
 
 
@@ -307,6 +361,7 @@ def test_diagonal_shortcut_changes_nothing(La, read_len, sigma, hdr_on):
     c = Context(0)
     try:
         c.set_traceback_budget(24 << 20)
+        c.set_exact_shortcut(False)                       # (its reads would leave the plan: the pair counts below are of all reads)
         c.set_diag_shortcut(False)
         ref = hotpath.run_hot_path(c, amp, packed, hdr_amplicon=hdr, flags=flags, want_rows=True, min_identity_score=40.0)
         total, left = c.last_diag()
