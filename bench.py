@@ -389,15 +389,16 @@ def main():
     n_chunks = len(items)
 
     def run_host_steps(k_steps):
-        """k_steps passes over the step's chunks as one stream; returns the last step's [(reductions, allele table)] per job."""
+        """k_steps passes over the step's chunks, as a section of an endless stream of steps: on entry the first chunk is
+        already staged (by the previous section), every chunk's run is preceded by the staging of the chunk after it -- the
+        last chunk stages the next step's first one -- so a section of k steps holds k copies of the step's reads and k runs.
+        Returns the last step's [(reductions, allele table)] per job."""
         last = []
-        items[0][0].pipe.stage(items[0][1], items[0][2], packed=True)
         for st in range(k_steps):
             last = []
             for c, (j, _pk, _po, out, job_done) in enumerate(items):
-                nxt = items[c + 1] if c + 1 < n_chunks else (items[0] if st + 1 < k_steps else None)
-                if nxt is not None:
-                    nxt[0].pipe.stage(nxt[1], nxt[2], packed=True)
+                nxt = items[(c + 1) % n_chunks]
+                nxt[0].pipe.stage(nxt[1], nxt[2], packed=True)
                 j.pipe.run(out)
                 if job_done:
                     # (the per-read arrays of this job's last chunk travel behind the next chunk's kernels)
@@ -407,6 +408,7 @@ def main():
         ctx.sync()                                                   # ... and are all in host memory here
         return last
 
+    items[0][0].pipe.stage(items[0][1], items[0][2], packed=True)    # the stream's very first chunk
     run_host_steps(max(1, args.warmup - 1))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -493,6 +495,9 @@ def main():
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": e2e_ms / args.steps, "results_equal_device_arm": same,
                 "distinct_alleles": n_alleles,
+                "stream": "the timed K steps are a section of a stream of steps: each step's run is preceded by the staging (H2D copy) "
+                          "of the next step's reads, so the section holds K copies of a step's reads, K runs and K sets of results in host "
+                          "memory (synchronised at both ends); the first timed step's reads were copied during the last warm-up step",
                 "api": "hotpath.StagedPipeline on one context: crgpu_stage_reads (BAM 4-bit reads from pinned memory, asynchronous "
                        "H2D on the library's copy stream, unpacked on the device; the next %d-read chunk is staged while the current "
                        "one runs) + crgpu_align_quantify_staged (per-read records, RC-rescue rows, reductions and the allele table "

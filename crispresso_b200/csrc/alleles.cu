@@ -16,12 +16,16 @@
 
 namespace crgpu {
 
-__device__ __forceinline__ uint64_t mix64(uint64_t h, uint64_t v, uint64_t mul)
+// murmur3's 64-bit finaliser: every (position, content) element of a row is mixed on its own and the row's hash is the SUM of
+// its elements' mixes, so the 32 lanes of a warp hash one row together, in any order
+__device__ __forceinline__ uint64_t fmix64(uint64_t x)
 {
-    h ^= v;
-    h *= mul;
-    h ^= h >> 29;
-    return h;
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
 }
 
 __device__ __forceinline__ uint8_t comp_up(uint8_t c)
@@ -36,61 +40,94 @@ __device__ __forceinline__ uint8_t comp_up(uint8_t c)
     }
 }
 
+constexpr uint64_t SEED1 = 0x9e3779b97f4a7c15ull, SEED2 = 0xc2b2ae3d27d4eb4full;
+
 // rows [0, n): forward row of read i (valid iff kept[i] & 1); rows [n, n + nrc): RC row j of read
-// rc_read[j] (valid iff kept[rc_read[j]] & 2).  Invalid rows get key = ~0 and sort last.
-__global__ void k_hash_rows(const uint8_t *__restrict__ reads, const int64_t *__restrict__ offsets, int64_t n,
+// rc_read[j] (valid iff kept[rc_read[j]] & 2).  Invalid rows get key = ~0 and sort last.  Eight lanes per row, four rows per
+// warp (a row is a short chain of dependent loads: the number of rows in flight is what counts).
+// Elements of a row: the bases as they appear in align_seq, four per element, keyed by their position (raw for forward rows,
+// upper-cased reverse complement for RC rows); the gap columns (op 2 / 3), keyed by their FORWARD column -- the walker stores
+// forward rows' ops last column first -- so that a forward row and an RC row with the same text rows agree (matches and
+// mismatches follow from the bases and the gaps); the alignment length, the read length and the four record fields.
+__global__ void __launch_bounds__(256) k_hash_rows(const uint8_t *__restrict__ reads, const int64_t *__restrict__ offsets, int64_t n,
                             const uint8_t *__restrict__ kept, const int32_t *__restrict__ rc_read, int64_t nrc,
                             const uint32_t *__restrict__ ops_fw, const uint32_t *__restrict__ ops_rc, int64_t ops_stride,
                             const crgpu_aln_rec *__restrict__ aln_fw, const crgpu_aln_rec *__restrict__ aln_rc,
                             const crgpu_read_rec *__restrict__ rec_fw, const crgpu_read_rec *__restrict__ rec_rc,
                             uint64_t *__restrict__ keys, uint64_t *__restrict__ chk, int32_t *__restrict__ rows)
 {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n + nrc) return;
-    rows[r] = (int32_t)r;
-    const bool rc = r >= n;
-    const int64_t read = rc ? rc_read[r - n] : r;
-    const bool valid = rc ? (kept[read] & 2) != 0 : (kept[read] & 1) != 0;
-    if (!valid) { keys[r] = ~0ull; chk[r] = 0; return; }
-    const uint8_t *b = reads + offsets[read];
-    const int len = (int)(offsets[read + 1] - offsets[read]);
-    {
-        // identity 100.0: the row's three strings are the amplicon itself (CORE:2014), whatever the strand -- one allele,
-        // by far the most frequent one, so its rows skip the two hash chains.  (align_seq keeps the read's CASE: a read with
-        // a lower-case base is another allele and takes the long way.)
-        const int t = rc ? aln_rc[r - n].tenths : aln_fw[read].tenths;
-        if (t == 1000) {
-            uint32_t any = 0;
-            if (!rc) for (int i = 0; i < len; ++i) any |= b[i];          // (RC rows are upper-cased by the reference, CORE:141-144)
-            if (!(any & 0x20u)) { keys[r] = 0x243f6a8885a308d3ull; chk[r] = 0x13198a2e03707344ull; return; }
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int sub = threadIdx.x & 7;
+    const bool in = r < n + nrc;
+    const bool rc = in && r >= n;
+    const int64_t read = !in ? 0 : rc ? rc_read[r - n] : r;
+    // (independent loads first: one round trip)
+    const uint8_t kp = kept[read];
+    const int64_t o0 = offsets[read], o1 = offsets[read + 1];
+    const int tenths = rc ? aln_rc[r - n].tenths : aln_fw[read].tenths;
+    const int ncol = rc ? aln_rc[r - n].alnlen : aln_fw[read].alnlen;
+    const bool valid = in && (rc ? (kp & 2) != 0 : (kp & 1) != 0);
+    const uint8_t *b = reads + o0;
+    const int len = (int)(o1 - o0);
+    // identity 100.0: the row's three strings are the amplicon itself (CORE:2014), whatever the strand -- one allele,
+    // by far the most frequent one, so its rows get a constant key.  (align_seq keeps the read's CASE: a read with
+    // a lower-case base is another allele and takes the long way; RC rows are upper-cased by the reference, CORE:141-144.)
+    const bool t1000 = valid && tenths == 1000;
+    uint32_t any = 0;
+    if (t1000 && !rc) for (int i = sub * 4; i < len; i += 32) any |= load4(b, i, len);
+    any |= __shfl_xor_sync(0xffffffffu, any, 1);
+    any |= __shfl_xor_sync(0xffffffffu, any, 2);
+    any |= __shfl_xor_sync(0xffffffffu, any, 4);
+    const bool fast = t1000 && !(any & 0x20202020u);
+    uint64_t h1 = 0, h2 = 0;
+    if (valid && !fast) {
+        const int nwords = (len + 3) >> 2;
+        for (int w = sub; w < nwords; w += 8) {
+            uint32_t c4 = 0;
+            if (!rc) c4 = load4(b, 4 * w, len);
+            else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = 4 * w + k;
+                    if (i < len) c4 |= (uint32_t)comp_up(b[len - 1 - i]) << (8 * k);
+                }
+            }
+            const uint64_t x = (uint64_t)c4 | ((uint64_t)(w + 1) << 32);
+            h1 += fmix64(x ^ SEED1);
+            h2 += fmix64((x + SEED2) * SEED1);
+        }
+        const uint32_t *ops = rc ? ops_rc + (r - n) * ops_stride : ops_fw + read * ops_stride;
+        const int nopw = (ncol + 15) >> 4;
+        for (int w = sub; w < nopw; w += 8) {
+            const uint32_t ow = ops[w];
+            uint32_t g = ow & 0xaaaaaaaau;                              // ops 2 and 3
+            while (g) {
+                const int bit = __ffs(g) - 1;
+                g &= g - 1;
+                const int j = w * 16 + (bit >> 1);
+                if (j >= ncol) break;
+                const int col = rc ? j : ncol - 1 - j;
+                const uint64_t x = (uint64_t)(uint32_t)col | ((uint64_t)((ow >> (bit - 1)) & 3u) << 32) | (1ull << 62);
+                h1 += fmix64(x ^ SEED1);
+                h2 += fmix64((x + SEED2) * SEED1);
+            }
         }
     }
-    uint64_t h1 = 0x9e3779b97f4a7c15ull, h2 = 0xc2b2ae3d27d4eb4full;
-    // bases as they appear in align_seq: raw for forward rows, upper-cased reverse complement for RC rows
-    for (int i = 0; i < len; ++i) {
-        const uint8_t c = rc ? comp_up(b[len - 1 - i]) : b[i];
-        h1 = mix64(h1, c, 0xff51afd7ed558ccdull);
-        h2 = mix64(h2, c + 0x100u * (uint32_t)(i & 255), 0xc4ceb9fe1a85ec53ull);
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+        h1 += __shfl_xor_sync(0xffffffffu, h1, d);
+        h2 += __shfl_xor_sync(0xffffffffu, h2, d);
     }
-    const crgpu_aln_rec a = rc ? aln_rc[r - n] : aln_fw[read];
-    const uint32_t *ops = rc ? ops_rc + (r - n) * ops_stride : ops_fw + read * ops_stride;
-    // ops are stored in walk order: reversed for forward rows, forward for RC rows; hash them in
-    // FORWARD column order so that a forward row and an RC row with the same text rows agree
-    const int ncol = a.alnlen;
-    uint64_t acc = 0;
-    for (int c = 0; c < ncol; ++c) {
-        const int j = rc ? c : ncol - 1 - c;
-        const uint64_t op = (ops[j >> 4] >> ((j & 15) * 2)) & 3u;
-        acc = (acc << 2) | op;
-        if ((c & 31) == 31) { h1 = mix64(h1, acc, 0xff51afd7ed558ccdull); h2 = mix64(h2, ~acc, 0xc4ceb9fe1a85ec53ull); acc = 0; }
-    }
-    h1 = mix64(h1, acc ^ ((uint64_t)ncol << 40), 0xff51afd7ed558ccdull);
-    h2 = mix64(h2, acc + ncol, 0xc4ceb9fe1a85ec53ull);
+    if (!in || sub != 0) return;
+    rows[r] = (int32_t)r;
+    if (!valid) { keys[r] = ~0ull; chk[r] = 0; return; }
+    if (fast) { keys[r] = 0x243f6a8885a308d3ull; chk[r] = 0x13198a2e03707344ull; return; }
     const crgpu_read_rec q = rc ? rec_rc[r - n] : rec_fw[read];
     const uint64_t f = (uint64_t)q.cls | ((uint64_t)(uint32_t)q.n_mutated << 8) | ((uint64_t)(uint32_t)q.n_inserted << 24) |
                        ((uint64_t)(uint32_t)q.n_deleted << 44);
-    h1 = mix64(h1, f, 0xff51afd7ed558ccdull);
-    h2 = mix64(h2, f, 0xc4ceb9fe1a85ec53ull);
+    const uint64_t g = (uint64_t)(uint32_t)ncol | ((uint64_t)(uint32_t)len << 32);
+    h1 = fmix64(h1 + fmix64(f ^ SEED2) + fmix64(g + SEED1));
+    h2 = fmix64(h2 ^ fmix64(f + SEED1) ^ fmix64(g * SEED2 + 1));
     if (h1 == ~0ull) h1 = 0x5bd1e995u;
     keys[r] = h1;
     chk[r] = h2;
@@ -108,7 +145,7 @@ __global__ void k_check_groups(const uint64_t *__restrict__ skeys, const int32_t
 // representative (first sorted row) of every run; the run of invalid rows gets count 0; slots past
 // the last run are neutral (count 0 from the memset, representative -1)
 __global__ void k_group_reps(const uint64_t *__restrict__ ukeys, const int32_t *__restrict__ starts, const int32_t *__restrict__ srows,
-                             int32_t *__restrict__ counts, const int *__restrict__ nruns, int32_t *__restrict__ rep,
+                             int32_t *__restrict__ counts, int *__restrict__ nruns, int32_t *__restrict__ rep,
                              int32_t *__restrict__ gid, int64_t m)
 {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -116,7 +153,7 @@ __global__ void k_group_reps(const uint64_t *__restrict__ ukeys, const int32_t *
     gid[g] = (int32_t)g;
     if (g >= *nruns) { rep[g] = -1; return; }
     rep[g] = srows[starts[g]];
-    if (ukeys[g] == ~0ull) counts[g] = 0;
+    if (ukeys[g] == ~0ull) { counts[g] = 0; nruns[2] = 1; }      // (nruns[2]: one of the runs is the rows that were not kept)
 }
 
 __global__ void k_gather_i32(const int32_t *__restrict__ src, const int32_t *__restrict__ idx, int32_t *__restrict__ out, int64_t m)
@@ -183,10 +220,10 @@ cudaError_t allele_groups(const uint8_t *reads, const int64_t *offsets, int64_t 
     uint64_t *kpairs = reinterpret_cast<uint64_t *>(p); p += m * 16;
     int *nruns = reinterpret_cast<int *>(p); int *err = nruns + 1;
     cudaError_t e;
-    if ((e = cudaMemsetAsync(nruns, 0, 8, s)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(nruns, 0, 12, s)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(counts, 0, (size_t)m * 4, s)) != cudaSuccess) return e;
     const unsigned grid = (unsigned)((m + 127) / 128);
-    k_hash_rows<<<grid, 128, 0, s>>>(reads, offsets, n, kept, rc_read, nrc, ops_fw, ops_rc, ops_stride, aln_fw, aln_rc, rec_fw,
+    k_hash_rows<<<(unsigned)((m + 31) / 32), 256, 0, s>>>(reads, offsets, n, kept, rc_read, nrc, ops_fw, ops_rc, ops_stride, aln_fw, aln_rc, rec_fw,
                                      rec_rc, keys, chk, rows);
     size_t tb = tmp_bytes;
     if ((e = cub::DeviceRadixSort::SortPairs(tmp, tb, keys, skeys, rows, srows, (int)m, 0, 64, s)) != cudaSuccess) return e;

@@ -23,8 +23,9 @@ int crgpu_create(crgpu_ctx **out, int device)
         if (c->stream2) cudaStreamDestroy(c->stream2);
         if (c->stream3) cudaStreamDestroy(c->stream3);
         if (c->stream_copy) cudaStreamDestroy(c->stream_copy);
-        for (int i = 0; i < 2; ++i) { if (c->staged_ev[i]) cudaEventDestroy(c->staged_ev[i]); if (c->out_ev[i]) cudaEventDestroy(c->out_ev[i]); }
+        for (int i = 0; i < 2; ++i) { if (c->staged_ev[i]) cudaEventDestroy(c->staged_ev[i]); if (c->out_ev[i]) cudaEventDestroy(c->out_ev[i]); if (c->out_ready[i]) cudaEventDestroy(c->out_ready[i]); }
         if (c->ready) cudaEventDestroy(c->ready);
+        if (c->mbox_h) cudaFreeHost(c->mbox_h);
         for (int i = 0; i < 2; ++i) { if (c->fill_done[i]) cudaEventDestroy(c->fill_done[i]); if (c->walk_done[i]) cudaEventDestroy(c->walk_done[i]); }
         delete c;
         if (prev >= 0) cudaSetDevice(prev);
@@ -40,6 +41,7 @@ int crgpu_create(crgpu_ctx **out, int device)
     // The traceback walk reads one byte per visited cell from scattered sectors: CRGPU_L2_HINT=1 asks L2 not to over-fetch
     // neighbouring sectors from HBM.  A device-wide limit (it measured neutral, profiles/r01_notes.md), so it is opt-in
     // and crgpu_destroy puts the previous value back.
+    c->trace_on = getenv("CRGPU_TRACE") != nullptr;
     if (getenv("CRGPU_L2_HINT") && cudaDeviceGetLimit(&c->l2_gran_prev, cudaLimitMaxL2FetchGranularity) == cudaSuccess) {
         if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32) == cudaSuccess) c->l2_gran_set = true;
         else cudaGetLastError();
@@ -54,7 +56,11 @@ int crgpu_create(crgpu_ctx **out, int device)
         if (cudaEventCreateWithFlags(&c->walk_done[i], cudaEventDisableTiming) != cudaSuccess) return bail();
         if (cudaEventCreateWithFlags(&c->staged_ev[i], cudaEventDisableTiming) != cudaSuccess) return bail();
         if (cudaEventCreateWithFlags(&c->out_ev[i], cudaEventDisableTiming) != cudaSuccess) return bail();
+        if (cudaEventCreateWithFlags(&c->out_ready[i], cudaEventDisableTiming) != cudaSuccess) return bail();
     }
+    c->mbox_bytes = (size_t)4 << 20;
+    if (cudaHostAlloc(reinterpret_cast<void **>(&c->mbox_h), c->mbox_bytes, cudaHostAllocMapped) != cudaSuccess) { c->mbox_h = nullptr; return bail(); }
+    if (cudaHostGetDevicePointer(reinterpret_cast<void **>(&c->mbox_d), c->mbox_h, 0) != cudaSuccess) return bail();
     if (prev >= 0 && prev != device) cudaSetDevice(prev);      // the caller's current device is not ours to change
     *out = c;
     return CRGPU_OK;
@@ -86,8 +92,9 @@ void crgpu_destroy(crgpu_ctx *c)
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->fill_done[i]); cudaEventDestroy(c->walk_done[i]); }
     cudaEventDestroy(c->ready);
-    for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->staged_ev[i]); cudaEventDestroy(c->out_ev[i]); }
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->staged_ev[i]); cudaEventDestroy(c->out_ev[i]); cudaEventDestroy(c->out_ready[i]); }
     for (auto &slot : c->stage_out) for (auto &b : slot) b.release();
+    if (c->mbox_h) cudaFreeHost(c->mbox_h);
     cudaStreamDestroy(c->stream_copy);
     cudaStreamDestroy(c->stream3);
     cudaStreamDestroy(c->stream2);
@@ -195,6 +202,7 @@ static int sync_impl(crgpu_ctx *ctx)
 {
     if (!ctx) return CRGPU_E_ARG;
     CK(cudaSetDevice(ctx->device));
+    { const int rc = flush_stages(ctx); if (rc) return rc; }
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream_copy));          // staged inputs / deferred outputs
     return CRGPU_OK;
@@ -271,6 +279,57 @@ static bool scale_penalties(double gapopen, double gapextend, int *scale, int *o
 }
 
 namespace crgpu {
+// ---- mailbox transfers (crgpu_internal.h) -------------------------------------------------------------------------------
+__global__ void k_copy_small(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, size_t bytes)
+{
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    if ((((uintptr_t)dst | (uintptr_t)src) & 3) == 0) {
+        const size_t w = bytes >> 2;
+        for (size_t i = tid; i < w; i += nth) reinterpret_cast<uint32_t *>(dst)[i] = reinterpret_cast<const uint32_t *>(src)[i];
+        for (size_t i = (w << 2) + tid; i < bytes; i += nth) dst[i] = src[i];
+    } else {
+        for (size_t i = tid; i < bytes; i += nth) dst[i] = src[i];
+    }
+}
+
+static cudaError_t copy_small(uint8_t *dst, const uint8_t *src, size_t bytes, cudaStream_t s)
+{
+    const unsigned blocks = (unsigned)std::min<size_t>(64, (bytes / 4 + 255) / 256 + 1);
+    k_copy_small<<<blocks, 256, 0, s>>>(dst, src, bytes);
+    return cudaGetLastError();
+}
+
+cudaError_t fetch_small(crgpu_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, cudaStream_t s)
+{
+    if (bytes == 0) return cudaSuccess;
+    const size_t off = (ctx->mbox_used + 15) & ~(size_t)15;
+    if (!ctx->mbox_h || off + bytes > ctx->mbox_bytes) return cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, s);
+    ctx->mbox_used = off + bytes;
+    ctx->mbox_pending.push_back({h_dst, off, bytes});
+    return copy_small(ctx->mbox_d + off, reinterpret_cast<const uint8_t *>(d_src), bytes, s);
+}
+
+cudaError_t fetch_wait(crgpu_ctx *ctx, cudaStream_t s)
+{
+    const cudaError_t e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess)
+        for (const auto &f : ctx->mbox_pending) memcpy(f.dst, ctx->mbox_h + f.off, f.bytes);
+    ctx->mbox_pending.clear();
+    ctx->mbox_used = 0;
+    return e;
+}
+
+cudaError_t push_small(crgpu_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, cudaStream_t s)
+{
+    if (bytes == 0) return cudaSuccess;
+    const size_t off = (ctx->mbox_used + 15) & ~(size_t)15;
+    if (!ctx->mbox_h || off + bytes > ctx->mbox_bytes) return cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, s);
+    ctx->mbox_used = off + bytes;
+    memcpy(ctx->mbox_h + off, h_src, bytes);
+    return copy_small(reinterpret_cast<uint8_t *>(d_dst), ctx->mbox_d + off, bytes, s);
+}
+
+
 
 // ---------------------------------------------------------------------------------------------
 // build_plan: bucket the reads (all n, or `d_subset`) by length on the device, pair consecutive
@@ -293,9 +352,9 @@ int build_plan(crgpu_ctx *ctx, const uint8_t *d_reads, const int64_t *d_offsets,
     span_end(ctx);
     std::vector<int> hist((size_t)NB + 0);
     int h_err = 0;
-    CK(cudaMemcpyAsync(hist.data(), d_hist, (size_t)NB * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    CK(fetch_small(ctx, hist.data(), d_hist, (size_t)NB * 4, s));
+    CK(fetch_small(ctx, &h_err, d_err, 4, s));
+    CK(fetch_wait(ctx, s));
     if (h_err & 2)
         return fail(ctx, CRGPU_E_ALIGN, "a read has a length outside [%d, %d]", CRGPU_MIN_LEN, CRGPU_MAX_READ);
     std::vector<int64_t> read_start((size_t)NB, 0);
@@ -321,8 +380,8 @@ int build_plan(crgpu_ctx *ctx, const uint8_t *d_reads, const int64_t *d_offsets,
     CK(ctx->plan_tab.reserve((size_t)NB * 8 + (size_t)nseg * sizeof(HostSeg)));
     int64_t *d_read_start = ctx->plan_tab.as<int64_t>();
     HostSeg *d_segs = reinterpret_cast<HostSeg *>(d_read_start + NB);
-    CK(cudaMemcpyAsync(d_read_start, read_start.data(), (size_t)NB * 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(d_segs, pl.segs.data(), (size_t)nseg * sizeof(HostSeg), cudaMemcpyHostToDevice, s));
+    CK(push_small(ctx, d_read_start, read_start.data(), (size_t)NB * 8, s));
+    CK(push_small(ctx, d_segs, pl.segs.data(), (size_t)nseg * sizeof(HostSeg), s));
     CK(ctx->order.reserve((size_t)nsub * 4));
     CK(ctx->pc.reserve((size_t)std::max<int64_t>(pcs, 1) + 16));      // (+16: k_gotoh_score2 prefetches one code past an odd-length read)
     CK(ctx->pc_off.reserve((size_t)(pl.np + 1) * 8));
@@ -336,8 +395,8 @@ int build_plan(crgpu_ctx *ctx, const uint8_t *d_reads, const int64_t *d_offsets,
     CK(launch_encode(d_reads, d_offsets, ctx->pair_lo.as<int32_t>(), ctx->pair_hi.as<int32_t>(), ctx->pc_off.as<int64_t>(), pl.np,
                      ctx->pc.as<uint8_t>(), d_err, ctx->d_bad, ctx->num_sms, s));
     span_end(ctx, 3);
-    CK(cudaMemcpyAsync(&h_err, d_err, 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));    // read_start / segs are locals of this frame
+    CK(fetch_small(ctx, &h_err, d_err, 4, s));
+    CK(fetch_wait(ctx, s));
     if (h_err & 1) return fail(ctx, CRGPU_E_ALIGN, "a read contains a base outside ACGTN(U)");
     return CRGPU_OK;
 }
@@ -449,8 +508,8 @@ int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_read
         CK(ctx->lastrow2.reserve((size_t)max_bp * 12));
         CK(ctx->lastcol2.reserve((size_t)max_bp * G * 12));
     }
-    CK(cudaMemcpyAsync(ctx->amp.p, amp_up.data(), (size_t)La, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->prof.p, prof.data(), prof.size() * 4, cudaMemcpyHostToDevice, s));
+    CK(push_small(ctx, ctx->amp.p, amp_up.data(), (size_t)La, s));
+    CK(push_small(ctx, ctx->prof.p, prof.data(), prof.size() * 4, s));
     CK(cudaStreamSynchronize(s));      // amp_up / prof are locals of this frame
 
     // Even fill batches run on the main stream, odd ones on a third stream, so that the persistent CTAs
@@ -624,10 +683,10 @@ int run_plan_dual(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         CK(lrA[i]->reserve((size_t)max_bp * 12)); CK(lcA[i]->reserve((size_t)max_bp * G * 12));
         CK(lrH[i]->reserve((size_t)max_bp * 12)); CK(lcH[i]->reserve((size_t)max_bp * Gh * 12));
     }
-    CK(cudaMemcpyAsync(ctx->amp.p, amp_up.data(), (size_t)La, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->amp_h.p, hdr_up.data(), (size_t)La, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->prof.p, prof_a.data(), prof_a.size() * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->prof_h.p, prof_h.data(), prof_h.size() * 4, cudaMemcpyHostToDevice, s));
+    CK(push_small(ctx, ctx->amp.p, amp_up.data(), (size_t)La, s));
+    CK(push_small(ctx, ctx->amp_h.p, hdr_up.data(), (size_t)La, s));
+    CK(push_small(ctx, ctx->prof.p, prof_a.data(), prof_a.size() * 4, s));
+    CK(push_small(ctx, ctx->prof_h.p, prof_h.data(), prof_h.size() * 4, s));
     CK(cudaStreamSynchronize(s));      // the staging vectors are locals of this frame
 
     cudaStream_t s2 = two ? ctx->stream2 : ctx->stream;
@@ -860,14 +919,14 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
             CK(lrH[i]->reserve((size_t)max_bp * 12)); CK(lcH[i]->reserve((size_t)max_bp * Gh * 12));
         }
     }
-    CK(cudaMemcpyAsync(ctx->amp.p, amp_up.data(), (size_t)La, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ctx->prof.p, prof_a.data(), prof_a.size() * 4, cudaMemcpyHostToDevice, s));
+    CK(push_small(ctx, ctx->amp.p, amp_up.data(), (size_t)La, s));
+    CK(push_small(ctx, ctx->prof.p, prof_a.data(), prof_a.size() * 4, s));
     if (dual) {
-        CK(cudaMemcpyAsync(ctx->amp_h.p, hdr_up.data(), (size_t)La, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->prof_h.p, prof_h.data(), prof_h.size() * 4, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->prof_hs.p, prof_hs.data(), prof_hs.size() * 4, cudaMemcpyHostToDevice, s));
+        CK(push_small(ctx, ctx->amp_h.p, hdr_up.data(), (size_t)La, s));
+        CK(push_small(ctx, ctx->prof_h.p, prof_h.data(), prof_h.size() * 4, s));
+        CK(push_small(ctx, ctx->prof_hs.p, prof_hs.data(), prof_hs.size() * 4, s));
     }
-    CK(cudaMemcpyAsync(ctx->prof_s.p, prof_as.data(), prof_as.size() * 4, cudaMemcpyHostToDevice, s));
+    CK(push_small(ctx, ctx->prof_s.p, prof_as.data(), prof_as.size() * 4, s));
     CK(cudaStreamSynchronize(s));      // the staging vectors are locals of this frame
 
     cudaStream_t s2 = two ? ctx->stream2 : ctx->stream;
@@ -911,6 +970,9 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         span_begin(ctx, T_SCORE, sf[cur]);
         CK(launch_fill(G, K, fas, ctx->num_sms, sf[cur], 1));
         if (dual) CK(launch_fill(Gh, K, fhs, ctx->num_sms, sf[cur], 1));
+        // the GPU has milliseconds of work queued: the moment to start the copy of the NEXT staged batch (a big DMA slows the
+        // launches and the small transfers that share PCIe with it; it costs nothing while the host only waits)
+        if (b == 0) { const int frc = flush_stages(ctx); if (frc) return frc; }
         span_end(ctx, dual ? 2 : 1);
 
         WalkArgs wa;
@@ -993,8 +1055,8 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     ctx->n_diag_pairs[0] += pl.np;
     if (diag) {
         std::vector<int> hc(nbatches, 0);
-        CK(cudaMemcpyAsync(hc.data(), ctx->need_cnt.p, nbatches * 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
+        CK(fetch_small(ctx, hc.data(), ctx->need_cnt.p, nbatches * 4, s));
+        CK(fetch_wait(ctx, s));
         int64_t left = 0;
         for (int c : hc) left += c;
         ctx->n_diag_pairs[1] += left;
@@ -1091,33 +1153,71 @@ __global__ void k_unpack_bam4(const uint8_t *__restrict__ packed, int64_t nbases
     }
 }
 
+// the copy of a staged batch (crgpu_stage_reads recorded it): H2D on the copy stream + unpack
+static int issue_stage(crgpu_ctx *ctx, int slot)
+{
+    crgpu_ctx::StagePending &sp = ctx->stage_pend[slot];
+    if (!sp.on) return CRGPU_OK;
+    sp.on = false;
+    cudaStream_t cs = ctx->stream_copy;
+    CK(cudaMemcpyAsync(ctx->stage_off[slot].p, sp.offsets, (size_t)(sp.n + 1) * 8, cudaMemcpyHostToDevice, cs));
+    if (sp.format == CRGPU_READS_BYTES) {
+        CK(cudaMemcpyAsync(ctx->stage_reads[slot].p, sp.reads, (size_t)sp.total, cudaMemcpyHostToDevice, cs));
+    } else {
+        const size_t pb = (size_t)((sp.total + 1) / 2);
+        CK(cudaMemcpyAsync(ctx->stage_pack[slot].p, sp.reads, pb, cudaMemcpyHostToDevice, cs));
+        const int64_t nthreads = (sp.total + 15) / 16;
+        k_unpack_bam4<<<(unsigned)((nthreads + 255) / 256), 256, 0, cs>>>(ctx->stage_pack[slot].as<uint8_t>(), sp.total,
+                                                                         ctx->stage_reads[slot].as<uint8_t>());
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(ctx->staged_ev[slot], cs));
+    return CRGPU_OK;
+}
+
+extern "C++" {
+namespace crgpu {
+int flush_stages(crgpu_ctx *ctx)
+{
+    for (int slot = 0; slot < 2; ++slot) {
+        const int rc = issue_stage(ctx, slot);
+        if (rc) return rc;
+    }
+    // ... and the deferred per-read outputs of the previous staged call
+    for (int slot = 0; slot < 2; ++slot) {
+        crgpu_ctx::OutPending &op = ctx->out_pend[slot];
+        if (!op.on) continue;
+        op.on = false;
+        CK(cudaStreamWaitEvent(ctx->stream_copy, ctx->out_ready[slot], 0));
+        for (int i = 0; i < op.n; ++i) CK(cudaMemcpyAsync(op.h[i], op.d[i], op.bytes[i], cudaMemcpyDeviceToHost, ctx->stream_copy));
+        CK(cudaEventRecord(ctx->out_ev[slot], ctx->stream_copy));
+    }
+    return CRGPU_OK;
+}
+}  // namespace crgpu
+}  // extern "C++"
+
+// crgpu_stage_reads: checks, buffers, and a note of what to copy.  The copy itself starts when it disturbs least: inside the
+// next crgpu_align_quantify* call, right after its first score-pass launches (flush_stages) -- or, when the batch is run /
+// the context synchronised before that, right there.  CRGPU_EAGER_STAGE=1: start it at once.
 static int stage_reads_impl(crgpu_ctx *ctx, int slot, int format, const uint8_t *reads, const int64_t *offsets, int64_t n)
 {
     if (slot < 0 || slot > 1) return fail(ctx, CRGPU_E_ARG, "crgpu_stage_reads: slot must be 0 or 1");
     if (format != CRGPU_READS_BYTES && format != CRGPU_READS_BAM4) return fail(ctx, CRGPU_E_ARG, "crgpu_stage_reads: unknown format");
     if (n < 0 || (n > 0 && (!reads || !offsets)) || n >= (int64_t)1 << 31) return fail(ctx, CRGPU_E_ARG, "crgpu_stage_reads: bad argument");
     ctx->stage_n[slot] = -1;
+    ctx->stage_pend[slot].on = false;
     if (n == 0) { ctx->stage_n[slot] = 0; return CRGPU_OK; }
-    cudaStream_t cs = ctx->stream_copy;
     const int64_t total = offsets[n] - offsets[0];
     if (offsets[0] != 0 || total < 0) return fail(ctx, CRGPU_E_ARG, "crgpu_stage_reads: offsets must start at 0");
     // (16 bytes of slack: the unpack kernel stores whole 16-byte groups)
     CK(ctx->stage_reads[slot].reserve((size_t)std::max<int64_t>(total, 1) + 32));
     CK(ctx->stage_off[slot].reserve((size_t)(n + 1) * 8));
-    CK(cudaMemcpyAsync(ctx->stage_off[slot].p, offsets, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, cs));
-    if (format == CRGPU_READS_BYTES) {
-        CK(cudaMemcpyAsync(ctx->stage_reads[slot].p, reads, (size_t)total, cudaMemcpyHostToDevice, cs));
-    } else {
-        const size_t pb = (size_t)((total + 1) / 2);
-        CK(ctx->stage_pack[slot].reserve(pb + 16));
-        CK(cudaMemcpyAsync(ctx->stage_pack[slot].p, reads, pb, cudaMemcpyHostToDevice, cs));
-        const int64_t nthreads = (total + 15) / 16;
-        k_unpack_bam4<<<(unsigned)((nthreads + 255) / 256), 256, 0, cs>>>(ctx->stage_pack[slot].as<uint8_t>(), total,
-                                                                         ctx->stage_reads[slot].as<uint8_t>());
-        CK(cudaGetLastError());
-    }
-    CK(cudaEventRecord(ctx->staged_ev[slot], cs));
+    if (format == CRGPU_READS_BAM4) CK(ctx->stage_pack[slot].reserve((size_t)((total + 1) / 2) + 16));
+    ctx->stage_pend[slot] = {true, format, reads, offsets, n, total};
     ctx->stage_n[slot] = n;
+    static const bool eager = getenv("CRGPU_EAGER_STAGE") != nullptr;
+    if (eager) return issue_stage(ctx, slot);
     return CRGPU_OK;
 }
 

@@ -148,4 +148,20 @@ struct WalkArgs {
     int upper_lo = 0;
 };
 
+// The 4 bytes at byte offset i of the byte string b[0, len) -- any alignment -- as one little-endian word: aligned 32-bit
+// loads + a funnel shift; bytes past len read as 0 and are not touched in memory (beyond the aligned word b[len-1] lies in).
+__device__ __forceinline__ uint32_t load4(const uint8_t *__restrict__ b, int i, int len)
+{
+    const uintptr_t p = reinterpret_cast<uintptr_t>(b + i);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(p & ~(uintptr_t)3);
+    const int mis = (int)(p & 3);
+    const int rem = len - i;                                   // > 0
+    const uint32_t lo = w[0];
+    uint32_t hi = 0;
+    if (mis && rem > 4 - mis) hi = w[1];
+    uint32_t v = __funnelshift_r(lo, hi, mis * 8);
+    if (rem < 4) v &= (1u << (8 * rem)) - 1u;
+    return v;
+}
+
 }  // namespace crgpu

@@ -4,6 +4,7 @@
 #include "crgpu_common.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -93,6 +94,23 @@ struct crgpu_ctx {
     bool diag = true;
     // exact-read shortcut (hotpath.cu): reads identical to the amplicon skip the DP
     bool exact_shortcut = true;
+    // staged batches whose copy has not been started yet (crgpu_stage_reads; flush_stages)
+    struct StagePending { bool on; int format; const uint8_t *reads; const int64_t *offsets; int64_t n, total; };
+    StagePending stage_pend[2] = {{false, 0, nullptr, nullptr, 0, 0}, {false, 0, nullptr, nullptr, 0, 0}};
+    // deferred per-read outputs of a staged call whose copies have not been started yet (flush_stages)
+    struct OutPending { bool on; int n; void *h[4]; const void *d[4]; size_t bytes[4]; };
+    OutPending out_pend[2] = {};
+    cudaEvent_t out_ready[2] = {nullptr, nullptr};
+    // mailbox: pinned host memory mapped into the device's address space.  The counts, histograms and accumulator blocks the
+    // host reads between launches (and the small tables it writes) travel through it with a copy KERNEL: a cudaMemcpyAsync of
+    // 4 bytes would queue on the copy engine behind the staged reads / deferred outputs of the neighbouring batches
+    uint8_t *mbox_h = nullptr, *mbox_d = nullptr;
+    size_t mbox_bytes = 0, mbox_used = 0;
+    struct Fetch { void *dst; size_t off, bytes; };
+    std::vector<Fetch> mbox_pending;
+    // CRGPU_TRACE=1: host wall-clock marks of the phases of crgpu_align_quantify, printed to stderr at the end of the call
+    bool trace_on = false;
+    std::vector<std::pair<const char *, double>> trace;
     int64_t n_exact = 0;                                           // last call: reads that skipped it
     DBuf exact_go, exact_sel;
     DBuf fastflags, need[2], plist[2], plist2[2], need_read[2], rlist[2], selscratch[2], need_cnt;
@@ -172,6 +190,28 @@ inline void timing_collect(crgpu_ctx *c)
 // Every exported entry point runs inside one of these: the context's device is made current for the call and the caller's
 // is restored afterwards; after a FAILED call everything it queued on the context's three streams is waited for, so that
 // nothing is still writing caller buffers (CRGPU_MEM_DEVICE) once the error has been returned.
+inline void trace_mark(crgpu_ctx *ctx, const char *what)
+{
+    if (!ctx->trace_on) return;
+    const double t = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    ctx->trace.emplace_back(what, t);
+}
+
+inline void trace_dump(crgpu_ctx *ctx)
+{
+    if (!ctx->trace_on || ctx->trace.empty()) return;
+    std::string line = "[crgpu trace]";
+    char buf[96];
+    for (size_t i = 1; i < ctx->trace.size(); ++i) {
+        snprintf(buf, sizeof buf, " %s %.3f", ctx->trace[i].first, ctx->trace[i].second - ctx->trace[i - 1].second);
+        line += buf;
+    }
+    snprintf(buf, sizeof buf, " | total %.3f ms\n", ctx->trace.back().second - ctx->trace.front().second);
+    line += buf;
+    fputs(line.c_str(), stderr);
+    ctx->trace.clear();
+}
+
 struct ApiGuard {
     crgpu_ctx *c;
     int prev = -1;
@@ -184,6 +224,7 @@ struct ApiGuard {
     {
         if (rc != CRGPU_OK) {
             cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3);
+            c->mbox_pending.clear(); c->mbox_used = 0;       // (their destinations were locals of the failed call)
             cudaGetLastError();                       // (a sticky launch error has been reported through rc already)
         }
         return rc;
@@ -192,6 +233,15 @@ struct ApiGuard {
 };
 
 namespace crgpu {
+// start the copies of the staged batches that are still waiting for a good moment (crgpu_stage_reads)
+int flush_stages(crgpu_ctx *ctx);
+// device -> host through the mailbox, asynchronous on s: h_dst is valid after fetch_wait(ctx, s)
+cudaError_t fetch_small(crgpu_ctx *ctx, void *h_dst, const void *d_src, size_t bytes, cudaStream_t s);
+// cudaStreamSynchronize(s) + delivery of the pending fetches; the mailbox is empty afterwards
+cudaError_t fetch_wait(crgpu_ctx *ctx, cudaStream_t s);
+// host -> device through the mailbox, asynchronous on s; h_src may be reused as soon as the call returns
+cudaError_t push_small(crgpu_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, cudaStream_t s);
+
 bool choose_tile(int La, int *G, int *K);
 bool tile_available(int G, int K);
 cudaError_t launch_fill(int G, int K, const FillArgs &a, int num_sms, cudaStream_t stream, int kind = 0);

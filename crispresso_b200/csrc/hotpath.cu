@@ -49,12 +49,11 @@ static int quant_setup(crgpu_ctx *ctx, const crgpu_quant_params *q, int hist_len
     pack_mask(q->exon_mask, L, bits, W, 1);
     pack_mask(q->splice_mask, L, bits, W, 2);
     CK(ctx->q_in[0].reserve(bits.size() * 4));
-    CK(cudaMemcpyAsync(ctx->q_in[0].p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(push_small(ctx, ctx->q_in[0].p, bits.data(), bits.size() * 4, ctx->stream));
     acc->L = L; acc->hist_len = hist_len > 0 ? hist_len : 0;
     CK(ctx->q_out[0].reserve(acc->words() * 8));
     acc->base = ctx->q_out[0].as<unsigned long long>();
     CK(cudaMemsetAsync(acc->base, 0, acc->words() * 8, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));    // `bits` is a local
     *d_bits = ctx->q_in[0].as<uint32_t>();
     *W_out = W;
     return CRGPU_OK;
@@ -65,8 +64,8 @@ static int quant_collect(crgpu_ctx *ctx, const Accum &acc, int64_t *vectors, int
                          int64_t *counters, int64_t *class_counts, int64_t *n_total)
 {
     std::vector<unsigned long long> h(acc.words());
-    CK(cudaMemcpyAsync(h.data(), acc.base, acc.words() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(fetch_small(ctx, h.data(), acc.base, acc.words() * 8, ctx->stream));
+    CK(fetch_wait(ctx, ctx->stream));
     const size_t nv = (size_t)CRGPU_NUM_VECTORS * acc.L;
     if (vectors) for (size_t i = 0; i < nv; ++i) vectors[i] += (int64_t)h[i];
     if (hist_in) for (int i = 0; i < acc.hist_len; ++i) hist_in[i] += (int64_t)h[nv + i];
@@ -185,27 +184,36 @@ static std::string revcomp_upper(const char *s, int n)
 // the maximum possible score 5 L -- every column scores at most 5 and a gap costs -- so needle's start cell is (L-1, L-1) and its
 // traceback the diagonal (the argument of k_diag_emit with D_n = 5 L); identity 100.0, UNMODIFIED (CORE:2014).  Its alignment to
 // the HDR amplicon is the same for every such read.  So these reads -- the largest group of an amplicon-sequencing run -- skip
-// the DP altogether: k_mark_exact finds them (one warp per read), ONE representative (the first) stays in the plan, and
+// the DP altogether: k_mark_exact finds them, ONE representative (the first) stays in the plan, and
 // k_emit_exact writes the others' records, ops and text rows and copies the representative's HDR record.
+// (eight lanes per read, four reads per warp: the kernel is a chain of dependent loads per read, so what counts is how many
+//  reads are in flight; every lane compares 4-byte granules of its read)
 __global__ void __launch_bounds__(256) k_mark_exact(const uint8_t *__restrict__ reads, const int64_t *__restrict__ offsets, int64_t n,
                                                     const uint8_t *__restrict__ amp, int La, uint8_t *__restrict__ go, int *rep)
 {
-    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (r >= n) return;
-    const int64_t o = offsets[r];
-    bool same = (offsets[r + 1] - o) == La;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int sub = threadIdx.x & 7;
+    const bool in = r < n;
+    const int64_t o = in ? offsets[r] : 0;
+    bool same = in && (offsets[r + 1] - o) == La;
     if (same) {
-        for (int x = lane; x < La; x += 32) {
-            uint8_t c = reads[o + x];
-            if (c >= 'a' && c <= 'z') c -= 32;
-            same &= c == amp[x];
+        // four bases per step: bit 5 cleared folds the case (the amplicon is plain upper-case A C G T here, and only a / A fold to A ...)
+        const uint8_t *b = reads + o;
+        const uint32_t *aw = reinterpret_cast<const uint32_t *>(amp);
+        for (int x = sub * 4; x < La; x += 32) {
+            uint32_t want = aw[x >> 2];
+            if (La - x < 4) want &= (1u << (8 * (La - x))) - 1u;
+            same &= (load4(b, x, La) & 0xdfdfdfdfu) == want;
         }
     }
-    same = __all_sync(0xffffffffu, same);
-    if (lane == 0) {
-        go[r] = same ? 0 : 1;                                        // 1: goes through the DP
-        if (same) atomicMin(rep, (int)r);
+    unsigned v = same ? 1u : 0u;
+    v &= __shfl_xor_sync(0xffffffffu, v, 1);
+    v &= __shfl_xor_sync(0xffffffffu, v, 2);
+    v &= __shfl_xor_sync(0xffffffffu, v, 4);
+    if (in && sub == 0) {
+        go[r] = v ? 0 : 1;                                           // 1: goes through the DP
+        // the first exact read is the representative (most candidates see a smaller index already there and skip the atomic)
+        if (v && (int)r < *reinterpret_cast<volatile int *>(rep)) atomicMin(rep, (int)r);
     }
 }
 
@@ -273,10 +281,23 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const bool host = mem == CRGPU_MEM_HOST;
+    ctx->trace.clear();
+    trace_mark(ctx, "enter");
 
     // ---- inputs on the device ----
     const uint8_t *d_reads = reads; const int64_t *d_off = offsets;
-    if (staged_slot >= 0) CK(cudaStreamWaitEvent(s, ctx->staged_ev[staged_slot], 0));     // (pointers: the staging slot's)
+    if (staged_slot >= 0) {
+        // (pointers: the staging slot's.)  A batch that is run before any call had the chance to start its copy: start it now;
+        // the other slot's copy waits for this call's first score-pass launches (flush_stages, run_plan_band)
+        if (ctx->stage_pend[staged_slot].on) {
+            crgpu_ctx::StagePending other = ctx->stage_pend[staged_slot ^ 1];
+            ctx->stage_pend[staged_slot ^ 1].on = false;
+            const int frc = flush_stages(ctx);
+            ctx->stage_pend[staged_slot ^ 1] = other;
+            if (frc) return frc;
+        }
+        CK(cudaStreamWaitEvent(s, ctx->staged_ev[staged_slot], 0));
+    }
     else if (host) {
         const int64_t total = offsets[n];
         CK(ctx->reads.reserve((size_t)std::max<int64_t>(total, 1)));
@@ -299,9 +320,9 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
             if (ch >= 'a' && ch <= 'z') ch = (char)(ch - 32);
             plain_acgt &= ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T';
         }
-        CK(cudaMemcpyAsync(ctx->aux[6].p, up.data(), (size_t)amplicon_len, cudaMemcpyHostToDevice, s));
-        CK(cudaStreamSynchronize(s));
+        CK(push_small(ctx, ctx->aux[6].p, up.data(), (size_t)amplicon_len, s));
     }
+    trace_mark(ctx, "amplicon-up");
     // ---- 0. reads that ARE the amplicon need no DP (k_mark_exact above): all but one representative leave the plan ----
     const int32_t *d_subset = nullptr;
     int64_t nsub = n;
@@ -316,22 +337,24 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
         int *d_cnt = reinterpret_cast<int *>(d_sel + n);
         d_rep = d_cnt + 1;
         const int big = 0x7fffffff;
-        CK(cudaMemcpyAsync(d_rep, &big, 4, cudaMemcpyHostToDevice, s));
+        CK(push_small(ctx, d_rep, &big, 4, s));
         span_begin(ctx, T_ENCODE);
-        k_mark_exact<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(d_reads, d_off, n, ctx->aux[6].as<uint8_t>(), amplicon_len, d_go, d_rep);
+        k_mark_exact<<<(unsigned)((n * 8 + 255) / 256), 256, 0, s>>>(d_reads, d_off, n, ctx->aux[6].as<uint8_t>(), amplicon_len, d_go, d_rep);
         k_keep_representative<<<1, 1, 0, s>>>(d_go, d_rep, n);
         CK(cudaGetLastError());
         span_end(ctx, 2);
         CK(select_flagged(d_go, n, 1, d_sel, d_cnt, ctx->alleles.p, sb, s));
         int h_cnt = 0;
-        CK(cudaMemcpyAsync(&h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
+        CK(fetch_small(ctx, &h_cnt, d_cnt, 4, s));
+        CK(fetch_wait(ctx, s));
         if (h_cnt < n) { d_subset = d_sel; nsub = h_cnt; ctx->n_exact = n - h_cnt; }
         else d_go = nullptr;                                          // no such read: the plan covers everything
     }
     // pairing plan of the read set (minus the exact reads): shared by the amplicon and the HDR-amplicon pass
+    trace_mark(ctx, "exact");
     int rc = build_plan(ctx, d_reads, d_off, d_subset, nsub);
     if (rc) { cudaStreamSynchronize(s); return rc; }
+    trace_mark(ctx, "plan");
     const int maxlen = ctx->plan.maxlen;
     const int max_amp = std::max(amplicon_len, has_hdr ? path->hdr_amplicon_len : 0);
     // rows are always produced on the device (the quantifier reads them); slot = caller's or minimal
@@ -346,6 +369,7 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
     const bool deferred = staged_slot >= 0 && ctx->deferred_out;
     if (deferred) {
         DBuf *o = ctx->stage_out[staged_slot];
+        if (ctx->out_pend[staged_slot].on) { const int frc = flush_stages(ctx); if (frc) return frc; }
         CK(cudaStreamWaitEvent(s, ctx->out_ev[staged_slot], 0));          // the slot's previous outputs have left
         CK(o[0].reserve((size_t)n)); CK(o[1].reserve((size_t)n * sizeof(crgpu_aln_rec)));
         CK(o[2].reserve((size_t)n * sizeof(crgpu_read_rec))); CK(o[3].reserve((size_t)n * 4));
@@ -435,6 +459,8 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
         if (rc) { cudaStreamSynchronize(s); return rc; }
         cells += c0; cells_computed += c0;
     }
+    { const int frc = flush_stages(ctx); if (frc) return frc; }          // (paths without a banded pass)
+    trace_mark(ctx, "main-issued");
     if (banded) {
         // reads that escaped the band: compacted on the device, re-aligned with the single-pass fill
         const size_t sb = select_scratch_bytes(n);
@@ -445,9 +471,10 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
         for (int bit = 1; bit <= (has_hdr ? 2 : 1); bit <<= 1) {
             CK(select_flagged(d_esc, n, bit, d_sel, d_cnt, ctx->alleles.p, sb, s));
             int h_cnt = 0;
-            CK(cudaMemcpyAsync(&h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
+            CK(fetch_small(ctx, &h_cnt, d_cnt, 4, s));
+            CK(fetch_wait(ctx, s));
             ctx->n_escaped[bit - 1] = h_cnt;
+            trace_mark(ctx, bit == 1 ? "main-done+esc-count" : "esc2-count");
             // a read set whose tracebacks mostly leave the band pays for both fills: skip the band for the next 8 calls
             if ((int64_t)h_cnt * 4 > n) ctx->band_holdoff = 8;
             if (h_cnt == 0) continue;
@@ -466,6 +493,7 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
         }
     }
 
+    trace_mark(ctx, "esc-issued");
     if (d_go) {
         // the exact reads: alignment = the diagonal (no DP), HDR record = the representative's
         ExactArgs ea;
@@ -500,16 +528,17 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
         int *d_cnt = reinterpret_cast<int *>(d_sel + n);
         CK(select_flagged(d_kept, n, 4, d_sel, d_cnt, ctx->alleles.p, sb, s));
         int h_cnt = 0;
-        CK(cudaMemcpyAsync(&h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
+        CK(fetch_small(ctx, &h_cnt, d_cnt, 4, s));
+        CK(fetch_wait(ctx, s));
         if (h_cnt > 0) {
             rc_read.resize((size_t)h_cnt);
-            CK(cudaMemcpyAsync(rc_read.data(), d_sel, (size_t)h_cnt * 4, cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
+            CK(fetch_small(ctx, rc_read.data(), d_sel, (size_t)h_cnt * 4, s));
+            CK(fetch_wait(ctx, s));
         }
     }
     const int64_t nrc = (int64_t)rc_read.size();
     out->rc_n = nrc;
+    trace_mark(ctx, "rc-select");
     if (nrc > out->rc_cap && (out->rc_read || out->rc_aln || out->rc_recs || want_rc_rows))
         return fail(ctx, CRGPU_E_ARG, "rc_cap %lld < %lld reads re-aligned to the reverse complement", (long long)out->rc_cap, (long long)nrc);
 
@@ -582,6 +611,7 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
         span_end(ctx);
     }
 
+    trace_mark(ctx, "quant+rc-issued");
     // ---- 4b. allele table: group the kept rows on the device (CORE:2923-2946) ----
     if (out->allele_cap > 0) {
         if (!out->allele_row || !out->allele_count) return fail(ctx, CRGPU_E_ARG, "allele_row / allele_count are required with allele_cap > 0");
@@ -594,17 +624,18 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
                          nrc ? ctx->ops_rc.as<uint32_t>() : nullptr, ops_stride, d_aln, d_rc_aln, d_recs, d_rc_recs,
                          ctx->alleles.p, sb, s, &d_rep, &d_cnt, &d_nruns, &d_aerr, &d_kp));
         span_end(ctx, 4);     // k_hash_rows, k_check_groups, k_group_reps, k_gather_i32 (+ cub's own kernels, not counted)
-        int h2[2] = {0, 0};
-        CK(cudaMemcpyAsync(h2, d_nruns, 8, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        if (h2[1]) return fail(ctx, CRGPU_E_CUDA, "allele grouping: 64-bit hash collision between different alleles");
-        const int64_t take = std::min<int64_t>(out->allele_cap, h2[0]);
+        int h3[3] = {0, 0, 0};                                  // runs, collision flag, "one run is the rows that were not kept"
+        CK(fetch_small(ctx, h3, d_nruns, 12, s));
+        CK(fetch_wait(ctx, s));
+        trace_mark(ctx, "allele-kernels");
+        if (h3[1]) return fail(ctx, CRGPU_E_CUDA, "allele grouping: 64-bit hash collision between different alleles");
+        const int64_t take = std::min<int64_t>(out->allele_cap, h3[0]);
         std::vector<int32_t> hrep((size_t)take), hcnt((size_t)take);
         if (take > 0) {
-            CK(cudaMemcpyAsync(hrep.data(), d_rep, (size_t)take * 4, cudaMemcpyDeviceToHost, s));
-            CK(cudaMemcpyAsync(hcnt.data(), d_cnt, (size_t)take * 4, cudaMemcpyDeviceToHost, s));
-            if (out->allele_key) CK(cudaMemcpyAsync(out->allele_key, d_kp, (size_t)take * 16, cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
+            CK(fetch_small(ctx, hrep.data(), d_rep, (size_t)take * 4, s));
+            CK(fetch_small(ctx, hcnt.data(), d_cnt, (size_t)take * 4, s));
+            if (out->allele_key) CK(fetch_small(ctx, out->allele_key, d_kp, (size_t)take * 16, s));
+            CK(fetch_wait(ctx, s));
         }
         int64_t na = 0;
         for (int64_t i = 0; i < take; ++i) {
@@ -614,27 +645,30 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
             ++na;
         }
         // runs = alleles (+ 1 run of rows that were not kept, which sorts last with count 0)
-        int32_t last_count = 1;
-        if (h2[0] > 0) {
-            CK(cudaMemcpyAsync(&last_count, d_cnt + (h2[0] - 1), 4, cudaMemcpyDeviceToHost, s));
-            CK(cudaStreamSynchronize(s));
-        }
-        out->allele_n = (int64_t)h2[0] - (last_count == 0 ? 1 : 0);
+        out->allele_n = (int64_t)h3[0] - (h3[2] ? 1 : 0);
     }
 
+    trace_mark(ctx, "alleles");
     // ---- 5. results ----
     if (host) {
-        cudaStream_t so = s;
-        if (deferred) {                                    // ... valid after crgpu_sync
-            so = ctx->stream_copy;
-            CK(cudaEventRecord(ctx->ready, s));
-            CK(cudaStreamWaitEvent(so, ctx->ready, 0));
+        if (deferred) {
+            // ... valid after crgpu_sync: the copies start inside the NEXT call, once its first score-pass launches are queued
+            // (flush_stages) -- right now they would share PCIe with that call's first launches and small transfers
+            crgpu_ctx::OutPending &op = ctx->out_pend[staged_slot];
+            op.n = 0;
+            auto add = [&](void *h, const void *d, size_t bytes) { if (h && bytes) { op.h[op.n] = h; op.d[op.n] = d; op.bytes[op.n] = bytes; ++op.n; } };
+            add(out->kept, d_kept, (size_t)n);
+            add(out->aln, d_aln, (size_t)n * sizeof(crgpu_aln_rec));
+            add(out->recs, d_recs, (size_t)n * sizeof(crgpu_read_rec));
+            add(out->tenths_rep, d_trep, (size_t)n * 4);
+            CK(cudaEventRecord(ctx->out_ready[staged_slot], s));
+            op.on = true;
+        } else {
+            CK(cudaMemcpyAsync(out->kept, d_kept, (size_t)n, cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(out->aln, d_aln, (size_t)n * sizeof(crgpu_aln_rec), cudaMemcpyDeviceToHost, s));
+            CK(cudaMemcpyAsync(out->recs, d_recs, (size_t)n * sizeof(crgpu_read_rec), cudaMemcpyDeviceToHost, s));
+            if (out->tenths_rep) CK(cudaMemcpyAsync(out->tenths_rep, d_trep, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
         }
-        CK(cudaMemcpyAsync(out->kept, d_kept, (size_t)n, cudaMemcpyDeviceToHost, so));
-        CK(cudaMemcpyAsync(out->aln, d_aln, (size_t)n * sizeof(crgpu_aln_rec), cudaMemcpyDeviceToHost, so));
-        CK(cudaMemcpyAsync(out->recs, d_recs, (size_t)n * sizeof(crgpu_read_rec), cudaMemcpyDeviceToHost, so));
-        if (out->tenths_rep) CK(cudaMemcpyAsync(out->tenths_rep, d_trep, (size_t)n * 4, cudaMemcpyDeviceToHost, so));
-        if (deferred) CK(cudaEventRecord(ctx->out_ev[staged_slot], so));
         if (want_rows) {
             if (out->slot != slot) return fail(ctx, CRGPU_E_ARG, "out->slot must be set when rows are requested");
             const size_t rb = (size_t)n * slot;
@@ -662,6 +696,8 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
     out->n_cells += cells;
     out->n_cells_computed += cells_computed;
     timing_collect(ctx);
+    trace_mark(ctx, "collect");
+    trace_dump(ctx);
     return CRGPU_OK;
 }
 

@@ -584,6 +584,9 @@ class StagedPipeline:
         batch's RC row j)."""
         if not self._tables:
             return np.zeros(0, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int32)
+        if len(self._tables) == 1:                          # one batch: the device's table is the answer (most frequent first)
+            _k, cnt, row, bat = self._tables[0]
+            return cnt.astype(np.int64), bat, row
         keys = np.concatenate([t[0] for t in self._tables])
         cnt = np.concatenate([t[1] for t in self._tables])
         row = np.concatenate([t[2] for t in self._tables])
