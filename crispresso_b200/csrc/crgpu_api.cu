@@ -510,7 +510,6 @@ int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_read
     }
     CK(push_small(ctx, ctx->amp.p, amp_up.data(), (size_t)La, s));
     CK(push_small(ctx, ctx->prof.p, prof.data(), prof.size() * 4, s));
-    CK(cudaStreamSynchronize(s));      // amp_up / prof are locals of this frame
 
     // Even fill batches run on the main stream, odd ones on a third stream, so that the persistent CTAs
     // of batch b+1 back-fill the SMs that the tail of batch b vacates (a fill launch is ~9 waves; its
@@ -687,7 +686,6 @@ int run_plan_dual(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     CK(push_small(ctx, ctx->amp_h.p, hdr_up.data(), (size_t)La, s));
     CK(push_small(ctx, ctx->prof.p, prof_a.data(), prof_a.size() * 4, s));
     CK(push_small(ctx, ctx->prof_h.p, prof_h.data(), prof_h.size() * 4, s));
-    CK(cudaStreamSynchronize(s));      // the staging vectors are locals of this frame
 
     cudaStream_t s2 = two ? ctx->stream2 : ctx->stream;
     cudaStream_t sf[2] = {s, two ? ctx->stream3 : s};
@@ -927,7 +925,6 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         CK(push_small(ctx, ctx->prof_hs.p, prof_hs.data(), prof_hs.size() * 4, s));
     }
     CK(push_small(ctx, ctx->prof_s.p, prof_as.data(), prof_as.size() * 4, s));
-    CK(cudaStreamSynchronize(s));      // the staging vectors are locals of this frame
 
     cudaStream_t s2 = two ? ctx->stream2 : ctx->stream;
     cudaStream_t sf[2] = {s, two ? ctx->stream3 : s};

@@ -217,6 +217,19 @@ __global__ void __launch_bounds__(256) k_mark_exact(const uint8_t *__restrict__ 
     }
 }
 
+// reads whose traceback left the band in the amplicon pass (bit 0) / the HDR pass (bit 1): out[0], out[1]
+__global__ void k_count_escapes(const uint8_t *__restrict__ esc, int64_t n, int *out)
+{
+    int c1 = 0, c2 = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint8_t e = esc[i];
+        c1 += e & 1; c2 += (e >> 1) & 1;
+    }
+    c1 = __reduce_add_sync(0xffffffffu, c1);
+    c2 = __reduce_add_sync(0xffffffffu, c2);
+    if ((threadIdx.x & 31) == 0) { if (c1) atomicAdd(out, c1); if (c2) atomicAdd(out + 1, c2); }
+}
+
 __global__ void k_keep_representative(uint8_t *go, const int *rep, int64_t n)
 {
     if (*rep >= 0 && *rep < n) go[*rep] = 3;                         // through the DP, and the source of the others' HDR record
@@ -468,26 +481,29 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
         CK(ctx->alleles.reserve(sb));
         int32_t *d_sel = ctx->aux[3].as<int32_t>();
         int *d_cnt = reinterpret_cast<int *>(d_sel + n);
-        for (int bit = 1; bit <= (has_hdr ? 2 : 1); bit <<= 1) {
-            CK(select_flagged(d_esc, n, bit, d_sel, d_cnt, ctx->alleles.p, sb, s));
-            int h_cnt = 0;
-            CK(fetch_small(ctx, &h_cnt, d_cnt, 4, s));
-            CK(fetch_wait(ctx, s));
-            ctx->n_escaped[bit - 1] = h_cnt;
-            trace_mark(ctx, bit == 1 ? "main-done+esc-count" : "esc2-count");
-            // a read set whose tracebacks mostly leave the band pays for both fills: skip the band for the next 8 calls
-            if ((int64_t)h_cnt * 4 > n) ctx->band_holdoff = 8;
-            if (h_cnt == 0) continue;
+        // ONE plan over the reads that escaped in either pass: a read that escaped only one of them is re-aligned to both
+        // amplicons (the single-pass fill gives the same records as the band did; cheaper than a second plan and its syncs)
+        CK(cudaMemsetAsync(d_cnt + 1, 0, 8, s));
+        k_count_escapes<<<(unsigned)std::min<int64_t>((n + 255) / 256, 1024), 256, 0, s>>>(d_esc, n, d_cnt + 1);
+        CK(cudaGetLastError());
+        CK(select_flagged(d_esc, n, has_hdr ? 3 : 1, d_sel, d_cnt, ctx->alleles.p, sb, s));
+        int h_cnt[3] = {0, 0, 0};                           // union, amplicon pass, HDR pass
+        CK(fetch_small(ctx, h_cnt, d_cnt, 12, s));
+        CK(fetch_wait(ctx, s));
+        trace_mark(ctx, "main-done+esc-count");
+        ctx->n_escaped[0] = h_cnt[1];
+        ctx->n_escaped[1] = has_hdr ? h_cnt[2] : 0;
+        // a read set whose tracebacks mostly leave the band pays for both fills: skip the band for the next 8 calls
+        if ((int64_t)std::max(h_cnt[1], h_cnt[2]) * 4 > n) ctx->band_holdoff = 8;
+        if (h_cnt[0] > 0) {
             int64_t c0 = 0;
-            rc = build_plan(ctx, d_reads, d_off, d_sel, h_cnt);
-            if (rc == CRGPU_OK) {
-                if (bit == 1)
-                    rc = run_plan(ctx, amplicon, amplicon_len, d_reads, d_off, nullptr, 0, path->gapopen, path->gapextend, d_aln, d_ref,
-                                  d_mark, d_qry, slot, &c0, d_ops, ops_stride);
-                else
-                    rc = run_plan(ctx, path->hdr_amplicon, path->hdr_amplicon_len, d_reads, d_off, nullptr, 0, path->gapopen,
-                                  path->gapextend, d_aln_hdr, nullptr, nullptr, nullptr, slot, &c0);
-            }
+            rc = build_plan(ctx, d_reads, d_off, d_sel, h_cnt[0]);
+            if (rc == CRGPU_OK && h_cnt[1] > 0)
+                rc = run_plan(ctx, amplicon, amplicon_len, d_reads, d_off, nullptr, 0, path->gapopen, path->gapextend, d_aln, d_ref,
+                              d_mark, d_qry, slot, &c0, d_ops, ops_stride);
+            if (rc == CRGPU_OK && has_hdr && h_cnt[2] > 0)
+                rc = run_plan(ctx, path->hdr_amplicon, path->hdr_amplicon_len, d_reads, d_off, nullptr, 0, path->gapopen,
+                              path->gapextend, d_aln_hdr, nullptr, nullptr, nullptr, slot, &c0);
             if (rc) { cudaStreamSynchronize(s); return rc; }
             cells_computed += c0;
         }

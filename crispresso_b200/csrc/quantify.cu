@@ -79,6 +79,25 @@ struct OpReader {
 };
 constexpr int OP_MATCH = 0, OP_MISMATCH = 1, OP_INS = 2, OP_DEL = 3;
 
+// Columns from c on that are matches, up to the end of the op word c lies in (0: column c is not a match).  Most of a row
+// is matches: the passes below step over them a word (16 columns) at a time.
+__device__ __forceinline__ int match_run(const OpReader &ops, int c)
+{
+    if (ops.rev) {
+        const int j = ops.n - 1 - c, k = j & 15;
+        const uint32_t word = __ldg(ops.w + (j >> 4));
+        const uint32_t m = k == 15 ? word : (word & ((1u << (2 * k + 2)) - 1u));
+        if (m == 0) return k + 1;
+        return (31 - __clz(m)) / 2 < k ? k - (31 - __clz(m)) / 2 : 0;          // matches above the highest non-match op
+    }
+    const int k = c & 15;
+    const int avail = min(16 - k, ops.n - c);
+    uint32_t m = __ldg(ops.w + (c >> 4)) >> (2 * k);
+    if (avail < 16) m &= (1u << (2 * avail)) - 1u;
+    if (m == 0) return avail;
+    return (__ffs(m) - 1) / 2;                                                  // matches below the lowest non-match op
+}
+
 // One kept row.  `sc`: the CTA's shared-memory copy of the nine scalar counters (4 frameshift counters, 4 class counts,
 // rows seen) -- every row bumps two or three of them, so they are reduced per warp (ptxas aggregates the uniform-address
 // shared atomics) and per CTA before one global atomic each; the per-position vectors and the histograms get few,
@@ -133,6 +152,7 @@ __device__ __forceinline__ void quantify_row(const QuantArgs &a, const int64_t i
         int idx = 0;              // amplicon bases consumed so far == ref_positions of the next base column
         int c = 0;
         while (c < n) {
+            { const int run = match_run(ops, c); if (run) { idx += run; c += run; continue; } }
             const int op = ops.at(c);
             if (op == OP_INS) {
                 // maximal '-' run in the amplicon row: an insertion [st, en)
@@ -200,6 +220,7 @@ __device__ __forceinline__ void quantify_row(const QuantArgs &a, const int64_t i
     {
         int idx = 0, c = 0;
         while (c < n) {
+            { const int run = match_run(ops, c); if (run) { idx += run; c += run; continue; } }
             const int op = ops.at(c);
             if (op == OP_INS) {
                 const int st = c;
