@@ -420,7 +420,7 @@ static int64_t plan_pc_off(const PairPlan &pl, int64_t p)
 int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_reads, const int64_t *d_offsets,
              const int32_t *d_out_index, int rc_out, double gapopen, double gapextend, crgpu_aln_rec *d_recs,
              uint8_t *d_ref, uint8_t *d_mark, uint8_t *d_qry, int64_t slot, int64_t *n_cells, uint32_t *d_ops,
-             int64_t ops_stride)
+             int64_t ops_stride, int lane)
 {
     const PairPlan &pl = ctx->plan;
     if (La < CRGPU_MIN_LEN || La > CRGPU_MAX_AMPLICON)
@@ -497,36 +497,41 @@ int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_read
         }
     }
     cudaStream_t s = ctx->stream;
-    CK(ctx->amp.reserve((size_t)La));
-    CK(ctx->prof.reserve(prof.size() * 4));
-    const bool two = batch_start.size() > 2 && ctx->overlap && !getenv("CRGPU_NO_OVERLAP");     // double-buffer only when there is a second batch to overlap with
-    CK(ctx->tb.reserve((size_t)max_tb_words * 4));
-    CK(ctx->lastrow.reserve((size_t)max_bp * 12));
-    CK(ctx->lastcol.reserve((size_t)max_bp * G * 12));
-    if (two) {
+    // lane 1 (a second, small pass that runs BESIDE a lane-0 pass over the same plan: the HDR re-alignment of the reads that
+    // left the band): its own tables, the second scratch set, the third stream; the caller joins ctx->walk_done[1]
+    DBuf &ampb = lane ? ctx->amp_h : ctx->amp, &profb = lane ? ctx->prof_h : ctx->prof;
+    CK(ampb.reserve((size_t)La));
+    CK(profb.reserve(prof.size() * 4));
+    const bool two = !lane && batch_start.size() > 2 && ctx->overlap && !getenv("CRGPU_NO_OVERLAP");     // double-buffer only when there is a second batch to overlap with
+    if (!lane) {
+        CK(ctx->tb.reserve((size_t)max_tb_words * 4));
+        CK(ctx->lastrow.reserve((size_t)max_bp * 12));
+        CK(ctx->lastcol.reserve((size_t)max_bp * G * 12));
+    }
+    if (two || lane) {
         CK(ctx->tb2.reserve((size_t)max_tb_words * 4));
         CK(ctx->lastrow2.reserve((size_t)max_bp * 12));
         CK(ctx->lastcol2.reserve((size_t)max_bp * G * 12));
     }
-    CK(push_small(ctx, ctx->amp.p, amp_up.data(), (size_t)La, s));
-    CK(push_small(ctx, ctx->prof.p, prof.data(), prof.size() * 4, s));
+    CK(push_small(ctx, ampb.p, amp_up.data(), (size_t)La, s));          // (always on the main stream: the mailbox is its)
+    CK(push_small(ctx, profb.p, prof.data(), prof.size() * 4, s));
 
     // Even fill batches run on the main stream, odd ones on a third stream, so that the persistent CTAs
     // of batch b+1 back-fill the SMs that the tail of batch b vacates (a fill launch is ~9 waves; its
     // last partial wave would otherwise leave most of the chip idle for one pair-time).  The traceback
     // walk of batch b runs on the second stream, overlapped with the fill of batch b+1 (the walk is
     // DRAM-latency bound, the fill integer-issue bound).  Two sets of traceback scratch alternate.
-    cudaStream_t s2 = two ? ctx->stream2 : ctx->stream;
-    cudaStream_t sf[2] = {s, two ? ctx->stream3 : s};
-    if (two) {
+    cudaStream_t s2 = two ? ctx->stream2 : lane ? ctx->stream3 : ctx->stream;
+    cudaStream_t sf[2] = {s, (two || lane) ? ctx->stream3 : s};
+    if (two || lane) {
         CK(cudaEventRecord(ctx->ready, s));                   // plan, profile, amplicon are in place
         CK(cudaStreamWaitEvent(sf[1], ctx->ready, 0));
     }
     bool used[2] = {false, false};
     for (size_t b = 0; b + 1 < batch_start.size(); ++b) {
-        const int cur = two ? (int)(b & 1) : 0;
+        const int cur = two ? (int)(b & 1) : lane;
         FillArgs fa;
-        fa.prof = ctx->prof.as<int32_t>();
+        fa.prof = profb.as<int32_t>();
         fa.pc = ctx->pc.as<uint8_t>();
         fa.pc_off = ctx->pc_off.as<int64_t>();
         fa.plen = ctx->plen.as<int32_t>();
@@ -550,7 +555,7 @@ int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_read
         wa.band_B = 0; wa.band_W = 0; wa.band_K = 0; wa.kdiv_magic = 0; wa.escaped = nullptr; wa.escape_bit = 0;
         wa.pc_off = fa.pc_off; wa.plen = fa.plen;
         wa.pair_lo = ctx->pair_lo.as<int32_t>(); wa.pair_hi = ctx->pair_hi.as<int32_t>();
-        wa.reads = d_reads; wa.offsets = d_offsets; wa.amplicon = ctx->amp.as<uint8_t>();
+        wa.reads = d_reads; wa.offsets = d_offsets; wa.amplicon = ampb.as<uint8_t>();
         wa.La = La; wa.GK = GK; wa.P = P; wa.G = G; wa.K = K; wa.p0 = fa.p0; wa.p1 = fa.p1;
         wa.open = open_s; wa.ext = ext_s; wa.scale = scale;
         wa.recs = d_recs; wa.ref_out = d_ref; wa.mark_out = d_mark; wa.qry_out = d_qry; wa.slot = slot;
@@ -563,7 +568,7 @@ int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_read
         used[cur] = true;
     }
     // everything queued later on the main stream (next pass, quantification, copies) sees the walks' results
-    for (int i = 0; i < 2; ++i) if (used[i]) CK(cudaStreamWaitEvent(s, ctx->walk_done[i], 0));
+    if (!lane) for (int i = 0; i < 2; ++i) if (used[i]) CK(cudaStreamWaitEvent(s, ctx->walk_done[i], 0));
     (void)plan_pc_off;
     return CRGPU_OK;
 }

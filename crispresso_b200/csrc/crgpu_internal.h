@@ -275,7 +275,7 @@ int build_plan(crgpu_ctx *ctx, const uint8_t *d_reads, const int64_t *d_offsets,
 int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_reads, const int64_t *d_offsets,
              const int32_t *d_out_index, int rc_out, double gapopen, double gapextend, crgpu_aln_rec *d_recs,
              uint8_t *d_ref, uint8_t *d_mark, uint8_t *d_qry, int64_t slot, int64_t *n_cells,
-             uint32_t *d_ops = nullptr, int64_t ops_stride = 0);
+             uint32_t *d_ops = nullptr, int64_t ops_stride = 0, int lane = 0);
 // amplicon + HDR amplicon in one sweep over the batches; the HDR pass reuses the DP rows it shares with
 // the amplicon pass.  Returns CRGPU_OK and *done = false when the two amplicons cannot share a prefix
 // (the caller then runs two plain passes).

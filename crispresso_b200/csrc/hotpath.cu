@@ -498,12 +498,16 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
         if (h_cnt[0] > 0) {
             int64_t c0 = 0;
             rc = build_plan(ctx, d_reads, d_off, d_sel, h_cnt[0]);
+            // both passes are a single wave of a few thousand pairs, bound by the latency of one pair's fill and walk: they
+            // run side by side (the HDR pass as lane 1: third stream, second scratch set)
+            const bool both = h_cnt[1] > 0 && has_hdr && h_cnt[2] > 0;
+            if (rc == CRGPU_OK && has_hdr && h_cnt[2] > 0)
+                rc = run_plan(ctx, path->hdr_amplicon, path->hdr_amplicon_len, d_reads, d_off, nullptr, 0, path->gapopen,
+                              path->gapextend, d_aln_hdr, nullptr, nullptr, nullptr, slot, &c0, nullptr, 0, both ? 1 : 0);
             if (rc == CRGPU_OK && h_cnt[1] > 0)
                 rc = run_plan(ctx, amplicon, amplicon_len, d_reads, d_off, nullptr, 0, path->gapopen, path->gapextend, d_aln, d_ref,
                               d_mark, d_qry, slot, &c0, d_ops, ops_stride);
-            if (rc == CRGPU_OK && has_hdr && h_cnt[2] > 0)
-                rc = run_plan(ctx, path->hdr_amplicon, path->hdr_amplicon_len, d_reads, d_off, nullptr, 0, path->gapopen,
-                              path->gapextend, d_aln_hdr, nullptr, nullptr, nullptr, slot, &c0);
+            if (rc == CRGPU_OK && both) CK(cudaStreamWaitEvent(s, ctx->walk_done[1], 0));
             if (rc) { cudaStreamSynchronize(s); return rc; }
             cells_computed += c0;
         }

@@ -55,17 +55,26 @@ cudaError_t launch_rows_to_ops(const uint8_t *ref, const uint8_t *mark, const ui
 __device__ __forceinline__ void set_bit(uint32_t *bits, int v) { bits[v >> 5] |= 1u << (v & 31); }
 __device__ __forceinline__ bool get_bit(const uint32_t *bits, int v) { return (bits[v >> 5] >> (v & 31)) & 1u; }
 
-__device__ __forceinline__ void add_bits(unsigned long long *vec, const uint32_t *bits, int W)
-{
-    for (int w = 0; w < W; ++w) {
-        uint32_t x = bits[w];
-        while (x) {
-            const int b = __ffs(x) - 1;
-            x &= x - 1;
-            atomicAdd(vec + w * 32 + b, 1ull);
+// The per-position vectors: rows pile their events onto the few dozen positions around the cut site, so global atomics
+// would queue on those addresses (~30 M adds on ~60 addresses per 2^20 reads).  Every CTA keeps the 15 vectors in shared
+// memory (32-bit, `sv`) and adds what it gathered to the global 64-bit vectors once, at its end.
+struct VecAcc {
+    unsigned *sv;
+    int L;
+    __device__ __forceinline__ void add(int vec, int pos, unsigned val) const { atomicAdd(sv + vec * L + pos, val); }
+    __device__ __forceinline__ void add_bits(int vec, const uint32_t *bits, int W) const
+    {
+        unsigned *v = sv + vec * L;
+        for (int w = 0; w < W; ++w) {
+            uint32_t x = bits[w];
+            while (x) {
+                const int b = __ffs(x) - 1;
+                x &= x - 1;
+                atomicAdd(v + w * 32 + b, 1u);
+            }
         }
     }
-}
+};
 
 struct OpReader {
     const uint32_t *w;
@@ -103,7 +112,21 @@ __device__ __forceinline__ int match_run(const OpReader &ops, int c)
 // shared atomics) and per CTA before one global atomic each; the per-position vectors and the histograms get few,
 // scattered hits per row and go straight to global memory.
 constexpr int NSCALAR = CRGPU_NUM_COUNTERS + 5;
-__device__ __forceinline__ void quantify_row(const QuantArgs &a, const int64_t i, unsigned *sc)
+// The light part: a row that came in UNMODIFIED (identity 100, CORE:2014) only bumps two counters.  Returns true when the
+// row needs quantify_row.  (With an N in the amplicon every row takes the long way: its markup is re-read first.)
+__device__ __forceinline__ bool quantify_row_light(const QuantArgs &a, const int64_t i, unsigned *sc)
+{
+    if (!a.unmod_in[i]) return true;
+    crgpu_read_rec rec;
+    rec.cls = CRGPU_C_UNMODIFIED; rec.pad[0] = rec.pad[1] = rec.pad[2] = 0;
+    rec.n_mutated = rec.n_inserted = rec.n_deleted = 0;
+    a.recs[i] = rec;
+    atomicAdd(sc + CRGPU_NUM_COUNTERS + 4, 1u);            // rows seen (n_total)
+    atomicAdd(sc + CRGPU_NUM_COUNTERS + 0, 1u);            // CORE:480-481
+    return false;
+}
+
+__device__ __forceinline__ void quantify_row(const QuantArgs &a, const int64_t i, unsigned *sc, const VecAcc V)
 {
     const int L = a.L, W = a.W, flags = a.flags;
     const int n = a.alnlen[i];
@@ -188,23 +211,22 @@ __device__ __forceinline__ void quantify_row(const QuantArgs &a, const int64_t i
     rec.cls = (uint8_t)cls;
     const bool hide = flags & CRGPU_Q_HIDE_OUTSIDE;
     const bool windowed = cls == CRGPU_C_NHEJ && (flags & CRGPU_Q_WINDOW);
-    unsigned long long *V = a.vectors;
 
     // ---- vectors that show every event (CORE:578-606) ----
     if (cls == CRGPU_C_MIXED) {
-        add_bits(V + (size_t)CRGPU_V_MUT_MIXED * L, S, W); add_bits(V + (size_t)CRGPU_V_DEL_MIXED * L, D, W);
-        add_bits(V + (size_t)CRGPU_V_INS_MIXED * L, I, W);
+        V.add_bits(CRGPU_V_MUT_MIXED, S, W); V.add_bits(CRGPU_V_DEL_MIXED, D, W);
+        V.add_bits(CRGPU_V_INS_MIXED, I, W);
     } else if (cls == CRGPU_C_HDR) {
-        add_bits(V + (size_t)CRGPU_V_MUT_HDR * L, S, W); add_bits(V + (size_t)CRGPU_V_DEL_HDR * L, D, W);
-        add_bits(V + (size_t)CRGPU_V_INS_HDR * L, I, W);
+        V.add_bits(CRGPU_V_MUT_HDR, S, W); V.add_bits(CRGPU_V_DEL_HDR, D, W);
+        V.add_bits(CRGPU_V_INS_HDR, I, W);
     } else if (cls == CRGPU_C_NHEJ && !hide) {
-        add_bits(V + (size_t)CRGPU_V_MUT * L, S, W); add_bits(V + (size_t)CRGPU_V_DEL * L, D, W);
-        add_bits(V + (size_t)CRGPU_V_INS * L, I, W);
+        V.add_bits(CRGPU_V_MUT, S, W); V.add_bits(CRGPU_V_DEL, D, W);
+        V.add_bits(CRGPU_V_INS, I, W);
     }
     {
         uint32_t A[MAXW];
         for (int w = 0; w < W; ++w) A[w] = S[w] | D[w] | I[w];
-        add_bits(V + (size_t)CRGPU_V_ANY * L, A, W);                  // also for rows re-classified UNMODIFIED (Q8)
+        V.add_bits(CRGPU_V_ANY, A, W);                  // also for rows re-classified UNMODIFIED (Q8)
     }
     const int cls_slot = cls == CRGPU_C_UNMODIFIED ? 0 : cls == CRGPU_C_NHEJ ? 1 : cls == CRGPU_C_HDR ? 2 : 3;
     atomicAdd(sc + CRGPU_NUM_COUNTERS + cls_slot, 1u);
@@ -234,8 +256,8 @@ __device__ __forceinline__ void quantify_row(const QuantArgs &a, const int64_t i
                     if (keep) {
                         n_ins += size;
                         const int wl = fl >= 0 ? fl : L + fl, wr = fr >= 0 ? fr : L + fr;
-                        atomicAdd(V + (size_t)CRGPU_V_AVG_INS * L + wl, (unsigned long long)size);
-                        if (wr != wl) atomicAdd(V + (size_t)CRGPU_V_AVG_INS * L + wr, (unsigned long long)size);
+                        V.add(CRGPU_V_AVG_INS, wl, (unsigned)size);
+                        if (wr != wl) V.add(CRGPU_V_AVG_INS, wr, (unsigned)size);
                         if (fs && ((fl >= 0 && get_bit(a.exon, fl)) || (fr >= 0 && get_bit(a.exon, fr)))) {
                             exon_len += size; have_len = true; exons_modified = true;        // CORE:665-670
                         }
@@ -257,7 +279,7 @@ __device__ __forceinline__ void quantify_row(const QuantArgs &a, const int64_t i
                     any_del_kept = true;
                     for (int p = p0; p < p0 + size; ++p) {
                         set_bit(Dk, p);
-                        atomicAdd(V + (size_t)CRGPU_V_AVG_DEL * L + p, (unsigned long long)size);
+                        V.add(CRGPU_V_AVG_DEL, p, (unsigned)size);
                     }
                 }
                 continue;
@@ -269,8 +291,8 @@ __device__ __forceinline__ void quantify_row(const QuantArgs &a, const int64_t i
     const uint32_t *Dflat = (windowed && any_del_kept) ? Dk : D;
 
     if (cls == CRGPU_C_NHEJ && hide) {                                 // CORE:643-649 (Q5)
-        add_bits(V + (size_t)CRGPU_V_MUT * L, S, W); add_bits(V + (size_t)CRGPU_V_DEL * L, Dflat, W);
-        add_bits(V + (size_t)CRGPU_V_INS * L, I, W);
+        V.add_bits(CRGPU_V_MUT, S, W); V.add_bits(CRGPU_V_DEL, Dflat, W);
+        V.add_bits(CRGPU_V_INS, I, W);
     }
     int n_mut = 0;
     for (int w = 0; w < W; ++w) n_mut += __popc(S[w]);
@@ -302,28 +324,56 @@ __device__ __forceinline__ void quantify_row(const QuantArgs &a, const int64_t i
             }
         } else {
             atomicAdd(sc + CRGPU_K_NON_MOD_NON_FRAMESHIFT, 1u);
-            add_bits(V + (size_t)CRGPU_V_INS_NONCODING * L, I, W);
-            add_bits(V + (size_t)CRGPU_V_DEL_NONCODING * L, Dflat, W);
-            add_bits(V + (size_t)CRGPU_V_MUT_NONCODING * L, S, W);
+            V.add_bits(CRGPU_V_INS_NONCODING, I, W);
+            V.add_bits(CRGPU_V_DEL_NONCODING, Dflat, W);
+            V.add_bits(CRGPU_V_MUT_NONCODING, S, W);
         }
     }
 }
 
-__global__ void __launch_bounds__(128) k_quantify(const QuantArgs a)
+// Rows that need the long way are a fraction of a CTA's rows, spread over its warps: they are gathered first, so that the
+// warps that walk op rows are full (thread-per-row over all rows ran with 4.6 of 32 lanes active on average).
+// A few CTAs per SM walk over the rows in chunks of QUANT_THREADS (fewer flushes of the shared vectors).
+constexpr int QUANT_THREADS = 256;
+__global__ void __launch_bounds__(QUANT_THREADS) k_quantify(const QuantArgs a)
 {
+    extern __shared__ unsigned sv[];                       // [CRGPU_NUM_VECTORS][L]
     __shared__ unsigned sc[NSCALAR];
+    __shared__ int heavy[QUANT_THREADS];
+    __shared__ int nheavy;
+    const int nv = CRGPU_NUM_VECTORS * a.L;
+    for (int k = threadIdx.x; k < nv; k += QUANT_THREADS) sv[k] = 0;
     if (threadIdx.x < NSCALAR) sc[threadIdx.x] = 0;
-    __syncthreads();
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < a.n && (!a.active || (a.active[i] & a.active_bit))) quantify_row(a, i, sc);
-    __syncthreads();
+    const VecAcc V{sv, a.L};
+    for (int64_t base = (int64_t)blockIdx.x * QUANT_THREADS; base < a.n; base += (int64_t)gridDim.x * QUANT_THREADS) {
+        if (threadIdx.x == 0) nheavy = 0;
+        __syncthreads();
+        const int64_t i = base + threadIdx.x;
+        if (i < a.n && (!a.active || (a.active[i] & a.active_bit)) && quantify_row_light(a, i, sc))
+            heavy[atomicAdd(&nheavy, 1)] = threadIdx.x;
+        __syncthreads();
+        if ((int)threadIdx.x < nheavy) quantify_row(a, base + heavy[threadIdx.x], sc, V);
+        __syncthreads();
+    }
     if (threadIdx.x < NSCALAR && sc[threadIdx.x]) atomicAdd(a.counters + threadIdx.x, (unsigned long long)sc[threadIdx.x]);
+    for (int k = threadIdx.x; k < nv; k += QUANT_THREADS)
+        if (sv[k]) atomicAdd(a.vectors + k, (unsigned long long)sv[k]);
 }
 
 cudaError_t launch_quantify(const QuantArgs &a, cudaStream_t s)
 {
     if (a.n <= 0) return cudaSuccess;
-    k_quantify<<<(unsigned)((a.n + 127) / 128), 128, 0, s>>>(a);
+    int dev = 0, sms = 0;
+    cudaError_t e;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    const size_t smem = (size_t)CRGPU_NUM_VECTORS * a.L * sizeof(unsigned);
+    if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k_quantify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    // every row adds at most L to a 32-bit shared counter: a CTA must see fewer than 2^32 / L rows (2^22 with L = 1024)
+    const int64_t chunks = (a.n + QUANT_THREADS - 1) / QUANT_THREADS;
+    const int64_t min_grid = (a.n + ((int64_t)1 << 21) - 1) >> 21;
+    const unsigned grid = (unsigned)std::max<int64_t>(min_grid, std::min<int64_t>(chunks, (int64_t)sms * 6));
+    k_quantify<<<grid, QUANT_THREADS, smem, s>>>(a);
     return cudaGetLastError();
 }
 
