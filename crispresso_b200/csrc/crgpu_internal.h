@@ -268,7 +268,7 @@ cudaError_t select_flagged(const uint8_t *flags, int64_t n, int bit, int32_t *ou
 cudaError_t allele_groups(const uint8_t *reads, const int64_t *offsets, int64_t n, const uint8_t *kept, const int32_t *rc_read,
                           int64_t nrc, const uint32_t *ops_fw, const uint32_t *ops_rc, int64_t ops_stride,
                           const crgpu_aln_rec *aln_fw, const crgpu_aln_rec *aln_rc, const crgpu_read_rec *rec_fw,
-                          const crgpu_read_rec *rec_rc, void *scratch, size_t scratch_bytes, cudaStream_t s,
+                          const crgpu_read_rec *rec_rc, int reads_upper, void *scratch, size_t scratch_bytes, cudaStream_t s,
                           int32_t **d_rep_sorted, int32_t **d_count_sorted, int **d_nruns, int **d_err, uint64_t **d_key_pairs);
 // alignment core (crgpu_api.cu): device pointers only
 int build_plan(crgpu_ctx *ctx, const uint8_t *d_reads, const int64_t *d_offsets, const int32_t *d_subset, int64_t nsub);

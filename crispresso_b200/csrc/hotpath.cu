@@ -642,8 +642,10 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
         span_begin(ctx, T_OTHER);
         CK(allele_groups(d_reads, d_off, n, d_kept, nrc ? ctx->aux[3].as<int32_t>() : nullptr, nrc, d_ops,
                          nrc ? ctx->ops_rc.as<uint32_t>() : nullptr, ops_stride, d_aln, d_rc_aln, d_recs, d_rc_recs,
+                         // (reads that came as BAM 4-bit codes were unpacked to upper case)
+                         staged_slot >= 0 && ctx->stage_pend[staged_slot].format == CRGPU_READS_BAM4 ? 1 : 0,
                          ctx->alleles.p, sb, s, &d_rep, &d_cnt, &d_nruns, &d_aerr, &d_kp));
-        span_end(ctx, 4);     // k_hash_rows, k_check_groups, k_group_reps, k_gather_i32 (+ cub's own kernels, not counted)
+        span_end(ctx, 5);     // k_hash_rows, k_check_groups, k_group_reps, k_gather_i32, k_allele_keys (+ cub's own kernels, not counted)
         int h3[3] = {0, 0, 0};                                  // runs, collision flag, "one run is the rows that were not kept"
         CK(fetch_small(ctx, h3, d_nruns, 12, s));
         CK(fetch_wait(ctx, s));
