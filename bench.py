@@ -232,6 +232,29 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """One process per GPU: run on the cores of the NUMA node the GPU's PCIe root hangs off, so that the pinned staging
+    buffers (first touch) and the library's mailbox live in that node's memory -- eight ranks copying ~200 MB per step each
+    through one node's memory controller is what the end-to-end arm scaled against.  Best effort: returns the node or None."""
+    try:
+        props = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def main():
     args = parse()
@@ -249,6 +272,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = Context(local)
@@ -491,7 +515,8 @@ def main():
                    "alignments_per_read": n_alignments / max(n, 1), "calls_per_step": len(jobs),
                    "l2": "inputs and traceback exceed L2 (reads %d MB per GPU per step, traceback scratch up to 8 GB per batch)" % (
                        sum(j.buf.nbytes for j in jobs) >> 20),
-                   "parallelism": "reads sharded x%d (%s scaling)" % (world, args.scaling)},
+                   "parallelism": "reads sharded x%d (%s scaling)" % (world, args.scaling),
+                   "numa_node_of_rank0": numa},
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": e2e_ms / args.steps, "results_equal_device_arm": same,
                 "distinct_alleles": n_alleles,

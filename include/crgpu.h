@@ -267,10 +267,11 @@ int crgpu_align_quantify(crgpu_ctx *ctx, int mem, const char *amplicon, int ampl
                          const uint8_t *reads, const int64_t *offsets, int64_t n, crgpu_path_out *out);
 
 /* ---- staged inputs: the NEXT batch of reads is copied while the current one is computed ------- *
- * crgpu_stage_reads starts the host-to-device copy of a batch on the context's copy stream into staging slot 0 or 1
- * and returns at once (`reads` / `offsets` must stay valid -- and should be pinned -- until the batch has been
- * consumed); crgpu_align_quantify_staged waits for that copy and runs crgpu_align_quantify on the batch, with every
- * output in HOST memory.  Typical loop: stage(0, b0); for k: stage((k+1)&1, b[k+1]); align_quantify_staged(k&1).
+ * crgpu_stage_reads registers a batch for the host-to-device copy into staging slot 0 or 1 (on the context's copy
+ * stream) and returns at once; `reads` / `offsets` must stay valid and unchanged -- and should be pinned -- until the
+ * batch has been consumed.  The copy itself starts inside the next crgpu_align_quantify* call of the context, behind its
+ * first kernel launches (or when the batch is run / crgpu_sync is called before that); crgpu_align_quantify_staged waits
+ * for it and runs crgpu_align_quantify on the batch, with every output in HOST memory.  Typical loop: stage(0, b0); for k: stage((k+1)&1, b[k+1]); align_quantify_staged(k&1).
  * format: CRGPU_READS_BYTES = one base per byte, as everywhere else; CRGPU_READS_BAM4 = two bases per byte in BAM's
  * 4-bit codes "=ACMGRSVTWYHKDBN", high nibble first, dense (base j of the batch is nibble j; offsets count BASES):
  * half the bytes over PCIe, unpacked on the device.  Codes other than A C G T N are reported per read (kept bit 3). */
