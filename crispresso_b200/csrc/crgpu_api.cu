@@ -395,6 +395,7 @@ int build_plan(crgpu_ctx *ctx, const uint8_t *d_reads, const int64_t *d_offsets,
     CK(launch_encode(d_reads, d_offsets, ctx->pair_lo.as<int32_t>(), ctx->pair_hi.as<int32_t>(), ctx->pc_off.as<int64_t>(), pl.np,
                      ctx->pc.as<uint8_t>(), d_err, ctx->d_bad, ctx->num_sms, s));
     span_end(ctx, 3);
+    if (ctx->d_bad) return CRGPU_OK;            // bases outside ACGTN(U) are flagged per read: nothing to wait for
     CK(fetch_small(ctx, &h_err, d_err, 4, s));
     CK(fetch_wait(ctx, s));
     if (h_err & 1) return fail(ctx, CRGPU_E_ALIGN, "a read contains a base outside ACGTN(U)");
@@ -442,6 +443,13 @@ int run_plan(crgpu_ctx *ctx, const char *amplicon, int La, const uint8_t *d_read
     if (pl.np == 0) return CRGPU_OK;
     int G, K;
     if (!choose_tile(La, &G, &K)) return fail(ctx, CRGPU_E_ALIGN, "no kernel tile for amplicon length %d", La);
+    // A plan of a few thousand pairs (band escapes, RC rescue) is a single wave whatever the tile: it lasts as long as one
+    // pair's systolic sweep, (read length + G) steps of K rows.  Take the flattest compiled tile that covers the amplicon.
+    if (pl.np <= 4096 && !getenv("CRGPU_TILE")) {
+        static const int flat[][2] = {{16, 16}, {16, 24}, {32, 24}};
+        for (const auto &t : flat)
+            if (t[1] < K && t[0] * t[1] >= La && tile_available(t[0], t[1])) { G = t[0]; K = t[1]; break; }
+    }
     const int GK = G * K, P = GK - La;
     const int maxlen = pl.maxlen;
     if ((int64_t)scale * 5 * std::min(La, maxlen) + 64 >= MAX_ABS_SCORE ||
