@@ -85,6 +85,14 @@ __device__ __forceinline__ uint8_t comp_upper(uint8_t c)
 
 __device__ __forceinline__ int half16(uint32_t w, int h) { return (int)((w >> (16 * h)) & 0xffffu); }
 
+// base_code(x) == base_code(y) for bases of the accepted alphabet (A C G T U N, either case; reads with anything else are
+// flagged by k_encode_pairs and their records cleared): upper case, U read as T
+__device__ __forceinline__ uint32_t fold_base(uint32_t c)
+{
+    c &= 0xdfu;
+    return c == 'U' ? (uint32_t)'T' : c;
+}
+
 // ix[0, j] of needle's first row (App. A.2), true scaled value.
 __device__ int row0_ix(const uint8_t *b, int ca0, int j, int open, int ext, int scale)
 {
@@ -244,19 +252,17 @@ __global__ void __launch_bounds__(128, 9) k_traceback_walk(const WalkArgs a)    
             a.escaped[r] |= (uint8_t)a.escape_bit;
             return;
         }
-        int dir;
-        if (prev == 1 && contL) dir = 1;
-        else if (prev == 2 && contD) dir = 2;
-        else if (!(f & F_NM)) {
-            if (prev == 1 && !(f & F_NX)) dir = 1;
-            else if (prev == 2 && !(f & F_NY)) dir = 2;
-            else dir = 0;
-        }
-        else if (!(f & F_NX)) dir = 1;
-        else dir = 2;
+        // (selects, no branches: as an if-chain the three-way decision of App. A.4 was a fifth of the step's instructions)
+        const bool nm = (f & F_NM) != 0, nx = (f & F_NX) != 0, ny = (f & F_NY) != 0;
+        const bool wasL = prev == 1, wasD = prev == 2;
+        const int dir_m = (wasL & !nx) ? 1 : (wasD & !ny) ? 2 : 0;       // m is a maximum: stay in the gap state that also is
+        const int dir_g = nx ? 2 : 1;
+        int dir = nm ? dir_g : dir_m;
+        dir = (wasD & contD) ? 2 : dir;
+        dir = (wasL & contL) ? 1 : dir;
         if (dir == 0) {
             const uint8_t ca = amp[y], cb = b[x];
-            const bool same = base_code(ca) == base_code(cb);
+            const bool same = fold_base(ca) == fold_base(cb);
             ident += same;
             if (want) { ro[dirn * n] = OUTC(ca); mo[dirn * n] = same ? '|' : '.'; qo[dirn * n] = OUTC(cb); }
             EMIT_OP(same ? 0 : 1);
