@@ -392,3 +392,42 @@ def test_diagonal_shortcut_changes_nothing(La, read_len, sigma, hdr_on):
             assert np.array_equal(lean.recs, ref.recs) and np.array_equal(lean.tenths_rep, ref.tenths_rep)
     finally:
         c.close()
+
+
+def test_staged_batches_in_any_call_order(ctx):
+    """crgpu_stage_reads only registers a batch; its copy starts inside the next call (or at crgpu_sync, or when the batch itself
+    is run first).  Whatever the order of stage / sync / run, every batch must give what the plain call gives, and deferred
+    per-read outputs must be in host memory after crgpu_sync."""
+    amp, guide, cut, hdr = synth.make_case(91, 180)
+    inc = hotpath.include_mask(len(amp), hotpath.cut_points_from_guides(amp, guide), 1, 15, 15)
+    flags = hotpath.quant_flags(hdr)
+    sets = [synth.make_reads(amp, hdr, cut, n, seed=92 + k, read_len=180, rc_frac=0.05) for k, n in enumerate((900, 500, 1300))]
+    want = [hotpath.run_hot_path(ctx, amp, s, hdr_amplicon=hdr, flags=flags, inc=inc) for s in sets]
+
+    def outputs(n):
+        return {"kept": np.zeros(n, np.uint8), "aln": np.zeros(n, _lib.ALN_REC), "recs": np.zeros(n, _lib.READ_REC),
+                "tenths_rep": np.zeros(n, np.int32), "rc_read": np.zeros(n, np.int32), "rc_aln": np.zeros(n, _lib.ALN_REC),
+                "rc_recs": np.zeros(n, _lib.READ_REC)}
+
+    def same(out, ref):
+        assert np.array_equal(out["kept"], ref.kept) and out["recs"].tobytes() == ref.recs.tobytes()
+        for f in _lib.ALN_REC.names:
+            if f != "aln_off":
+                assert np.array_equal(out["aln"][f], ref.aln[f]), f
+        assert np.array_equal(out["tenths_rep"], ref.tenths_rep)
+
+    for deferred in (False, True):
+        pipe = hotpath.StagedPipeline(ctx, amp, hdr_amplicon=hdr, flags=flags, inc=inc, deferred=deferred)
+        outs = [outputs(len(s[1]) - 1) for s in sets]
+        # two batches staged back to back, then run: the first one's copy starts when it is run, the second one's inside that call
+        pipe.stage(*sets[0]); pipe.stage(*sets[1])
+        pipe.run(outs[0]); pipe.run(outs[1])
+        # a batch staged, the context synchronised (copy forced), then run; its outputs fetched by the final sync
+        pipe.stage(*sets[2])
+        ctx.sync()
+        pipe.run(outs[2])
+        red, _table = pipe.take_results(sync=True)
+        for o, w in zip(outs, want):
+            same(o, w)
+        total = want[0].red.results() + want[1].red.results() + want[2].red.results()
+        assert np.array_equal(red.results(), total)
