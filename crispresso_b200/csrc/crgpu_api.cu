@@ -22,6 +22,8 @@ int crgpu_create(crgpu_ctx **out, int device)
         if (c->stream) cudaStreamDestroy(c->stream);
         if (c->stream2) cudaStreamDestroy(c->stream2);
         if (c->stream3) cudaStreamDestroy(c->stream3);
+        if (c->stream4) cudaStreamDestroy(c->stream4);
+        for (int i = 0; i < 2; ++i) if (c->walk_side[i]) cudaEventDestroy(c->walk_side[i]);
         if (c->stream_copy) cudaStreamDestroy(c->stream_copy);
         for (int i = 0; i < 2; ++i) { if (c->staged_ev[i]) cudaEventDestroy(c->staged_ev[i]); if (c->out_ev[i]) cudaEventDestroy(c->out_ev[i]); if (c->out_ready[i]) cudaEventDestroy(c->out_ready[i]); }
         if (c->ready) cudaEventDestroy(c->ready);
@@ -49,6 +51,8 @@ int crgpu_create(crgpu_ctx **out, int device)
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail();
     if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) return bail();
     if (cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking) != cudaSuccess) return bail();
+    if (cudaStreamCreateWithFlags(&c->stream4, cudaStreamNonBlocking) != cudaSuccess) return bail();
+    for (int i = 0; i < 2; ++i) if (cudaEventCreateWithFlags(&c->walk_side[i], cudaEventDisableTiming) != cudaSuccess) return bail();
     if (cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking) != cudaSuccess) return bail();
     if (cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming) != cudaSuccess) return bail();
     for (int i = 0; i < 2; ++i) {
@@ -76,6 +80,7 @@ void crgpu_destroy(crgpu_ctx *c)
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->stream2);
     cudaStreamSynchronize(c->stream3);
+    cudaStreamSynchronize(c->stream4);
     cudaStreamSynchronize(c->stream_copy);
     DBuf *all[] = {&c->reads, &c->offsets, &c->amp, &c->prof, &c->pc, &c->pc_off, &c->plen, &c->pair_lo, &c->pair_hi,
                    &c->order, &c->plan_hist, &c->plan_tab, &c->tb2, &c->lastrow2, &c->lastcol2, &c->tb, &c->lastrow, &c->lastcol, &c->errflag, &c->recs, &c->sref, &c->smark, &c->sqry, &c->ops, &c->ops_rc, &c->alleles, &c->prof_h, &c->amp_h, &c->tbh, &c->tbh2,
@@ -96,6 +101,8 @@ void crgpu_destroy(crgpu_ctx *c)
     for (auto &slot : c->stage_out) for (auto &b : slot) b.release();
     if (c->mbox_h) cudaFreeHost(c->mbox_h);
     cudaStreamDestroy(c->stream_copy);
+    cudaStreamDestroy(c->stream4);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->walk_side[i]); c->rlist_side[i].release(); }
     cudaStreamDestroy(c->stream3);
     cudaStreamDestroy(c->stream2);
     cudaStreamDestroy(c->stream);
@@ -906,8 +913,8 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
     const size_t selbytes = select_scratch_bytes((int64_t)max_bp * 2);
     if (diag) {
         if (!d_fast) return fail(ctx, CRGPU_E_ARG, "run_plan_band: the diagonal shortcut needs the per-read flag array");
-        CK(ctx->need_cnt.reserve(nbatches * 12));
-        CK(cudaMemsetAsync(ctx->need_cnt.p, 0, nbatches * 12, ctx->stream));
+        CK(ctx->need_cnt.reserve(nbatches * 16));
+        CK(cudaMemsetAsync(ctx->need_cnt.p, 0, nbatches * 16, ctx->stream));
     }
     for (int i = 0; i < (two ? 2 : 1); ++i) {
         CK(tbA[i]->reserve((size_t)max_bp * G * W * K * 2));
@@ -919,7 +926,7 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         if (diag) {
             CK(ctx->need[i].reserve((size_t)max_bp)); CK(ctx->plist[i].reserve((size_t)max_bp * 4));
             CK(ctx->need_read[i].reserve((size_t)max_bp * 2)); CK(ctx->rlist[i].reserve((size_t)max_bp * 8));
-            if (dual) CK(ctx->plist2[i].reserve((size_t)max_bp * 4));
+            if (dual) { CK(ctx->plist2[i].reserve((size_t)max_bp * 4)); CK(ctx->rlist_side[i].reserve((size_t)max_bp * 8)); }
             CK(ctx->selscratch[i].reserve(selbytes));
         }
         if (dual) {
@@ -1009,6 +1016,7 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
             wh.recs = d_recs_hdr; wh.ref_out = wh.mark_out = wh.qry_out = nullptr; wh.ops_out = nullptr;
         }
         FillArgs fa_up;                                                 // (amplicon band of the shortcut pairs: rows above the split)
+        const int32_t *side_list = nullptr; const int *side_n = nullptr;
         if (wa.join_out) CK(cudaMemsetAsync(wa.join_out, 0, (size_t)(fa.p1 - fa.p0) * 2 * JOIN_STRIDE * 4, sf[cur]));
         if (diag) {
             // diagonal shortcut: amplicon alignments whose traceback is provably the diagonal through the start cell are
@@ -1033,6 +1041,11 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
             wa.read_list = ctx->rlist[cur].as<int32_t>(); wa.read_list_n = d_cnt3;
             wa.fast = d_fast; wa.fast_bit = escape_bit;
             if (dual) {
+                // the HDR walks of the reads whose amplicon alignment was emitted above (need_read == 2) wait for nothing but
+                // the band pass: they run beside the amplicon walks of the other reads, on a stream of their own
+                int *d_cnt4 = ctx->need_cnt.as<int>() + 3 * nbatches + b;
+                CK(select_flagged(wd.need_read, 2 * (fa.p1 - fa.p0), 2, ctx->rlist_side[cur].as<int32_t>(), d_cnt4, ctx->selscratch[cur].p, selbytes, sf[cur]));
+                side_list = ctx->rlist_side[cur].as<int32_t>(); side_n = d_cnt4;
                 // the HDR walk of such a pair still needs the amplicon pass's flags for the rows right above the split, until it
                 // meets the amplicon alignment's diagonal at a join checkpoint: ~32 rows of sub-strips for those pairs
                 int *d_cnt2 = ctx->need_cnt.as<int>() + nbatches + b;
@@ -1052,10 +1065,22 @@ int run_plan_band(crgpu_ctx *ctx, const char *amplicon, const char *hdr_amplicon
         CK(cudaEventRecord(ctx->fill_done[cur], sf[cur]));
 
         CK(cudaStreamWaitEvent(s2, ctx->fill_done[cur], 0));
+        if (side_list) {
+            cudaStream_t s4 = two ? ctx->stream4 : s2;
+            WalkArgs ws = wh;
+            ws.read_list = side_list; ws.read_list_n = side_n;
+            if (two) CK(cudaStreamWaitEvent(s4, ctx->fill_done[cur], 0));
+            span_begin(ctx, T_WALK, s4);
+            CK(launch_walk(ws, s4));
+            span_end(ctx, 1);
+            if (two) CK(cudaEventRecord(ctx->walk_side[cur], s4));
+            wh.read_list = wa.read_list; wh.read_list_n = wa.read_list_n;      // ... and behind the amplicon walks, the HDR walks of their reads
+        }
         span_begin(ctx, T_WALK, s2);
         CK(launch_walk(wa, s2));
         if (dual) CK(launch_walk(wh, s2));
         span_end(ctx, dual ? 2 : 1);
+        if (side_list && two) CK(cudaStreamWaitEvent(s2, ctx->walk_side[cur], 0));
         CK(cudaEventRecord(ctx->walk_done[cur], s2));
         used[cur] = true;
     }

@@ -54,6 +54,9 @@ struct crgpu_ctx {
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;      // traceback walks run here, overlapped with the next batch's fill
+    cudaStream_t stream4 = nullptr;      // HDR walks of the reads whose amplicon alignment took the diagonal shortcut (beside the amplicon walks)
+    cudaEvent_t walk_side[2] = {nullptr, nullptr};
+    DBuf rlist_side[2];                  // those reads, per batch
     cudaStream_t stream3 = nullptr;      // odd fill batches: their CTAs back-fill the SMs the previous fill's tail vacates
     cudaEvent_t ready = nullptr;
     size_t l2_gran_prev = 0;             // CRGPU_L2_HINT: the device's L2 fetch granularity before crgpu_create changed it
@@ -223,7 +226,7 @@ struct ApiGuard {
     int done(int rc)
     {
         if (rc != CRGPU_OK) {
-            cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3);
+            cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(c->stream3); cudaStreamSynchronize(c->stream4);
             c->mbox_pending.clear(); c->mbox_used = 0;       // (their destinations were locals of the failed call)
             cudaGetLastError();                       // (a sticky launch error has been reported through rc already)
         }

@@ -562,6 +562,7 @@ __global__ void __launch_bounds__(256) k_diag_emit(const WalkArgs a)
     }
     if (lane != 0) return;
     a.fast[r] |= (uint8_t)a.fast_bit;
+    if (a.need_read) a.need_read[2 * pj + h] = 2;                    // emitted: this read's HDR walk need not wait for an amplicon walk
     crgpu_aln_rec rec;
     rec.score = (float)(best - BIAS) / (float)a.scale;
     rec.alnlen = n;
