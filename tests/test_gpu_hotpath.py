@@ -431,3 +431,13 @@ def test_staged_batches_in_any_call_order(ctx):
             same(o, w)
         total = want[0].red.results() + want[1].red.results() + want[2].red.results()
         assert np.array_equal(red.results(), total)
+
+
+def test_longest_amplicons_quantify_in_shared_memory(ctx):
+    """k_quantify keeps the 15 per-position vectors of a CTA in shared memory: above 819 bp that is more than the default 48 KB
+    (opt-in size, set per launch).  A 1000-bp amplicon -- close to CRGPU_MAX_AMPLICON -- against the oracle."""
+    amp, guide, cut, hdr = synth.make_case(4321, 1000)
+    packed = synth.make_reads(amp, hdr, cut, 160, seed=4321, read_len=1000)
+    res, ora = _run_both(ctx, amp, packed, hdr_amp=hdr, guide=guide, want_rows=False)
+    _assert_same(res, ora, has_hdr=True, amp=amp)
+    assert ora["classes"]["NHEJ"] > 5
