@@ -313,6 +313,7 @@ cudaError_t fetch_small(crgpu_ctx *ctx, void *h_dst, const void *d_src, size_t b
     if (!ctx->mbox_h || off + bytes > ctx->mbox_bytes) return cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, s);
     ctx->mbox_used = off + bytes;
     ctx->mbox_pending.push_back({h_dst, off, bytes});
+    ctx->launches[T_OTHER] += 1;                                  // (k_copy_small: counted, not timed)
     return copy_small(ctx->mbox_d + off, reinterpret_cast<const uint8_t *>(d_src), bytes, s);
 }
 
@@ -333,6 +334,7 @@ cudaError_t push_small(crgpu_ctx *ctx, void *d_dst, const void *h_src, size_t by
     if (!ctx->mbox_h || off + bytes > ctx->mbox_bytes) return cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, s);
     ctx->mbox_used = off + bytes;
     memcpy(ctx->mbox_h + off, h_src, bytes);
+    ctx->launches[T_OTHER] += 1;
     return copy_small(reinterpret_cast<uint8_t *>(d_dst), ctx->mbox_d + off, bytes, s);
 }
 
@@ -1205,6 +1207,7 @@ static int issue_stage(crgpu_ctx *ctx, int slot)
         k_unpack_bam4<<<(unsigned)((nthreads + 255) / 256), 256, 0, cs>>>(ctx->stage_pack[slot].as<uint8_t>(), sp.total,
                                                                          ctx->stage_reads[slot].as<uint8_t>());
         CK(cudaGetLastError());
+        ctx->launches[T_OTHER] += 1;                              // (k_unpack_bam4)
     }
     CK(cudaEventRecord(ctx->staged_ev[slot], cs));
     return CRGPU_OK;

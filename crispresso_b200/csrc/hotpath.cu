@@ -486,6 +486,7 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
         CK(cudaMemsetAsync(d_cnt + 1, 0, 8, s));
         k_count_escapes<<<(unsigned)std::min<int64_t>((n + 255) / 256, 1024), 256, 0, s>>>(d_esc, n, d_cnt + 1);
         CK(cudaGetLastError());
+        ctx->launches[T_OTHER] += 1;
         CK(select_flagged(d_esc, n, has_hdr ? 3 : 1, d_sel, d_cnt, ctx->alleles.p, sb, s));
         int h_cnt[3] = {0, 0, 0};                           // union, amplicon pass, HDR pass
         CK(fetch_small(ctx, h_cnt, d_cnt, 12, s));
@@ -639,13 +640,14 @@ static int align_quantify_impl(crgpu_ctx *ctx, int mem, const char *amplicon, in
         const size_t sb = allele_scratch_bytes(m);
         CK(ctx->alleles.reserve(sb));
         int32_t *d_rep, *d_cnt; int *d_nruns, *d_aerr; uint64_t *d_kp;
+        const bool reads_upper = staged_slot >= 0 && ctx->stage_pend[staged_slot].format == CRGPU_READS_BAM4;
         span_begin(ctx, T_OTHER);
         CK(allele_groups(d_reads, d_off, n, d_kept, nrc ? ctx->aux[3].as<int32_t>() : nullptr, nrc, d_ops,
                          nrc ? ctx->ops_rc.as<uint32_t>() : nullptr, ops_stride, d_aln, d_rc_aln, d_recs, d_rc_recs,
                          // (reads that came as BAM 4-bit codes were unpacked to upper case)
-                         staged_slot >= 0 && ctx->stage_pend[staged_slot].format == CRGPU_READS_BAM4 ? 1 : 0,
+                         reads_upper ? 1 : 0,
                          ctx->alleles.p, sb, s, &d_rep, &d_cnt, &d_nruns, &d_aerr, &d_kp));
-        span_end(ctx, 5);     // k_hash_rows, k_check_groups, k_group_reps, k_gather_i32, k_allele_keys (+ cub's own kernels, not counted)
+        span_end(ctx, reads_upper ? 5 : 6);     // (k_any_lower,) k_hash_rows, k_check_groups, k_group_reps, k_gather_i32, k_allele_keys (+ cub's own kernels, not counted)
         int h3[3] = {0, 0, 0};                                  // runs, collision flag, "one run is the rows that were not kept"
         CK(fetch_small(ctx, h3, d_nruns, 12, s));
         CK(fetch_wait(ctx, s));
