@@ -230,3 +230,58 @@ def test_a_forward_row_and_an_rc_row_with_the_same_text_hash_alike():
         # a lower-case copy of a forward read is another allele (align_seq keeps the case); RC rows are upper-cased
         assert row_hash_model(read.lower(), fwd[::-1], False, fields) != fw
         assert row_hash_model(_revcomp(read).lower(), fwd, True, fields) == rc
+
+
+# ---- traceback_walk.cu: the walk's three-way decision (App. A.4) ------------------------------------------------------------
+F_NM, F_NX, F_NY = 1, 2, 4
+
+
+def direction_if_chain(prev, contL, contD, f):
+    """The decision as SURVEY App. A.4 states it (and as the walker had it before it became branch-free)."""
+    if prev == 1 and contL:
+        return 1
+    if prev == 2 and contD:
+        return 2
+    if not (f & F_NM):
+        if prev == 1 and not (f & F_NX):
+            return 1
+        if prev == 2 and not (f & F_NY):
+            return 2
+        return 0
+    if not (f & F_NX):
+        return 1
+    return 2
+
+
+def direction_selects(prev, contL, contD, f):
+    """traceback_walk.cu: the same decision as selects."""
+    nm, nx, ny = (f & F_NM) != 0, (f & F_NX) != 0, (f & F_NY) != 0
+    wasL, wasD = prev == 1, prev == 2
+    dir_m = 1 if (wasL and not nx) else 2 if (wasD and not ny) else 0
+    dir_g = 2 if nx else 1
+    d = dir_g if nm else dir_m
+    d = 2 if (wasD and contD) else d
+    d = 1 if (wasL and contL) else d
+    return d
+
+
+def test_branch_free_direction_equals_the_if_chain_on_every_input():
+    for prev in (0, 1, 2):
+        for contL in (False, True):
+            for contD in (False, True):
+                for f in range(32):
+                    assert direction_selects(prev, contL, contD, f) == direction_if_chain(prev, contL, contD, f)
+
+
+def test_case_folded_identity_equals_the_base_code_compare():
+    """fold_base(x) == fold_base(y) <=> base_code(x) == base_code(y) on the accepted alphabet (A C G T U N, either case)."""
+    code = {"A": 0, "C": 1, "G": 2, "T": 3, "U": 3, "N": 4}
+
+    def fold(c):
+        c &= 0xDF
+        return ord("T") if c == ord("U") else c
+
+    alphabet = [ord(ch) for ch in "ACGTUNacgtun"]
+    for x in alphabet:
+        for y in alphabet:
+            assert (fold(x) == fold(y)) == (code[chr(x).upper()] == code[chr(y).upper()])
